@@ -1,0 +1,151 @@
+"""Generate tests/golden/* by EXECUTING THE REFERENCE (TEST INFRASTRUCTURE; build container only).
+
+    python -m oracle.make_golden
+
+Inputs are seeded synthetic minibatches from adapted_b200.synth.make_reads; each golden file records the
+generator arguments and a sha256 of the generated ADC blob (so a drifting generator is detected instead
+of silently comparing different inputs) together with what the reference returned for every
+DetectResults field.  The reference is run from the patched scratch copy built by oracle/build_ref.py
+with this container's numpy/scipy/torch/pandas (versions recorded in the file) and the
+oracle's bottleneck stand-in (third-party, absent from the image: PARITY UNPINNED for that dependency).
+"""
+from __future__ import annotations
+
+import gzip
+import hashlib
+import json
+import logging
+import os
+import sys
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from adapted_b200.config import config_as_dict  # noqa: E402
+from adapted_b200.synth import make_reads  # noqa: E402
+from oracle import build_ref  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+CASES = [
+    # name, seam, chemistry/config, n, seed, generator kwargs
+    ("llr_rna002_basic", "llr2", "rna002", 48, 11, {}),
+    ("llr_rna002_stress", "llr2", "rna002", 32, 12, {"stress": True}),
+    ("llr_rna002_lost_minibatch", "llr2", "rna002", 8, 13, {"short_frac": 1.0}),
+    ("cnn_rna004_basic", "cnn", "rna004", 48, 21, {}),
+    ("cnn_rna004_short", "cnn", "rna004", 64, 22, {"short_frac": 0.3}),
+    ("cnn_rna004_stress", "cnn", "rna004", 32, 23, {"stress": True}),
+    ("start_peak_rna004_basic", "start_peak", "rna004", 48, 31, {}),
+    ("start_peak_rna004_poisoned", "start_peak", "rna004", 8, 32, {"short_frac": 0.5}),
+]
+
+
+def _jsonable(v):
+    if v is None or isinstance(v, (str, bool)):
+        return v
+    if isinstance(v, np.ndarray):
+        return {"array": v.tolist(), "dtype": str(v.dtype)}
+    if isinstance(v, (np.bool_,)):
+        return bool(v)
+    if isinstance(v, (int, np.integer)):
+        return int(v)
+    if isinstance(v, (float, np.floating)):
+        return float(v)  # float32 -> float64 is exact; repr round-trips
+    raise TypeError(type(v))
+
+
+def reference_configs():
+    from adapted.config.base import nested_config_from_dict
+    from adapted.config.sig_proc import SigProcConfig, config_name_to_dict, get_chemistry_specific_config
+
+    out = {}
+    for chem in ("rna002", "rna004"):
+        spc = get_chemistry_specific_config(chem)
+        spc.update_primary_method()
+        spc.update_sig_preload_size()
+        out[("plain", chem)] = spc
+        d = config_name_to_dict({"rna002": "rna002_70bps@v0.2.4", "rna004": "rna004_130bps@v0.2.4"}[chem])
+        d["rna_start_peak"]["detect_rna_start_peak"] = True
+        d["llr_boundaries"]["llr_detect"] = False
+        d["cnn_boundaries"]["cnn_detect"] = False
+        d["mvs_polya"]["mvs_detect_check"] = False
+        d["med_shift"]["detect_med_shift"] = True
+        sp = nested_config_from_dict(d, SigProcConfig)
+        sp.update_primary_method()
+        sp.update_sig_preload_size()
+        out[("start_peak", chem)] = sp
+    return out
+
+
+def main():
+    if not build_ref.reference_present():
+        sys.exit("needs /root/reference")
+    build_ref.import_reference()
+    logging.disable(logging.CRITICAL)
+    warnings.simplefilter("ignore")
+    import pandas
+    import scipy
+    import torch
+    from adapted.detect.cnn import load_cnn_model
+    from adapted.detect.combined import combined_detect_cnn, combined_detect_llr2, combined_detect_start_peak
+
+    os.makedirs(GOLDEN, exist_ok=True)
+    cfgs = reference_configs()
+    model = load_cnn_model(cfgs[("plain", "rna004")].cnn_boundaries.model_name)
+    np.savez_compressed(
+        os.path.join(GOLDEN, "cnn_weights_rna004_130bps_v0.2.4.npz"),
+        **{k: v.detach().numpy() for k, v in model.state_dict().items()},
+    )
+    versions = dict(numpy=np.__version__, scipy=scipy.__version__, torch=torch.__version__,
+                    pandas=pandas.__version__, reference="KleistLab/ADAPTed v0.2.4",
+                    bottleneck="oracle.bn_restate stand-in (unpinned)")
+    for name, seam, chem, n, seed, kw in CASES:
+        spc = cfgs[("start_peak" if seam == "start_peak" else "plain", chem)]
+        batch = make_reads(n, chem, spc.sig_preload_size, seed=seed, **kw)
+        x = batch.to_dense_pa()
+        rec = dict(name=name, seam=seam, chemistry=chem, n=n, seed=seed, gen_kwargs=kw,
+                   m=int(spc.sig_preload_size), adc_sha256=hashlib.sha256(batch.adc.tobytes()).hexdigest(),
+                   config=config_as_dict(spc), versions=versions)
+        try:
+            if seam == "llr2":
+                res = combined_detect_llr2(x, batch.full_lens, spc)
+            elif seam == "cnn":
+                res = combined_detect_cnn(x, batch.full_lens, model, spc)
+            else:
+                res = combined_detect_start_peak(x, batch.full_lens, spc)
+            rec["results"] = [{k: _jsonable(v) for k, v in r.to_dict().items()} for r in res]
+            n_pass = sum(bool(r.success) for r in res)
+        except Exception as e:  # whole-minibatch failure
+            rec["raises"] = dict(type=type(e).__name__, message=str(e))
+            n_pass = -1
+        path = os.path.join(GOLDEN, name + ".json.gz")
+        with gzip.GzipFile(path, "wb", mtime=0) as f:
+            f.write(json.dumps(rec).encode())
+        print(f"{name}: n={n} pass={n_pass} -> {os.path.relpath(path, ROOT)} ({os.path.getsize(path)} B)")
+
+    # kernel-level golden vectors for c_llr_trace incl. the early-stop dispatch branches
+    from adapted.detect._c_llr import c_llr_trace
+
+    rng = np.random.default_rng(99)
+    arrays = {}
+    for i in range(6):
+        nn = int(rng.integers(300, 1650))
+        k1, k2 = sorted(rng.integers(20, nn - 20, size=2))
+        sig = np.concatenate([rng.normal(-1, 1, k1), rng.normal(1.5, .3, k2 - k1), rng.normal(.5, 1.4, nn - k2)])
+        sig = sig.astype(np.float32).astype(np.float64)
+        arrays[f"x{i}"] = sig
+        for tag, args in (("full", (0, nn - 1, 5, 5, 1, 0, 0, 0, 0, 0, 0)),
+                          ("aes", (0, nn - 1, 5, 5, 1, 1, 100, 20, 0, 0, 0)),
+                          ("pes", (0, nn - 1, 5, 5, 1, 1, 100, 20, 1, 30, 10)),
+                          ("tail", (int(k1), nn - 1, 1, 1, 1, 0, 0, 0, 0, 0, 0))):
+            arrays[f"g{i}_{tag}"] = c_llr_trace(sig, *args, 0)
+            arrays[f"a{i}_{tag}"] = np.asarray(args, dtype=np.int64)
+    np.savez_compressed(os.path.join(GOLDEN, "c_llr_trace.npz"), **arrays)
+    print("c_llr_trace.npz written")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,50 @@
+"""Load tests/golden/*.json.gz (written by oracle/make_golden.py from the executed reference)."""
+from __future__ import annotations
+
+import gzip
+import hashlib
+import json
+import os
+from typing import Any, Dict
+
+import numpy as np
+
+from adapted_b200.config import config_from_dict
+from adapted_b200.synth import make_reads
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+SEAM_CASES = {
+    "llr2": ["llr_rna002_basic", "llr_rna002_stress", "llr_rna002_lost_minibatch"],
+    "cnn": ["cnn_rna004_basic", "cnn_rna004_short", "cnn_rna004_stress"],
+    "start_peak": ["start_peak_rna004_basic", "start_peak_rna004_poisoned"],
+}
+
+
+def _decode(v):
+    if isinstance(v, dict) and "array" in v:
+        return np.asarray(v["array"], dtype=v["dtype"])
+    return v
+
+
+def load_case(name: str) -> Dict[str, Any]:
+    with gzip.open(os.path.join(GOLDEN, name + ".json.gz"), "rb") as f:
+        rec = json.loads(f.read().decode())
+    if "results" in rec:
+        rec["results"] = [{k: _decode(v) for k, v in r.items()} for r in rec["results"]]
+    cfg = rec["config"]
+    for sec in cfg.values():
+        for k, v in sec.items():
+            if isinstance(v, list):
+                sec[k] = tuple(v)
+    rec["spc"] = config_from_dict(cfg)
+    batch = make_reads(rec["n"], rec["chemistry"], rec["m"], seed=rec["seed"], **rec["gen_kwargs"])
+    sha = hashlib.sha256(batch.adc.tobytes()).hexdigest()
+    assert sha == rec["adc_sha256"], "synthetic generator drifted: golden inputs cannot be regenerated"
+    rec["batch"] = batch
+    return rec
+
+
+def load_cnn_weights() -> Dict[str, np.ndarray]:
+    with np.load(os.path.join(GOLDEN, "cnn_weights_rna004_130bps_v0.2.4.npz")) as z:
+        return {k: z[k] for k in z.files}
