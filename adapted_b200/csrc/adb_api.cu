@@ -1,0 +1,414 @@
+// C ABI of libadapted_b200.so (see include/adapted_b200.h).  Single translation unit: the kernels live in the
+// .cuh files included below.  Build: adapted_b200/csrc/build.py (nvcc -gencode arch=compute_100a,code=sm_100a).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/adapted_b200.h"
+#include "adb_common.cuh"
+#include "adb_ctx.cuh"
+#include "adb_global.cuh"
+#include "adb_llr.cuh"
+#include "adb_read_kernel.cuh"
+#include "adb_cnn.cuh"
+#include "adb_start_peak.cuh"
+
+extern "C" int adb_abi_version(void) { return ADB_ABI_VERSION; }
+extern "C" const char *adb_last_error(void) { return adb_err_string().c_str(); }
+extern "C" int adb_record_size(void) { return (int)sizeof(adb_record); }
+extern "C" int adb_config_size(void) { return (int)sizeof(adb_config); }
+extern "C" int adb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int adb_ctx_create(int device, adb_ctx **out) {
+    if (!out) return ADB_ERR_ARG;
+    *out = nullptr;
+    int n = adb_device_count();
+    if (n <= 0) {
+        set_err("no CUDA device available: adapted_b200 has no CPU fallback");
+        return ADB_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) {
+        set_err("invalid device index");
+        return ADB_ERR_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    adb_ctx *c = new adb_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    *out = c;
+    return ADB_OK;
+}
+
+extern "C" void adb_ctx_destroy(adb_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    DevBuf *all[] = {&c->states, &c->hist, &c->series, &c->given, &c->status, &c->cnn_x, &c->cnn_act0,
+                     &c->cnn_act1, &c->cnn_scores, &c->cnn_w, &c->cnn_aux, &c->h_signal, &c->h_offsets,
+                     &c->h_lens, &c->h_coff, &c->h_cscale, &c->h_records, &c->h_misc, &c->h_misc2, &c->h_misc3};
+    for (DevBuf *b : all) b->release();
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int64_t adb_ctx_launch_count(const adb_ctx *c) { return c ? c->launches : 0; }
+
+static BatchDev to_dev_view(const adb_batch &b) {
+    BatchDev d;
+    d.signal = b.signal;
+    d.sig_type = b.sig_type;
+    d.n_reads = b.n_reads;
+    d.m = b.m;
+    d.batch_size = b.batch_size;
+    d.offsets = b.offsets;
+    d.full_lens = b.full_lens;
+    d.calib_offset = b.calib_offset;
+    d.calib_scale = b.calib_scale;
+    return d;
+}
+
+static int check_batch(const adb_batch *b) {
+    if (!b || !b->signal || !b->full_lens || b->n_reads < 0 || b->m <= 0 || b->batch_size <= 0) {
+        set_err("invalid adb_batch");
+        return ADB_ERR_ARG;
+    }
+    if (b->sig_type == ADB_SIG_I16 && (!b->offsets || !b->calib_offset || !b->calib_scale)) {
+        set_err("ADB_SIG_I16 needs offsets and calibration");
+        return ADB_ERR_ARG;
+    }
+    if (b->sig_type != ADB_SIG_I16 && b->sig_type != ADB_SIG_F32) {
+        set_err("unknown sig_type");
+        return ADB_ERR_ARG;
+    }
+    return ADB_OK;
+}
+
+static int check_config(const adb_config *cfg) {
+    if (!cfg) return ADB_ERR_ARG;
+    if (cfg->mvs_detect_check && cfg->mvs_detect_overwrite) {
+        set_err("mvs_detect_overwrite=true (mean_var_shift_polyA_detect_at_loc) is outside the built scope");
+        return ADB_ERR_UNSUPPORTED;
+    }
+    if (cfg->downscale_factor < 1 || cfg->downscale_factor > 128 || cfg->sp_downscale_factor < 1 ||
+        cfg->sp_downscale_factor > 128) {
+        set_err("downscale_factor must be in [1, 128]");
+        return ADB_ERR_UNSUPPORTED;
+    }
+    if (cfg->mean_window > ADB_STAGE_CHUNK || cfg->pA_var_window > ADB_STAGE_HIST ||
+        cfg->pA_mean_window > ADB_STAGE_HIST || cfg->pA_var_window < 1 || cfg->pA_mean_window < 1) {
+        set_err("window sizes outside the supported range (mean_window <= 1024, pA_*_window in [1, 128])");
+        return ADB_ERR_UNSUPPORTED;
+    }
+    if (cfg->polya_cand_k > ADB_MAX_CAND) {
+        set_err("polya_cand_k exceeds ADB_MAX_CAND");
+        return ADB_ERR_UNSUPPORTED;
+    }
+    return ADB_OK;
+}
+
+// ---- global median / MAD -------------------------------------------------------------------------------------
+static int run_global_med_mad(adb_ctx *ctx, const BatchDev &B, int n_batches, int max_obs_trace, cudaStream_t st) {
+    if (ctx->states.ensure(sizeof(GselState) * (size_t)n_batches)) { set_err("cudaMalloc states"); return ADB_ERR_CUDA; }
+    if (ctx->hist.ensure(sizeof(unsigned) * 2 * GSEL_BINS * (size_t)n_batches)) { set_err("cudaMalloc hist"); return ADB_ERR_CUDA; }
+    CUDA_TRY(cudaMemsetAsync(ctx->states.p, 0, sizeof(GselState) * (size_t)n_batches, st));
+    CUDA_TRY(cudaMemsetAsync(ctx->hist.p, 0, sizeof(unsigned) * 2 * GSEL_BINS * (size_t)n_batches, st));
+    int gx = std::max(1, std::min(B.batch_size, (ctx->sm_count * 8 + n_batches - 1) / n_batches));
+    dim3 grid(gx, n_batches);
+    for (int stage = 0; stage < 2; stage++) {
+        for (int pass = 0; pass < 3; pass++) {
+            gsel_hist_kernel<<<grid, 256, 0, st>>>(B, max_obs_trace, stage, pass, (const GselState *)ctx->states.p,
+                                                   (unsigned *)ctx->hist.p);
+            gsel_scan_kernel<<<n_batches, 256, 0, st>>>(stage, pass, (GselState *)ctx->states.p, (unsigned *)ctx->hist.p);
+            ctx->launches += 2;
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    return ADB_OK;
+}
+
+__global__ void merge_status_kernel(const GselState *states, int *batch_status, int n_batches) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_batches) {
+        int s = states[i].status;
+        if (s != ADB_OK) atomicMin(&batch_status[i], s);
+    }
+}
+
+// ---- the detect entry point (device pointers) -----------------------------------------------------------------
+static int launch_read_kernel(adb_ctx *ctx, const BatchDev &B, const adb_config &cfg, int mode, const int *given,
+                              int given_stride, int given_ntopk, adb_record *out, int *batch_status,
+                              cudaStream_t st) {
+    ReadKernelArgs A;
+    A.B = B;
+    A.gstates = (const GselState *)ctx->states.p;
+    A.given = given;
+    A.given_stride = given_stride;
+    A.given_ntopk = given_ntopk;
+    A.mode = mode;
+    int span = std::max(cfg.max_obs_trace - cfg.min_obs_adapter, 0);
+    if (mode == ADB_METHOD_CNN) span = std::max(span, B.m);  // hail mary slices up to the whole window
+    A.nds_max = std::max(64, (span + cfg.downscale_factor - 1) / cfg.downscale_factor + 2);
+    A.peak_cap = A.nds_max / 2 + 8;
+    A.out = out;
+    A.batch_status = batch_status;
+    size_t smem = read_kernel_smem_bytes(A.nds_max, A.peak_cap);
+    if ((int)smem > ctx->max_smem_optin) {
+        set_err("downscaled window does not fit in shared memory");
+        return ADB_ERR_UNSUPPORTED;
+    }
+    CUDA_TRY(cudaFuncSetAttribute(read_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, read_kernel, ADB_READ_THREADS, smem));
+    if (occ < 1) occ = 1;
+    int grid = std::max(1, std::min(B.n_reads, ctx->sm_count * occ));
+    if (ctx->series.ensure((size_t)grid * 2 * B.m * sizeof(float))) { set_err("cudaMalloc series"); return ADB_ERR_CUDA; }
+    A.series = (float *)ctx->series.p;
+    read_kernel<<<grid, ADB_READ_THREADS, smem, st>>>(A, cfg);
+    ctx->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return ADB_OK;
+}
+
+extern "C" int adb_detect_dev(adb_ctx *ctx, const adb_batch *batch, const adb_config *cfg, const float *cnn_weights,
+                              adb_record *out_records, int32_t *batch_status, void *cuda_stream) {
+    if (!ctx || !out_records) { set_err("null argument"); return ADB_ERR_ARG; }
+    int rc = check_batch(batch);
+    if (rc) return rc;
+    rc = check_config(cfg);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    if (batch->n_reads == 0) return ADB_OK;
+    const int n_batches = (batch->n_reads + batch->batch_size - 1) / batch->batch_size;
+    BatchDev B = to_dev_view(*batch);
+    int *status = batch_status;
+    if (!status) {
+        if (ctx->status.ensure(sizeof(int) * (size_t)n_batches)) { set_err("cudaMalloc status"); return ADB_ERR_CUDA; }
+        status = (int *)ctx->status.p;
+    }
+    CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int) * (size_t)n_batches, st));
+    if (cfg->primary_method == ADB_METHOD_LLR) {
+        rc = run_global_med_mad(ctx, B, n_batches, cfg->max_obs_trace, st);
+        if (rc) return rc;
+        merge_status_kernel<<<(n_batches + 127) / 128, 128, 0, st>>>((const GselState *)ctx->states.p, status, n_batches);
+        ctx->launches += 1;
+        return launch_read_kernel(ctx, B, *cfg, ADB_METHOD_LLR, nullptr, 0, -1, out_records, status, st);
+    } else if (cfg->primary_method == ADB_METHOD_CNN) {
+        if (!cnn_weights) { set_err("cnn_weights required for the CNN primary method"); return ADB_ERR_ARG; }
+        const int stride = 1 + cfg->polya_cand_k;
+        if (ctx->given.ensure(sizeof(int) * (size_t)batch->n_reads * stride)) { set_err("cudaMalloc given"); return ADB_ERR_CUDA; }
+        rc = cnn_primary_boundaries(ctx, B, *cfg, cnn_weights, (int *)ctx->given.p, st);
+        if (rc) return rc;
+        return launch_read_kernel(ctx, B, *cfg, ADB_METHOD_CNN, (const int *)ctx->given.p, stride,
+                                  cfg->polya_cand_k >= 1 ? std::max(1, cfg->polya_cand_k) : 1, out_records, status, st);
+    } else if (cfg->primary_method == ADB_METHOD_START_PEAK) {
+        if (ctx->given.ensure(sizeof(int) * (size_t)batch->n_reads * 2)) { set_err("cudaMalloc given"); return ADB_ERR_CUDA; }
+        rc = start_peak_primary(ctx, B, *cfg, (int *)ctx->given.p, out_records, status, st);
+        if (rc) return rc;
+        rc = launch_read_kernel(ctx, B, *cfg, ADB_METHOD_START_PEAK, (const int *)ctx->given.p, 2, -1, out_records, status, st);
+        if (rc) return rc;
+        return start_peak_finish(ctx, B, *cfg, out_records, st);
+    }
+    set_err("unknown primary_method");
+    return ADB_ERR_ARG;
+}
+
+// ---- host-buffer convenience wrappers ------------------------------------------------------------------------------
+struct StagedBatch {
+    adb_batch dev;
+    size_t signal_bytes;
+};
+
+static int stage_batch(adb_ctx *ctx, const adb_batch *b, StagedBatch *out, cudaStream_t st) {
+    adb_batch d = *b;
+    size_t sig_bytes;
+    if (b->sig_type == ADB_SIG_F32) sig_bytes = (size_t)b->n_reads * b->m * sizeof(float);
+    else sig_bytes = (size_t)b->offsets[b->n_reads] * sizeof(int16_t);
+    if (ctx->h_signal.ensure(sig_bytes + 64)) { set_err("cudaMalloc signal staging"); return ADB_ERR_CUDA; }
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_signal.p, b->signal, sig_bytes, cudaMemcpyHostToDevice, st));
+    d.signal = ctx->h_signal.p;
+    if (ctx->h_lens.ensure(sizeof(int32_t) * (size_t)b->n_reads + 16)) { set_err("cudaMalloc lens"); return ADB_ERR_CUDA; }
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_lens.p, b->full_lens, sizeof(int32_t) * (size_t)b->n_reads, cudaMemcpyHostToDevice, st));
+    d.full_lens = (const int32_t *)ctx->h_lens.p;
+    if (b->sig_type == ADB_SIG_I16) {
+        if (ctx->h_offsets.ensure(sizeof(int64_t) * ((size_t)b->n_reads + 1)) || ctx->h_coff.ensure(sizeof(float) * (size_t)b->n_reads + 16) ||
+            ctx->h_cscale.ensure(sizeof(float) * (size_t)b->n_reads + 16)) { set_err("cudaMalloc staging"); return ADB_ERR_CUDA; }
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_offsets.p, b->offsets, sizeof(int64_t) * ((size_t)b->n_reads + 1), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_coff.p, b->calib_offset, sizeof(float) * (size_t)b->n_reads, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_cscale.p, b->calib_scale, sizeof(float) * (size_t)b->n_reads, cudaMemcpyHostToDevice, st));
+        d.offsets = (const int64_t *)ctx->h_offsets.p;
+        d.calib_offset = (const float *)ctx->h_coff.p;
+        d.calib_scale = (const float *)ctx->h_cscale.p;
+    } else {
+        d.offsets = nullptr;
+        d.calib_offset = d.calib_scale = nullptr;
+    }
+    out->dev = d;
+    out->signal_bytes = sig_bytes;
+    return ADB_OK;
+}
+
+extern "C" int adb_detect_host(adb_ctx *ctx, const adb_batch *batch, const adb_config *cfg, const float *cnn_weights,
+                               adb_record *out_records, int32_t *batch_status) {
+    if (!ctx || !out_records) { set_err("null argument"); return ADB_ERR_ARG; }
+    int rc = check_batch(batch);
+    if (rc) return rc;
+    rc = check_config(cfg);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (batch->n_reads == 0) return ADB_OK;
+    cudaStream_t st = ctx->stream;
+    StagedBatch sb;
+    rc = stage_batch(ctx, batch, &sb, st);
+    if (rc) return rc;
+    const int n_batches = (batch->n_reads + batch->batch_size - 1) / batch->batch_size;
+    if (ctx->h_records.ensure(sizeof(adb_record) * (size_t)batch->n_reads)) { set_err("cudaMalloc records"); return ADB_ERR_CUDA; }
+    if (ctx->h_misc.ensure(sizeof(int) * (size_t)n_batches + 16)) { set_err("cudaMalloc status"); return ADB_ERR_CUDA; }
+    const float *w_dev = nullptr;
+    if (cnn_weights && cfg->primary_method == ADB_METHOD_CNN) {
+        if (ctx->h_misc2.ensure(sizeof(float) * ADB_CNN_NPARAMS)) { set_err("cudaMalloc weights"); return ADB_ERR_CUDA; }
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_misc2.p, cnn_weights, sizeof(float) * ADB_CNN_NPARAMS, cudaMemcpyHostToDevice, st));
+        w_dev = (const float *)ctx->h_misc2.p;
+    }
+    rc = adb_detect_dev(ctx, &sb.dev, cfg, w_dev, (adb_record *)ctx->h_records.p, (int *)ctx->h_misc.p, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_records, ctx->h_records.p, sizeof(adb_record) * (size_t)batch->n_reads, cudaMemcpyDeviceToHost, st));
+    if (batch_status)
+        CUDA_TRY(cudaMemcpyAsync(batch_status, ctx->h_misc.p, sizeof(int) * (size_t)n_batches, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return ADB_OK;
+}
+
+extern "C" int adb_global_med_mad_host(adb_ctx *ctx, const adb_batch *batch, int32_t max_obs_trace, float *med_mad) {
+    if (!ctx || !med_mad) { set_err("null argument"); return ADB_ERR_ARG; }
+    int rc = check_batch(batch);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    StagedBatch sb;
+    rc = stage_batch(ctx, batch, &sb, st);
+    if (rc) return rc;
+    const int n_batches = (batch->n_reads + batch->batch_size - 1) / batch->batch_size;
+    rc = run_global_med_mad(ctx, to_dev_view(sb.dev), n_batches, max_obs_trace, st);
+    if (rc) return rc;
+    std::vector<GselState> hs(n_batches);
+    CUDA_TRY(cudaMemcpyAsync(hs.data(), ctx->states.p, sizeof(GselState) * (size_t)n_batches, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int i = 0; i < n_batches; i++) { med_mad[2 * i] = hs[i].med; med_mad[2 * i + 1] = hs[i].mad; }
+    return ADB_OK;
+}
+
+// ---- c_llr_trace ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) llr_trace_kernel(const double *signals, const int64_t *offs, const int64_t *params,
+                                                        double *gains, double *c_out, double *c2_out, double *c_tmp,
+                                                        double *c2_tmp) {
+    __shared__ int tmp[2];
+    const int t = blockIdx.x;
+    const int64_t o = offs[t];
+    const int n = (int)(offs[t + 1] - o);
+    const int64_t *p = params + (size_t)t * 11;
+    const int start = (int)p[0], end = (int)p[1], head = (int)p[2], tail = (int)p[3], stride = (int)max((int64_t)1, p[4]);
+    const int aes = (int)p[5], aw = (int)p[6], as_ = (int)p[7], pes = (int)p[8], pw = (int)p[9], ps = (int)p[10];
+    const double *x = signals + o;
+    double *c = (c_out ? c_out : c_tmp) + o, *c2 = (c2_out ? c2_out : c2_tmp) + o, *g = gains + o;
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < n; i++) { s = __dadd_rn(s, x[i]); c[i] = s; }
+    } else if (threadIdx.x == 32) {
+        double s2 = 0.0;
+        for (int i = 0; i < n; i++) { s2 = __dadd_rn(s2, __dmul_rn(x[i], x[i])); c2[i] = s2; }
+    }
+    __threadfence_block();
+    __syncthreads();
+    if (n <= 0 || end > n || start < 0 || end < 1) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) g[i] = 0.0;
+        return;
+    }
+    cta_llr_gains(c, c2, n, start, end, head, tail, stride, g);
+    const int mode = pes > 0 ? 2 : (aes > 0 ? 1 : 0);
+    if (mode) cta_llr_early_stop(g, n, start, end, head, tail, stride, mode, aw, max(as_, 1), pw, max(ps, 1), tmp);
+}
+
+extern "C" int adb_llr_trace_host(adb_ctx *ctx, const double *signals, const int64_t *sig_offsets, int32_t n_traces,
+                                  const int64_t *params, double *gains, double *c, double *c2) {
+    if (!ctx || !signals || !sig_offsets || !params || !gains || n_traces < 0) { set_err("null argument"); return ADB_ERR_ARG; }
+    if (n_traces == 0) return ADB_OK;
+    for (int t = 0; t < n_traces; t++) {
+        const int64_t *p = params + (size_t)t * 11;
+        const int64_t stride = std::max<int64_t>(1, p[4]);
+        if ((p[8] > 0 || p[5] > 0) && (p[7] <= 0 || p[7] % stride != 0)) { set_err("early_stop_stride % stride != 0"); return ADB_ERR_ARG; }
+        if (p[8] > 0 && (p[10] <= 0 || p[10] % stride != 0)) { set_err("polya early_stop_stride % stride != 0"); return ADB_ERR_ARG; }
+    }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t total = (size_t)sig_offsets[n_traces];
+    DevBuf &dx = ctx->h_signal, &dg = ctx->h_records, &dc = ctx->h_misc2, &dc2 = ctx->h_misc3, &doff = ctx->h_offsets, &dp = ctx->h_misc;
+    if (dx.ensure(total * 8 + 8) || dg.ensure(total * 8 + 8) || dc.ensure(total * 8 + 8) || dc2.ensure(total * 8 + 8) ||
+        doff.ensure(sizeof(int64_t) * ((size_t)n_traces + 1)) || dp.ensure(sizeof(int64_t) * 11 * (size_t)n_traces)) {
+        set_err("cudaMalloc llr trace buffers");
+        return ADB_ERR_CUDA;
+    }
+    CUDA_TRY(cudaMemcpyAsync(dx.p, signals, total * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(doff.p, sig_offsets, sizeof(int64_t) * ((size_t)n_traces + 1), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dp.p, params, sizeof(int64_t) * 11 * (size_t)n_traces, cudaMemcpyHostToDevice, st));
+    llr_trace_kernel<<<n_traces, 128, 0, st>>>((const double *)dx.p, (const int64_t *)doff.p, (const int64_t *)dp.p,
+                                               (double *)dg.p, nullptr, nullptr, (double *)dc.p, (double *)dc2.p);
+    ctx->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(gains, dg.p, total * 8, cudaMemcpyDeviceToHost, st));
+    if (c) CUDA_TRY(cudaMemcpyAsync(c, dc.p, total * 8, cudaMemcpyDeviceToHost, st));
+    if (c2) CUDA_TRY(cudaMemcpyAsync(c2, dc2.p, total * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return ADB_OK;
+}
+
+// ---- downscale ------------------------------------------------------------------------------------------------------
+__global__ void downscale_kernel(BatchDev B, int col0, int factor, int ncols_out, float *out) {
+    const int r = blockIdx.y;
+    const ReadSrc src = make_src(B, r);
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < ncols_out; b += gridDim.x * blockDim.x) {
+        const int j0 = col0 + b * factor;
+        bool nan = false;
+        for (int k = 0; k < factor; k++) { int j = j0 + k; if (j < B.m && j >= src.n) nan = true; }
+        float v;
+        if (nan) v = CUDART_NAN_F;
+        else v = block_mean_f32([&](int k) { int j = j0 + k; return (j < B.m) ? src.pa(j) : 0.0f; }, factor);
+        out[(size_t)r * ncols_out + b] = v;
+    }
+}
+
+extern "C" int adb_downscale_host(adb_ctx *ctx, const adb_batch *batch, int32_t col0, int32_t factor, float *out) {
+    if (!ctx || !out || factor < 1 || factor > 128 || col0 < 0) { set_err("invalid argument"); return ADB_ERR_ARG; }
+    int rc = check_batch(batch);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    StagedBatch sb;
+    rc = stage_batch(ctx, batch, &sb, st);
+    if (rc) return rc;
+    const int ncols = (std::max(batch->m - col0, 0) + factor - 1) / factor;
+    if (ncols == 0 || batch->n_reads == 0) return ADB_OK;
+    if (ctx->h_records.ensure(sizeof(float) * (size_t)ncols * batch->n_reads)) { set_err("cudaMalloc downscale"); return ADB_ERR_CUDA; }
+    dim3 grid((ncols + 127) / 128, batch->n_reads);
+    downscale_kernel<<<grid, 128, 0, st>>>(to_dev_view(sb.dev), col0, factor, ncols, (float *)ctx->h_records.p);
+    ctx->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, ctx->h_records.p, sizeof(float) * (size_t)ncols * batch->n_reads, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return ADB_OK;
+}

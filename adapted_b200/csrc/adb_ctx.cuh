@@ -1,0 +1,59 @@
+// Host-side context shared by the entry points (not part of the ABI: adb_ctx is opaque to callers).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "../../include/adapted_b200.h"
+
+inline std::string &adb_err_string() {
+    static thread_local std::string s;
+    return s;
+}
+inline void set_err(const std::string &s) { adb_err_string() = s; }
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            set_err(std::string(#expr) + ": " + cudaGetErrorString(_e));                       \
+            return ADB_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4;
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            if (cudaMalloc(&p, bytes) != cudaSuccess) return -1;
+            want = bytes;
+        }
+        cap = want;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct adb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+    // scratch (device)
+    DevBuf states, hist, series, given, status;
+    DevBuf cnn_x, cnn_act0, cnn_act1, cnn_scores, cnn_w, cnn_aux;
+    // staging for the *_host entry points
+    DevBuf h_signal, h_offsets, h_lens, h_coff, h_cscale, h_records, h_misc, h_misc2, h_misc3;
+};
+

@@ -1,0 +1,234 @@
+// LLR changepoint trace and boundary picking -- device side.
+//
+// Reference: adapted/detect/_c_llr.pyx:22-236 (var_c, _gains*, c_llr_trace[_gains]),
+//            adapted/detect/llr.py:52-259,406-479 (LLRTrace, peak picking, corrections, poly(A) spike rule),
+//            adapted/detect/combined.py:145-211 (per-read loop of combined_detect_llr2).
+// Arithmetic contract: SURVEY.md A.2 -- sequential float64 prefix sums, individually rounded IEEE double
+// operations (no FMA), gains written only where the reference's loop visits.
+#pragma once
+#include "adb_common.cuh"
+#include "adb_peaks.cuh"
+
+// _c_llr.pyx:22-37
+__device__ __forceinline__ double var_c(int start, int end, const double *c, const double *c2) {
+    if (start == end) return 0.0;
+    if (start == 0) {
+        double m = __ddiv_rn(c[end - 1], (double)end);
+        return __dsub_rn(__ddiv_rn(c2[end - 1], (double)end), __dmul_rn(m, m));
+    }
+    double n = (double)(end - start);
+    double m = __ddiv_rn(__dsub_rn(c[end - 1], c[start - 1]), n);
+    return __dsub_rn(__ddiv_rn(__dsub_rn(c2[end - 1], c2[start - 1]), n), __dmul_rn(m, m));
+}
+
+// _c_llr.pyx:82-86 for every i the reference loop visits; gains[] zero elsewhere (np.zeros_like, :80).  CTA-wide.
+__device__ void cta_llr_gains(const double *c, const double *c2, int n, int start, int end, int head, int tail,
+                              int stride, double *gains) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) gains[i] = 0.0;
+    __syncthreads();
+    const int i0 = start + head, i1 = end - tail;
+    if (i0 < i1) {
+        const double var_summed = __dmul_rn((double)(end - start), log(var_c(start, end, c, c2)));
+        const int cnt = (i1 - i0 + stride - 1) / stride;
+        for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+            int i = i0 + k * stride;
+            double h = __dmul_rn((double)(i - start), log(var_c(start, i, c, c2)));
+            double t = __dmul_rn((double)(end - i), log(var_c(i, end, c, c2)));
+            gains[i] = __dsub_rn(var_summed, __dadd_rn(h, t));
+        }
+    }
+    __syncthreads();
+}
+
+// mean(diff(gains[lo:hi:stride])) with python slice semantics and numpy's pairwise float64 mean; one thread.
+__device__ double lane_mean_diff(const double *g, int n, int lo, int hi, int stride) {
+    if (lo < 0) { lo += n; if (lo < 0) lo = 0; }
+    if (hi > n) hi = n;
+    int cnt = (hi > lo) ? (hi - lo + stride - 1) / stride : 0;
+    int nd = cnt - 1;
+    if (nd <= 0) return CUDART_NAN;
+    double s = np_sum_f64([&](int k) { return __dsub_rn(g[lo + (k + 1) * stride], g[lo + k * stride]); }, nd);
+    return __ddiv_rn(s, (double)nd);
+}
+
+// Early-stop variants (_c_llr.pyx:91-173).  The gains themselves do not depend on the stop rule (an early-stopped
+// trace is a prefix of the full trace), so the full trace is computed in parallel, the stop position is found by
+// evaluating the reference's predicates at the positions its loop would test them, and the tail is zeroed.
+// mode 1: adapter early stop; mode 2: adapter + poly(A) early stop.  `tmp` = one int of shared memory.  CTA-wide.
+__device__ void cta_llr_early_stop(double *gains, int n, int start, int end, int head, int tail, int stride,
+                                   int mode, int a_window, int a_stride, int p_window, int p_stride, int *tmp) {
+    const int i0 = start + head, i1 = end - tail;
+    if (i0 >= i1) return;
+    const int cnt = (i1 - i0 + stride - 1) / stride;
+    if (threadIdx.x == 0) *tmp = 0x7fffffff;
+    __syncthreads();
+    // first loop index k (i = i0 + k*stride) whose adapter predicate fires
+    for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+        int i = i0 + k * stride;
+        if (i >= i0 + a_window && ((i - i0) % a_stride) == 0) {
+            if (lane_mean_diff(gains, n, i - a_window, i, stride) < 0) atomicMin(tmp, k);
+        }
+    }
+    __syncthreads();
+    int ka = *tmp;
+    __syncthreads();
+    int kstop = cnt;
+    if (mode == 1) {
+        kstop = min(ka, cnt);
+    } else if (ka < cnt) {
+        if (threadIdx.x == 0) *tmp = 0x7fffffff;
+        __syncthreads();
+        for (int k = ka + threadIdx.x; k < cnt; k += blockDim.x) {
+            int i = i0 + k * stride;
+            if (lane_mean_diff(gains, n, i - p_window, i, stride) > 0) atomicMin(tmp, k);
+        }
+        __syncthreads();
+        kstop = min(*tmp, cnt);
+        __syncthreads();
+    }
+    for (int k = kstop + threadIdx.x; k < cnt; k += blockDim.x) gains[i0 + k * stride] = 0.0;
+    __syncthreads();
+}
+
+// LLRTrace._trace_start_end (llr.py:135-142): first / last index whose value is not <= 0 (NaN counts as positive);
+// all <= 0 -> (0, n-1).  CTA-wide; `tmp` = 2 ints of shared memory.
+__device__ void cta_trace_support(const double *g, int n, int &start, int &end, int *tmp) {
+    if (threadIdx.x == 0) { tmp[0] = 0x7fffffff; tmp[1] = -1; }
+    __syncthreads();
+    int lo = 0x7fffffff, hi = -1;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (!(g[i] <= 0.0)) { lo = min(lo, i); hi = max(hi, i); }
+    }
+    if (hi >= 0) { atomicMin(&tmp[0], lo); atomicMax(&tmp[1], hi); }
+    __syncthreads();
+    start = (tmp[0] == 0x7fffffff) ? 0 : tmp[0];
+    end = (tmp[1] < 0) ? n - 1 : tmp[1];
+    __syncthreads();
+}
+
+// np.nanstd over g[lo:hi) (numpy/lib/_nanfunctions_impl.py _nanvar): NaN -> 0, pairwise sums; one thread.
+__device__ double lane_nanstd(const double *g, int lo, int hi) {
+    int n = hi - lo;
+    if (n <= 0) return CUDART_NAN;
+    int cnt = 0;
+    for (int i = lo; i < hi; i++) cnt += (g[i] == g[i]);
+    if (cnt == 0) return CUDART_NAN;
+    double avg = __ddiv_rn(np_sum_f64([&](int k) { double v = g[lo + k]; return v == v ? v : 0.0; }, n), (double)cnt);
+    double ss = np_sum_f64(
+        [&](int k) {
+            double v = g[lo + k];
+            if (!(v == v)) return 0.0;
+            double d = __dsub_rn(v, avg);
+            return __dmul_rn(d, d);
+        },
+        n);
+    return sqrt(__ddiv_rn(ss, (double)cnt));
+}
+
+// correct_for_plateau (llr.py:145-177), warp-wide.  Returns the corrected absolute index.
+__device__ int warp_plateau_fix(const double *g, int n, int peak) {
+    const int lane = threadIdx.x & 31;
+    const int L = min(peak + 500, n) - peak;  // len(trace_)
+    const int nch = L - 1;                    // len(changes)
+    const double thr = __dmul_rn(0.9, g[peak]);
+    int best = -1;
+    // candidates i = nch-10 .. 0 (descending); the first hit wins -> search from the top in chunks of 32
+    for (int top = nch - 10; top >= 0 && best < 0; top -= 32) {
+        int i = top - lane;
+        bool ok = false;
+        if (i >= 0) {
+            ok = g[peak + i + 9] > thr;
+            for (int k = 0; k < 9 && ok; k++) ok = (__dsub_rn(g[peak + i + k + 1], g[peak + i + k]) >= 0.0);
+        }
+        unsigned m = __ballot_sync(ADB_FULL, ok);
+        if (m) best = top - (__ffs(m) - 1);
+    }
+    int plateau_end = (best >= 0) ? best + 9 : -1;
+    return plateau_end > 0 ? peak + plateau_end : peak;
+}
+
+// correct_for_split_peak (llr.py:180-201), warp-wide.
+__device__ int warp_split_fix(const double *g, int n, int peak, const PeakScratch &PS) {
+    TraceView W;
+    W.x = g + peak;
+    W.n = min(peak + 500, n) - peak;
+    W.nan2num = 0;
+    int out[2];
+    int k = warp_find_first_peaks(W, 0, 1.0, 10.0, 0.5, 1, out, PS);
+    if (k > 0 && g[out[0] + peak] >= __dmul_rn(0.9, g[peak])) return out[0] + peak;
+    return peak;
+}
+
+// adapter_end_from_trace (llr.py:204-259) -> cands[0] or -1 if there is no candidate.  Warp-wide
+// (support [start, end) and the nanstd threshold are computed by the caller).
+__device__ int warp_adapter_end(const double *g, int n, int start, int end, double pmin, double wmin,
+                                double rel_height, const PeakScratch &PS) {
+    TraceView W;
+    W.x = g + start;
+    W.n = end - start;
+    W.nan2num = 0;
+    int out[2];
+    int k = warp_find_first_peaks(W, 0, pmin, wmin, rel_height, 1, out, PS);
+    if (k == 0) return -1;
+    int peak = out[0] + start;
+    peak = warp_plateau_fix(g, n, peak);
+    peak = warp_split_fix(g, n, peak, PS);
+    return peak;
+}
+
+// detect_full_polya_trace_peak_with_spike (llr.py:406-479) on the full-length trace g[0..n).  Warp-wide.
+// Returns the downscaled index (0 = none); *err is set when scipy.stats.linregress would raise.
+__device__ int warp_polya_end(const double *g, int n, const PeakScratch &PS, int *err) {
+    const int lane = threadIdx.x & 31;
+    TraceView W;
+    W.x = g;
+    W.n = n;
+    W.nan2num = 1;
+    int pk[2];
+    int k = warp_find_first_peaks(W, 10, 1.0, 10.0, 0.5, 2, pk, PS);
+    if (k == 0) return 0;
+    if (k == 1) return pk[0];
+    const double h0 = g[pk[0]], h1 = g[pk[1]];  // raw trace, not nan_to_num (llr.py:459)
+    if (h1 > h0) return pk[1];
+    if (h1 < __dmul_rn(h0, 0.5)) return pk[0];
+    // idx_min = argmin(trace[p0:p1]) (first minimum; numpy's argmin returns the first NaN if there is one)
+    double bv = CUDART_INF;
+    int bi = 0x7fffffff, nan_i = 0x7fffffff;
+    for (int i = pk[0] + lane; i < pk[1]; i += 32) {
+        double v = g[i];
+        if (!(v == v)) nan_i = min(nan_i, i);
+        else if (v < bv) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double ov = __shfl_xor_sync(ADB_FULL, bv, o);
+        int oi = __shfl_xor_sync(ADB_FULL, bi, o);
+        int on = __shfl_xor_sync(ADB_FULL, nan_i, o);
+        if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        nan_i = min(nan_i, on);
+    }
+    const int idx_min = (nan_i != 0x7fffffff) ? nan_i : bi;
+    const int cnt = pk[1] - idx_min;
+    if (cnt < 2) {  // linregress raises for fewer than two points / identical x
+        *err = 1;
+        return 0;
+    }
+    // r^2 of the regression of g[idx_min:p1] on its index (scipy.stats.linregress: r = ssxym / sqrt(ssxm*ssym))
+    double sx = 0, sy = 0;
+    for (int i = idx_min + lane; i < pk[1]; i += 32) { sx += (double)i; sy += g[i]; }
+    sx = warp_sum_d(sx); sy = warp_sum_d(sy);
+    const double mx = sx / cnt, my = sy / cnt;
+    double sxx = 0, sxy = 0, syy = 0;
+    for (int i = idx_min + lane; i < pk[1]; i += 32) {
+        double dx = (double)i - mx, dy = g[i] - my;
+        sxx += dx * dx; sxy += dx * dy; syy += dy * dy;
+    }
+    sxx = warp_sum_d(sxx); sxy = warp_sum_d(sxy); syy = warp_sum_d(syy);
+    double r;
+    if (sxx == 0.0 || syy == 0.0) r = 0.0;
+    else {
+        r = sxy / sqrt(sxx * syy);
+        if (r > 1.0) r = 1.0; else if (r < -1.0) r = -1.0;
+    }
+    return (r * r >= 0.99) ? pk[1] : 0;
+}

@@ -1,0 +1,591 @@
+// validate_boundaries + per-segment statistics, one CTA per read.
+//
+// Reference: adapted/detect/combined.py:358-631 with adapted/detect/anomalies.py:15-35 (open pores),
+// adapted/detect/real_range.py:33-63, adapted/detect/mvs.py:45-158 (mean/var/median-shift check, bottleneck
+// moving statistics restated from its move_template.c recurrences in float32), adapted/detect/utils.py:16-36,
+// adapted/partition/signal_partitions.py:65-96.  Control flow follows SURVEY.md A.8 including the
+// "success is never reset" behaviour of the top-k loop.
+#pragma once
+#include "adb_common.cuh"
+#include "adb_select.cuh"
+
+#define ADB_STAGE_HIST 128   // history kept in front of a staged chunk (>= moving windows)
+#define ADB_STAGE_CHUNK 1024 // samples staged per step for the sequential moving statistics
+
+struct ValCtx {
+    ReadSrc src;
+    const adb_config *cfg;
+    SelScratch S;
+    uint32_t *kbuf;      // shared: 4 keys + 4 ranks
+    float *stage;        // shared: [ADB_STAGE_HIST + ADB_STAGE_CHUNK]
+    float *series_a;     // global scratch [m] (moving variance)
+    float *series_b;     // global scratch [m] (moving mean)
+    int *itmp;           // shared: 8 ints
+    double *dtmp;        // shared: 8 doubles
+    bool int_keys;       // raw ADC keys usable (i16 source, scale > 0)
+    uint32_t wkmin, wkmax;  // key bounds of the whole window
+    float wvmin, wvmax;     // value bounds of the whole window
+};
+
+// ---- keys of a pA segment ----------------------------------------------------------------------------------
+struct PaKeys {
+    ReadSrc s;
+    int a;
+    bool ik;
+    __device__ __forceinline__ uint32_t operator()(int j) const {
+        if (ik) return (uint32_t)((int)__ldg(s.i16 + a + j) + 32768);
+        return f32_key(s.pa(a + j));
+    }
+};
+struct PaVal {
+    ReadSrc s;
+    bool ik;
+    __device__ __forceinline__ float operator()(uint32_t k) const {
+        if (ik) return __fmul_rn(__fadd_rn((float)((int)k - 32768), s.coff), s.cscale);
+        return key_f32(k);
+    }
+};
+struct DevKeys {  // |x - med| in float32
+    ReadSrc s;
+    int a;
+    float med;
+    __device__ __forceinline__ uint32_t operator()(int j) const { return f32_key(fabsf(__fsub_rn(s.pa(a + j), med))); }
+};
+struct BufKeys {
+    const float *p;
+    __device__ __forceinline__ uint32_t operator()(int j) const { return f32_key(p[j]); }
+};
+struct KeyToF32 {
+    __device__ __forceinline__ float operator()(uint32_t k) const { return key_f32(k); }
+};
+
+__device__ void val_window_bounds(ValCtx &C) {
+    PaKeys K{C.src, 0, C.int_keys};
+    PaVal V{C.src, C.int_keys};
+    cta_key_minmax(K, C.src.n, C.wkmin, C.wkmax, C.S);
+    if (C.src.n > 0) {
+        C.wvmin = V(C.wkmin);
+        C.wvmax = V(C.wkmax);
+    } else {
+        C.wvmin = C.wvmax = 0.f;
+        C.wkmin = C.wkmax = 0;
+    }
+}
+
+// python slice clipping of [a, b) to [0, size)
+__device__ __forceinline__ void clip_seg(int &a, int &b, int size) {
+    a = min(max(a, 0), size);
+    b = min(max(b, 0), size);
+    if (b < a) b = a;
+}
+
+__device__ float seg_median(ValCtx &C, int a, int b) {
+    clip_seg(a, b, C.src.n);
+    PaKeys K{C.src, a, C.int_keys};
+    PaVal V{C.src, C.int_keys};
+    return cta_median_keys(K, V, b - a, C.wkmin, C.wkmax, C.S, C.kbuf);
+}
+
+// median(|x - med|) in float32 (combined.py:399-400, signal_partitions.py:94)
+__device__ float seg_mad(ValCtx &C, int a, int b, float med) {
+    clip_seg(a, b, C.src.n);
+    if (b - a <= 0) return CUDART_NAN_F;
+    if (!(med == med)) return CUDART_NAN_F;
+    DevKeys K{C.src, a, med};
+    float dmax = fmaxf(fabsf(__fsub_rn(C.wvmax, med)), fabsf(__fsub_rn(C.wvmin, med)));
+    return cta_median_keys(K, KeyToF32(), b - a, f32_key(0.0f), f32_key(dmax), C.S, C.kbuf);
+}
+
+// np.subtract(*np.percentile(seg, (85, 15))) -> float64 (real_range.py:50-57, mvs.py:113-118)
+__device__ double seg_local_range(ValCtx &C, int a, int b) {
+    clip_seg(a, b, C.src.n);
+    const int n = b - a;
+    if (n <= 0) return CUDART_NAN;
+    int *ranks = (int *)(C.kbuf + 4);
+    // virtual indexes (n-1)*q in float64, q = 85/100, 15/100
+    const double v85 = __dmul_rn((double)(n - 1), 0.85), v15 = __dmul_rn((double)(n - 1), 0.15);
+    const int l85 = (int)floor(v85), l15 = (int)floor(v15);
+    const int h85 = min(l85 + 1, n - 1), h15 = min(l15 + 1, n - 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // ascending, possibly equal ranks: l15 <= h15 <= l85 <= h85
+        ranks[0] = l15; ranks[1] = h15; ranks[2] = l85; ranks[3] = h85;
+    }
+    __syncthreads();
+    PaKeys K{C.src, a, C.int_keys};
+    PaVal V{C.src, C.int_keys};
+    cta_select_ranks(K, n, C.wkmin, C.wkmax, ranks, 4, C.kbuf, C.S);
+    const float a15 = V(C.kbuf[0]), b15 = V(C.kbuf[1]), a85 = V(C.kbuf[2]), b85 = V(C.kbuf[3]);
+    const double p85 = np_lerp_f32(a85, b85, __dsub_rn(v85, (double)l85));
+    const double p15 = np_lerp_f32(a15, b15, __dsub_rn(v15, (double)l15));
+    __syncthreads();
+    return __dsub_rn(p85, p15);
+}
+
+// float32 numpy mean of `n` (<= ADB_STAGE_CHUNK) samples starting at a: staged to shared memory, summed in numpy's
+// pairwise order by one thread.  Returns the mean to all threads.
+__device__ float seg_mean_exact_small(ValCtx &C, int a, int n) {
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += blockDim.x) C.stage[j] = C.src.pa(a + j);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const float *st = C.stage;
+        float s = np_sum_f32([&](int i) { return st[i]; }, n);
+        ((float *)C.dtmp)[0] = __fdiv_rn(s, (float)n);
+    }
+    __syncthreads();
+    float r = ((float *)C.dtmp)[0];
+    __syncthreads();
+    return r;
+}
+
+// float32 np.var of n (<= ADB_STAGE_CHUNK) samples (numpy _var: mean, x - mean, x*x, pairwise sum / n)
+__device__ float seg_var_exact_small(ValCtx &C, int a, int n) {
+    float mean = seg_mean_exact_small(C, a, n);  // leaves the samples staged
+    if (threadIdx.x == 0) {
+        const float *st = C.stage;
+        float s = np_sum_f32([&](int i) { float d = __fsub_rn(st[i], mean); return __fmul_rn(d, d); }, n);
+        ((float *)C.dtmp)[0] = __fdiv_rn(s, (float)n);
+    }
+    __syncthreads();
+    float r = ((float *)C.dtmp)[0];
+    __syncthreads();
+    return r;
+}
+
+// mean / population std of a segment for the partition table (signal_partitions.py:91-92).  numpy accumulates
+// these in float32 pairwise order; they only have to agree to 1e-5 relative (north_star), so the sums are
+// taken in float64 and rounded to float32 at the end.
+__device__ void seg_mean_std(ValCtx &C, int a, int b, double &mean_out, double &std_out) {
+    clip_seg(a, b, C.src.n);
+    const int n = b - a;
+    if (n <= 0) { mean_out = CUDART_NAN; std_out = CUDART_NAN; return; }
+    double s = 0.0;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) s += (double)C.src.pa(a + j);
+    s = warp_sum_d(s);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) C.dtmp[threadIdx.x >> 5] = s;
+    __syncthreads();
+    double tot = 0.0;
+    for (int w = 0; w < (int)((blockDim.x + 31) >> 5); w++) tot += C.dtmp[w];
+    const float mean32 = (float)(tot / n);
+    __syncthreads();
+    double q = 0.0;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        double d = (double)__fsub_rn(C.src.pa(a + j), mean32);
+        q += d * d;
+    }
+    q = warp_sum_d(q);
+    if ((threadIdx.x & 31) == 0) C.dtmp[threadIdx.x >> 5] = q;
+    __syncthreads();
+    double qt = 0.0;
+    for (int w = 0; w < (int)((blockDim.x + 31) >> 5); w++) qt += C.dtmp[w];
+    __syncthreads();
+    mean_out = (double)mean32;
+    std_out = (double)sqrtf((float)(qt / n));
+}
+
+// ---- bottleneck moving statistics (float32 recurrences, one lane each) --------------------------------------
+struct MoveMeanState {
+    int count; float asum, count_inv;
+};
+struct MoveVarState {
+    int count; float amean, assqdm, count_inv, ddof_inv;
+};
+
+// Runs move_var(window wv) on thread 0 and move_mean(window wm) on thread 32 over src[a, a+L); writes the valid
+// entries (index >= window-1) compacted to series_a / series_b.  CTA-wide (all threads stage the data).
+__device__ void seg_moving_stats(ValCtx &C, int a, int L, int wv, int wm, bool do_var, bool do_mean) {
+    MoveMeanState M{0, 0.f, 0.f};
+    MoveVarState Vs{0, 0.f, 0.f, 0.f, 0.f};
+    float *st = C.stage + ADB_STAGE_HIST;  // st[-k] holds history
+    for (int base = 0; base < L; base += ADB_STAGE_CHUNK) {
+        const int len = min(ADB_STAGE_CHUNK, L - base);
+        __syncthreads();
+        // history: last ADB_STAGE_HIST samples before `base`
+        for (int j = threadIdx.x; j < ADB_STAGE_HIST; j += blockDim.x) {
+            int idx = base - ADB_STAGE_HIST + j;
+            C.stage[j] = (idx >= 0) ? C.src.pa(a + idx) : 0.f;
+        }
+        for (int j = threadIdx.x; j < len; j += blockDim.x) st[j] = C.src.pa(a + base + j);
+        __syncthreads();
+        if (threadIdx.x == 0 && do_var) {
+            for (int j = 0; j < len; j++) {
+                const int i = base + j;
+                float ai = st[j], yi;
+                if (i < wv) {  // WHILE0 / WHILE1 of move_template.c
+                    if (ai == ai) {
+                        Vs.count += 1;
+                        float delta = __fsub_rn(ai, Vs.amean);
+                        Vs.amean = __fadd_rn(Vs.amean, __fdiv_rn(delta, (float)Vs.count));
+                        Vs.assqdm = __fadd_rn(Vs.assqdm, __fmul_rn(delta, __fsub_rn(ai, Vs.amean)));
+                    }
+                    if (i == wv - 1) {
+                        if (Vs.count >= wv) {
+                            if (Vs.assqdm < 0) Vs.assqdm = 0;
+                            yi = __fdiv_rn(Vs.assqdm, (float)Vs.count);
+                        } else yi = CUDART_NAN_F;
+                        C.series_a[0] = yi;
+                        Vs.count_inv = (float)(1.0 / (double)Vs.count);
+                        Vs.ddof_inv = Vs.count_inv;
+                    }
+                } else {
+                    float aold = st[j - wv];
+                    if (ai == ai) {
+                        if (aold == aold) {
+                            float delta = __fsub_rn(ai, aold);
+                            aold = __fsub_rn(aold, Vs.amean);
+                            Vs.amean = __fadd_rn(Vs.amean, __fmul_rn(delta, Vs.count_inv));
+                            ai = __fsub_rn(ai, Vs.amean);
+                            Vs.assqdm = __fadd_rn(Vs.assqdm, __fmul_rn(__fadd_rn(ai, aold), delta));
+                        } else {
+                            Vs.count++;
+                            Vs.count_inv = (float)(1.0 / (double)Vs.count);
+                            Vs.ddof_inv = Vs.count_inv;
+                            float delta = __fsub_rn(ai, Vs.amean);
+                            Vs.amean = __fadd_rn(Vs.amean, __fmul_rn(delta, Vs.count_inv));
+                            Vs.assqdm = __fadd_rn(Vs.assqdm, __fmul_rn(delta, __fsub_rn(ai, Vs.amean)));
+                        }
+                    } else if (aold == aold) {
+                        Vs.count--;
+                        Vs.count_inv = (float)(1.0 / (double)Vs.count);
+                        Vs.ddof_inv = Vs.count_inv;
+                        if (Vs.count > 0) {
+                            float delta = __fsub_rn(aold, Vs.amean);
+                            Vs.amean = __fsub_rn(Vs.amean, __fmul_rn(delta, Vs.count_inv));
+                            Vs.assqdm = __fsub_rn(Vs.assqdm, __fmul_rn(delta, __fsub_rn(aold, Vs.amean)));
+                        } else {
+                            Vs.amean = 0;
+                            Vs.assqdm = 0;
+                        }
+                    }
+                    if (Vs.count >= wv) {
+                        if (Vs.assqdm < 0) Vs.assqdm = 0;
+                        yi = __fmul_rn(Vs.assqdm, Vs.ddof_inv);
+                    } else yi = CUDART_NAN_F;
+                    C.series_a[i - (wv - 1)] = yi;
+                }
+            }
+        }
+        if (threadIdx.x == 32 && do_mean) {
+            for (int j = 0; j < len; j++) {
+                const int i = base + j;
+                float ai = st[j];
+                if (i < wm) {
+                    if (ai == ai) { M.asum = __fadd_rn(M.asum, ai); M.count += 1; }
+                    if (i == wm - 1) {
+                        C.series_b[0] = (M.count >= wm) ? __fdiv_rn(M.asum, (float)M.count) : CUDART_NAN_F;
+                        M.count_inv = (float)(1.0 / (double)M.count);
+                    }
+                } else {
+                    float aold = st[j - wm];
+                    if (ai == ai) {
+                        if (aold == aold) M.asum = __fadd_rn(M.asum, __fsub_rn(ai, aold));
+                        else { M.asum = __fadd_rn(M.asum, ai); M.count++; M.count_inv = (float)(1.0 / (double)M.count); }
+                    } else if (aold == aold) {
+                        M.asum = __fsub_rn(M.asum, aold); M.count--; M.count_inv = (float)(1.0 / (double)M.count);
+                    }
+                    C.series_b[i - (wm - 1)] = (M.count >= wm) ? __fmul_rn(M.asum, M.count_inv) : CUDART_NAN_F;
+                }
+            }
+        }
+    }
+    __threadfence_block();
+    __syncthreads();
+}
+
+// np.nanmedian of a float32 series in global scratch (NaNs dropped; none occur for NaN-free input)
+__device__ float series_nanmedian(ValCtx &C, const float *p, int n) {
+    if (n <= 0) return CUDART_NAN_F;
+    BufKeys K{p};
+    uint32_t kmin, kmax;
+    cta_key_minmax(K, n, kmin, kmax, C.S);
+    return cta_median_keys(K, KeyToF32(), n, kmin, kmax, C.S, C.kbuf);
+}
+
+// ---- mean_var_shift_polyA_check (mvs.py:45-158) -------------------------------------------------------------
+struct MvsOut {
+    bool ok;
+    int fail_mask;   // bit i: check i failed (mean var med range shift)
+    double v[5];     // mean, var, med, local_range, med_shift (all 0 on early fail)
+};
+
+__device__ MvsOut mvs_check(ValCtx &C, int ae, int pe, double mean_lo, double mean_hi) {
+    const adb_config &cfg = *C.cfg;
+    MvsOut R;
+    R.ok = false; R.fail_mask = 0x1f;
+    for (int i = 0; i < 5; i++) R.v[i] = 0.0;
+    const int size = C.src.n;
+    if (pe == 0 || ae == 0 || pe < ae || pe - ae <= 2) return R;
+    if (size < ae + cfg.median_shift_window) return R;
+    int a = ae, b = pe;
+    clip_seg(a, b, size);
+    const int L = b - a;
+    float var32, mean32;
+    const bool win_var = !(pe - ae <= cfg.pA_var_window + 2);
+    const bool win_mean = !(pe - ae <= cfg.pA_mean_window + 2);
+    if (win_var || win_mean) seg_moving_stats(C, a, L, cfg.pA_var_window, cfg.pA_mean_window, win_var, win_mean);
+    if (win_var) var32 = series_nanmedian(C, C.series_a, L - (cfg.pA_var_window - 1));
+    else var32 = seg_var_exact_small(C, a, L);
+    if (win_mean) mean32 = series_nanmedian(C, C.series_b, L - (cfg.pA_mean_window - 1));
+    else mean32 = seg_mean_exact_small(C, a, L);
+    const float med32 = seg_median(C, ae, pe);
+    const double lr = seg_local_range(C, ae, pe);
+    const float m_after = seg_median(C, ae, min(ae + cfg.median_shift_window, size));
+    const float m_before = seg_median(C, max(ae - cfg.median_shift_window, 0), ae);
+    const float shift32 = __fsub_rn(m_after, m_before);
+    R.v[0] = (double)mean32; R.v[1] = (double)var32; R.v[2] = (double)med32; R.v[3] = lr; R.v[4] = (double)shift32;
+    const double mr[2] = {mean_lo, mean_hi};
+    int mask = 0;
+    if (!in_range_d(R.v[0], mr)) mask |= 1;
+    if (!in_range_d(R.v[1], cfg.pA_var_range)) mask |= 2;
+    if (!in_range_d(R.v[2], cfg.polyA_med_range)) mask |= 4;
+    if (!in_range_d(R.v[3], cfg.polyA_local_range)) mask |= 8;
+    if (!in_range_d(R.v[4], cfg.median_shift_range)) mask |= 16;
+    R.fail_mask = mask;
+    R.ok = (mask == 0);
+    return R;
+}
+
+// ---- find_open_pores (anomalies.py:15-35) on signal[a:b), absolute indices ------------------------------------
+// Returns the number of reported positions; *last = open_pores[-1]; the first ADB_MAX_OPEN_PORES go to rec.
+__device__ int open_pores_scan(ValCtx &C, int a, int b, adb_record *rec, int *last) {
+    clip_seg(a, b, C.src.n);
+    const int n = b - a;
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int chunk = (n + T - 1) / T;
+    const int j0 = min(tid * chunk, n), j1 = min(j0 + chunk, n);
+    int *sh = C.itmp;  // [0]=hits [1]=first hit [2]=last hit [3]=valid count [4]=last valid
+    __syncthreads();
+    if (tid == 0) { sh[0] = 0; sh[1] = 0x7fffffff; sh[2] = -1; sh[3] = 0; sh[4] = -1; }
+    __syncthreads();
+    // pass 1: hits, and "gap >= 10 to the previous hit" candidates (first-hit exclusion applied later)
+    int hits = 0, first = 0x7fffffff, lastp = -1, ncand = 0, lastc = -1;
+    for (int j = j0; j < j1; j++) {
+        float v = C.src.pa(a + j);
+        if (v >= 200.0f) {
+            hits++;
+            first = min(first, j);
+            lastp = j;
+            bool gap = true;
+            for (int k = 1; k < 10 && gap; k++)
+                if (j - k >= 0 && C.src.pa(a + j - k) >= 200.0f) gap = false;
+            if (gap) { ncand++; lastc = j; }
+        }
+    }
+    if (hits) {
+        atomicAdd(&sh[0], hits);
+        atomicMin(&sh[1], first);
+        atomicMax(&sh[2], lastp);
+    }
+    __syncthreads();
+    const int tot_hits = sh[0], first_hit = sh[1], last_hit = sh[2];
+    int result_n;
+    if (tot_hits == 0) {
+        result_n = 0;
+    } else if (tot_hits == 1) {
+        result_n = 1;
+        if (tid == 0) rec->open_pores[0] = a + first_hit;
+        *last = a + first_hit;
+    } else {
+        // the first hit is always a "gap" candidate but never reported (the loop starts at i = 1)
+        if (first_hit >= j0 && first_hit < j1) { ncand--; if (lastc == first_hit) lastc = -1; }
+        // ordered compaction of the reported positions
+        int incl = ncand;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(ADB_FULL, incl, o);
+            if ((tid & 31) >= o) incl += v;
+        }
+        __syncthreads();
+        if ((tid & 31) == 31) C.S.warp_tot[tid >> 5] = (uint32_t)incl;
+        if (lastc >= 0) atomicMax(&sh[4], lastc);
+        __syncthreads();
+        int wbase = 0, total = 0;
+        for (int w = 0; w < (int)((T + 31) >> 5); w++) {
+            if (w < (tid >> 5)) wbase += (int)C.S.warp_tot[w];
+            total += (int)C.S.warp_tot[w];
+        }
+        int pos = wbase + incl - ncand;
+        if (total > 0) {
+            if (ncand > 0 && pos < ADB_MAX_OPEN_PORES) {
+                for (int j = j0; j < j1 && pos < ADB_MAX_OPEN_PORES; j++) {
+                    if (j == first_hit) continue;
+                    if (C.src.pa(a + j) >= 200.0f) {
+                        bool gap = true;
+                        for (int k = 1; k < 10 && gap; k++)
+                            if (j - k >= 0 && C.src.pa(a + j - k) >= 200.0f) gap = false;
+                        if (gap) rec->open_pores[pos++] = a + j;
+                    }
+                }
+            }
+            result_n = total;
+            *last = a + sh[4];
+        } else {
+            result_n = 1;  // valid_pos = pos[-1]
+            if (tid == 0) rec->open_pores[0] = a + last_hit;
+            *last = a + last_hit;
+        }
+    }
+    __syncthreads();
+    return result_n;
+}
+
+struct PrimaryBounds {
+    int adapter_start, adapter_end, polya_end;
+    int n_topk;           // -1: polya_end_topk is None
+    const int *topk;      // n_topk entries (shared or global)
+};
+
+// validate_boundaries (combined.py:358-631).  Fills `rec` (thread 0 writes the scalars).  CTA-wide.
+__device__ void validate_boundaries_cta(ValCtx &C, const PrimaryBounds &B, int full_len, adb_record *rec) {
+    const adb_config &cfg = *C.cfg;
+    const int size = C.src.n;
+    int a_start = B.adapter_start, a_end = B.adapter_end, pe_best = B.polya_end;
+    bool success = true;
+    int fail = ADB_FAIL_NONE, fail_mask = 0;
+    uint32_t valid = ADB_V_FIELDS;
+    float a_med = CUDART_NAN_F, a_mad = CUDART_NAN_F;
+    bool have_amed = false;
+    double mvs_v[5] = {0, 0, 0, 0, 0};
+    double real_v[3] = {0, 0, 0};
+    double med_shift = 0.0;
+    int n_open = 0;
+    float polya_med_cache = 0.f; int polya_med_cache_pe = -1;
+
+    if (a_end == 0) {
+        success = false; fail = ADB_FAIL_NO_ADAPTER;
+    } else {
+        a_med = seg_median(C, a_start, a_end);
+        a_mad = seg_mad(C, a_start, a_end, a_med);
+        have_amed = true;
+    }
+    if (success && (a_mad != 0.0f) && !in_range_d((double)a_mad, cfg.adapter_mad_range)) {
+        success = false; fail = ADB_FAIL_ADAPTER_MAD;
+    }
+    const int a_start0 = a_start;
+    if (success && cfg.detect_open_pores) {
+        int last = 0;
+        n_open = open_pores_scan(C, a_start, a_end, rec, &last);
+        valid |= ADB_V_OPEN_PORES;
+        if (n_open > 0) {
+            a_start = last;
+            if (a_end - a_start < cfg.min_obs_adapter) { success = false; fail = ADB_FAIL_OPEN_PORE; }
+        }
+    }
+    if (success && cfg.real_signal_check) {
+        int a = a_start, b = a_end;
+        clip_seg(a, b, size);
+        const int len = b - a;
+        if (len < 2 * cfg.mean_window) {
+            success = false; fail = ADB_FAIL_REAL_RANGE;
+        } else {
+            const float m0 = seg_mean_exact_small(C, a, cfg.mean_window);
+            const float m1 = seg_mean_exact_small(C, b - cfg.mean_window, cfg.mean_window);
+            real_v[0] = (double)m0; real_v[1] = (double)m1;
+            valid |= ADB_V_REAL_MEANS;
+            if (in_range_d((double)m0, cfg.mean_start_range) && in_range_d((double)m1, cfg.mean_end_range)) {
+                const int w = min(cfg.max_obs_local_range, len);
+                const double lr = seg_local_range(C, b - w, b);
+                real_v[2] = lr;
+                valid |= ADB_V_REAL_RANGE;
+                if (!in_range_d(lr, cfg.local_range)) { success = false; fail = ADB_FAIL_REAL_RANGE; }
+            } else {
+                success = false; fail = ADB_FAIL_REAL_RANGE;
+            }
+        }
+    }
+    bool exception = false;
+    if (success && cfg.mvs_detect_check) {
+        if (pe_best == 0) {
+            success = false; fail = ADB_FAIL_NO_POLYA;
+        } else {
+            double mlo = cfg.pA_mean_range[0], mhi = cfg.pA_mean_range[1];
+            if (cfg.pA_mean_range_empty && !cfg.pA_mean_scale_range_empty) {
+                mlo = __dmul_rn(cfg.pA_mean_scale_range[0], (double)a_med);
+                mhi = __dmul_rn(cfg.pA_mean_scale_range[1], (double)a_med);
+            } else if (cfg.pA_mean_range_empty) {
+                exception = true; fail = ADB_FAIL_EXC_PA_MEAN_RANGE;
+            }
+            if (!exception && B.n_topk < 0) { exception = true; fail = ADB_FAIL_EXC_TOPK_NONE; }
+            if (!exception) {
+                for (int t = 0; t < B.n_topk; t++) {
+                    const int pe = B.topk[t];
+                    if (pe == 0) break;
+                    MvsOut R = mvs_check(C, a_end, pe, mlo, mhi);
+                    for (int i = 0; i < 5; i++) mvs_v[i] = R.v[i];
+                    valid |= ADB_V_MVS;
+                    if (R.ok || R.v[0] != 0.0) { polya_med_cache = (float)R.v[2]; polya_med_cache_pe = pe; }
+                    if (!R.ok) {
+                        success = false;
+                        if (R.v[0] == 0.0) { fail = ADB_FAIL_MVS_NOT_ENOUGH; fail_mask = 0; }
+                        else { fail = ADB_FAIL_MVS_CHECKS; fail_mask = R.fail_mask; }
+                    }
+                    if (success) { pe_best = pe; break; }
+                }
+            }
+        }
+    }
+    if (!exception && success && cfg.detect_med_shift) {
+        const int w = cfg.med_shift_window;
+        const float m_after = seg_median(C, a_end, min(a_end + w, full_len));
+        const float m_before = seg_median(C, max(a_end - w, 0), a_end);
+        const float sh = __fsub_rn(m_after, m_before);
+        med_shift = (double)sh;
+        valid |= ADB_V_MED_SHIFT;
+        if (!in_range_d(med_shift, cfg.med_shift_range)) { success = false; fail = ADB_FAIL_MED_SHIFT; }
+    }
+    if (exception) {
+        // combined.py:225-226 / 304-305 / 350-351: DetectResults(success=False, fail_reason=str(e)), all else None
+        if (threadIdx.x == 0) {
+            rec->success = 0; rec->fail_code = fail; rec->mvs_fail_mask = 0; rec->valid = 0;
+            rec->signal_len = full_len; rec->preloaded = min(full_len, size);
+        }
+        return;
+    }
+    // partition statistics (signal_partitions.py:65-96), with the updated adapter_start
+    double st[3][4];
+    for (int p = 0; p < 3; p++) for (int q = 0; q < 4; q++) st[p][q] = 0.0;
+    if (a_end > a_start) {
+        seg_mean_std(C, a_start, a_end, st[0][0], st[0][1]);
+        float med = (have_amed && a_start == a_start0) ? a_med : seg_median(C, a_start, a_end);
+        float mad = (have_amed && a_start == a_start0) ? a_mad : seg_mad(C, a_start, a_end, med);
+        st[0][2] = (double)med; st[0][3] = (double)mad;
+        valid |= ADB_V_ADAPTER_STATS;
+    }
+    if (pe_best > a_end) {
+        seg_mean_std(C, a_end, pe_best, st[1][0], st[1][1]);
+        float med = (polya_med_cache_pe == pe_best) ? polya_med_cache : seg_median(C, a_end, pe_best);
+        float mad = seg_mad(C, a_end, pe_best, med);
+        st[1][2] = (double)med; st[1][3] = (double)mad;
+        valid |= ADB_V_POLYA_STATS;
+    }
+    if (size > pe_best) {
+        seg_mean_std(C, pe_best, size, st[2][0], st[2][1]);
+        float med = seg_median(C, pe_best, size);
+        float mad = seg_mad(C, pe_best, size, med);
+        st[2][2] = (double)med; st[2][3] = (double)mad;
+        valid |= ADB_V_RNA_STATS;
+    }
+    if (threadIdx.x == 0) {
+        rec->success = success ? 1 : 0;
+        rec->fail_code = fail;
+        rec->mvs_fail_mask = fail_mask;
+        rec->valid = valid | (B.n_topk >= 0 ? ADB_V_CAND : 0);
+        rec->signal_len = full_len;
+        rec->preloaded = min(full_len, size);
+        rec->adapter_start = a_start;
+        rec->adapter_end = a_end;
+        rec->polya_end = pe_best;
+        rec->primary_adapter_end = B.adapter_end;
+        rec->primary_polya_end = B.polya_end;
+        rec->mvs_adapter_end = 0;
+        rec->n_cand = max(B.n_topk, 0);
+        for (int t = 0; t < ADB_MAX_CAND; t++) rec->cand[t] = (t < B.n_topk) ? B.topk[t] : 0;
+        rec->n_open_pores = n_open;
+        for (int p = 0; p < 3; p++) for (int q = 0; q < 4; q++) rec->stats[p][q] = st[p][q];
+        for (int i = 0; i < 5; i++) rec->mvs[i] = mvs_v[i];
+        for (int i = 0; i < 3; i++) rec->real[i] = real_v[i];
+        rec->med_shift = med_shift;
+    }
+}

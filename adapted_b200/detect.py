@@ -1,0 +1,214 @@
+"""Drop-in minibatch detectors: same names, arguments and error behaviour as the reference's seam functions
+(adapted/detect/combined.py:122-355), executed by the CUDA library.
+
+    combined_detect_llr2(batch_of_signals, full_signal_lens, spc)          -> List[DetectResults]
+    combined_detect_cnn(batch_of_signals, full_signal_lens, model, spc)    -> List[DetectResults] | DetectResults
+    combined_detect_start_peak(batch_of_signals, full_signal_lens, spc)    -> List[DetectResults]
+
+``batch_of_signals`` is the reference's float32 [N, m] NaN-padded pA matrix; ``spc`` may be this package's
+:class:`adapted_b200.config.SigProcConfig` or the reference's own object; ``model`` may be the reference's
+``BoundariesCNN`` (any object with ``state_dict()``), a state-dict-like mapping, or a flat float32 array.
+
+:func:`detect_reads` is the native ingest: ragged int16 ADC + per-read calibration, any number of
+minibatches per call.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, List, Optional, Sequence, Union
+
+import numpy as np
+
+from . import _lib
+from .config import flatten_config
+from .records import DetectResults, records_to_results
+
+_CNN_KEYS = ("0.weight", "0.bias", "2.weight", "2.bias", "4.weight", "4.bias", "6.weight", "6.bias")
+
+
+def flatten_cnn_weights(model: Any) -> np.ndarray:
+    """state dict of BoundariesCNN (adapted/detect/cnn.py:16-52) -> flat float32[58882] in ABI order."""
+    if isinstance(model, np.ndarray):
+        w = np.ascontiguousarray(model, dtype=np.float32).ravel()
+    else:
+        sd = model.state_dict() if hasattr(model, "state_dict") else model
+        if len(sd) == 0:
+            raise ValueError("Model weights were not loaded")  # cnn.py:90-91
+        parts = []
+        for k in _CNN_KEYS:
+            v = sd[k]
+            v = v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)
+            parts.append(np.ascontiguousarray(v, dtype=np.float32).ravel())
+        w = np.concatenate(parts)
+    if w.size != _lib.CNN_NPARAMS:
+        raise ValueError(f"expected {_lib.CNN_NPARAMS} CNN parameters, got {w.size}")
+    return w
+
+
+def _dense_batch(batch_of_signals: np.ndarray, full_signal_lens: np.ndarray):
+    x = np.ascontiguousarray(batch_of_signals, dtype=np.float32)
+    if x.ndim != 2:
+        raise ValueError("batch_of_signals must be a 2-D float32 array")
+    lens = np.ascontiguousarray(full_signal_lens, dtype=np.int32)
+    n, m = x.shape
+    b = _lib.AdbBatch(signal=x.ctypes.data, sig_type=_lib.SIG_F32, n_reads=n, m=m, batch_size=max(n, 1),
+                      offsets=None, full_lens=lens.ctypes.data, calib_offset=None, calib_scale=None)
+    return b, (x, lens)
+
+
+def _raise_minibatch_error(status: int) -> None:
+    # Failures the reference raises outside its per-read try: same exception type and text.
+    if status == -3:
+        raise ValueError("MAD normalization failed: scale is 0")
+    if status == -4:
+        raise ValueError("attempt to get argmin of an empty sequence")
+    if status != 0:
+        raise _lib.AdbError(status, "minibatch failed")
+
+
+def combined_detect_llr2(batch_of_signals: np.ndarray, full_signal_lens: np.ndarray, spc: Any,
+                         device: int = 0) -> List[Any]:
+    """adapted/detect/combined.py:122-227 on the GPU."""
+    b, keep = _dense_batch(batch_of_signals, full_signal_lens)
+    if b.n_reads == 0:
+        return []
+    flat = flatten_config(spc)
+    flat["primary_method"] = 0
+    recs, status, cfg = _run_flat(b, flat, None, device, keep)
+    _raise_minibatch_error(int(status[0]))
+    return records_to_results(recs, 0, "")
+
+
+def combined_detect_cnn(batch_of_signals: np.ndarray, full_signal_lens: np.ndarray, model: Any, spc: Any,
+                        device: int = 0) -> Union[List[Any], Any]:
+    """adapted/detect/combined.py:230-309 on the GPU (returns a bare object for N == 1, like :309)."""
+    b, keep = _dense_batch(batch_of_signals, full_signal_lens)
+    w = flatten_cnn_weights(model)
+    flat = flatten_config(spc)
+    flat["primary_method"] = 1
+    recs, status, cfg = _run_flat(b, flat, w, device, keep)
+    _raise_minibatch_error(int(status[0]))
+    res = records_to_results(recs, 1, None)
+    return res if len(res) > 1 else res[0]
+
+
+def combined_detect_start_peak(batch_of_signals: np.ndarray, full_signal_lens: np.ndarray, spc: Any,
+                               device: int = 0) -> List[Any]:
+    """adapted/detect/combined.py:312-355 on the GPU."""
+    b, keep = _dense_batch(batch_of_signals, full_signal_lens)
+    if b.n_reads == 0:
+        return []
+    flat = flatten_config(spc)
+    flat["primary_method"] = 2
+    recs, status, cfg = _run_flat(b, flat, None, device, keep)
+    if int(status[0]) == -4:
+        raise ValueError("attempt to get argmax of an empty sequence")  # start_peak.py:25-29, outside the try
+    _raise_minibatch_error(int(status[0]))
+    return records_to_results(recs, 2, None)
+
+
+def _run_flat(batch: _lib.AdbBatch, flat: dict, weights: Optional[np.ndarray], device: int, keep):
+    cfg = _lib.fill_config(flat)
+    ctx = _lib.default_context(device)
+    n_batches = (batch.n_reads + batch.batch_size - 1) // batch.batch_size
+    recs = np.zeros(batch.n_reads, dtype=_lib.RECORD_DTYPE)
+    status = np.zeros(max(n_batches, 1), dtype=np.int32)
+    wptr = weights.ctypes.data if weights is not None else None
+    _lib.check(_lib.load().adb_detect_host(ctx.handle, C.byref(batch), C.byref(cfg), wptr, recs.ctypes.data,
+                                           status.ctypes.data))
+    del keep
+    return recs, status, cfg
+
+
+def detect_reads(adc: np.ndarray, offsets: np.ndarray, full_lens: np.ndarray, calib_offset: np.ndarray,
+                 calib_scale: np.ndarray, spc: Any, model: Any = None, minibatch_size: int = 1000,
+                 device: int = 0, return_records: bool = False):
+    """Native ingest: ragged int16 ADC reads (pod5-equivalent information) -> per-read results.
+
+    Reads are processed in consecutive minibatches of ``minibatch_size`` (parser.py:95-99), which is the unit
+    the reference normalises / post-processes over.  Returns (results, batch_status) where a non-zero
+    batch_status marks a minibatch the reference would have lost (its reads are returned as None).
+    """
+    adc = np.ascontiguousarray(adc, dtype=np.int16)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    lens = np.ascontiguousarray(full_lens, dtype=np.int32)
+    coff = np.ascontiguousarray(calib_offset, dtype=np.float32)
+    cscale = np.ascontiguousarray(calib_scale, dtype=np.float32)
+    n = lens.size
+    flat = flatten_config(spc)
+    w = flatten_cnn_weights(model) if flat["primary_method"] == 1 else None
+    b = _lib.AdbBatch(signal=adc.ctypes.data, sig_type=_lib.SIG_I16, n_reads=n, m=int(flat["sig_preload_size"]),
+                      batch_size=int(minibatch_size), offsets=offsets.ctypes.data, full_lens=lens.ctypes.data,
+                      calib_offset=coff.ctypes.data, calib_scale=cscale.ctypes.data)
+    if n == 0:
+        return ([], np.zeros(0, np.int32))
+    recs, status, cfg = _run_flat(b, flat, w, device, (adc, offsets, lens, coff, cscale))
+    if return_records:
+        return recs, status
+    res = records_to_results(recs, flat["primary_method"], "" if flat["primary_method"] == 0 else None)
+    for bi, s in enumerate(status):
+        if s != 0:
+            for i in range(bi * minibatch_size, min((bi + 1) * minibatch_size, n)):
+                res[i] = None
+    return res, status
+
+
+# ---- kernel-level mirrors of the Cython module (adapted/detect/_c_llr.pyx) ---------------------------------------
+
+def c_llr_trace(raw_signal, start, end, min_obs, border_trim, stride=1, adapter_early_stopping=0,
+                adapter_early_stop_window=500, adapter_early_stop_stride=100, polya_early_stopping=0,
+                polya_early_stop_window=50, polya_early_stop_stride=10, return_c_c2=0, device: int = 0):
+    """_c_llr.pyx:202-236 on the GPU (one trace)."""
+    out = c_llr_trace_batch([raw_signal], [(start, end, min_obs, border_trim, stride, adapter_early_stopping,
+                                            adapter_early_stop_window, adapter_early_stop_stride,
+                                            polya_early_stopping, polya_early_stop_window,
+                                            polya_early_stop_stride)], bool(return_c_c2), device)
+    return out[0]
+
+
+def c_llr_trace_batch(signals, params, return_c_c2: bool = False, device: int = 0):
+    sigs = [np.ascontiguousarray(s, dtype=np.float64) for s in signals]
+    offs = np.zeros(len(sigs) + 1, dtype=np.int64)
+    np.cumsum([s.size for s in sigs], out=offs[1:])
+    blob = np.concatenate(sigs) if sigs else np.zeros(0)
+    p = np.ascontiguousarray(np.asarray(params, dtype=np.int64).reshape(len(sigs), 11))
+    for row in p:
+        stride = max(int(row[4]), 1)
+        if (row[8] > 0 or row[5] > 0) and (row[7] <= 0 or row[7] % stride != 0):
+            raise AssertionError("early_stop_stride % stride != 0")  # _c_llr.pyx:102,139
+        if row[8] > 0 and (row[10] <= 0 or row[10] % stride != 0):
+            raise AssertionError("early_stop_stride % stride != 0")  # _c_llr.pyx:140
+    g = np.empty_like(blob)
+    c = np.empty_like(blob) if return_c_c2 else None
+    c2 = np.empty_like(blob) if return_c_c2 else None
+    ctx = _lib.default_context(device)
+    _lib.check(_lib.load().adb_llr_trace_host(
+        ctx.handle, blob.ctypes.data, offs.ctypes.data, len(sigs), p.ctypes.data, g.ctypes.data,
+        c.ctypes.data if return_c_c2 else None, c2.ctypes.data if return_c_c2 else None))
+    out = []
+    for i in range(len(sigs)):
+        sl = slice(offs[i], offs[i + 1])
+        out.append((g[sl], c[sl], c2[sl]) if return_c_c2 else g[sl])
+    return out
+
+
+def global_med_mad(batch_of_signals: np.ndarray, full_signal_lens: np.ndarray, max_obs_trace: int, device: int = 0):
+    """med_mad(batch[:, :max_obs_trace], with_nan=True), adapted/detect/normalize.py:15-22."""
+    b, keep = _dense_batch(batch_of_signals, full_signal_lens)
+    out = np.zeros(2, dtype=np.float32)
+    ctx = _lib.default_context(device)
+    _lib.check(_lib.load().adb_global_med_mad_host(ctx.handle, C.byref(b), int(max_obs_trace), out.ctypes.data))
+    del keep
+    return float(out[0]), float(out[1])
+
+
+def downscale_signal(batch_of_signals: np.ndarray, full_signal_lens: np.ndarray, factor: int, col0: int = 0,
+                     device: int = 0) -> np.ndarray:
+    """downscale_signal(batch[:, col0:], factor), adapted/detect/downscale.py:37-41."""
+    b, keep = _dense_batch(batch_of_signals, full_signal_lens)
+    ncols = (max(b.m - col0, 0) + factor - 1) // factor
+    out = np.zeros((b.n_reads, ncols), dtype=np.float32)
+    ctx = _lib.default_context(device)
+    _lib.check(_lib.load().adb_downscale_host(ctx.handle, C.byref(b), int(col0), int(factor), out.ctypes.data))
+    del keep
+    return out

@@ -1,0 +1,200 @@
+/*
+ * adapted_b200 -- C ABI of the B200-native boundary-detection hot path (drop-in for KleistLab/ADAPTed v0.2.4).
+ *
+ * The reference has no FFI of its own (it is python + one Cython module); the entry points below are what a
+ * binding for the hot path replaces.  Each one cites the reference interface it stands in for
+ * (paths relative to the reference repository).  INTEGRATION.md shows the ctypes stub a maintainer adds.
+ *
+ * Conventions
+ *   - plain C, pointers + sizes, no torch / C++ types;
+ *   - every function returns 0 on success or a negative adb_status; adb_last_error() gives the text;
+ *   - "_host" variants take HOST buffers (pageable or pinned), do H2D / D2H themselves and are synchronous;
+ *   - "_dev" variants take DEVICE pointers and a cudaStream_t (as void*), and are asynchronous on that stream;
+ *   - all kernels are hand-written sm_100a CUDA; there is NO CPU fallback: without a CUDA device every compute
+ *     entry point fails with ADB_ERR_CUDA.
+ */
+#ifndef ADAPTED_B200_H
+#define ADAPTED_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADB_ABI_VERSION 1
+#define ADB_MAX_CAND 16        /* >= cnn_boundaries.polya_cand_k (10 / 15 in the shipped configs)            */
+#define ADB_MAX_OPEN_PORES 20  /* open-pore run starts kept per read in the record; n_open_pores is the true count */
+
+typedef enum adb_status {
+    ADB_OK = 0,
+    ADB_ERR_CUDA = -1,          /* no device / CUDA runtime error                                             */
+    ADB_ERR_ARG = -2,           /* invalid argument                                                            */
+    ADB_ERR_MAD_ZERO = -3,      /* global MAD == 0: the reference raises ValueError (normalize.py:56-59)        */
+    ADB_ERR_EMPTY_TRACE = -4,   /* a read has no downscaled sample: the reference raises ValueError (llr.py:136)
+                                   outside any try and loses the minibatch (combined.py:145-211)              */
+    ADB_ERR_UNSUPPORTED = -5    /* configuration outside the built scope (e.g. mvs_detect_overwrite)            */
+} adb_status;
+
+/* signal element types */
+#define ADB_SIG_F32 0 /* calibrated pA, float32, dense [n_reads, m] row-major, NaN-padded (file_proc.py:160-175) */
+#define ADB_SIG_I16 1 /* raw ADC int16, ragged: read i occupies [offsets[i], offsets[i+1]) of the blob         */
+
+/* primary method codes (config/sig_proc.py:192-208) */
+#define ADB_METHOD_LLR 0
+#define ADB_METHOD_CNN 1
+#define ADB_METHOD_START_PEAK 2
+
+/* Flattened SigProcConfig (adapted/config/sig_proc.py:22-221).  Open range ends are +-inf. */
+typedef struct adb_config {
+    /* [core] */
+    int32_t max_obs_trace, min_obs_adapter, max_obs_adapter, min_obs_polya, downscale_factor;
+    int32_t primary_method;
+    double sig_norm_outlier_thresh;
+    /* [llr_boundaries] */
+    double adapter_peak_prominence, adapter_peak_rel_height;
+    int32_t adapter_peak_width;
+    /* [cnn_boundaries] */
+    int32_t polya_cand_k, fallback_to_llr_short_reads;
+    /* [mvs_polya] */
+    int32_t mvs_detect_check, mvs_detect_overwrite, search_window, pA_mean_window, pA_var_window;
+    int32_t median_shift_window, polyA_window, pA_mean_range_empty, pA_mean_scale_range_empty;
+    double pA_mean_range[2], pA_var_range[2], median_shift_range[2], polyA_med_range[2], polyA_local_range[2];
+    double pA_mean_scale_range[2];
+    /* [real_range] */
+    int32_t detect_open_pores, real_signal_check, mean_window, max_obs_local_range;
+    double mean_start_range[2], mean_end_range[2], local_range[2], adapter_mad_range[2];
+    /* [med_shift] */
+    int32_t detect_med_shift, med_shift_window;
+    double med_shift_range[2];
+    /* [rna_start_peak] */
+    int32_t sp_downscale_factor, start_peak_max_idx, sp_offset1, sp_offset2;
+    double open_pore_pa;
+    int32_t sig_preload_size, _pad;
+} adb_config;
+
+/* fail_code values: the exact strings of combined.py:396-580 are produced by the host mirror */
+enum adb_fail_code {
+    ADB_FAIL_NONE = 0,
+    ADB_FAIL_NO_ADAPTER = 1,        /* "No adapter detected (primary)"                     combined.py:396 */
+    ADB_FAIL_ADAPTER_MAD = 2,       /* "adapter MAD check failed"                          combined.py:409 */
+    ADB_FAIL_OPEN_PORE = 3,         /* "Open pore too close to boundary"                   combined.py:423 */
+    ADB_FAIL_REAL_RANGE = 4,        /* "Real signal check failed"                          combined.py:439 */
+    ADB_FAIL_NO_POLYA = 5,          /* "No polya detected (primary)"                       combined.py:444 */
+    ADB_FAIL_MVS_NOT_ENOUGH = 6,    /* "MVS polya check failed: not enough signal"         combined.py:495 */
+    ADB_FAIL_MVS_CHECKS = 7,        /* "MVS polya check failed: <names from mvs_fail_mask>" combined.py:515 */
+    ADB_FAIL_MED_SHIFT = 9,         /* "Median shift check failed"                         combined.py:580 */
+    ADB_FAIL_EXC_PA_MEAN_RANGE = 20,/* ValueError("pA_mean_range is not specified")        combined.py:462 */
+    ADB_FAIL_EXC_TOPK_NONE = 21,    /* TypeError: 'NoneType' object is not iterable         combined.py:464 */
+    ADB_FAIL_EXC_EMPTY_TRACE = 22,  /* ValueError from the hail-mary trace on an empty slice combined.py:277 */
+    ADB_FAIL_EXC_SLICE_INDEX = 23,  /* TypeError: slice indices must be integers ... (start-peak, pandas)    */
+    ADB_FAIL_EXC_MAD_ZERO = 24      /* ValueError("MAD normalization failed: scale is 0") in the hail mary   */
+};
+
+/* valid bits: which optional groups of the record are set (unset == None in DetectResults) */
+#define ADB_V_ADAPTER_STATS (1u << 0)
+#define ADB_V_POLYA_STATS (1u << 1)
+#define ADB_V_RNA_STATS (1u << 2)
+#define ADB_V_MVS (1u << 3)
+#define ADB_V_REAL_MEANS (1u << 4)
+#define ADB_V_REAL_RANGE (1u << 5)
+#define ADB_V_OPEN_PORES (1u << 6)
+#define ADB_V_MED_SHIFT (1u << 7)
+#define ADB_V_CAND (1u << 8)
+#define ADB_V_START_PEAK (1u << 9)
+#define ADB_V_SP_OPEN_PORE (1u << 10)
+#define ADB_V_FIELDS (1u << 11) /* cleared for reads that died on an exception: every field but fail is None */
+
+/* Fixed-layout result record, one per read (container_types.py:22-94 DetectResults). 512 bytes. */
+typedef struct adb_record {
+    int32_t success, fail_code, mvs_fail_mask;
+    uint32_t valid;
+    int32_t signal_len, preloaded;
+    int32_t adapter_start, adapter_end, polya_end;    /* validated coordinates (combined.py:603-604,626) */
+    int32_t primary_adapter_end, primary_polya_end;   /* {llr,cnn,start_peak}_{adapter,polya}_end (590-593) */
+    int32_t mvs_adapter_end;
+    int32_t n_cand, cand[ADB_MAX_CAND];               /* polya_candidates */
+    int32_t n_open_pores, open_pores[ADB_MAX_OPEN_PORES];
+    int32_t sp_idx, sp_next_idx, sp_open_pore_idx, sp_flag; /* start_peak_* (333-338); sp_flag 1/2 = type */
+    float sp_pa, sp_next_pa;
+    double stats[3][4];  /* adapter / polya / rna_preloaded x mean, std, med, mad (signal_partitions.py:81-96) */
+    double mvs[5];       /* mvs_detect_{mean_at_loc,var_at_loc,polya_med,polya_local_range,med_shift}          */
+    double real[3];      /* real_adapter_{mean_start,mean_end,local_range}                                      */
+    double med_shift;    /* adapter_rna_median_shift                                                            */
+    uint8_t _reserved[120];
+} adb_record;
+
+/* ---- library ---------------------------------------------------------------------------------------- */
+int adb_abi_version(void);
+const char *adb_last_error(void);
+int adb_device_count(void);
+int adb_record_size(void);
+int adb_config_size(void);
+
+/* Opaque per-device context: owns the scratch arena, pinned staging buffers and two CUDA streams. */
+typedef struct adb_ctx adb_ctx;
+int adb_ctx_create(int device, adb_ctx **out);
+void adb_ctx_destroy(adb_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py: gpu_launches) */
+int64_t adb_ctx_launch_count(const adb_ctx *ctx);
+
+/* ---- minibatch detection ---------------------------------------------------------------------------- */
+/*
+ * One description of a batch of reads.  `n_batches` consecutive groups of `batch_size` reads (the last may be
+ * short) are independent minibatches: the LLR path normalises with ONE median/MAD per minibatch
+ * (combined.py:128-132) and the CNN path couples reads of a minibatch through a flattened peak search
+ * (cnn.py:140), so the reference's minibatch (default 1000 reads, parser.py:95-99) is the unit of work.
+ */
+typedef struct adb_batch {
+    const void *signal;          /* f32 dense matrix or i16 blob (host or device, see the function)   */
+    int32_t sig_type;            /* ADB_SIG_F32 | ADB_SIG_I16                                         */
+    int32_t n_reads;
+    int32_t m;                   /* preload window: row length (F32) / max samples per read (I16)     */
+    int32_t batch_size;          /* reads per minibatch                                               */
+    const int64_t *offsets;      /* I16: [n_reads+1] element offsets into the blob; F32: NULL         */
+    const int32_t *full_lens;    /* [n_reads] untruncated read lengths (file_proc.py:161,171)        */
+    const float *calib_offset;   /* I16: [n_reads] pA = (adc + offset) * scale in float32; F32: NULL  */
+    const float *calib_scale;
+} adb_batch;
+
+/*
+ * Drop-in for combined_detect_llr2(batch_of_signals, full_signal_lens, spc)   adapted/detect/combined.py:122-227
+ *          and combined_detect_cnn(batch, lens, model, spc)                   adapted/detect/combined.py:230-309
+ *          and combined_detect_start_peak(batch, lens, spc)                   adapted/detect/combined.py:312-355
+ * selected by cfg->primary_method.  `cnn_weights` (CNN only) is the model's state dict flattened in the order
+ * 0.weight[64,1,7] 0.bias[64] 2.weight[64,64,7] 2.bias[64] 4.weight[64,64,7] 4.bias[64] 6.weight[64,2,7] 6.bias[2]
+ * (58 882 floats, adapted/detect/cnn.py:16-52).  `batch_status` (optional, [n_batches]) receives the per-minibatch
+ * adb_status (where the reference raises outside its per-read try and loses the minibatch).
+ */
+int adb_detect_host(adb_ctx *ctx, const adb_batch *batch, const adb_config *cfg, const float *cnn_weights,
+                    adb_record *out_records, int32_t *batch_status);
+/* Same, all pointers inside `batch`, `cnn_weights`, `out_records`, `batch_status` are DEVICE pointers. */
+int adb_detect_dev(adb_ctx *ctx, const adb_batch *batch, const adb_config *cfg, const float *cnn_weights,
+                   adb_record *out_records, int32_t *batch_status, void *cuda_stream);
+
+/* ---- kernel-level entry points (differential tests against the Cython module) -------------------------- */
+/*
+ * Drop-in for c_llr_trace(raw_signal, start, end, min_obs, border_trim, stride, adapter_early_stopping,
+ *   adapter_early_stop_window, adapter_early_stop_stride, polya_early_stopping, polya_early_stop_window,
+ *   polya_early_stop_stride, return_c_c2)                                  adapted/detect/_c_llr.pyx:202-236
+ * for `n_traces` signals at once (signal i = signals[sig_offsets[i] .. sig_offsets[i+1]), float64, HOST).
+ * params[i*11 .. i*11+11) = start,end,min_obs,border_trim,stride,aes,aes_window,aes_stride,pes,pes_window,pes_stride.
+ * gains / c / c2 (c, c2 optional) use the same offsets.
+ */
+int adb_llr_trace_host(adb_ctx *ctx, const double *signals, const int64_t *sig_offsets, int32_t n_traces,
+                       const int64_t *params, double *gains, double *c, double *c2);
+
+/* Minibatch-global median / MAD of normalize_signal (adapted/detect/normalize.py:15-22,54), HOST buffers. */
+int adb_global_med_mad_host(adb_ctx *ctx, const adb_batch *batch, int32_t max_obs_trace, float *med_mad /*[n_batches*2]*/);
+
+/* mean-pool downscale of efficient_average_pooling (adapted/detect/downscale.py:4-41) on raw pA, HOST buffers:
+ * out[n_reads, ceil(m / factor)] float32 (NaN where the block has a NaN). */
+int adb_downscale_host(adb_ctx *ctx, const adb_batch *batch, int32_t col0, int32_t factor, float *out);
+
+/* CNN scores of BoundariesCNN (adapted/detect/cnn.py:16-52,85-98) on prepared inputs x[n, L] -> scores[n, 2, L_out] */
+int adb_cnn_scores_host(adb_ctx *ctx, const float *x, int32_t n, int32_t L, const float *cnn_weights, float *scores);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADAPTED_B200_H */
