@@ -105,11 +105,14 @@ def load() -> C.CDLL:
     L.adb_ctx_launch_count.restype = C.c_int64
     L.adb_detect_host.argtypes = [vp, C.POINTER(AdbBatch), C.POINTER(AdbConfig), vp, vp, vp]
     L.adb_detect_dev.argtypes = [vp, C.POINTER(AdbBatch), C.POINTER(AdbConfig), vp, vp, vp, vp]
+    L.adb_detect_pipelined_host.argtypes = [vp, C.POINTER(AdbBatch), C.POINTER(AdbConfig), vp, vp, vp, C.c_int32]
+    L.adb_ctx_set_timing.argtypes = [vp, ip]
+    L.adb_ctx_get_timing.argtypes = [vp, vp]
     L.adb_llr_trace_host.argtypes = [vp, vp, vp, C.c_int32, vp, vp, vp, vp]
     L.adb_global_med_mad_host.argtypes = [vp, C.POINTER(AdbBatch), C.c_int32, vp]
     L.adb_downscale_host.argtypes = [vp, C.POINTER(AdbBatch), C.c_int32, C.c_int32, vp]
     L.adb_cnn_scores_host.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, vp]
-    for f in ("adb_ctx_create", "adb_detect_host", "adb_detect_dev", "adb_llr_trace_host",
+    for f in ("adb_detect_pipelined_host", "adb_ctx_set_timing", "adb_ctx_get_timing", "adb_ctx_create", "adb_detect_host", "adb_detect_dev", "adb_llr_trace_host",
               "adb_global_med_mad_host", "adb_downscale_host", "adb_cnn_scores_host"):
         getattr(L, f).restype = ip
     assert L.adb_record_size() == RECORD_DTYPE.itemsize, "adb_record layout mismatch"

@@ -51,10 +51,16 @@ extern "C" int adb_ctx_create(int device, adb_ctx **out) {
     c->sm_count = prop.multiProcessorCount;
     c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+        CUDA_TRY(cudaEventCreateWithFlags(&c->p_done[k], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->p_copied[k], cudaEventDisableTiming));
+    }
     *out = c;
     return ADB_OK;
 }
 
+extern "C" int adb_ctx_set_timing(adb_ctx *c, int on);
 extern "C" void adb_ctx_destroy(adb_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
@@ -62,11 +68,68 @@ extern "C" void adb_ctx_destroy(adb_ctx *c) {
                      &c->cnn_act1, &c->cnn_scores, &c->cnn_w, &c->cnn_aux, &c->h_signal, &c->h_offsets,
                      &c->h_lens, &c->h_coff, &c->h_cscale, &c->h_records, &c->h_misc, &c->h_misc2, &c->h_misc3};
     for (DevBuf *b : all) b->release();
+    for (int k = 0; k < 2; k++) {
+        DevBuf *pb[] = {&c->p_signal[k], &c->p_offsets[k], &c->p_lens[k], &c->p_coff[k], &c->p_cscale[k], &c->p_records[k], &c->p_status[k]};
+        for (DevBuf *b : pb) b->release();
+        if (c->p_done[k]) cudaEventDestroy(c->p_done[k]);
+        if (c->p_copied[k]) cudaEventDestroy(c->p_copied[k]);
+    }
+    adb_ctx_set_timing(c, 0);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 
 extern "C" int64_t adb_ctx_launch_count(const adb_ctx *c) { return c ? c->launches : 0; }
+
+struct KernelTimer {  // brackets one launch with events when ctx->timing is on
+    adb_ctx *ctx;
+    int cls;
+    cudaStream_t st;
+    cudaEvent_t a = nullptr, b = nullptr;
+    KernelTimer(adb_ctx *c, int cls_, cudaStream_t s) : ctx(c), cls(cls_), st(s) {
+        if (ctx->timing) {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, st);
+        }
+    }
+    ~KernelTimer() {
+        if (ctx->timing) {
+            cudaEventRecord(b, st);
+            ctx->ev[cls].push_back({a, b});
+        }
+    }
+};
+
+extern "C" int adb_ctx_set_timing(adb_ctx *c, int on) {
+    if (!c) return ADB_ERR_ARG;
+    c->timing = on;
+    for (int k = 0; k < 4; k++) {
+        for (auto &p : c->ev[k]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+        c->ev[k].clear();
+        c->timing_ms[k] = 0;
+        c->timing_n[k] = 0;
+    }
+    return ADB_OK;
+}
+
+// out[8] = {ms, launches} for the 4 kernel classes; call after the stream has been synchronised
+extern "C" int adb_ctx_get_timing(adb_ctx *c, double *out) {
+    if (!c || !out) return ADB_ERR_ARG;
+    for (int k = 0; k < 4; k++) {
+        for (auto &p : c->ev[k]) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) { c->timing_ms[k] += ms; c->timing_n[k] += 1; }
+            cudaEventDestroy(p.first);
+            cudaEventDestroy(p.second);
+        }
+        c->ev[k].clear();
+        out[2 * k] = c->timing_ms[k];
+        out[2 * k + 1] = (double)c->timing_n[k];
+    }
+    return ADB_OK;
+}
 
 static BatchDev to_dev_view(const adb_batch &b) {
     BatchDev d;
@@ -131,9 +194,15 @@ static int run_global_med_mad(adb_ctx *ctx, const BatchDev &B, int n_batches, in
     dim3 grid(gx, n_batches);
     for (int stage = 0; stage < 2; stage++) {
         for (int pass = 0; pass < 3; pass++) {
-            gsel_hist_kernel<<<grid, 256, 0, st>>>(B, max_obs_trace, stage, pass, (const GselState *)ctx->states.p,
-                                                   (unsigned *)ctx->hist.p);
-            gsel_scan_kernel<<<n_batches, 256, 0, st>>>(stage, pass, (GselState *)ctx->states.p, (unsigned *)ctx->hist.p);
+            {
+                KernelTimer t(ctx, 0, st);
+                gsel_hist_kernel<<<grid, 256, 0, st>>>(B, max_obs_trace, stage, pass, (const GselState *)ctx->states.p,
+                                                       (unsigned *)ctx->hist.p);
+            }
+            {
+                KernelTimer t(ctx, 1, st);
+                gsel_scan_kernel<<<n_batches, 256, 0, st>>>(stage, pass, (GselState *)ctx->states.p, (unsigned *)ctx->hist.p);
+            }
             ctx->launches += 2;
         }
     }
@@ -178,7 +247,10 @@ static int launch_read_kernel(adb_ctx *ctx, const BatchDev &B, const adb_config 
     int grid = std::max(1, std::min(B.n_reads, ctx->sm_count * occ));
     if (ctx->series.ensure((size_t)grid * 2 * B.m * sizeof(float))) { set_err("cudaMalloc series"); return ADB_ERR_CUDA; }
     A.series = (float *)ctx->series.p;
-    read_kernel<<<grid, ADB_READ_THREADS, smem, st>>>(A, cfg);
+    {
+        KernelTimer t(ctx, 2, st);
+        read_kernel<<<grid, ADB_READ_THREADS, smem, st>>>(A, cfg);
+    }
     ctx->launches += 1;
     CUDA_TRY(cudaGetLastError());
     return ADB_OK;
@@ -291,6 +363,71 @@ extern "C" int adb_detect_host(adb_ctx *ctx, const adb_batch *batch, const adb_c
     if (batch_status)
         CUDA_TRY(cudaMemcpyAsync(batch_status, ctx->h_misc.p, sizeof(int) * (size_t)n_batches, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    return ADB_OK;
+}
+
+// Pipelined ingest for long jobs: the reads are cut into chunks of `chunk_batches` minibatches; the H2D copy of
+// chunk i+1 (copy stream) overlaps the kernels of chunk i (compute stream), records return per chunk.  Host buffers
+// should be pinned (cudaHostAlloc / torch pin_memory) for the copies to be asynchronous.  I16 ragged input only.
+extern "C" int adb_detect_pipelined_host(adb_ctx *ctx, const adb_batch *batch, const adb_config *cfg,
+                                         const float *cnn_weights, adb_record *out_records, int32_t *batch_status,
+                                         int32_t chunk_batches) {
+    if (!ctx || !out_records) { set_err("null argument"); return ADB_ERR_ARG; }
+    int rc = check_batch(batch);
+    if (rc) return rc;
+    rc = check_config(cfg);
+    if (rc) return rc;
+    if (batch->sig_type != ADB_SIG_I16) { set_err("pipelined ingest takes ragged int16 input"); return ADB_ERR_ARG; }
+    if (chunk_batches < 1) chunk_batches = 1;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (batch->n_reads == 0) return ADB_OK;
+    const float *w_dev = nullptr;
+    if (cfg->primary_method == ADB_METHOD_CNN) {
+        if (!cnn_weights) { set_err("cnn_weights required"); return ADB_ERR_ARG; }
+        if (ctx->h_misc2.ensure(sizeof(float) * ADB_CNN_NPARAMS)) { set_err("cudaMalloc weights"); return ADB_ERR_CUDA; }
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_misc2.p, cnn_weights, sizeof(float) * ADB_CNN_NPARAMS, cudaMemcpyHostToDevice, ctx->stream));
+        w_dev = (const float *)ctx->h_misc2.p;
+    }
+    const int n_batches = (batch->n_reads + batch->batch_size - 1) / batch->batch_size;
+    const int reads_per_chunk = chunk_batches * batch->batch_size;
+    const int n_chunks = (batch->n_reads + reads_per_chunk - 1) / reads_per_chunk;
+    cudaStream_t cs = ctx->copy_stream, ks = ctx->stream;
+    for (int ch = 0; ch < n_chunks; ch++) {
+        const int slot = ch & 1;
+        const int r0 = ch * reads_per_chunk, r1 = std::min(batch->n_reads, r0 + reads_per_chunk), nr = r1 - r0;
+        const int nb = (nr + batch->batch_size - 1) / batch->batch_size;
+        const int64_t e0 = batch->offsets[r0], e1 = batch->offsets[r1];
+        // the slot is free once the D2H of the chunk that used it two iterations ago has finished
+        if (ch >= 2) CUDA_TRY(cudaEventSynchronize(ctx->p_done[slot]));
+        if (ctx->p_signal[slot].ensure((size_t)(e1 - e0) * 2 + 64) || ctx->p_offsets[slot].ensure(sizeof(int64_t) * ((size_t)nr + 1)) ||
+            ctx->p_lens[slot].ensure(sizeof(int32_t) * (size_t)nr + 16) || ctx->p_coff[slot].ensure(sizeof(float) * (size_t)nr + 16) ||
+            ctx->p_cscale[slot].ensure(sizeof(float) * (size_t)nr + 16) || ctx->p_records[slot].ensure(sizeof(adb_record) * (size_t)nr) ||
+            ctx->p_status[slot].ensure(sizeof(int) * (size_t)nb + 16)) { set_err("cudaMalloc pipeline staging"); return ADB_ERR_CUDA; }
+        CUDA_TRY(cudaMemcpyAsync(ctx->p_signal[slot].p, (const int16_t *)batch->signal + e0, (size_t)(e1 - e0) * 2, cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(cudaMemcpyAsync(ctx->p_offsets[slot].p, batch->offsets + r0, sizeof(int64_t) * ((size_t)nr + 1), cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(cudaMemcpyAsync(ctx->p_lens[slot].p, batch->full_lens + r0, sizeof(int32_t) * (size_t)nr, cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(cudaMemcpyAsync(ctx->p_coff[slot].p, batch->calib_offset + r0, sizeof(float) * (size_t)nr, cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(cudaMemcpyAsync(ctx->p_cscale[slot].p, batch->calib_scale + r0, sizeof(float) * (size_t)nr, cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(cudaEventRecord(ctx->p_copied[slot], cs));
+        CUDA_TRY(cudaStreamWaitEvent(ks, ctx->p_copied[slot], 0));
+        adb_batch d = *batch;
+        // offsets stay absolute: rebase the blob pointer so that blob[offsets[i]] is the staged copy
+        d.signal = (const int16_t *)ctx->p_signal[slot].p - e0;
+        d.offsets = (const int64_t *)ctx->p_offsets[slot].p;
+        d.full_lens = (const int32_t *)ctx->p_lens[slot].p;
+        d.calib_offset = (const float *)ctx->p_coff[slot].p;
+        d.calib_scale = (const float *)ctx->p_cscale[slot].p;
+        d.n_reads = nr;
+        rc = adb_detect_dev(ctx, &d, cfg, w_dev, (adb_record *)ctx->p_records[slot].p, (int *)ctx->p_status[slot].p, ks);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(out_records + r0, ctx->p_records[slot].p, sizeof(adb_record) * (size_t)nr, cudaMemcpyDeviceToHost, ks));
+        if (batch_status)
+            CUDA_TRY(cudaMemcpyAsync(batch_status + (size_t)ch * chunk_batches, ctx->p_status[slot].p, sizeof(int) * (size_t)nb, cudaMemcpyDeviceToHost, ks));
+        CUDA_TRY(cudaEventRecord(ctx->p_done[slot], ks));
+    }
+    CUDA_TRY(cudaStreamSynchronize(ks));
+    CUDA_TRY(cudaStreamSynchronize(cs));
+    (void)n_batches;
     return ADB_OK;
 }
 

@@ -103,3 +103,50 @@ def make_reads(n: int, chemistry: str, m: int, seed: int, stress: bool = False,
         adc=np.concatenate(chunks) if chunks else np.zeros(0, np.int16),
         offsets=np.asarray(offs, dtype=np.int64), full_lens=np.asarray(lens, dtype=np.int32),
         calib_offset=c_off, calib_scale=c_scale, truth=np.asarray(truth, dtype=np.int32).reshape(-1, 3), m=m)
+
+
+def make_reads_torch(n: int, chemistry: str, m: int, seed: int, device="cuda", chunk: int = 4000):
+    """Same squiggle distribution as :func:`make_reads`, generated with torch on `device` (bench.py builds
+    10^5..10^7 reads directly in HBM).  Returns a dict of tensors: adc int16 [sum k_i], offsets int64 [n+1],
+    full_lens int32 [n], calib_offset / calib_scale float32 [n], truth int32 [n, 3]."""
+    import torch
+
+    spec = SPECS[chemistry.lower()]
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    dev = torch.device(device)
+
+    def randint(lo, hi, size):
+        return torch.randint(lo, hi, (size,), generator=g, device=dev)
+
+    parts, lens_all, k_all, off_all, truth_all = [], [], [], [], []
+    t = torch.arange(m, device=dev)[None, :]
+    for s in range(0, n, chunk):
+        c = min(chunk, n - s)
+        n_op, n_ad = randint(*spec.open_pore, c), randint(*spec.adapter, c)
+        n_pa, n_rna = randint(*spec.polya, c), randint(*spec.rna, c)
+        e0, e1, e2 = n_op, n_op + n_ad, n_op + n_ad + n_pa
+        full = e2 + n_rna
+        k = torch.clamp(full, max=m)
+        z = torch.randn((c, m), generator=g, device=dev)
+        nlev = m // spec.hold + 2
+        levels = 95.0 + 14.0 * torch.randn((c, nlev), generator=g, device=dev)
+        li = torch.clamp((t - e2[:, None]) // spec.hold, 0, nlev - 1)
+        pa = torch.gather(levels, 1, li) + 3.0 * z
+        pa = torch.where(t < e2[:, None], 108.0 + 2.5 * z, pa)
+        pa = torch.where(t < e1[:, None], 80.0 + 7.0 * z, pa)
+        pa = torch.where(t < e0[:, None], 220.0 + 3.0 * z, pa)
+        coff = -240.0 + 40.0 * torch.rand((c,), generator=g, device=dev)
+        adc = torch.clamp(torch.round(pa / SCALE - coff[:, None]), -32768, 32767).to(torch.int16)
+        parts.append(adc[t < k[:, None]])
+        lens_all.append(full.to(torch.int32))
+        k_all.append(k)
+        off_all.append(coff.to(torch.float32))
+        truth_all.append(torch.stack([e0, e1, e2], dim=1).to(torch.int32))
+        del z, levels, li, pa, adc
+    k = torch.cat(k_all)
+    offsets = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    offsets[1:] = torch.cumsum(k, 0)
+    return dict(adc=torch.cat(parts), offsets=offsets, full_lens=torch.cat(lens_all),
+                calib_offset=torch.cat(off_all), calib_scale=torch.full((n,), SCALE, dtype=torch.float32, device=dev),
+                truth=torch.cat(truth_all), m=m)

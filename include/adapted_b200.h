@@ -172,6 +172,20 @@ int adb_detect_host(adb_ctx *ctx, const adb_batch *batch, const adb_config *cfg,
 int adb_detect_dev(adb_ctx *ctx, const adb_batch *batch, const adb_config *cfg, const float *cnn_weights,
                    adb_record *out_records, int32_t *batch_status, void *cuda_stream);
 
+/*
+ * Streaming ingest (replaces the producer thread + process pool of adapted/file_proc.py:143-214,738-784 for one
+ * GPU): HOST (ideally pinned) ragged int16 reads are cut into chunks of `chunk_batches` minibatches; the H2D
+ * copy of chunk i+1 overlaps the kernels of chunk i, records are copied back per chunk.  Synchronous on return.
+ */
+int adb_detect_pipelined_host(adb_ctx *ctx, const adb_batch *batch, const adb_config *cfg, const float *cnn_weights,
+                              adb_record *out_records, int32_t *batch_status, int32_t chunk_batches);
+
+/* Per-kernel-class device timing (CUDA events around every launch; used by bench.py for the roofline):
+ * class 0 global-select histogram passes, 1 global-select scans, 2 per-read kernel, 3 other.
+ * adb_ctx_get_timing fills out[8] = {ms, launches} x 4; call it after synchronising the stream. */
+int adb_ctx_set_timing(adb_ctx *ctx, int on);
+int adb_ctx_get_timing(adb_ctx *ctx, double *out);
+
 /* ---- kernel-level entry points (differential tests against the Cython module) -------------------------- */
 /*
  * Drop-in for c_llr_trace(raw_signal, start, end, min_obs, border_trim, stride, adapter_early_stopping,
