@@ -172,9 +172,9 @@ static int check_config(const adb_config *cfg) {
         set_err("downscale_factor must be in [1, 128]");
         return ADB_ERR_UNSUPPORTED;
     }
-    if (cfg->mean_window > ADB_STAGE_CHUNK || cfg->pA_var_window > ADB_STAGE_HIST ||
-        cfg->pA_mean_window > ADB_STAGE_HIST || cfg->pA_var_window < 1 || cfg->pA_mean_window < 1) {
-        set_err("window sizes outside the supported range (mean_window <= 1024, pA_*_window in [1, 128])");
+    if (cfg->mean_window < 1 || cfg->mean_window > ADB_MAX_MEAN_WINDOW || cfg->pA_var_window > ADB_MAX_MOVE_WINDOW ||
+        cfg->pA_mean_window > ADB_MAX_MOVE_WINDOW || cfg->pA_var_window < 1 || cfg->pA_mean_window < 1) {
+        set_err("window sizes outside the supported range");
         return ADB_ERR_UNSUPPORTED;
     }
     if (cfg->polya_cand_k > ADB_MAX_CAND) {
@@ -219,37 +219,68 @@ __global__ void merge_status_kernel(const GselState *states, int *batch_status, 
 }
 
 // ---- the detect entry point (device pointers) -----------------------------------------------------------------
-static int launch_read_kernel(adb_ctx *ctx, const BatchDev &B, const adb_config &cfg, int mode, const int *given,
-                              int given_stride, int given_ntopk, adb_record *out, int *batch_status,
-                              cudaStream_t st) {
-    ReadKernelArgs A;
+static int trace_dims(const adb_config &cfg, int span, int *nds_max, int *peak_cap) {
+    *nds_max = std::max(64, (std::max(span, 0) + cfg.downscale_factor - 1) / cfg.downscale_factor + 2);
+    *peak_cap = *nds_max / 2 + 8;
+    return 0;
+}
+
+static int launch_llr_primary(adb_ctx *ctx, const BatchDev &B, const adb_config &cfg, int *given, int *ntopk,
+                              int *batch_status, cudaStream_t st) {
+    PrimaryArgs A;
     A.B = B;
     A.gstates = (const GselState *)ctx->states.p;
+    trace_dims(cfg, cfg.max_obs_trace - cfg.min_obs_adapter, &A.nds_max, &A.peak_cap);
+    A.given = given;
+    A.ntopk = ntopk;
+    A.batch_status = batch_status;
+    size_t smem = trace_smem_bytes(A.nds_max, A.peak_cap);
+    if ((int)smem > ctx->max_smem_optin) { set_err("downscaled trace does not fit in shared memory"); return ADB_ERR_UNSUPPORTED; }
+    CUDA_TRY(cudaFuncSetAttribute(llr_primary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, llr_primary_kernel, ADB_TRACE_THREADS, smem));
+    if (occ < 1) occ = 1;
+    int grid = std::max(1, std::min(B.n_reads, ctx->sm_count * occ));
+    {
+        KernelTimer t(ctx, 3, st);
+        llr_primary_kernel<<<grid, ADB_TRACE_THREADS, smem, st>>>(A, cfg);
+    }
+    ctx->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return ADB_OK;
+}
+
+static int launch_validate(adb_ctx *ctx, const BatchDev &B, const adb_config &cfg, int mode, const int *given,
+                           int given_stride, int given_ntopk, const int *ntopk_per_read, adb_record *out,
+                           const int *batch_status, cudaStream_t st) {
+    ValidateArgs A;
+    A.B = B;
     A.given = given;
     A.given_stride = given_stride;
     A.given_ntopk = given_ntopk;
+    A.ntopk_per_read = ntopk_per_read;
     A.mode = mode;
-    int span = std::max(cfg.max_obs_trace - cfg.min_obs_adapter, 0);
-    if (mode == ADB_METHOD_CNN) span = std::max(span, B.m);  // hail mary slices up to the whole window
-    A.nds_max = std::max(64, (span + cfg.downscale_factor - 1) / cfg.downscale_factor + 2);
-    A.peak_cap = A.nds_max / 2 + 8;
+    A.win_bytes = B.m * (B.sig_type == ADB_SIG_F32 ? 4 : 2);
+    A.nds_max = 0;
+    A.peak_cap = 0;
+    if (mode == ADB_METHOD_CNN && cfg.fallback_to_llr_short_reads) trace_dims(cfg, B.m, &A.nds_max, &A.peak_cap);
     A.out = out;
     A.batch_status = batch_status;
-    size_t smem = read_kernel_smem_bytes(A.nds_max, A.peak_cap);
+    size_t smem = validate_smem_bytes(A.win_bytes, A.nds_max, A.peak_cap);
     if ((int)smem > ctx->max_smem_optin) {
-        set_err("downscaled window does not fit in shared memory");
+        set_err("preload window does not fit in shared memory (sig_preload_size too large for this build)");
         return ADB_ERR_UNSUPPORTED;
     }
-    CUDA_TRY(cudaFuncSetAttribute(read_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(validate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, read_kernel, ADB_READ_THREADS, smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, validate_kernel, ADB_VAL_THREADS, smem));
     if (occ < 1) occ = 1;
     int grid = std::max(1, std::min(B.n_reads, ctx->sm_count * occ));
     if (ctx->series.ensure((size_t)grid * 2 * B.m * sizeof(float))) { set_err("cudaMalloc series"); return ADB_ERR_CUDA; }
     A.series = (float *)ctx->series.p;
     {
         KernelTimer t(ctx, 2, st);
-        read_kernel<<<grid, ADB_READ_THREADS, smem, st>>>(A, cfg);
+        validate_kernel<<<grid, ADB_VAL_THREADS, smem, st>>>(A, cfg);
     }
     ctx->launches += 1;
     CUDA_TRY(cudaGetLastError());
@@ -279,20 +310,24 @@ extern "C" int adb_detect_dev(adb_ctx *ctx, const adb_batch *batch, const adb_co
         if (rc) return rc;
         merge_status_kernel<<<(n_batches + 127) / 128, 128, 0, st>>>((const GselState *)ctx->states.p, status, n_batches);
         ctx->launches += 1;
-        return launch_read_kernel(ctx, B, *cfg, ADB_METHOD_LLR, nullptr, 0, -1, out_records, status, st);
+        if (ctx->given.ensure(sizeof(int) * (size_t)batch->n_reads * 3)) { set_err("cudaMalloc given"); return ADB_ERR_CUDA; }
+        int *given = (int *)ctx->given.p, *ntopk = given + (size_t)batch->n_reads * 2;
+        rc = launch_llr_primary(ctx, B, *cfg, given, ntopk, status, st);
+        if (rc) return rc;
+        return launch_validate(ctx, B, *cfg, ADB_METHOD_LLR, given, 2, -1, ntopk, out_records, status, st);
     } else if (cfg->primary_method == ADB_METHOD_CNN) {
         if (!cnn_weights) { set_err("cnn_weights required for the CNN primary method"); return ADB_ERR_ARG; }
         const int stride = 1 + cfg->polya_cand_k;
         if (ctx->given.ensure(sizeof(int) * (size_t)batch->n_reads * stride)) { set_err("cudaMalloc given"); return ADB_ERR_CUDA; }
         rc = cnn_primary_boundaries(ctx, B, *cfg, cnn_weights, (int *)ctx->given.p, st);
         if (rc) return rc;
-        return launch_read_kernel(ctx, B, *cfg, ADB_METHOD_CNN, (const int *)ctx->given.p, stride,
-                                  cfg->polya_cand_k >= 1 ? std::max(1, cfg->polya_cand_k) : 1, out_records, status, st);
+        return launch_validate(ctx, B, *cfg, ADB_METHOD_CNN, (const int *)ctx->given.p, stride,
+                               std::max(1, cfg->polya_cand_k), nullptr, out_records, status, st);
     } else if (cfg->primary_method == ADB_METHOD_START_PEAK) {
         if (ctx->given.ensure(sizeof(int) * (size_t)batch->n_reads * 2)) { set_err("cudaMalloc given"); return ADB_ERR_CUDA; }
         rc = start_peak_primary(ctx, B, *cfg, (int *)ctx->given.p, out_records, status, st);
         if (rc) return rc;
-        rc = launch_read_kernel(ctx, B, *cfg, ADB_METHOD_START_PEAK, (const int *)ctx->given.p, 2, -1, out_records, status, st);
+        rc = launch_validate(ctx, B, *cfg, ADB_METHOD_START_PEAK, (const int *)ctx->given.p, 2, -1, nullptr, out_records, status, st);
         if (rc) return rc;
         return start_peak_finish(ctx, B, *cfg, out_records, st);
     }

@@ -22,9 +22,10 @@ struct ReadSrc {
     int n;                // valid samples = min(full_len, m)
     float coff, cscale;   // pA = (adc + coff) * cscale, float32 ops
 
+    // plain loads: the pointers may address global memory or a window staged in shared memory
     __device__ __forceinline__ float pa(int j) const {
-        if (f32) return __ldg(f32 + j);
-        return __fmul_rn(__fadd_rn((float)__ldg(i16 + j), coff), cscale);
+        if (f32) return f32[j];
+        return __fmul_rn(__fadd_rn((float)i16[j], coff), cscale);
     }
 };
 
@@ -54,6 +55,73 @@ __device__ __forceinline__ ReadSrc make_src(const BatchDev &b, int r) {
         s.cscale = b.calib_scale[r];
     }
     return s;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// TMA bulk copy global -> shared (cp.async.bulk, SASS UBLKCP) completing on an mbarrier
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t phase) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+    while (!mbar_try_wait(bar, phase)) {
+    }
+}
+// dst (shared) and src (global) 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Stage `nbytes` bytes starting at the (arbitrarily aligned) global address `src` into shared memory so that the
+// shared copy has the same 16-byte phase as the source: returns the shared address of src[0].  `buf` is 16-byte
+// aligned with room for nbytes + 32.  The 16-byte aligned body goes through the TMA bulk engine (one thread issues,
+// everybody waits on the mbarrier), the unaligned head / tail with ordinary loads.  CTA-wide.
+__device__ unsigned char *cta_stage_window(unsigned char *buf, const unsigned char *src, int nbytes, uint64_t *bar,
+                                           uint32_t &phase) {
+    const int shift = (int)((uintptr_t)src & 15);
+    unsigned char *dst0 = buf + shift;  // dst0 == shared image of src[0]
+    if (nbytes <= 0) return dst0;
+    const unsigned char *body_src = src + ((16 - shift) & 15);
+    const int head = (int)(body_src - src);
+    int body = nbytes - head;
+    if (body < 0) body = 0;
+    body &= ~15;
+    const int tail0 = head + body;
+    if (threadIdx.x == 0 && body > 0) {
+        mbar_expect_tx(bar, (uint32_t)body);
+        const int CH = 16384;
+        for (int o = 0; o < body; o += CH)
+            tma_bulk_g2s(dst0 + head + o, body_src + o, (uint32_t)min(CH, body - o), bar);
+    }
+    for (int i = threadIdx.x; i < min(head, nbytes); i += blockDim.x) dst0[i] = src[i];
+    for (int i = tail0 + threadIdx.x; i < nbytes; i += blockDim.x) dst0[i] = src[i];
+    if (body > 0) {
+        mbar_wait(bar, phase);
+        phase ^= 1;
+    }
+    __syncthreads();
+    return dst0;
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -177,8 +177,8 @@ __device__ int warp_adapter_end(const double *g, int n, int start, int end, doub
 }
 
 // detect_full_polya_trace_peak_with_spike (llr.py:406-479) on the full-length trace g[0..n).  Warp-wide.
-// Returns the downscaled index (0 = none); *err is set when scipy.stats.linregress would raise.
-__device__ int warp_polya_end(const double *g, int n, const PeakScratch &PS, int *err) {
+// Returns the downscaled index (0 = none).
+__device__ int warp_polya_end(const double *g, int n, const PeakScratch &PS) {
     const int lane = threadIdx.x & 31;
     TraceView W;
     W.x = g;
@@ -208,11 +208,7 @@ __device__ int warp_polya_end(const double *g, int n, const PeakScratch &PS, int
         nan_i = min(nan_i, on);
     }
     const int idx_min = (nan_i != 0x7fffffff) ? nan_i : bi;
-    const int cnt = pk[1] - idx_min;
-    if (cnt < 2) {  // linregress raises for fewer than two points / identical x
-        *err = 1;
-        return 0;
-    }
+    const int cnt = pk[1] - idx_min;  // >= 1; a single point gives ssxm == 0 -> r = 0 -> 0 (scipy returns nan, same decision)
     // r^2 of the regression of g[idx_min:p1] on its index (scipy.stats.linregress: r = ssxym / sqrt(ssxm*ssym))
     double sx = 0, sy = 0;
     for (int i = idx_min + lane; i < pk[1]; i += 32) { sx += (double)i; sy += g[i]; }

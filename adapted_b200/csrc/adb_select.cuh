@@ -44,10 +44,19 @@ __device__ __forceinline__ SelScratch sel_scratch_from(unsigned char *base) {
 template <class KeyF>
 __device__ void cta_key_minmax(KeyF key, int n, uint32_t &kmin, uint32_t &kmax, SelScratch &S) {
     uint32_t lo = 0xffffffffu, hi = 0u;
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-        uint32_t k = key(j);
-        lo = min(lo, k);
-        hi = max(hi, k);
+    {
+        const int T = blockDim.x;
+        int j = threadIdx.x;
+        for (; j + 3 * T < n; j += 4 * T) {
+            const uint32_t k0 = key(j), k1 = key(j + T), k2 = key(j + 2 * T), k3 = key(j + 3 * T);
+            lo = min(min(lo, k0), min(k1, min(k2, k3)));
+            hi = max(max(hi, k0), max(k1, max(k2, k3)));
+        }
+        for (; j < n; j += T) {
+            const uint32_t k = key(j);
+            lo = min(lo, k);
+            hi = max(hi, k);
+        }
     }
     lo = warp_min_u(lo);
     hi = warp_max_u(hi);
@@ -97,9 +106,20 @@ __device__ void cta_select_ranks(KeyF key, int n, uint32_t kmin, uint32_t kmax, 
         for (int b = tid; b < ADB_SEL_NB; b += T) S.hist[b] = 0;
         if (tid == 0) *S.g_count = gc - 1;
         __syncthreads();
-        for (int j = tid; j < n; j += T) {
-            uint32_t d = key(j) - lo;  // wraps for keys below lo -> large -> filtered by the span test
-            if (d <= span) atomicAdd(&S.hist[d >> s], 1u);
+        {
+            // keys below lo wrap to large values and are filtered by the span test; 4 loads in flight per thread
+            int j = tid;
+            for (; j + 3 * T < n; j += 4 * T) {
+                const uint32_t d0 = key(j) - lo, d1 = key(j + T) - lo, d2 = key(j + 2 * T) - lo, d3 = key(j + 3 * T) - lo;
+                if (d0 <= span) atomicAdd(&S.hist[d0 >> s], 1u);
+                if (d1 <= span) atomicAdd(&S.hist[d1 >> s], 1u);
+                if (d2 <= span) atomicAdd(&S.hist[d2 >> s], 1u);
+                if (d3 <= span) atomicAdd(&S.hist[d3 >> s], 1u);
+            }
+            for (; j < n; j += T) {
+                const uint32_t d = key(j) - lo;
+                if (d <= span) atomicAdd(&S.hist[d >> s], 1u);
+            }
         }
         __syncthreads();
         // exclusive prefix over the bins: each thread owns a contiguous chunk

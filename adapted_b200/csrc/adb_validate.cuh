@@ -9,15 +9,14 @@
 #include "adb_common.cuh"
 #include "adb_select.cuh"
 
-#define ADB_STAGE_HIST 128   // history kept in front of a staged chunk (>= moving windows)
-#define ADB_STAGE_CHUNK 1024 // samples staged per step for the sequential moving statistics
+#define ADB_MAX_MOVE_WINDOW 4096   // bottleneck window sizes accepted (any value up to the segment length works)
+#define ADB_MAX_MEAN_WINDOW 65536
 
 struct ValCtx {
-    ReadSrc src;
+    ReadSrc src;         // the read's preload window, STAGED IN SHARED MEMORY (pointers address smem)
     const adb_config *cfg;
     SelScratch S;
     uint32_t *kbuf;      // shared: 4 keys + 4 ranks
-    float *stage;        // shared: [ADB_STAGE_HIST + ADB_STAGE_CHUNK]
     float *series_a;     // global scratch [m] (moving variance)
     float *series_b;     // global scratch [m] (moving mean)
     int *itmp;           // shared: 8 ints
@@ -33,7 +32,7 @@ struct PaKeys {
     int a;
     bool ik;
     __device__ __forceinline__ uint32_t operator()(int j) const {
-        if (ik) return (uint32_t)((int)__ldg(s.i16 + a + j) + 32768);
+        if (ik) return (uint32_t)((int)s.i16[a + j] + 32768);
         return f32_key(s.pa(a + j));
     }
 };
@@ -122,15 +121,13 @@ __device__ double seg_local_range(ValCtx &C, int a, int b) {
     return __dsub_rn(p85, p15);
 }
 
-// float32 numpy mean of `n` (<= ADB_STAGE_CHUNK) samples starting at a: staged to shared memory, summed in numpy's
-// pairwise order by one thread.  Returns the mean to all threads.
+// float32 numpy mean of `n` samples starting at a, summed in numpy's pairwise order by one thread (the window is
+// in shared memory).  Returns the mean to all threads.
 __device__ float seg_mean_exact_small(ValCtx &C, int a, int n) {
     __syncthreads();
-    for (int j = threadIdx.x; j < n; j += blockDim.x) C.stage[j] = C.src.pa(a + j);
-    __syncthreads();
     if (threadIdx.x == 0) {
-        const float *st = C.stage;
-        float s = np_sum_f32([&](int i) { return st[i]; }, n);
+        const ReadSrc &src = C.src;
+        float s = np_sum_f32([&](int i) { return src.pa(a + i); }, n);
         ((float *)C.dtmp)[0] = __fdiv_rn(s, (float)n);
     }
     __syncthreads();
@@ -139,12 +136,27 @@ __device__ float seg_mean_exact_small(ValCtx &C, int a, int n) {
     return r;
 }
 
-// float32 np.var of n (<= ADB_STAGE_CHUNK) samples (numpy _var: mean, x - mean, x*x, pairwise sum / n)
+// two means at once (real_range_check: first / last mean_window samples), threads 0 and 32
+__device__ void seg_mean_exact_pair(ValCtx &C, int a0, int a1, int n, float &m0, float &m1) {
+    __syncthreads();
+    if (threadIdx.x == 0 || threadIdx.x == 32) {
+        const ReadSrc &src = C.src;
+        const int a = threadIdx.x == 0 ? a0 : a1;
+        float s = np_sum_f32([&](int i) { return src.pa(a + i); }, n);
+        ((float *)C.dtmp)[threadIdx.x == 0 ? 0 : 1] = __fdiv_rn(s, (float)n);
+    }
+    __syncthreads();
+    m0 = ((float *)C.dtmp)[0];
+    m1 = ((float *)C.dtmp)[1];
+    __syncthreads();
+}
+
+// float32 np.var of n samples (numpy _var: mean, x - mean, x*x, pairwise sum / n)
 __device__ float seg_var_exact_small(ValCtx &C, int a, int n) {
-    float mean = seg_mean_exact_small(C, a, n);  // leaves the samples staged
+    float mean = seg_mean_exact_small(C, a, n);
     if (threadIdx.x == 0) {
-        const float *st = C.stage;
-        float s = np_sum_f32([&](int i) { float d = __fsub_rn(st[i], mean); return __fmul_rn(d, d); }, n);
+        const ReadSrc &src = C.src;
+        float s = np_sum_f32([&](int i) { float d = __fsub_rn(src.pa(a + i), mean); return __fmul_rn(d, d); }, n);
         ((float *)C.dtmp)[0] = __fdiv_rn(s, (float)n);
     }
     __syncthreads();
@@ -186,106 +198,133 @@ __device__ void seg_mean_std(ValCtx &C, int a, int b, double &mean_out, double &
 }
 
 // ---- bottleneck moving statistics (float32 recurrences, one lane each) --------------------------------------
-struct MoveMeanState {
-    int count; float asum, count_inv;
-};
-struct MoveVarState {
-    int count; float amean, assqdm, count_inv, ddof_inv;
-};
-
-// Runs move_var(window wv) on thread 0 and move_mean(window wm) on thread 32 over src[a, a+L); writes the valid
-// entries (index >= window-1) compacted to series_a / series_b.  CTA-wide (all threads stage the data).
+// move_var(window wv) on thread 0 and move_mean(window wm) on thread 32 over src[a, a+L), reading the window from
+// shared memory; the valid entries (index >= window-1) go, compacted, to series_a / series_b (global scratch).
+// NaN-free segments (the only case real ADC data produces) take a branch-free loop whose only loop-carried
+// dependencies are the float32 accumulators themselves; segments with NaN take the general path with bottleneck's
+// count bookkeeping.  CTA-wide.
 __device__ void seg_moving_stats(ValCtx &C, int a, int L, int wv, int wm, bool do_var, bool do_mean) {
-    MoveMeanState M{0, 0.f, 0.f};
-    MoveVarState Vs{0, 0.f, 0.f, 0.f, 0.f};
-    float *st = C.stage + ADB_STAGE_HIST;  // st[-k] holds history
-    for (int base = 0; base < L; base += ADB_STAGE_CHUNK) {
-        const int len = min(ADB_STAGE_CHUNK, L - base);
-        __syncthreads();
-        // history: last ADB_STAGE_HIST samples before `base`
-        for (int j = threadIdx.x; j < ADB_STAGE_HIST; j += blockDim.x) {
-            int idx = base - ADB_STAGE_HIST + j;
-            C.stage[j] = (idx >= 0) ? C.src.pa(a + idx) : 0.f;
-        }
-        for (int j = threadIdx.x; j < len; j += blockDim.x) st[j] = C.src.pa(a + base + j);
-        __syncthreads();
-        if (threadIdx.x == 0 && do_var) {
-            for (int j = 0; j < len; j++) {
-                const int i = base + j;
-                float ai = st[j], yi;
-                if (i < wv) {  // WHILE0 / WHILE1 of move_template.c
+    const ReadSrc &src = C.src;
+    // any NaN in the segment?
+    __syncthreads();
+    if (threadIdx.x == 0) C.itmp[6] = 0;
+    __syncthreads();
+    {
+        bool bad = false;
+        for (int j = threadIdx.x; j < L; j += blockDim.x) { float v = src.pa(a + j); bad |= !(v == v); }
+        if (bad) C.itmp[6] = 1;
+    }
+    __syncthreads();
+    const bool has_nan = C.itmp[6] != 0;
+    if (threadIdx.x == 0 && do_var) {
+        float *y = C.series_a;
+        if (!has_nan) {
+            float amean = 0.f, assqdm = 0.f;
+            for (int i = 0; i < wv; i++) {  // Welford accumulation of the first window
+                const float ai = src.pa(a + i);
+                const float delta = __fsub_rn(ai, amean);
+                amean = __fadd_rn(amean, __fdiv_rn(delta, (float)(i + 1)));
+                assqdm = __fadd_rn(assqdm, __fmul_rn(delta, __fsub_rn(ai, amean)));
+            }
+            if (assqdm < 0) assqdm = 0;
+            y[0] = __fdiv_rn(assqdm, (float)wv);
+            const float count_inv = (float)(1.0 / (double)wv);
+#pragma unroll 4
+            for (int i = wv; i < L; i++) {
+                float ai = src.pa(a + i), aold = src.pa(a + i - wv);
+                const float delta = __fsub_rn(ai, aold);
+                aold = __fsub_rn(aold, amean);
+                amean = __fadd_rn(amean, __fmul_rn(delta, count_inv));
+                ai = __fsub_rn(ai, amean);
+                assqdm = __fadd_rn(assqdm, __fmul_rn(__fadd_rn(ai, aold), delta));
+                if (assqdm < 0) assqdm = 0;
+                y[i - (wv - 1)] = __fmul_rn(assqdm, count_inv);
+            }
+        } else {
+            int count = 0;
+            float amean = 0.f, assqdm = 0.f, count_inv = 0.f, ddof_inv = 0.f;
+            for (int i = 0; i < L; i++) {
+                float ai = src.pa(a + i), yi;
+                if (i < wv) {
                     if (ai == ai) {
-                        Vs.count += 1;
-                        float delta = __fsub_rn(ai, Vs.amean);
-                        Vs.amean = __fadd_rn(Vs.amean, __fdiv_rn(delta, (float)Vs.count));
-                        Vs.assqdm = __fadd_rn(Vs.assqdm, __fmul_rn(delta, __fsub_rn(ai, Vs.amean)));
+                        count += 1;
+                        const float delta = __fsub_rn(ai, amean);
+                        amean = __fadd_rn(amean, __fdiv_rn(delta, (float)count));
+                        assqdm = __fadd_rn(assqdm, __fmul_rn(delta, __fsub_rn(ai, amean)));
                     }
                     if (i == wv - 1) {
-                        if (Vs.count >= wv) {
-                            if (Vs.assqdm < 0) Vs.assqdm = 0;
-                            yi = __fdiv_rn(Vs.assqdm, (float)Vs.count);
-                        } else yi = CUDART_NAN_F;
-                        C.series_a[0] = yi;
-                        Vs.count_inv = (float)(1.0 / (double)Vs.count);
-                        Vs.ddof_inv = Vs.count_inv;
+                        if (count >= wv) { if (assqdm < 0) assqdm = 0; yi = __fdiv_rn(assqdm, (float)count); }
+                        else yi = CUDART_NAN_F;
+                        y[0] = yi;
+                        count_inv = (float)(1.0 / (double)count);
+                        ddof_inv = count_inv;
                     }
                 } else {
-                    float aold = st[j - wv];
+                    float aold = src.pa(a + i - wv);
                     if (ai == ai) {
                         if (aold == aold) {
-                            float delta = __fsub_rn(ai, aold);
-                            aold = __fsub_rn(aold, Vs.amean);
-                            Vs.amean = __fadd_rn(Vs.amean, __fmul_rn(delta, Vs.count_inv));
-                            ai = __fsub_rn(ai, Vs.amean);
-                            Vs.assqdm = __fadd_rn(Vs.assqdm, __fmul_rn(__fadd_rn(ai, aold), delta));
+                            const float delta = __fsub_rn(ai, aold);
+                            aold = __fsub_rn(aold, amean);
+                            amean = __fadd_rn(amean, __fmul_rn(delta, count_inv));
+                            ai = __fsub_rn(ai, amean);
+                            assqdm = __fadd_rn(assqdm, __fmul_rn(__fadd_rn(ai, aold), delta));
                         } else {
-                            Vs.count++;
-                            Vs.count_inv = (float)(1.0 / (double)Vs.count);
-                            Vs.ddof_inv = Vs.count_inv;
-                            float delta = __fsub_rn(ai, Vs.amean);
-                            Vs.amean = __fadd_rn(Vs.amean, __fmul_rn(delta, Vs.count_inv));
-                            Vs.assqdm = __fadd_rn(Vs.assqdm, __fmul_rn(delta, __fsub_rn(ai, Vs.amean)));
+                            count++;
+                            count_inv = (float)(1.0 / (double)count);
+                            ddof_inv = count_inv;
+                            const float delta = __fsub_rn(ai, amean);
+                            amean = __fadd_rn(amean, __fmul_rn(delta, count_inv));
+                            assqdm = __fadd_rn(assqdm, __fmul_rn(delta, __fsub_rn(ai, amean)));
                         }
                     } else if (aold == aold) {
-                        Vs.count--;
-                        Vs.count_inv = (float)(1.0 / (double)Vs.count);
-                        Vs.ddof_inv = Vs.count_inv;
-                        if (Vs.count > 0) {
-                            float delta = __fsub_rn(aold, Vs.amean);
-                            Vs.amean = __fsub_rn(Vs.amean, __fmul_rn(delta, Vs.count_inv));
-                            Vs.assqdm = __fsub_rn(Vs.assqdm, __fmul_rn(delta, __fsub_rn(aold, Vs.amean)));
-                        } else {
-                            Vs.amean = 0;
-                            Vs.assqdm = 0;
-                        }
+                        count--;
+                        count_inv = (float)(1.0 / (double)count);
+                        ddof_inv = count_inv;
+                        if (count > 0) {
+                            const float delta = __fsub_rn(aold, amean);
+                            amean = __fsub_rn(amean, __fmul_rn(delta, count_inv));
+                            assqdm = __fsub_rn(assqdm, __fmul_rn(delta, __fsub_rn(aold, amean)));
+                        } else { amean = 0; assqdm = 0; }
                     }
-                    if (Vs.count >= wv) {
-                        if (Vs.assqdm < 0) Vs.assqdm = 0;
-                        yi = __fmul_rn(Vs.assqdm, Vs.ddof_inv);
-                    } else yi = CUDART_NAN_F;
-                    C.series_a[i - (wv - 1)] = yi;
+                    if (count >= wv) { if (assqdm < 0) assqdm = 0; yi = __fmul_rn(assqdm, ddof_inv); }
+                    else yi = CUDART_NAN_F;
+                    y[i - (wv - 1)] = yi;
                 }
             }
         }
-        if (threadIdx.x == 32 && do_mean) {
-            for (int j = 0; j < len; j++) {
-                const int i = base + j;
-                float ai = st[j];
+    }
+    if (threadIdx.x == 32 && do_mean) {
+        float *y = C.series_b;
+        if (!has_nan) {
+            float asum = 0.f;
+            for (int i = 0; i < wm; i++) asum = __fadd_rn(asum, src.pa(a + i));
+            y[0] = __fdiv_rn(asum, (float)wm);
+            const float count_inv = (float)(1.0 / (double)wm);
+#pragma unroll 8
+            for (int i = wm; i < L; i++) {
+                asum = __fadd_rn(asum, __fsub_rn(src.pa(a + i), src.pa(a + i - wm)));
+                y[i - (wm - 1)] = __fmul_rn(asum, count_inv);
+            }
+        } else {
+            int count = 0;
+            float asum = 0.f, count_inv = 0.f;
+            for (int i = 0; i < L; i++) {
+                const float ai = src.pa(a + i);
                 if (i < wm) {
-                    if (ai == ai) { M.asum = __fadd_rn(M.asum, ai); M.count += 1; }
+                    if (ai == ai) { asum = __fadd_rn(asum, ai); count += 1; }
                     if (i == wm - 1) {
-                        C.series_b[0] = (M.count >= wm) ? __fdiv_rn(M.asum, (float)M.count) : CUDART_NAN_F;
-                        M.count_inv = (float)(1.0 / (double)M.count);
+                        y[0] = (count >= wm) ? __fdiv_rn(asum, (float)count) : CUDART_NAN_F;
+                        count_inv = (float)(1.0 / (double)count);
                     }
                 } else {
-                    float aold = st[j - wm];
+                    const float aold = src.pa(a + i - wm);
                     if (ai == ai) {
-                        if (aold == aold) M.asum = __fadd_rn(M.asum, __fsub_rn(ai, aold));
-                        else { M.asum = __fadd_rn(M.asum, ai); M.count++; M.count_inv = (float)(1.0 / (double)M.count); }
+                        if (aold == aold) asum = __fadd_rn(asum, __fsub_rn(ai, aold));
+                        else { asum = __fadd_rn(asum, ai); count++; count_inv = (float)(1.0 / (double)count); }
                     } else if (aold == aold) {
-                        M.asum = __fsub_rn(M.asum, aold); M.count--; M.count_inv = (float)(1.0 / (double)M.count);
+                        asum = __fsub_rn(asum, aold); count--; count_inv = (float)(1.0 / (double)count);
                     }
-                    C.series_b[i - (wm - 1)] = (M.count >= wm) ? __fmul_rn(M.asum, M.count_inv) : CUDART_NAN_F;
+                    y[i - (wm - 1)] = (count >= wm) ? __fmul_rn(asum, count_inv) : CUDART_NAN_F;
                 }
             }
         }
@@ -294,13 +333,37 @@ __device__ void seg_moving_stats(ValCtx &C, int a, int L, int wv, int wm, bool d
     __syncthreads();
 }
 
-// np.nanmedian of a float32 series in global scratch (NaNs dropped; none occur for NaN-free input)
+// keys of a float32 series that may contain NaN: NaNs sort last (key 0xffffffff) and are not counted
+struct BufKeysNan {
+    const float *p;
+    __device__ __forceinline__ uint32_t operator()(int j) const { float v = p[j]; return (v == v) ? f32_key(v) : 0xffffffffu; }
+};
+
+// np.nanmedian of a float32 series in global scratch: NaNs are dropped (they get the largest key and the ranks
+// are taken among the non-NaN count)
 __device__ float series_nanmedian(ValCtx &C, const float *p, int n) {
     if (n <= 0) return CUDART_NAN_F;
-    BufKeys K{p};
+    __syncthreads();
+    if (threadIdx.x == 0) C.itmp[7] = 0;
+    __syncthreads();
+    int cnt = 0;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) { float v = p[j]; cnt += (v == v); }
+    cnt = warp_sum_i(cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&C.itmp[7], cnt);
+    __syncthreads();
+    const int nvalid = C.itmp[7];
+    __syncthreads();
+    if (nvalid == 0) return CUDART_NAN_F;
+    BufKeysNan K{p};
     uint32_t kmin, kmax;
     cta_key_minmax(K, n, kmin, kmax, C.S);
-    return cta_median_keys(K, KeyToF32(), n, kmin, kmax, C.S, C.kbuf);
+    int *ranks = (int *)(C.kbuf + 4);
+    if (threadIdx.x == 0) { ranks[0] = (nvalid - 1) / 2; ranks[1] = nvalid / 2; }
+    __syncthreads();
+    cta_select_ranks(K, n, kmin, kmax, ranks, (nvalid & 1) ? 1 : 2, C.kbuf, C.S);
+    const float x0 = key_f32(C.kbuf[0]);
+    if (nvalid & 1) return x0;
+    return __fdiv_rn(__fadd_rn(x0, key_f32(C.kbuf[1])), 2.0f);
 }
 
 // ---- mean_var_shift_polyA_check (mvs.py:45-158) -------------------------------------------------------------
@@ -480,8 +543,8 @@ __device__ void validate_boundaries_cta(ValCtx &C, const PrimaryBounds &B, int f
         if (len < 2 * cfg.mean_window) {
             success = false; fail = ADB_FAIL_REAL_RANGE;
         } else {
-            const float m0 = seg_mean_exact_small(C, a, cfg.mean_window);
-            const float m1 = seg_mean_exact_small(C, b - cfg.mean_window, cfg.mean_window);
+            float m0, m1;
+            seg_mean_exact_pair(C, a, b - cfg.mean_window, cfg.mean_window, m0, m1);
             real_v[0] = (double)m0; real_v[1] = (double)m1;
             valid |= ADB_V_REAL_MEANS;
             if (in_range_d((double)m0, cfg.mean_start_range) && in_range_d((double)m1, cfg.mean_end_range)) {

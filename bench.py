@@ -192,7 +192,11 @@ def main():
                           batch_size=args.minibatch, offsets=data["offsets"].data_ptr(),
                           full_lens=data["full_lens"].data_ptr(), calib_offset=data["calib_offset"].data_ptr(),
                           calib_scale=data["calib_scale"].data_ptr())
-    stream = torch.cuda.current_stream().cuda_stream
+    # a non-default torch stream: its handle is passed to the C ABI, so torch's events bracket the kernels
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def step():
         _lib.check(L.adb_detect_dev(ctx.handle, C.byref(batch), C.byref(cfg), None, records.data_ptr(),
@@ -269,11 +273,11 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    cls_names = ["global_select_hist", "global_select_scan", "read_kernel", "other"]
+    cls_names = ["global_select_hist", "global_select_scan", "validate_kernel", "llr_primary_kernel"]
     per_cls = {cls_names[i]: {"ms": tim[2 * i], "launches": int(tim[2 * i + 1])} for i in range(4)}
-    dom = max(range(3), key=lambda i: tim[2 * i])
+    dom = max(range(4), key=lambda i: tim[2 * i])
     alg_bytes_per_step = 2.0 * samples + (8 + 4 + 512) * n
-    if dom == 0:  # each histogram pass streams the first max_obs_trace samples of every read once
+    if dom in (0, 3):  # these kernels stream the first max_obs_trace samples of every read once per launch
         launches_dom = max(per_cls[cls_names[0]]["launches"], 1)
         alg_launch = 2.0 * float(torch.clamp(data["offsets"][1:] - data["offsets"][:-1], max=flat["max_obs_trace"]).sum().item())
     else:
