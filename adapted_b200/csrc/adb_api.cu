@@ -105,7 +105,7 @@ struct KernelTimer {  // brackets one launch with events when ctx->timing is on
 extern "C" int adb_ctx_set_timing(adb_ctx *c, int on) {
     if (!c) return ADB_ERR_ARG;
     c->timing = on;
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < 8; k++) {
         for (auto &p : c->ev[k]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
         c->ev[k].clear();
         c->timing_ms[k] = 0;
@@ -114,10 +114,10 @@ extern "C" int adb_ctx_set_timing(adb_ctx *c, int on) {
     return ADB_OK;
 }
 
-// out[8] = {ms, launches} for the 4 kernel classes; call after the stream has been synchronised
+// out[16] = {ms, launches} for the 8 kernel classes; call after the stream has been synchronised
 extern "C" int adb_ctx_get_timing(adb_ctx *c, double *out) {
     if (!c || !out) return ADB_ERR_ARG;
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < 8; k++) {
         for (auto &p : c->ev[k]) {
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) { c->timing_ms[k] += ms; c->timing_n[k] += 1; }
@@ -275,10 +275,53 @@ static int launch_validate(adb_ctx *ctx, const BatchDev &B, const adb_config &cf
     int occ = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, validate_kernel, ADB_VAL_THREADS, smem));
     if (occ < 1) occ = 1;
-    int grid = std::max(1, std::min(B.n_reads, ctx->sm_count * occ));
-    if (ctx->series.ensure((size_t)grid * 2 * B.m * sizeof(float))) { set_err("cudaMalloc series"); return ADB_ERR_CUDA; }
+    // moving statistics of the first poly(A) candidate are precomputed thread-per-read into compact pools sized for
+    // an average poly(A) share of 1/4 of the window; reads that do not fit fall back to the in-CTA path (same result)
+    const bool pre = cfg.mvs_detect_check != 0;
+    const long long pool_cap = std::max<long long>(1 << 20, (long long)B.n_reads * B.m / 4);
+    if (pre && (ctx->cnn_aux.ensure((size_t)pool_cap * sizeof(float) * 2) ||
+                ctx->h_misc3.ensure(sizeof(int) * 2 * (size_t)B.n_reads + sizeof(long long) * ((size_t)B.n_reads + 2)))) {
+        set_err("cudaMalloc moving-statistics scratch");
+        return ADB_ERR_CUDA;
+    }
+    int grid_max = std::max(1, ctx->sm_count * occ);
+    const size_t row = (size_t)B.m * sizeof(float);
+    if (ctx->series.ensure((size_t)grid_max * 2 * row)) { set_err("cudaMalloc series"); return ADB_ERR_CUDA; }
     A.series = (float *)ctx->series.p;
+    A.pre_var = A.pre_mean = nullptr;
+    A.pre_off = nullptr;
+    A.pre_meta = nullptr;
+    if (pre) {
+        MvsSeriesArgs M;
+        M.B = B;
+        M.given = given;
+        M.given_stride = given_stride;
+        M.n_reads = B.n_reads;
+        M.var_pool = (float *)ctx->cnn_aux.p;
+        M.mean_pool = M.var_pool + pool_cap;
+        M.pool_cap = pool_cap;
+        long long *lbase = (long long *)ctx->h_misc3.p;
+        M.cursor = (unsigned long long *)lbase;
+        M.row_off = lbase + 2;
+        M.meta = (int *)(lbase + 2 + B.n_reads);
+        CUDA_TRY(cudaMemsetAsync(M.cursor, 0, 16, st));
+        {
+            KernelTimer t(ctx, 4, st);
+            if (B.sig_type == ADB_SIG_I16) {
+                CUDA_TRY(cudaFuncSetAttribute(mvs_series_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mvs_smem_bytes()));
+                mvs_series_kernel<<<(B.n_reads + MVS_LANES - 1) / MVS_LANES, MVS_LANES, mvs_smem_bytes(), st>>>(M, cfg);
+            } else {
+                mvs_series_f32_kernel<<<(B.n_reads + 127) / 128, 128, 0, st>>>(M, cfg);
+            }
+        }
+        ctx->launches += 1;
+        A.pre_var = M.var_pool;
+        A.pre_mean = M.mean_pool;
+        A.pre_off = M.row_off;
+        A.pre_meta = M.meta;
+    }
     {
+        int grid = std::max(1, std::min(B.n_reads, grid_max));
         KernelTimer t(ctx, 2, st);
         validate_kernel<<<grid, ADB_VAL_THREADS, smem, st>>>(A, cfg);
     }

@@ -55,9 +55,9 @@ struct adb_ctx {
     int64_t launches = 0;
     // optional per-kernel-class timing (bench.py roofline): events bracket every launch of a class
     int timing = 0;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[4];  // 0 global-select hist, 1 global-select scan, 2 read kernel, 3 other
-    double timing_ms[4] = {0, 0, 0, 0};
-    int64_t timing_n[4] = {0, 0, 0, 0};
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[8];  // see ADB_TC_* in adb_api.cu
+    double timing_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int64_t timing_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // double-buffered staging for the pipelined host entry point
     DevBuf p_signal[2], p_offsets[2], p_lens[2], p_coff[2], p_cscale[2], p_records[2], p_status[2];
     cudaEvent_t p_done[2] = {nullptr, nullptr}, p_copied[2] = {nullptr, nullptr};

@@ -41,30 +41,63 @@ __global__ void __launch_bounds__(256) gsel_hist_kernel(BatchDev B, int max_obs_
     const int pshift = (pass == 0) ? 32 : (pass == 1 ? 21 : 10);
     const bool same = (pass == 0) || (st.prefix[0] == st.prefix[1]);
     const float med = st.med;
-    for (int r = r0 + blockIdx.x; r < r1; r += gridDim.x) {
-        ReadSrc src = make_src(B, r);
-        const int n = min(src.n, max_obs_trace);
-        // run-length aggregation: consecutive samples of a thread mostly fall into the same bin
-        int cur0 = -1, cnt0 = 0, cur1 = -1, cnt1 = 0;
-        for (int j = threadIdx.x; j < n; j += blockDim.x) {
-            float v = src.pa(j);
-            if (!(v == v)) continue;
-            if (stage == 1) v = fabsf(__fsub_rn(v, med));
-            const uint32_t k = f32_key(v);
-            const uint32_t hi = (pshift >= 32) ? 0u : (k >> pshift);
-            const int bin = (int)((k >> shift) & mask);
-            if (pass == 0 || hi == st.prefix[0]) {
-                if (bin == cur0) cnt0++;
-                else { if (cnt0) atomicAdd(&sh[0][cur0], (unsigned)cnt0); cur0 = bin; cnt0 = 1; }
-            }
-            if (!same && hi == st.prefix[1]) {
-                if (bin == cur1) cnt1++;
-                else { if (cnt1) atomicAdd(&sh[1][cur1], (unsigned)cnt1); cur1 = bin; cnt1 = 1; }
-            }
+    // run-length aggregation: consecutive samples mostly fall into the same bin, so a thread only touches the
+    // shared histogram when its bin changes
+    int cur0 = -1, cnt0 = 0, cur1 = -1, cnt1 = 0;
+    auto consume = [&](float v) {
+        if (!(v == v)) return;
+        if (stage == 1) v = fabsf(__fsub_rn(v, med));
+        const uint32_t k = f32_key(v);
+        const uint32_t hi = (pshift >= 32) ? 0u : (k >> pshift);
+        const int bin = (int)((k >> shift) & mask);
+        if (pass == 0 || hi == st.prefix[0]) {
+            if (bin == cur0) cnt0++;
+            else { if (cnt0) atomicAdd(&sh[0][cur0], (unsigned)cnt0); cur0 = bin; cnt0 = 1; }
         }
-        if (cnt0) atomicAdd(&sh[0][cur0], (unsigned)cnt0);
-        if (cnt1) atomicAdd(&sh[1][cur1], (unsigned)cnt1);
+        if (!same && hi == st.prefix[1]) {
+            if (bin == cur1) cnt1++;
+            else { if (cnt1) atomicAdd(&sh[1][cur1], (unsigned)cnt1); cur1 = bin; cnt1 = 1; }
+        }
+    };
+    for (int r = r0 + blockIdx.x; r < r1; r += gridDim.x) {
+        const ReadSrc src = make_src(B, r);
+        const int n = min(src.n, max_obs_trace);
+        if (n <= 0) continue;
+        if (src.i16) {
+            // 16-byte vector loads (8 samples) over the aligned body, scalar head / tail
+            const int16_t *p = src.i16;
+            const int head = min(n, (int)(((16 - ((uintptr_t)p & 15)) & 15) >> 1));
+            const int nvec = (n - head) >> 3;
+            const uint4 *pv = (const uint4 *)(p + head);
+            const float co = src.coff, cs = src.cscale;
+            for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+                const uint4 q = __ldg(pv + v);
+                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    consume(__fmul_rn(__fadd_rn((float)(int16_t)(w[t] & 0xffffu), co), cs));
+                    consume(__fmul_rn(__fadd_rn((float)(int16_t)(w[t] >> 16), co), cs));
+                }
+            }
+            const int tail0 = head + (nvec << 3);
+            for (int j = threadIdx.x; j < head; j += blockDim.x) consume(src.pa(j));
+            for (int j = tail0 + threadIdx.x; j < n; j += blockDim.x) consume(src.pa(j));
+        } else {
+            const float *p = src.f32;
+            const int head = min(n, (int)(((16 - ((uintptr_t)p & 15)) & 15) >> 2));
+            const int nvec = (n - head) >> 2;
+            const float4 *pv = (const float4 *)(p + head);
+            for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+                const float4 q = __ldg(pv + v);
+                consume(q.x); consume(q.y); consume(q.z); consume(q.w);
+            }
+            const int tail0 = head + (nvec << 2);
+            for (int j = threadIdx.x; j < head; j += blockDim.x) consume(p[j]);
+            for (int j = tail0 + threadIdx.x; j < n; j += blockDim.x) consume(p[j]);
+        }
     }
+    if (cnt0) atomicAdd(&sh[0][cur0], (unsigned)cnt0);
+    if (cnt1) atomicAdd(&sh[1][cur1], (unsigned)cnt1);
     __syncthreads();
     unsigned int *gh = hist + (size_t)mb * 2 * GSEL_BINS;
     for (int b = threadIdx.x; b < 2 * GSEL_BINS; b += blockDim.x) {

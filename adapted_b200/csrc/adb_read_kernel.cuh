@@ -201,6 +201,9 @@ struct ValidateArgs {
     adb_record *out;
     float *series;        // [gridDim.x][2][m]
     const int *batch_status;
+    const float *pre_var, *pre_mean;  // compact pools of precomputed moving statistics (mvs_series_kernel)
+    const long long *pre_off;         // [n_reads] row offset into the pools, -1: none
+    const int *pre_meta;              // [n_reads][2] = (adapter_end, polya_end) of the row
 };
 
 __host__ __device__ inline size_t validate_smem_bytes(int win_bytes, int nds_max, int peak_cap) {
@@ -247,6 +250,13 @@ __global__ void __launch_bounds__(ADB_VAL_THREADS) validate_kernel(ValidateArgs 
         const int mb = r / A.B.batch_size;
         adb_record *rec = A.out + r;
         __syncthreads();
+        {
+            const long long po = A.pre_off ? A.pre_off[r] : -1;
+            C.pre_var = (po >= 0) ? A.pre_var + po : nullptr;
+            C.pre_mean = (po >= 0) ? A.pre_mean + po : nullptr;
+            C.pre_ae = (po >= 0) ? A.pre_meta[2 * r] : -1;
+            C.pre_pe = (po >= 0) ? A.pre_meta[2 * r + 1] : -1;
+        }
         // zero the record (so unset groups read as zeros) -- 512 B = 128 words
         for (int w = threadIdx.x; w < (int)(sizeof(adb_record) / 4); w += blockDim.x) ((uint32_t *)rec)[w] = 0;
         if (A.batch_status[mb] != ADB_OK) continue;  // minibatch lost (host raises)

@@ -17,8 +17,11 @@ struct ValCtx {
     const adb_config *cfg;
     SelScratch S;
     uint32_t *kbuf;      // shared: 4 keys + 4 ranks
-    float *series_a;     // global scratch [m] (moving variance)
+    float *series_a;     // global scratch [m] (moving variance)  -- in-CTA fallback path
     float *series_b;     // global scratch [m] (moving mean)
+    const float *pre_var;   // moving variance of candidate 0 precomputed by mvs_series_kernel (or nullptr)
+    const float *pre_mean;  // moving mean of candidate 0
+    int pre_ae, pre_pe;     // the (adapter_end, polya_end) pair the precomputed series belong to (-1: none)
     int *itmp;           // shared: 8 ints
     double *dtmp;        // shared: 8 doubles
     bool int_keys;       // raw ADC keys usable (i16 source, scale > 0)
@@ -333,6 +336,258 @@ __device__ void seg_moving_stats(ValCtx &C, int a, int L, int wv, int wm, bool d
     __syncthreads();
 }
 
+// ---- thread-per-read moving statistics -------------------------------------------------------------------------
+// The two bottleneck recurrences are strictly sequential in float32 (each output depends on every earlier sample),
+// but reads are independent: one THREAD per read runs both recurrences over [ae, pe) straight from global memory
+// (the lagging a[i-window] stream hits L1/L2) and writes the valid entries of both series to a per-read scratch row.
+// Only NaN-free segments are handled here (real ADC data); anything else, and candidates other than the first,
+// falls back to the in-CTA path above.  Conditions mirror mvs.py:76-107.
+struct MvsSeriesArgs {
+    BatchDev B;
+    const int *given;
+    int given_stride;
+    int n_reads;
+    float *var_pool;          // [pool_cap] compact rows of moving variance
+    float *mean_pool;         // [pool_cap] compact rows of moving mean (same offsets)
+    long long pool_cap;       // floats per pool
+    unsigned long long *cursor;  // allocation cursor (zeroed before the launch)
+    long long *row_off;       // [n_reads] offset of the read's row in the pools, or -1 (not precomputed)
+    int *meta;                // [n_reads][2] = ae, pe the row belongs to
+};
+
+#define MVS_LANES 128   // reads per CTA (one lane each)
+#define MVS_C 32        // samples staged per step
+#define MVS_RING 256    // circular input columns per read (>= window + MVS_C), power of two
+#define MVS_RING_STRIDE 258  // int16 units: 516 B = 129 words, odd -> lanes walking their own row hit distinct banks
+#define MVS_OUT_STRIDE 33    // float units
+
+__host__ __device__ inline size_t mvs_smem_bytes() {
+    return (size_t)MVS_LANES * MVS_RING_STRIDE * 2 + 2 * (size_t)MVS_LANES * MVS_OUT_STRIDE * 4 + MVS_LANES * 24 + 64;
+}
+
+// eligibility of a read for the precomputed series (mirrors the early exits of mvs.py:76-107)
+__device__ __forceinline__ bool mvs_plan(const adb_config &cfg, const ReadSrc &src, int ae, int pe, int &a, int &L,
+                                         bool &win_var, bool &win_mean) {
+    if (!cfg.mvs_detect_check) return false;
+    const int size = src.n;
+    if (pe == 0 || ae == 0 || pe < ae || pe - ae <= 2) return false;
+    if (size < ae + cfg.median_shift_window) return false;
+    win_var = !(pe - ae <= cfg.pA_var_window + 2);
+    win_mean = !(pe - ae <= cfg.pA_mean_window + 2);
+    if (!win_var && !win_mean) return false;
+    a = min(ae, size);
+    L = min(pe, size) - a;
+    if (L < max(cfg.pA_var_window, cfg.pA_mean_window)) return false;
+    return true;
+}
+
+// int16 sources: 128 reads per CTA, one lane per read.  The input is staged through shared memory in chunks of
+// MVS_C samples per read (coalesced row loads, circular history for a[i - window]) and the outputs leave through
+// a shared tile (coalesced row stores), so neither side pays 32 L1 wavefronts per access.
+__global__ void __launch_bounds__(MVS_LANES) mvs_series_kernel(MvsSeriesArgs A, adb_config cfg) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    int16_t *ring = (int16_t *)smem;
+    float *ov = (float *)(smem + (size_t)MVS_LANES * MVS_RING_STRIDE * 2);
+    float *om = ov + MVS_LANES * MVS_OUT_STRIDE;
+    const int16_t **rptr = (const int16_t **)(om + MVS_LANES * MVS_OUT_STRIDE);
+    int *rlen = (int *)(rptr + MVS_LANES);
+    int *rflag = rlen + MVS_LANES;
+    __shared__ int lmax_sh;
+    __shared__ long long base_sh;
+    __shared__ int wsum_sh[MVS_LANES / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q = blockIdx.x * MVS_LANES + tid;
+    const int wv = cfg.pA_var_window, wm = cfg.pA_mean_window;
+    bool active = false, win_var = false, win_mean = false;
+    int a = 0, L = 0, ae = 0, pe = 0;
+    float coff = 0.f, cscale = 1.f;
+    if (tid == 0) lmax_sh = 0;
+    __syncthreads();
+    if (q < A.n_reads) {
+        const int r = q;
+        const int *g = A.given + (size_t)r * A.given_stride;
+        ae = g[0]; pe = g[1];
+        const ReadSrc src = make_src(A.B, r);
+        active = (src.i16 != nullptr) && mvs_plan(cfg, src, ae, pe, a, L, win_var, win_mean) &&
+                 isfinite(src.coff) && isfinite(src.cscale);
+        coff = src.coff; cscale = src.cscale;
+        rptr[tid] = active ? src.i16 + a : nullptr;
+    } else {
+        rptr[tid] = nullptr;
+    }
+    // compact row allocation: in-CTA exclusive scan of the (4-float aligned) row lengths + one atomic per CTA
+    const int need = active ? ((L + 3) & ~3) : 0;
+    int incl = need;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(ADB_FULL, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) wsum_sh[warp] = incl;
+    __syncthreads();
+    int wbase = 0, total = 0;
+    for (int w = 0; w < MVS_LANES / 32; w++) { if (w < warp) wbase += wsum_sh[w]; total += wsum_sh[w]; }
+    if (tid == 0) base_sh = (long long)atomicAdd(A.cursor, (unsigned long long)total);
+    __syncthreads();
+    long long myoff = base_sh + wbase + incl - need;
+    if (active && myoff + need > A.pool_cap) active = false;  // pool exhausted: the validate kernel falls back
+    if (q < A.n_reads) {
+        A.row_off[q] = active ? myoff : -1;
+        A.meta[2 * (size_t)q] = active ? ae : -1;
+        A.meta[2 * (size_t)q + 1] = active ? pe : -1;
+    }
+    if (!active) rptr[tid] = nullptr;
+    rlen[tid] = active ? L : 0;
+    rflag[tid] = (win_var ? 1 : 0) | (win_mean ? 2 : 0);
+    long long *roff_sh = (long long *)(rflag + MVS_LANES);
+    roff_sh[tid] = myoff;
+    if (active) atomicMax(&lmax_sh, L);
+    __syncthreads();
+    const int Lmax = lmax_sh;
+    float amean = 0.f, assqdm = 0.f, asum = 0.f;
+    const float cinv_v = (float)(1.0 / (double)wv), cinv_m = (float)(1.0 / (double)wm);
+    const int16_t *myrow = ring + (size_t)tid * MVS_RING_STRIDE;
+    float *myov = ov + tid * MVS_OUT_STRIDE, *myom = om + tid * MVS_OUT_STRIDE;
+    float *gv = A.var_pool, *gm = A.mean_pool;
+    for (int base = 0; base < Lmax; base += MVS_C) {
+        // ---- stage MVS_C samples of every row (warp w loads rows w, w+4, ...; 8 loads in flight) ----
+        {
+            const int i = base + lane;
+            for (int row0 = warp; row0 < MVS_LANES; row0 += 8 * (MVS_LANES / 32)) {
+                int16_t v[8];
+                bool ok[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int row = row0 + u * (MVS_LANES / 32);
+                    const int16_t *p = (row < MVS_LANES) ? rptr[row] : nullptr;
+                    ok[u] = (p != nullptr) && (i < rlen[row]);
+                    v[u] = ok[u] ? p[i] : (int16_t)0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int row = row0 + u * (MVS_LANES / 32);
+                    if (ok[u]) ring[(size_t)row * MVS_RING_STRIDE + (i & (MVS_RING - 1))] = v[u];
+                }
+            }
+        }
+        __syncthreads();
+        // ---- each lane advances its own recurrences ----
+        if (active) {
+            const int iend = min(base + MVS_C, L);
+            for (int i = base; i < iend; i++) {
+                const float x = __fmul_rn(__fadd_rn((float)myrow[i & (MVS_RING - 1)], coff), cscale);
+                if (win_var) {
+                    if (i < wv) {
+                        const float delta = __fsub_rn(x, amean);
+                        amean = __fadd_rn(amean, __fdiv_rn(delta, (float)(i + 1)));
+                        assqdm = __fadd_rn(assqdm, __fmul_rn(delta, __fsub_rn(x, amean)));
+                        if (i == wv - 1) {
+                            if (assqdm < 0) assqdm = 0;
+                            myov[i - base] = __fdiv_rn(assqdm, (float)wv);
+                        }
+                    } else {
+                        float ai = x;
+                        float aold = __fmul_rn(__fadd_rn((float)myrow[(i - wv) & (MVS_RING - 1)], coff), cscale);
+                        const float delta = __fsub_rn(ai, aold);
+                        aold = __fsub_rn(aold, amean);
+                        amean = __fadd_rn(amean, __fmul_rn(delta, cinv_v));
+                        ai = __fsub_rn(ai, amean);
+                        assqdm = __fadd_rn(assqdm, __fmul_rn(__fadd_rn(ai, aold), delta));
+                        if (assqdm < 0) assqdm = 0;
+                        myov[i - base] = __fmul_rn(assqdm, cinv_v);
+                    }
+                }
+                if (win_mean) {
+                    if (i < wm) {
+                        asum = __fadd_rn(asum, x);
+                        if (i == wm - 1) myom[i - base] = __fdiv_rn(asum, (float)wm);
+                    } else {
+                        const float aold = __fmul_rn(__fadd_rn((float)myrow[(i - wm) & (MVS_RING - 1)], coff), cscale);
+                        asum = __fadd_rn(asum, __fsub_rn(x, aold));
+                        myom[i - base] = __fmul_rn(asum, cinv_m);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- coalesced row stores of the valid entries ----
+        for (int row = warp; row < MVS_LANES; row += MVS_LANES / 32) {
+            const int Lr = rlen[row];
+            const int i = base + lane;
+            if (i < Lr) {
+                const long long rowoff = roff_sh[row];
+                const int fl = rflag[row];
+                if ((fl & 1) && i >= wv - 1) gv[rowoff + i - (wv - 1)] = ov[row * MVS_OUT_STRIDE + lane];
+                if ((fl & 2) && i >= wm - 1) gm[rowoff + i - (wm - 1)] = om[row * MVS_OUT_STRIDE + lane];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// float32 sources (the reference seam): one thread per read straight from global memory.  This path is PCIe-bound
+// anyway (106 MB per minibatch over the bus), so it keeps the simple form.
+__global__ void __launch_bounds__(128) mvs_series_f32_kernel(MvsSeriesArgs A, adb_config cfg) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= A.n_reads) return;
+    const int r = q;
+    int *meta = A.meta + 2 * (size_t)q;
+    meta[0] = -1;
+    meta[1] = -1;
+    A.row_off[q] = -1;
+    const int *g = A.given + (size_t)r * A.given_stride;
+    const int ae = g[0], pe = g[1];
+    const ReadSrc src = make_src(A.B, r);
+    if (!src.f32) return;
+    int a, L;
+    bool win_var, win_mean;
+    if (!mvs_plan(cfg, src, ae, pe, a, L, win_var, win_mean)) return;
+    const int wv = cfg.pA_var_window, wm = cfg.pA_mean_window;
+    const float *__restrict__ x = src.f32 + a;
+    for (int i = 0; i < L; i++) { float v = x[i]; if (!(v == v)) return; }
+    const int need = (L + 3) & ~3;
+    const long long off = (long long)atomicAdd(A.cursor, (unsigned long long)need);
+    if (off + need > A.pool_cap) return;
+    A.row_off[q] = off;
+    float *__restrict__ yv = A.var_pool + off;
+    float *__restrict__ ym = A.mean_pool + off;
+    const float cinv_v = (float)(1.0 / (double)wv), cinv_m = (float)(1.0 / (double)wm);
+    if (win_var) {
+        float amean = 0.f, assqdm = 0.f;
+        for (int i = 0; i < wv; i++) {
+            const float ai = x[i];
+            const float delta = __fsub_rn(ai, amean);
+            amean = __fadd_rn(amean, __fdiv_rn(delta, (float)(i + 1)));
+            assqdm = __fadd_rn(assqdm, __fmul_rn(delta, __fsub_rn(ai, amean)));
+        }
+        if (assqdm < 0) assqdm = 0;
+        yv[0] = __fdiv_rn(assqdm, (float)wv);
+#pragma unroll 4
+        for (int i = wv; i < L; i++) {
+            float ai = x[i], aold = x[i - wv];
+            const float delta = __fsub_rn(ai, aold);
+            aold = __fsub_rn(aold, amean);
+            amean = __fadd_rn(amean, __fmul_rn(delta, cinv_v));
+            ai = __fsub_rn(ai, amean);
+            assqdm = __fadd_rn(assqdm, __fmul_rn(__fadd_rn(ai, aold), delta));
+            if (assqdm < 0) assqdm = 0;
+            yv[i - (wv - 1)] = __fmul_rn(assqdm, cinv_v);
+        }
+    }
+    if (win_mean) {
+        float asum = 0.f;
+        for (int i = 0; i < wm; i++) asum = __fadd_rn(asum, x[i]);
+        ym[0] = __fdiv_rn(asum, (float)wm);
+#pragma unroll 4
+        for (int i = wm; i < L; i++) {
+            asum = __fadd_rn(asum, __fsub_rn(x[i], x[i - wm]));
+            ym[i - (wm - 1)] = __fmul_rn(asum, cinv_m);
+        }
+    }
+    meta[0] = ae;
+    meta[1] = pe;
+}
+
 // keys of a float32 series that may contain NaN: NaNs sort last (key 0xffffffff) and are not counted
 struct BufKeysNan {
     const float *p;
@@ -387,10 +642,12 @@ __device__ MvsOut mvs_check(ValCtx &C, int ae, int pe, double mean_lo, double me
     float var32, mean32;
     const bool win_var = !(pe - ae <= cfg.pA_var_window + 2);
     const bool win_mean = !(pe - ae <= cfg.pA_mean_window + 2);
-    if (win_var || win_mean) seg_moving_stats(C, a, L, cfg.pA_var_window, cfg.pA_mean_window, win_var, win_mean);
-    if (win_var) var32 = series_nanmedian(C, C.series_a, L - (cfg.pA_var_window - 1));
+    const bool pre = (C.pre_var != nullptr) && C.pre_ae == ae && C.pre_pe == pe;
+    if (!pre && (win_var || win_mean))
+        seg_moving_stats(C, a, L, cfg.pA_var_window, cfg.pA_mean_window, win_var, win_mean);
+    if (win_var) var32 = series_nanmedian(C, pre ? C.pre_var : C.series_a, L - (cfg.pA_var_window - 1));
     else var32 = seg_var_exact_small(C, a, L);
-    if (win_mean) mean32 = series_nanmedian(C, C.series_b, L - (cfg.pA_mean_window - 1));
+    if (win_mean) mean32 = series_nanmedian(C, pre ? C.pre_mean : C.series_b, L - (cfg.pA_mean_window - 1));
     else mean32 = seg_mean_exact_small(C, a, L);
     const float med32 = seg_median(C, ae, pe);
     const double lr = seg_local_range(C, ae, pe);

@@ -220,7 +220,7 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = ctx.launches - launches0
-    tim = (C.c_double * 8)()
+    tim = (C.c_double * 16)()
     L.adb_ctx_get_timing(ctx.handle, tim)
     L.adb_ctx_set_timing(ctx.handle, 0)
     n_pass = int(torch.frombuffer(records.cpu().numpy(), dtype=torch.int32).reshape(n, 128)[:, 0].sum().item())
@@ -273,9 +273,10 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    cls_names = ["global_select_hist", "global_select_scan", "validate_kernel", "llr_primary_kernel"]
-    per_cls = {cls_names[i]: {"ms": tim[2 * i], "launches": int(tim[2 * i + 1])} for i in range(4)}
-    dom = max(range(4), key=lambda i: tim[2 * i])
+    cls_names = ["global_select_hist", "global_select_scan", "validate_kernel", "llr_primary_kernel",
+                 "mvs_series_kernel", "cnn", "start_peak", "other"]
+    per_cls = {cls_names[i]: {"ms": tim[2 * i], "launches": int(tim[2 * i + 1])} for i in range(8) if tim[2 * i + 1] > 0}
+    dom = max(range(8), key=lambda i: tim[2 * i])
     alg_bytes_per_step = 2.0 * samples + (8 + 4 + 512) * n
     if dom in (0, 3):  # these kernels stream the first max_obs_trace samples of every read once per launch
         launches_dom = max(per_cls[cls_names[0]]["launches"], 1)

@@ -181,8 +181,9 @@ int adb_detect_pipelined_host(adb_ctx *ctx, const adb_batch *batch, const adb_co
                               adb_record *out_records, int32_t *batch_status, int32_t chunk_batches);
 
 /* Per-kernel-class device timing (CUDA events around every launch; used by bench.py for the roofline):
- * class 0 global-select histogram passes, 1 global-select scans, 2 per-read kernel, 3 other.
- * adb_ctx_get_timing fills out[8] = {ms, launches} x 4; call it after synchronising the stream. */
+ * class 0 global-select histogram passes, 1 global-select scans, 2 validate kernel, 3 LLR-primary kernel,
+ * 4 moving-statistics kernel, 5 CNN kernels, 6 start-peak kernels, 7 other.
+ * adb_ctx_get_timing fills out[16] = {ms, launches} x 8; call it after synchronising the stream. */
 int adb_ctx_set_timing(adb_ctx *ctx, int on);
 int adb_ctx_get_timing(adb_ctx *ctx, double *out);
 
