@@ -298,8 +298,8 @@ __global__ void __launch_bounds__(ADB_VAL_THREADS) validate_kernel(ValidateArgs 
                 // per-read normalisation over signal[:min(max_obs_trace, full_len)] (NaN padding dropped)
                 const int nn = min(min(cfg.max_obs_trace, full_len), A.B.m);
                 const int nvalid = min(nn, src.n);
-                const float med = seg_median(C, 0, nvalid);
-                const float mad = seg_mad(C, 0, nvalid, med);
+                const SegStats N0 = seg_stats(C, 0, nvalid, SS_MED | SS_MAD);
+                const float med = N0.med, mad = N0.mad;
                 if (nvalid > 0 && mad == 0.0f) {
                     // normalize_signal raises ValueError("MAD normalization failed: scale is 0") inside the try
                     __syncthreads();

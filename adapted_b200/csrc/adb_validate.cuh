@@ -124,6 +124,143 @@ __device__ double seg_local_range(ValCtx &C, int a, int b) {
     return __dsub_rn(p85, p15);
 }
 
+// ---- segment statistics from ONE histogram pass (int16 sources) -------------------------------------------------
+// pA = (adc + offset) * scale is monotone in the ADC code for scale > 0, so order statistics can be taken in the
+// integer domain and mapped back exactly.  A read spans 1-2 k distinct codes, so one shared-memory histogram over
+// [wkmin, wkmax] holds a whole segment; after an in-place inclusive scan it answers, without touching the samples
+// again:  median (two rank look-ups), p85 - p15 (four look-ups + numpy's float64 lerp), and the MAD -- the k-th
+// smallest |pA(code) - med| found by counting, with two binary searches per occupied code, how many samples deviate
+// less (deviations are monotone on either side of the median).  Sources that do not qualify (float32 input,
+// non-positive scale, > ADB_SEL_NB codes) use the generic multi-level select above.
+#define SS_MED 1
+#define SS_MAD 2
+#define SS_LR 4
+struct SegStats {
+    float med, mad;
+    double lr;
+};
+
+__device__ __forceinline__ int ihist_bin_of_rank(const uint32_t *cum, int nb, uint32_t k) {
+    int lo = 0, hi = nb - 1;  // smallest b with cum[b] > k
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (cum[mid] > k) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+__device__ SegStats seg_stats(ValCtx &C, int a, int b, int flags) {
+    SegStats R;
+    R.med = CUDART_NAN_F; R.mad = CUDART_NAN_F; R.lr = CUDART_NAN;
+    clip_seg(a, b, C.src.n);
+    const int n = b - a;
+    if (n <= 0) return R;
+    const bool fast = C.int_keys && (C.wkmax - C.wkmin) < (uint32_t)ADB_SEL_NB;
+    if (!fast) {
+        R.med = seg_median(C, a, b);
+        if (flags & SS_MAD) R.mad = seg_mad(C, a, b, R.med);
+        if (flags & SS_LR) R.lr = seg_local_range(C, a, b);
+        return R;
+    }
+    const int T = blockDim.x, tid = threadIdx.x;
+    uint32_t *hist = C.S.hist;
+    const uint32_t kmin = C.wkmin;
+    const int nb = (int)(C.wkmax - C.wkmin) + 1;
+    const float coff = C.src.coff, cscale = C.src.cscale;
+    const int16_t *p = C.src.i16 + a;
+    __syncthreads();
+    for (int q = tid; q < ADB_SEL_NB; q += T) hist[q] = 0;
+    __syncthreads();
+    {
+        const uint32_t bias = 32768u - kmin;
+        int j = tid;
+        for (; j + 3 * T < n; j += 4 * T) {
+            const int v0 = p[j], v1 = p[j + T], v2 = p[j + 2 * T], v3 = p[j + 3 * T];
+            atomicAdd(&hist[(uint32_t)v0 + bias], 1u);
+            atomicAdd(&hist[(uint32_t)v1 + bias], 1u);
+            atomicAdd(&hist[(uint32_t)v2 + bias], 1u);
+            atomicAdd(&hist[(uint32_t)v3 + bias], 1u);
+        }
+        for (; j < n; j += T) atomicAdd(&hist[(uint32_t)(int)p[j] + bias], 1u);
+    }
+    __syncthreads();
+    // in-place inclusive scan over ADB_SEL_NB bins: contiguous chunk per thread + warp/block offsets
+    {
+        const int per = ADB_SEL_NB / T;  // 8 for 256 threads
+        const int q0 = tid * per;
+        uint32_t loc = 0;
+        for (int q = q0; q < q0 + per; q++) { loc += hist[q]; hist[q] = loc; }
+        uint32_t incl = loc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(ADB_FULL, incl, o);
+            if ((tid & 31) >= o) incl += v;
+        }
+        if ((tid & 31) == 31) C.S.warp_tot[tid >> 5] = incl;
+        __syncthreads();
+        uint32_t wbase = 0;
+        for (int w = 0; w < (tid >> 5); w++) wbase += C.S.warp_tot[w];
+        const uint32_t add = wbase + incl - loc;
+        if (add) for (int q = q0; q < q0 + per; q++) hist[q] += add;
+    }
+    __syncthreads();
+    auto val = [&](int bin) { return __fmul_rn(__fadd_rn((float)((int)((uint32_t)bin + kmin) - 32768), coff), cscale); };
+    // median: odd -> s[n/2]; even -> f32(f32(a+b)/2); every thread computes it (uniform)
+    {
+        const float x0 = val(ihist_bin_of_rank(hist, nb, (uint32_t)((n - 1) / 2)));
+        if (n & 1) R.med = x0;
+        else R.med = __fdiv_rn(__fadd_rn(x0, val(ihist_bin_of_rank(hist, nb, (uint32_t)(n / 2)))), 2.0f);
+    }
+    if (flags & SS_LR) {
+        const double v85 = __dmul_rn((double)(n - 1), 0.85), v15 = __dmul_rn((double)(n - 1), 0.15);
+        const int l85 = (int)floor(v85), l15 = (int)floor(v15);
+        const int h85 = min(l85 + 1, n - 1), h15 = min(l15 + 1, n - 1);
+        const float a15 = val(ihist_bin_of_rank(hist, nb, l15)), b15 = val(ihist_bin_of_rank(hist, nb, h15));
+        const float a85 = val(ihist_bin_of_rank(hist, nb, l85)), b85 = val(ihist_bin_of_rank(hist, nb, h85));
+        R.lr = __dsub_rn(np_lerp_f32(a85, b85, __dsub_rn(v85, (double)l85)), np_lerp_f32(a15, b15, __dsub_rn(v15, (double)l15)));
+    }
+    if (flags & SS_MAD) {
+        const float med = R.med;
+        auto dev = [&](int bin) { return fabsf(__fsub_rn(val(bin), med)); };
+        auto cum = [&](int x) -> uint32_t { return x < 0 ? 0u : hist[x]; };
+        // pivot: first bin whose value is >= med
+        int pv;
+        {
+            int lo = 0, hi = nb;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (val(mid) >= med) hi = mid; else lo = mid + 1; }
+            pv = lo;
+        }
+        const uint32_t k0 = (uint32_t)((n - 1) / 2), k1 = (uint32_t)(n / 2);
+        for (int bin = tid; bin < nb; bin += T) {
+            if (cum(bin) == cum(bin - 1)) continue;  // empty code
+            const float t = dev(bin);
+            // right side [pv, nb): deviations non-decreasing
+            int lo = pv, hi = nb;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (dev(mid) >= t) hi = mid; else lo = mid + 1; }
+            const int r_ge = lo;
+            lo = r_ge; hi = nb;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (dev(mid) > t) hi = mid; else lo = mid + 1; }
+            const int r_gt = lo;
+            // left side [0, pv): deviations non-increasing
+            lo = 0; hi = pv;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (dev(mid) <= t) hi = mid; else lo = mid + 1; }
+            const int l_le = lo;
+            lo = l_le; hi = pv;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (dev(mid) < t) hi = mid; else lo = mid + 1; }
+            const int l_lt = lo;
+            const uint32_t cnt_lt = cum(r_ge - 1) - cum(l_lt - 1);
+            const uint32_t cnt_le = cum(r_gt - 1) - cum(l_le - 1);
+            if (cnt_lt <= k0 && k0 < cnt_le) ((float *)C.kbuf)[0] = t;
+            if (cnt_lt <= k1 && k1 < cnt_le) ((float *)C.kbuf)[1] = t;
+        }
+        __syncthreads();
+        const float d0 = ((float *)C.kbuf)[0], d1 = ((float *)C.kbuf)[1];
+        R.mad = (n & 1) ? d0 : __fdiv_rn(__fadd_rn(d0, d1), 2.0f);
+    }
+    __syncthreads();
+    return R;
+}
+
 // float32 numpy mean of `n` samples starting at a, summed in numpy's pairwise order by one thread (the window is
 // in shared memory).  Returns the mean to all threads.
 __device__ float seg_mean_exact_small(ValCtx &C, int a, int n) {
@@ -602,7 +739,15 @@ __device__ float series_nanmedian(ValCtx &C, const float *p, int n) {
     if (threadIdx.x == 0) C.itmp[7] = 0;
     __syncthreads();
     int cnt = 0;
-    for (int j = threadIdx.x; j < n; j += blockDim.x) { float v = p[j]; cnt += (v == v); }
+    {
+        const int T = blockDim.x;
+        int j = threadIdx.x;
+        for (; j + 3 * T < n; j += 4 * T) {
+            const float v0 = p[j], v1 = p[j + T], v2 = p[j + 2 * T], v3 = p[j + 3 * T];
+            cnt += (v0 == v0) + (v1 == v1) + (v2 == v2) + (v3 == v3);
+        }
+        for (; j < n; j += T) { const float v = p[j]; cnt += (v == v); }
+    }
     cnt = warp_sum_i(cnt);
     if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&C.itmp[7], cnt);
     __syncthreads();
@@ -626,12 +771,13 @@ struct MvsOut {
     bool ok;
     int fail_mask;   // bit i: check i failed (mean var med range shift)
     double v[5];     // mean, var, med, local_range, med_shift (all 0 on early fail)
+    float polya_mad; // MAD of signal[ae:pe) from the same histogram (reused by the partition table)
 };
 
 __device__ MvsOut mvs_check(ValCtx &C, int ae, int pe, double mean_lo, double mean_hi) {
     const adb_config &cfg = *C.cfg;
     MvsOut R;
-    R.ok = false; R.fail_mask = 0x1f;
+    R.ok = false; R.fail_mask = 0x1f; R.polya_mad = 0.f;
     for (int i = 0; i < 5; i++) R.v[i] = 0.0;
     const int size = C.src.n;
     if (pe == 0 || ae == 0 || pe < ae || pe - ae <= 2) return R;
@@ -649,10 +795,12 @@ __device__ MvsOut mvs_check(ValCtx &C, int ae, int pe, double mean_lo, double me
     else var32 = seg_var_exact_small(C, a, L);
     if (win_mean) mean32 = series_nanmedian(C, pre ? C.pre_mean : C.series_b, L - (cfg.pA_mean_window - 1));
     else mean32 = seg_mean_exact_small(C, a, L);
-    const float med32 = seg_median(C, ae, pe);
-    const double lr = seg_local_range(C, ae, pe);
-    const float m_after = seg_median(C, ae, min(ae + cfg.median_shift_window, size));
-    const float m_before = seg_median(C, max(ae - cfg.median_shift_window, 0), ae);
+    const SegStats P = seg_stats(C, ae, pe, SS_MED | SS_LR | SS_MAD);
+    const float med32 = P.med;
+    const double lr = P.lr;
+    R.polya_mad = P.mad;
+    const float m_after = seg_stats(C, ae, min(ae + cfg.median_shift_window, size), SS_MED).med;
+    const float m_before = seg_stats(C, max(ae - cfg.median_shift_window, 0), ae, SS_MED).med;
     const float shift32 = __fsub_rn(m_after, m_before);
     R.v[0] = (double)mean32; R.v[1] = (double)var32; R.v[2] = (double)med32; R.v[3] = lr; R.v[4] = (double)shift32;
     const double mr[2] = {mean_lo, mean_hi};
@@ -771,13 +919,19 @@ __device__ void validate_boundaries_cta(ValCtx &C, const PrimaryBounds &B, int f
     double real_v[3] = {0, 0, 0};
     double med_shift = 0.0;
     int n_open = 0;
-    float polya_med_cache = 0.f; int polya_med_cache_pe = -1;
+    float polya_med_cache = 0.f, polya_mad_cache = 0.f; int polya_med_cache_pe = -1;
+    bool lr0_ok = false; double lr0 = 0.0;
 
     if (a_end == 0) {
         success = false; fail = ADB_FAIL_NO_ADAPTER;
     } else {
-        a_med = seg_median(C, a_start, a_end);
-        a_mad = seg_mad(C, a_start, a_end, a_med);
+        // the local range of real_range_check covers the same samples when the adapter is short and no open
+        // pore moves its start: take it from the same histogram
+        int ca = a_start, cb = a_end;
+        clip_seg(ca, cb, size);
+        lr0_ok = cfg.real_signal_check && (cb - ca) <= cfg.max_obs_local_range;
+        const SegStats A0 = seg_stats(C, a_start, a_end, SS_MED | SS_MAD | (lr0_ok ? SS_LR : 0));
+        a_med = A0.med; a_mad = A0.mad; lr0 = A0.lr;
         have_amed = true;
     }
     if (success && (a_mad != 0.0f) && !in_range_d((double)a_mad, cfg.adapter_mad_range)) {
@@ -806,7 +960,7 @@ __device__ void validate_boundaries_cta(ValCtx &C, const PrimaryBounds &B, int f
             valid |= ADB_V_REAL_MEANS;
             if (in_range_d((double)m0, cfg.mean_start_range) && in_range_d((double)m1, cfg.mean_end_range)) {
                 const int w = min(cfg.max_obs_local_range, len);
-                const double lr = seg_local_range(C, b - w, b);
+                const double lr = (lr0_ok && a_start == a_start0 && w == len) ? lr0 : seg_stats(C, b - w, b, SS_MED | SS_LR).lr;
                 real_v[2] = lr;
                 valid |= ADB_V_REAL_RANGE;
                 if (!in_range_d(lr, cfg.local_range)) { success = false; fail = ADB_FAIL_REAL_RANGE; }
@@ -835,7 +989,7 @@ __device__ void validate_boundaries_cta(ValCtx &C, const PrimaryBounds &B, int f
                     MvsOut R = mvs_check(C, a_end, pe, mlo, mhi);
                     for (int i = 0; i < 5; i++) mvs_v[i] = R.v[i];
                     valid |= ADB_V_MVS;
-                    if (R.ok || R.v[0] != 0.0) { polya_med_cache = (float)R.v[2]; polya_med_cache_pe = pe; }
+                    if (R.ok || R.v[0] != 0.0) { polya_med_cache = (float)R.v[2]; polya_mad_cache = R.polya_mad; polya_med_cache_pe = pe; }
                     if (!R.ok) {
                         success = false;
                         if (R.v[0] == 0.0) { fail = ADB_FAIL_MVS_NOT_ENOUGH; fail_mask = 0; }
@@ -848,8 +1002,8 @@ __device__ void validate_boundaries_cta(ValCtx &C, const PrimaryBounds &B, int f
     }
     if (!exception && success && cfg.detect_med_shift) {
         const int w = cfg.med_shift_window;
-        const float m_after = seg_median(C, a_end, min(a_end + w, full_len));
-        const float m_before = seg_median(C, max(a_end - w, 0), a_end);
+        const float m_after = seg_stats(C, a_end, min(a_end + w, full_len), SS_MED).med;
+        const float m_before = seg_stats(C, max(a_end - w, 0), a_end, SS_MED).med;
         const float sh = __fsub_rn(m_after, m_before);
         med_shift = (double)sh;
         valid |= ADB_V_MED_SHIFT;
@@ -868,22 +1022,28 @@ __device__ void validate_boundaries_cta(ValCtx &C, const PrimaryBounds &B, int f
     for (int p = 0; p < 3; p++) for (int q = 0; q < 4; q++) st[p][q] = 0.0;
     if (a_end > a_start) {
         seg_mean_std(C, a_start, a_end, st[0][0], st[0][1]);
-        float med = (have_amed && a_start == a_start0) ? a_med : seg_median(C, a_start, a_end);
-        float mad = (have_amed && a_start == a_start0) ? a_mad : seg_mad(C, a_start, a_end, med);
+        float med = a_med, mad = a_mad;
+        if (!(have_amed && a_start == a_start0)) {
+            const SegStats Q = seg_stats(C, a_start, a_end, SS_MED | SS_MAD);
+            med = Q.med; mad = Q.mad;
+        }
         st[0][2] = (double)med; st[0][3] = (double)mad;
         valid |= ADB_V_ADAPTER_STATS;
     }
     if (pe_best > a_end) {
         seg_mean_std(C, a_end, pe_best, st[1][0], st[1][1]);
-        float med = (polya_med_cache_pe == pe_best) ? polya_med_cache : seg_median(C, a_end, pe_best);
-        float mad = seg_mad(C, a_end, pe_best, med);
+        float med = polya_med_cache, mad = polya_mad_cache;
+        if (polya_med_cache_pe != pe_best) {
+            const SegStats Q = seg_stats(C, a_end, pe_best, SS_MED | SS_MAD);
+            med = Q.med; mad = Q.mad;
+        }
         st[1][2] = (double)med; st[1][3] = (double)mad;
         valid |= ADB_V_POLYA_STATS;
     }
     if (size > pe_best) {
         seg_mean_std(C, pe_best, size, st[2][0], st[2][1]);
-        float med = seg_median(C, pe_best, size);
-        float mad = seg_mad(C, pe_best, size, med);
+        const SegStats Q = seg_stats(C, pe_best, size, SS_MED | SS_MAD);
+        const float med = Q.med, mad = Q.mad;
         st[2][2] = (double)med; st[2][3] = (double)mad;
         valid |= ADB_V_RNA_STATS;
     }
