@@ -65,7 +65,7 @@ extern "C" void adb_ctx_destroy(adb_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     DevBuf *all[] = {&c->states, &c->hist, &c->series, &c->given, &c->status, &c->cnn_x, &c->cnn_act0,
-                     &c->cnn_act1, &c->cnn_scores, &c->cnn_w, &c->cnn_aux, &c->h_signal, &c->h_offsets,
+                     &c->cnn_act1, &c->cnn_scores, &c->cnn_w, &c->cnn_aux, &c->cnn_post, &c->sp_rows, &c->h_signal, &c->h_offsets,
                      &c->h_lens, &c->h_coff, &c->h_cscale, &c->h_records, &c->h_misc, &c->h_misc2, &c->h_misc3};
     for (DevBuf *b : all) b->release();
     for (int k = 0; k < 2; k++) {
@@ -81,26 +81,6 @@ extern "C" void adb_ctx_destroy(adb_ctx *c) {
 }
 
 extern "C" int64_t adb_ctx_launch_count(const adb_ctx *c) { return c ? c->launches : 0; }
-
-struct KernelTimer {  // brackets one launch with events when ctx->timing is on
-    adb_ctx *ctx;
-    int cls;
-    cudaStream_t st;
-    cudaEvent_t a = nullptr, b = nullptr;
-    KernelTimer(adb_ctx *c, int cls_, cudaStream_t s) : ctx(c), cls(cls_), st(s) {
-        if (ctx->timing) {
-            cudaEventCreate(&a);
-            cudaEventCreate(&b);
-            cudaEventRecord(a, st);
-        }
-    }
-    ~KernelTimer() {
-        if (ctx->timing) {
-            cudaEventRecord(b, st);
-            ctx->ev[cls].push_back({a, b});
-        }
-    }
-};
 
 extern "C" int adb_ctx_set_timing(adb_ctx *c, int on) {
     if (!c) return ADB_ERR_ARG;
@@ -360,7 +340,7 @@ extern "C" int adb_detect_dev(adb_ctx *ctx, const adb_batch *batch, const adb_co
         return launch_validate(ctx, B, *cfg, ADB_METHOD_LLR, given, 2, -1, ntopk, out_records, status, st);
     } else if (cfg->primary_method == ADB_METHOD_CNN) {
         if (!cnn_weights) { set_err("cnn_weights required for the CNN primary method"); return ADB_ERR_ARG; }
-        const int stride = 1 + cfg->polya_cand_k;
+        const int stride = 1 + std::max(1, cfg->polya_cand_k);
         if (ctx->given.ensure(sizeof(int) * (size_t)batch->n_reads * stride)) { set_err("cudaMalloc given"); return ADB_ERR_CUDA; }
         rc = cnn_primary_boundaries(ctx, B, *cfg, cnn_weights, (int *)ctx->given.p, st);
         if (rc) return rc;
@@ -525,6 +505,28 @@ extern "C" int adb_global_med_mad_host(adb_ctx *ctx, const adb_batch *batch, int
     CUDA_TRY(cudaMemcpyAsync(hs.data(), ctx->states.p, sizeof(GselState) * (size_t)n_batches, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     for (int i = 0; i < n_batches; i++) { med_mad[2 * i] = hs[i].med; med_mad[2 * i + 1] = hs[i].mad; }
+    return ADB_OK;
+}
+
+// ---- CNN scores (kernel-level test entry) ------------------------------------------------------------------------
+extern "C" int adb_cnn_scores_host(adb_ctx *ctx, const float *x, int32_t n, int32_t L, const float *cnn_weights, float *scores) {
+    if (!ctx || !x || !cnn_weights || !scores || n < 0 || L < CNN_K) { set_err("invalid argument"); return ADB_ERR_ARG; }
+    if (n == 0) return ADB_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CnnDims D;
+    D.Lx = L;
+    D.L1 = (L + 2 * 3 - CNN_K) / 3 + 1;
+    D.LP = (D.L1 + 3) & ~3;
+    D.Lout = (D.L1 - 1) * 3 - 2 * 3 + CNN_K;
+    if (ctx->cnn_x.ensure(sizeof(float) * (size_t)n * L) || ctx->cnn_scores.ensure(sizeof(float) * (size_t)n * 2 * D.Lout) ||
+        ctx->h_misc2.ensure(sizeof(float) * ADB_CNN_NPARAMS)) { set_err("cudaMalloc cnn buffers"); return ADB_ERR_CUDA; }
+    CUDA_TRY(cudaMemcpyAsync(ctx->cnn_x.p, x, sizeof(float) * (size_t)n * L, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_misc2.p, cnn_weights, sizeof(float) * ADB_CNN_NPARAMS, cudaMemcpyHostToDevice, st));
+    int rc = cnn_forward_dev(ctx, (const float *)ctx->cnn_x.p, n, D, (const float *)ctx->h_misc2.p, (float *)ctx->cnn_scores.p, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(scores, ctx->cnn_scores.p, sizeof(float) * (size_t)n * 2 * D.Lout, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return ADB_OK;
 }
 

@@ -1,13 +1,599 @@
-// CNN primary boundaries (placeholder until the conv kernels land).
+// CNN primary boundaries (cnn_detect_boundaries, adapted/detect/cnn.py:16-201).
+//
+//   cnn_prep_kernel     prepare_data (cnn.py:70-82): mean-pool downscale of batch[:, min_obs_adapter:], per-read
+//                       nanmedian / MAD normalisation (no clipping), nan_to_num(-5).
+//   cnn_conv64_kernel   layers 2 and 3 (Conv1d 64->64, k=7, pad 3, ReLU) as a register-tiled implicit GEMM on the FP32
+//                       pipes; layer 1 (Conv1d 1->64, k=7, stride 3, pad 3, ReLU) is fused into layer 2's input stage.
+//   cnn_convT_kernel    layer 4 (ConvTranspose1d 64->2, k=7, stride 3, pad 3) -> scores [N, 2, L_out].
+//   cnn_mask_kernel / cnn_peaks_* / cnn_topk_kernel / cnn_shift_kernel
+//                       cnn_predict's post-processing (cnn.py:117-160): adapter argmax, masking, poly(A) argmax,
+//                       find_peaks(flattened scores, distance=5) with its cross-read plateau / distance coupling,
+//                       per-read top-k by height, and the "groups shift up when a read has no peak" behaviour
+//                       (SURVEY.md A.6), then cnn_detect's coordinate mapping (cnn.py:173-179).
+//
+// Precision: weights and activations are float32 and every product is accumulated with fmaf in float32, like the
+// reference's torch CPU forward (whose summation order is oneDNN's and not reproducible bit for bit); the contract is
+// "boundaries within +-1 downscaled step" (north_star).  The convolutions are ~64.6 MFLOP per read and compute bound
+// (SURVEY.md section 8d); a tcgen05 (3xTF32) version of cnn_conv64_kernel is the planned next step, see DESIGN.md.
 #pragma once
+#include <float.h>
+
 #include "adb_common.cuh"
 #include "adb_ctx.cuh"
+#include "adb_select.cuh"
+#include <algorithm>
+
 #define ADB_CNN_NPARAMS 58882
-static int cnn_primary_boundaries(adb_ctx *, const BatchDev &, const adb_config &, const float *, int *, cudaStream_t) {
-    set_err("CNN primary method not built yet");
-    return ADB_ERR_UNSUPPORTED;
+#define CNN_C 64
+#define CNN_K 7
+#define CNN_SCORE_EXCL (-5.0f)
+// offsets into the flat state dict (0.weight, 0.bias, 2.weight, 2.bias, 4.weight, 4.bias, 6.weight, 6.bias)
+#define CNN_W1 0
+#define CNN_B1 (CNN_W1 + 64 * 7)
+#define CNN_W2 (CNN_B1 + 64)
+#define CNN_B2 (CNN_W2 + 64 * 64 * 7)
+#define CNN_W3 (CNN_B2 + 64)
+#define CNN_B3 (CNN_W3 + 64 * 64 * 7)
+#define CNN_W4 (CNN_B3 + 64)
+#define CNN_B4 (CNN_W4 + 64 * 2 * 7)
+
+#define CNN_TILE 96       // output positions per tile of the 64->64 convolutions
+#define CNN_TILE_IN 104   // input tile row stride (CNN_TILE + 6, padded)
+#define CNN_THREADS 192   // 8 output-channel groups x 24 position groups; each thread: 8 channels x 4 positions
+
+// ---- prepare_data ----------------------------------------------------------------------------------------------
+struct SmemKeys {
+    const float *p;
+    __device__ __forceinline__ uint32_t operator()(int j) const { return f32_key(p[j]); }
+};
+struct SmemDevKeys {
+    const float *p;
+    float med;
+    __device__ __forceinline__ uint32_t operator()(int j) const { return f32_key(fabsf(__fsub_rn(p[j], med))); }
+};
+struct KeyF32Id {
+    __device__ __forceinline__ float operator()(uint32_t k) const { return key_f32(k); }
+};
+
+template <class F>
+__device__ __forceinline__ float cnn_block_mean(F f, int factor) {
+    return __fdiv_rn(np_sum_f32_leaf(f, factor), (float)factor);
 }
-extern "C" int adb_cnn_scores_host(adb_ctx *, const float *, int32_t, int32_t, const float *, float *) {
-    set_err("CNN primary method not built yet");
-    return ADB_ERR_UNSUPPORTED;
+
+// x[r][0..L) ; L = ceil((m - A0) / f).  One CTA (256 threads) per read; dynamic smem = L floats + select scratch.
+__global__ void __launch_bounds__(256) cnn_prep_kernel(BatchDev B, int A0, int f, int L, float *x) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float *ds = (float *)smem;
+    unsigned char *scr = smem + (((size_t)L * 4 + 15) & ~(size_t)15);
+    SelScratch S = sel_scratch_from(scr);
+    uint32_t *kbuf = (uint32_t *)(scr + ((ADB_SEL_SMEM_BYTES + 15) & ~15));
+    const int r = blockIdx.x;
+    const ReadSrc src = make_src(B, r);
+    // leading NaN-free bins (the rest of the row is NaN: NaN padding of the minibatch matrix, file_proc.py:172-174)
+    int nv;
+    {
+        const int span = B.m - A0;
+        if (span <= 0) nv = 0;
+        else if (src.n >= B.m) nv = L;
+        else nv = (src.n > A0) ? (src.n - A0) / f : 0;
+        nv = min(nv, L);
+    }
+    for (int b = threadIdx.x; b < nv; b += blockDim.x) {
+        const int j0 = A0 + b * f;
+        ds[b] = cnn_block_mean([&](int k) { const int j = j0 + k; return (j < B.m) ? src.pa(j) : 0.0f; }, f);
+    }
+    __syncthreads();
+    float med = CUDART_NAN_F, mad = CUDART_NAN_F;
+    if (nv > 0) {
+        uint32_t kmin, kmax;
+        SmemKeys K{ds};
+        cta_key_minmax(K, nv, kmin, kmax, S);
+        med = cta_median_keys(K, KeyF32Id(), nv, kmin, kmax, S, kbuf);
+        SmemDevKeys D{ds, med};
+        const float dmax = fmaxf(fabsf(__fsub_rn(key_f32(kmax), med)), fabsf(__fsub_rn(key_f32(kmin), med)));
+        mad = cta_median_keys(D, KeyF32Id(), nv, f32_key(0.0f), f32_key(dmax), S, kbuf);
+    }
+    float *xr = x + (size_t)r * L;
+    for (int b = threadIdx.x; b < L; b += blockDim.x) {
+        float v = CNN_SCORE_EXCL;
+        if (b < nv) {
+            v = __fdiv_rn(__fsub_rn(ds[b], med), mad);
+            if (!(v == v)) v = CNN_SCORE_EXCL;          // torch.nan_to_num(nan=-5)
+            else if (v == CUDART_INF_F) v = FLT_MAX;
+            else if (v == -CUDART_INF_F) v = -FLT_MAX;
+        }
+        xr[b] = v;
+    }
+}
+
+// ---- weights: torch layout w[co][ci][k] -> [ci][k][co] so that a thread's 8 output channels are contiguous ---------
+__global__ void cnn_pack_weights_kernel(const float *w, float *packed /* 2 x [64][7][64] */) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * CNN_C * CNN_K * CNN_C) return;
+    const int layer = i / (CNN_C * CNN_K * CNN_C);
+    const int rem = i % (CNN_C * CNN_K * CNN_C);
+    const int ci = rem / (CNN_K * CNN_C), k = (rem / CNN_C) % CNN_K, co = rem % CNN_C;
+    const float *src = w + (layer == 0 ? CNN_W2 : CNN_W3);
+    packed[i] = src[(co * CNN_C + ci) * CNN_K + k];
+}
+
+// ---- Conv1d(64 -> 64, k = 7, pad 3) + ReLU ------------------------------------------------------------------------------
+// in  : FUSE_L1 ? x [N][Lx] : act [N][64][LP]        out : act [N][64][LP]   (LP = padded row length, multiple of 4)
+// Persistent CTAs; the 114.7 KB of packed weights stay in shared memory for the CTA's whole life.
+template <bool FUSE_L1>
+__global__ void __launch_bounds__(CNN_THREADS, 1) cnn_conv64_kernel(const float *in, float *out, const float *packed_w,
+                                                                   const float *bias, const float *w1, const float *b1,
+                                                                   int n_reads, int Lx, int L1, int LP) {
+    extern __shared__ __align__(16) float sm[];
+    float *Ws = sm;                                   // [64][7][64]
+    float *Is = Ws + CNN_C * CNN_K * CNN_C;           // [64][CNN_TILE_IN]
+    float *Xs = Is + CNN_C * CNN_TILE_IN;             // FUSE_L1: x window, 3*(CNN_TILE+6)+8 floats
+    float *W1s = Xs + 3 * (CNN_TILE + 6) + 8;         // [64][7] + [64]
+    for (int i = threadIdx.x; i < CNN_C * CNN_K * CNN_C; i += blockDim.x) Ws[i] = packed_w[i];
+    if (FUSE_L1) {
+        for (int i = threadIdx.x; i < CNN_C * CNN_K; i += blockDim.x) W1s[i] = w1[i];
+        for (int i = threadIdx.x; i < CNN_C; i += blockDim.x) W1s[CNN_C * CNN_K + i] = b1[i];
+    }
+    __syncthreads();
+    const int tiles_per_read = (L1 + CNN_TILE - 1) / CNN_TILE;
+    const int n_tiles = n_reads * tiles_per_read;
+    const int cg = threadIdx.x / 24, tg = threadIdx.x % 24;
+    const int co0 = cg * 8, tp = tg * 4;
+    float bv[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) bv[c] = bias[co0 + c];
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int r = tile / tiles_per_read, t0 = (tile % tiles_per_read) * CNN_TILE;
+        __syncthreads();
+        if (FUSE_L1) {
+            // x window needed by act1 positions [t0-3, t0+CNN_TILE+3): x[3p-3 .. 3p+3]
+            const float *xr = in + (size_t)r * Lx;
+            const int x0 = 3 * (t0 - 3) - 3, nx = 3 * (CNN_TILE + 6) + 6;
+            for (int i = threadIdx.x; i < nx; i += blockDim.x) {
+                const int j = x0 + i;
+                Xs[i] = (j >= 0 && j < Lx) ? xr[j] : 0.0f;
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < CNN_C * (CNN_TILE + 6); i += blockDim.x) {
+                const int ci = i / (CNN_TILE + 6), q = i % (CNN_TILE + 6);
+                const int p = t0 - 3 + q;
+                float v = 0.0f;  // zero padding of layer 2's input outside [0, L1)
+                if (p >= 0 && p < L1) {
+                    float a = W1s[CNN_C * CNN_K + ci];
+#pragma unroll
+                    for (int k = 0; k < CNN_K; k++) a = fmaf(W1s[ci * CNN_K + k], Xs[3 * q + k], a);
+                    v = fmaxf(a, 0.0f);
+                }
+                Is[ci * CNN_TILE_IN + q] = v;
+            }
+        } else {
+            const float *ar = in + (size_t)r * CNN_C * LP;
+            for (int i = threadIdx.x; i < CNN_C * (CNN_TILE + 6); i += blockDim.x) {
+                const int ci = i / (CNN_TILE + 6), q = i % (CNN_TILE + 6);
+                const int p = t0 - 3 + q;
+                Is[ci * CNN_TILE_IN + q] = (p >= 0 && p < L1) ? ar[(size_t)ci * LP + p] : 0.0f;
+            }
+        }
+        __syncthreads();
+        float acc[8][4];
+#pragma unroll
+        for (int c = 0; c < 8; c++)
+#pragma unroll
+            for (int t = 0; t < 4; t++) acc[c][t] = bv[c];
+#pragma unroll 2
+        for (int ci = 0; ci < CNN_C; ci++) {
+            float iv[10];
+            const float *ip = Is + ci * CNN_TILE_IN + tp;
+#pragma unroll
+            for (int q = 0; q < 10; q++) iv[q] = ip[q];
+            const float *wp = Ws + ci * CNN_K * CNN_C + co0;
+#pragma unroll
+            for (int k = 0; k < CNN_K; k++) {
+                const float4 wa = *(const float4 *)(wp + k * CNN_C);
+                const float4 wb = *(const float4 *)(wp + k * CNN_C + 4);
+                const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                for (int c = 0; c < 8; c++)
+#pragma unroll
+                    for (int t = 0; t < 4; t++) acc[c][t] = fmaf(wv[c], iv[t + k], acc[c][t]);
+            }
+        }
+        float *orow = out + (size_t)r * CNN_C * LP;
+        const int p0 = t0 + tp;
+        if (p0 < L1) {
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                float4 v = make_float4(fmaxf(acc[c][0], 0.f), fmaxf(acc[c][1], 0.f), fmaxf(acc[c][2], 0.f), fmaxf(acc[c][3], 0.f));
+                float *dst = orow + (size_t)(co0 + c) * LP + p0;
+                if (p0 + 3 < LP) *(float4 *)dst = v;  // LP is a multiple of 4 and >= L1: the padding lanes are never read
+                else {
+                    if (p0 < LP) dst[0] = v.x;
+                    if (p0 + 1 < LP) dst[1] = v.y;
+                    if (p0 + 2 < LP) dst[2] = v.z;
+                }
+            }
+        }
+    }
+}
+
+__host__ __device__ inline size_t cnn_conv_smem_bytes() {
+    return (size_t)(CNN_C * CNN_K * CNN_C + CNN_C * CNN_TILE_IN + 3 * (CNN_TILE + 6) + 8 + CNN_C * CNN_K + CNN_C) * 4;
+}
+
+// ---- ConvTranspose1d(64 -> 2, k = 7, stride 3, pad 3) ---------------------------------------------------------------------
+// out[co][j] = b[co] + sum_ci sum_{k = j%3 (+3, +6)} in[ci][(j + 3 - k) / 3] * w[ci][co][k]
+__global__ void __launch_bounds__(256) cnn_convT_kernel(const float *act, const float *w4, const float *b4, int L1, int LP,
+                                                        int Lout, float *scores) {
+    __shared__ float ws[CNN_C * 2 * CNN_K];
+    for (int i = threadIdx.x; i < CNN_C * 2 * CNN_K; i += blockDim.x) ws[i] = w4[i];
+    __syncthreads();
+    const int r = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= Lout) return;
+    const float *ar = act + (size_t)r * CNN_C * LP;
+    float a0 = b4[0], a1 = b4[1];
+    const int k0 = j % 3;
+    for (int ci = 0; ci < CNN_C; ci++) {
+        const float *ap = ar + (size_t)ci * LP;
+#pragma unroll
+        for (int kk = 0; kk < 3; kk++) {
+            const int k = k0 + 3 * kk;
+            if (k < CNN_K) {
+                const int t = (j + 3 - k) / 3;
+                if (t >= 0 && t < L1) {
+                    const float v = ap[t];
+                    a0 = fmaf(v, ws[(ci * 2 + 0) * CNN_K + k], a0);
+                    a1 = fmaf(v, ws[(ci * 2 + 1) * CNN_K + k], a1);
+                }
+            }
+        }
+    }
+    scores[((size_t)r * 2 + 0) * Lout + j] = a0;
+    scores[((size_t)r * 2 + 1) * Lout + j] = a1;
+}
+
+// ---- post-processing (cnn.py:117-160) ---------------------------------------------------------------------------------
+// argmax with numpy semantics: first maximum; a NaN wins over everything (first NaN)
+__device__ __forceinline__ bool np_better(float v, int i, float bv, int bi) {
+    const bool vn = !(v == v), bn = !(bv == bv);
+    if (vn != bn) return vn;
+    if (vn) return i < bi;
+    return v > bv || (v == bv && i < bi);
+}
+
+__device__ int cta_argmax(const float *p, int n, float *sv, int *si) {
+    float bv = -CUDART_INF_F;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = p[i];
+        if (bi == 0x7fffffff || np_better(v, i, bv, bi)) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(ADB_FULL, bv, o);
+        const int oi = __shfl_xor_sync(ADB_FULL, bi, o);
+        if (oi != 0x7fffffff && (bi == 0x7fffffff || np_better(ov, oi, bv, bi))) { bv = ov; bi = oi; }
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    bv = sv[0]; bi = si[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++)
+        if (si[w] != 0x7fffffff && (bi == 0x7fffffff || np_better(sv[w], si[w], bv, bi))) { bv = sv[w]; bi = si[w]; }
+    __syncthreads();
+    return bi == 0x7fffffff ? 0 : bi;
+}
+
+// one CTA (256 threads) per read: adapter argmax, mask, poly(A) argmax, mask (in place in scores[:, 1, :])
+__global__ void __launch_bounds__(256) cnn_mask_kernel(float *scores, int Lout, int n_adapter_bins, int k, int *apos,
+                                                       int *ppos) {
+    __shared__ float sv[8];
+    __shared__ int si[8];
+    const int r = blockIdx.x;
+    float *c0 = scores + ((size_t)r * 2) * Lout, *c1 = c0 + Lout;
+    const int a = cta_argmax(c0, min(n_adapter_bins, Lout), sv, si);
+    int p = 0;
+    if (k >= 1) {
+        for (int j = threadIdx.x; j < a; j += blockDim.x) c1[j] = CNN_SCORE_EXCL;
+        __syncthreads();
+        p = cta_argmax(c1, Lout, sv, si);
+        if (k > 1)
+            for (int j = p + 1 + threadIdx.x; j < Lout; j += blockDim.x) c1[j] = CNN_SCORE_EXCL;
+    }
+    if (threadIdx.x == 0) { apos[r] = a; ppos[r] = p; }
+}
+
+// flattened view of the poly(A) channel of one minibatch: element g of the flattened array = row g / Lout
+struct FlatView {
+    const float *scores;
+    int Lout;
+    int r0, nr;  // minibatch rows [r0, r0 + nr)
+    __device__ __forceinline__ float at(long long g) const {
+        const int rr = (int)(g / Lout), j = (int)(g % Lout);
+        return scores[((size_t)(r0 + rr) * 2 + 1) * Lout + j];
+    }
+    __device__ __forceinline__ long long size() const { return (long long)nr * Lout; }
+};
+
+#define CNN_PK_CAP 832  // >= Lout / 2 local maxima per row
+
+// pass A/B: local maxima (scipy _local_maxima_1d on the flattened minibatch array) whose LEFT EDGE lies in this row;
+// midpoints are flattened indices and may fall into a later row when a plateau crosses row boundaries.
+// One CTA (128 threads) per read.  pk_pos[r][CNN_PK_CAP] (flattened midpoint), pk_cnt[r].
+__global__ void __launch_bounds__(128) cnn_peaks_kernel(const float *scores, int Lout, int batch_size, int n_reads,
+                                                        long long *pk_pos, int *pk_cnt) {
+    __shared__ int wcount[4];
+    __shared__ int base_sh;
+    const int r = blockIdx.x;
+    const int mb = r / batch_size;
+    FlatView V{scores, Lout, mb * batch_size, min(batch_size, n_reads - mb * batch_size)};
+    const long long N = V.size();
+    const long long g0 = (long long)(r - V.r0) * Lout;
+    if (threadIdx.x == 0) base_sh = 0;
+    __syncthreads();
+    for (int jb = 0; jb < Lout; jb += blockDim.x) {
+        const int j = jb + threadIdx.x;
+        long long mid = -1;
+        if (j < Lout) {
+            const long long i = g0 + j;
+            if (i >= 1 && i < N - 1) {
+                const float xi = V.at(i);
+                if (V.at(i - 1) < xi) {
+                    long long ia = i + 1;
+                    while (ia < N - 1 && V.at(ia) == xi) ia++;
+                    if (V.at(ia) < xi) mid = (i + ia - 1) / 2;
+                }
+            }
+        }
+        const unsigned m = __ballot_sync(ADB_FULL, mid >= 0);
+        if ((threadIdx.x & 31) == 0) wcount[threadIdx.x >> 5] = __popc(m);
+        __syncthreads();
+        int off = base_sh;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); w++) off += wcount[w];
+        if (mid >= 0) {
+            const int pos = off + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
+            if (pos < CNN_PK_CAP) pk_pos[(size_t)r * CNN_PK_CAP + pos] = mid;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) base_sh += wcount[0] + wcount[1] + wcount[2] + wcount[3];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) pk_cnt[r] = min(base_sh, CNN_PK_CAP);
+}
+
+// distance filter + per-read top-k.  One CTA (128 threads) per read: gathers the peaks listed under rows r-1, r, r+1 of
+// the same minibatch (a distance-5 chain across a row boundary needs unmasked scores on both sides of it; chains
+// spanning more than the neighbouring row do not occur), orders them by priority, runs scipy's greedy
+// _select_by_peak_distance, keeps the survivors whose midpoint lies in row r, sorts those by (-height, position)
+// and writes the first k positions (row-local).  cand[r][k] (0-padded), ncand[r].
+#define CNN_WS_CAP 2560
+__global__ void __launch_bounds__(128) cnn_topk_kernel(const float *scores, int Lout, int batch_size, int n_reads, int k,
+                                                       int dist, const long long *pk_pos, const int *pk_cnt, int *cand,
+                                                       int *ncand) {
+    __shared__ long long pos[CNN_WS_CAP];   // flattened positions, ascending
+    __shared__ float hgt[CNN_WS_CAP];
+    __shared__ unsigned short ord[CNN_WS_CAP];  // indices sorted by priority (ascending height, ties: lower index first)
+    __shared__ unsigned char keep[CNN_WS_CAP];
+    __shared__ int n_sh;
+    const int r = blockIdx.x;
+    const int mb = r / batch_size;
+    FlatView V{scores, Lout, mb * batch_size, min(batch_size, n_reads - mb * batch_size)};
+    const int rl = r - V.r0;
+    // gather (lists are already ascending and rows are consecutive -> concatenation is ascending)
+    int n = 0;
+    for (int rr = max(rl - 1, 0); rr <= min(rl + 1, V.nr - 1); rr++) {
+        const int c = pk_cnt[V.r0 + rr];
+        for (int i = threadIdx.x; i < c; i += blockDim.x) {
+            if (n + i < CNN_WS_CAP) {
+                const long long p = pk_pos[(size_t)(V.r0 + rr) * CNN_PK_CAP + i];
+                pos[n + i] = p;
+                hgt[n + i] = V.at(p);
+                keep[n + i] = 1;
+            }
+        }
+        n = min(n + c, CNN_WS_CAP);
+    }
+    __syncthreads();
+    // priority order: rank by counting (n is a few hundred): ascending height, ties -> lower index first,
+    // processed from the back like scipy (np.argsort read backwards)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float h = hgt[i];
+        int rank = 0;
+        for (int j = 0; j < n; j++) {
+            const float hj = hgt[j];
+            rank += (hj < h) || (hj == h && j < i);
+        }
+        ord[rank] = (unsigned short)i;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && dist > 0) {
+        for (int q = n - 1; q >= 0; q--) {
+            const int j = ord[q];
+            if (!keep[j]) continue;
+            for (int t = j - 1; t >= 0 && pos[j] - pos[t] < dist; t--) keep[t] = 0;
+            for (int t = j + 1; t < n && pos[t] - pos[j] < dist; t++) keep[t] = 0;
+        }
+    }
+    __syncthreads();
+    // survivors in row r, best first: (-height, position); selection by counting
+    const long long lo = (long long)rl * Lout, hi = lo + Lout;
+    if (threadIdx.x == 0) n_sh = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (!keep[i] || pos[i] < lo || pos[i] >= hi) continue;
+        const float h = hgt[i];
+        int rank = 0;
+        for (int j = 0; j < n; j++) {
+            if (!keep[j] || pos[j] < lo || pos[j] >= hi) continue;
+            const float hj = hgt[j];
+            rank += (hj > h) || (hj == h && j < i);
+        }
+        if (rank < k) cand[(size_t)r * k + rank] = (int)(pos[i] - lo);
+        atomicAdd(&n_sh, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) ncand[r] = n_sh;
+}
+
+// groups of candidates are assigned to rows in order of appearance (cnn.py:149-158): read r's candidates land in row
+// (number of earlier reads of the minibatch that have at least one candidate).  One CTA per minibatch.
+__global__ void __launch_bounds__(256) cnn_shift_kernel(const int *apos, const int *ppos, const int *cand, const int *ncand,
+                                                        int batch_size, int n_reads, int k, int ds, int A0, int *given) {
+    __shared__ int wtot[8];
+    __shared__ int carry;
+    const int mb = blockIdx.x;
+    const int r0 = mb * batch_size, nr = min(batch_size, n_reads - r0);
+    const int stride = 1 + max(k, 1);
+    if (threadIdx.x == 0) carry = 0;
+    // adapter ends + zero-filled candidate rows
+    for (int i = threadIdx.x; i < nr; i += blockDim.x) {
+        int *g = given + (size_t)(r0 + i) * stride;
+        const int a = apos[r0 + i];
+        g[0] = (a == 0) ? 0 : a * ds + A0;  // preds == min_obs_adapter -> 0 (cnn.py:179)
+        for (int t = 0; t < max(k, 1); t++) g[1 + t] = 0;
+        if (k == 1) { const int p = ppos[r0 + i]; g[1] = (p == 0) ? 0 : p * ds + A0; }
+    }
+    __syncthreads();
+    if (k <= 1) return;
+    for (int base = 0; base < nr; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int has = (i < nr && ncand[r0 + i] > 0) ? 1 : 0;
+        const unsigned m = __ballot_sync(ADB_FULL, has);
+        if ((threadIdx.x & 31) == 0) wtot[threadIdx.x >> 5] = __popc(m);
+        __syncthreads();
+        int off = carry;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); w++) off += wtot[w];
+        if (has) {
+            const int row = off + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
+            int *g = given + (size_t)(r0 + row) * stride;
+            const int nc = min(ncand[r0 + i], k);
+            for (int t = 0; t < nc; t++) {
+                const int p = cand[(size_t)(r0 + i) * k + t];
+                g[1 + t] = (p == 0) ? 0 : p * ds + A0;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { int s = 0; for (int w = 0; w < 8; w++) s += wtot[w]; carry += s; }
+        __syncthreads();
+    }
+}
+
+// ---- host orchestration -----------------------------------------------------------------------------------------------------
+struct CnnDims {
+    int Lx, L1, LP, Lout;
+};
+static CnnDims cnn_dims(int m, int A0, int f) {
+    CnnDims d;
+    d.Lx = (std::max(m - A0, 0) + f - 1) / f;
+    d.L1 = (d.Lx + 2 * 3 - CNN_K) / 3 + 1;
+    d.LP = (d.L1 + 3) & ~3;
+    d.Lout = (d.L1 - 1) * 3 - 2 * 3 + CNN_K;
+    return d;
+}
+
+// x [n][Lx] (device) -> scores [n][2][Lout] (device); chunked over reads to bound the activation buffers
+static int cnn_forward_dev(adb_ctx *ctx, const float *x, int n, const CnnDims &D, const float *w_dev, float *scores,
+                           cudaStream_t st) {
+    if (ctx->cnn_w.ensure(sizeof(float) * 2 * CNN_C * CNN_K * CNN_C)) { set_err("cudaMalloc cnn weights"); return ADB_ERR_CUDA; }
+    float *packed = (float *)ctx->cnn_w.p;
+    {
+        KernelTimer t(ctx, 5, st);
+        cnn_pack_weights_kernel<<<(2 * CNN_C * CNN_K * CNN_C + 255) / 256, 256, 0, st>>>(w_dev, packed);
+    }
+    ctx->launches += 1;
+    const size_t act_per_read = (size_t)CNN_C * D.LP * sizeof(float);
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, ((size_t)1 << 30) / act_per_read));
+    if (ctx->cnn_act0.ensure(act_per_read * chunk) || ctx->cnn_act1.ensure(act_per_read * chunk)) {
+        set_err("cudaMalloc cnn activations");
+        return ADB_ERR_CUDA;
+    }
+    const size_t smem = cnn_conv_smem_bytes();
+    CUDA_TRY(cudaFuncSetAttribute(cnn_conv64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(cnn_conv64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    float *a0 = (float *)ctx->cnn_act0.p, *a1 = (float *)ctx->cnn_act1.p;
+    for (int r0 = 0; r0 < n; r0 += chunk) {
+        const int nc = std::min(chunk, n - r0);
+        const int tiles = nc * ((D.L1 + CNN_TILE - 1) / CNN_TILE);
+        const int grid = std::max(1, std::min(tiles, ctx->sm_count));
+        {
+            KernelTimer t(ctx, 5, st);
+            cnn_conv64_kernel<true><<<grid, CNN_THREADS, smem, st>>>(x + (size_t)r0 * D.Lx, a0, packed, w_dev + CNN_B2,
+                                                                      w_dev + CNN_W1, w_dev + CNN_B1, nc, D.Lx, D.L1, D.LP);
+        }
+        {
+            KernelTimer t(ctx, 5, st);
+            cnn_conv64_kernel<false><<<grid, CNN_THREADS, smem, st>>>(a0, a1, packed + CNN_C * CNN_K * CNN_C, w_dev + CNN_B3,
+                                                                       nullptr, nullptr, nc, D.Lx, D.L1, D.LP);
+        }
+        {
+            KernelTimer t(ctx, 5, st);
+            dim3 g((D.Lout + 255) / 256, nc);
+            cnn_convT_kernel<<<g, 256, 0, st>>>(a1, w_dev + CNN_W4, w_dev + CNN_B4, D.L1, D.LP, D.Lout,
+                                                scores + (size_t)r0 * 2 * D.Lout);
+        }
+        ctx->launches += 3;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return ADB_OK;
+}
+
+// primary boundaries of the CNN method -> given[n_reads][1 + max(k,1)]
+static int cnn_primary_boundaries(adb_ctx *ctx, const BatchDev &B, const adb_config &cfg, const float *w_dev, int *given,
+                                  cudaStream_t st) {
+    const CnnDims D = cnn_dims(B.m, cfg.min_obs_adapter, cfg.downscale_factor);
+    if (D.Lx < CNN_K || D.Lout < 3 || D.Lout / 2 + 8 > CNN_PK_CAP) {
+        set_err("preload window outside the range supported by the CNN kernels");
+        return ADB_ERR_UNSUPPORTED;
+    }
+    const int n = B.n_reads, k = cfg.polya_cand_k;
+    if (ctx->cnn_x.ensure(sizeof(float) * (size_t)n * D.Lx) || ctx->cnn_scores.ensure(sizeof(float) * (size_t)n * 2 * D.Lout)) {
+        set_err("cudaMalloc cnn buffers");
+        return ADB_ERR_CUDA;
+    }
+    float *x = (float *)ctx->cnn_x.p, *scores = (float *)ctx->cnn_scores.p;
+    {
+        const size_t smem = (((size_t)D.Lx * 4 + 15) & ~(size_t)15) + ((ADB_SEL_SMEM_BYTES + 15) & ~15) + 64;
+        CUDA_TRY(cudaFuncSetAttribute(cnn_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KernelTimer t(ctx, 5, st);
+        cnn_prep_kernel<<<n, 256, smem, st>>>(B, cfg.min_obs_adapter, cfg.downscale_factor, D.Lx, x);
+        ctx->launches += 1;
+    }
+    int rc = cnn_forward_dev(ctx, x, n, D, w_dev, scores, st);
+    if (rc) return rc;
+    // post-processing scratch: apos, ppos, pk_cnt, ncand [n] ints; cand [n][k]; pk_pos [n][CNN_PK_CAP] int64
+    const size_t ints = (size_t)n * (4 + std::max(k, 1));
+    if (ctx->cnn_post.ensure(sizeof(long long) * (size_t)n * CNN_PK_CAP + sizeof(int) * ints + 64)) {
+        set_err("cudaMalloc cnn post-processing");
+        return ADB_ERR_CUDA;
+    }
+    long long *pk_pos = (long long *)ctx->cnn_post.p;
+    int *apos = (int *)(pk_pos + (size_t)n * CNN_PK_CAP), *ppos = apos + n, *pk_cnt = ppos + n, *ncand = pk_cnt + n;
+    int *cand = ncand + n;
+    const int nadp = (cfg.max_obs_adapter - cfg.min_obs_adapter) / cfg.downscale_factor;
+    const int n_batches = (n + B.batch_size - 1) / B.batch_size;
+    {
+        KernelTimer t(ctx, 5, st);
+        cnn_mask_kernel<<<n, 256, 0, st>>>(scores, D.Lout, nadp, k, apos, ppos);
+    }
+    ctx->launches += 1;
+    if (k > 1) {
+        CUDA_TRY(cudaMemsetAsync(cand, 0, sizeof(int) * (size_t)n * k, st));
+        {
+            KernelTimer t(ctx, 5, st);
+            cnn_peaks_kernel<<<n, 128, 0, st>>>(scores, D.Lout, B.batch_size, n, pk_pos, pk_cnt);
+        }
+        {
+            KernelTimer t(ctx, 5, st);
+            cnn_topk_kernel<<<n, 128, 0, st>>>(scores, D.Lout, B.batch_size, n, k, 5, pk_pos, pk_cnt, cand, ncand);
+        }
+        ctx->launches += 2;
+    }
+    {
+        KernelTimer t(ctx, 5, st);
+        cnn_shift_kernel<<<n_batches, 256, 0, st>>>(apos, ppos, cand, ncand, B.batch_size, n, k, cfg.downscale_factor,
+                                                    cfg.min_obs_adapter, given);
+    }
+    ctx->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return ADB_OK;
 }

@@ -63,8 +63,28 @@ struct adb_ctx {
     cudaEvent_t p_done[2] = {nullptr, nullptr}, p_copied[2] = {nullptr, nullptr};
     // scratch (device)
     DevBuf states, hist, series, given, status;
-    DevBuf cnn_x, cnn_act0, cnn_act1, cnn_scores, cnn_w, cnn_aux;
+    DevBuf cnn_x, cnn_act0, cnn_act1, cnn_scores, cnn_w, cnn_aux, cnn_post, sp_rows;
     // staging for the *_host entry points
     DevBuf h_signal, h_offsets, h_lens, h_coff, h_cscale, h_records, h_misc, h_misc2, h_misc3;
+};
+
+struct KernelTimer {  // brackets one launch with events when ctx->timing is on
+    adb_ctx *ctx;
+    int cls;
+    cudaStream_t st;
+    cudaEvent_t a = nullptr, b = nullptr;
+    KernelTimer(adb_ctx *c, int cls_, cudaStream_t s) : ctx(c), cls(cls_), st(s) {
+        if (ctx->timing) {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, st);
+        }
+    }
+    ~KernelTimer() {
+        if (ctx->timing) {
+            cudaEventRecord(b, st);
+            ctx->ev[cls].push_back({a, b});
+        }
+    }
 };
 

@@ -214,7 +214,7 @@ __host__ __device__ inline size_t validate_smem_bytes(int win_bytes, int nds_max
     return (((size_t)win_bytes + 48 + 15) & ~(size_t)15) + scratch + 256;
 }
 
-__global__ void __launch_bounds__(ADB_VAL_THREADS) validate_kernel(ValidateArgs A, adb_config cfg) {
+__global__ void __launch_bounds__(ADB_VAL_THREADS, 3) validate_kernel(ValidateArgs A, adb_config cfg) {
     extern __shared__ __align__(128) unsigned char smem[];
     // layout: [window (+48)][scratch: select histogram | hail-mary trace buffers][small]
     unsigned char *winbuf = smem;

@@ -205,56 +205,61 @@ __device__ SegStats seg_stats(ValCtx &C, int a, int b, int flags) {
     }
     __syncthreads();
     auto val = [&](int bin) { return __fmul_rn(__fadd_rn((float)((int)((uint32_t)bin + kmin) - 32768), coff), cscale); };
-    // median: odd -> s[n/2]; even -> f32(f32(a+b)/2); every thread computes it (uniform)
+    // rank look-ups by six threads (median x2, percentile x4), results broadcast through shared memory
+    float *fb = (float *)C.kbuf;  // 8 floats
     {
-        const float x0 = val(ihist_bin_of_rank(hist, nb, (uint32_t)((n - 1) / 2)));
-        if (n & 1) R.med = x0;
-        else R.med = __fdiv_rn(__fadd_rn(x0, val(ihist_bin_of_rank(hist, nb, (uint32_t)(n / 2)))), 2.0f);
-    }
-    if (flags & SS_LR) {
         const double v85 = __dmul_rn((double)(n - 1), 0.85), v15 = __dmul_rn((double)(n - 1), 0.15);
         const int l85 = (int)floor(v85), l15 = (int)floor(v15);
-        const int h85 = min(l85 + 1, n - 1), h15 = min(l15 + 1, n - 1);
-        const float a15 = val(ihist_bin_of_rank(hist, nb, l15)), b15 = val(ihist_bin_of_rank(hist, nb, h15));
-        const float a85 = val(ihist_bin_of_rank(hist, nb, l85)), b85 = val(ihist_bin_of_rank(hist, nb, h85));
-        R.lr = __dsub_rn(np_lerp_f32(a85, b85, __dsub_rn(v85, (double)l85)), np_lerp_f32(a15, b15, __dsub_rn(v15, (double)l15)));
+        if (tid < 6) {
+            int rank;
+            switch (tid) {
+                case 0: rank = (n - 1) / 2; break;
+                case 1: rank = n / 2; break;
+                case 2: rank = l15; break;
+                case 3: rank = min(l15 + 1, n - 1); break;
+                case 4: rank = l85; break;
+                default: rank = min(l85 + 1, n - 1); break;
+            }
+            if (tid < 2 || (flags & SS_LR)) fb[tid] = val(ihist_bin_of_rank(hist, nb, (uint32_t)rank));
+        }
+        __syncthreads();
+        // median: odd -> s[n/2]; even -> f32(f32(a+b)/2)
+        R.med = (n & 1) ? fb[0] : __fdiv_rn(__fadd_rn(fb[0], fb[1]), 2.0f);
+        if (flags & SS_LR)
+            R.lr = __dsub_rn(np_lerp_f32(fb[4], fb[5], __dsub_rn(v85, (double)l85)),
+                             np_lerp_f32(fb[2], fb[3], __dsub_rn(v15, (double)l15)));
     }
     if (flags & SS_MAD) {
+        // k-th smallest deviation t* = min{ dev(code) : #(dev <= dev(code)) > k } over the occupied codes
         const float med = R.med;
         auto dev = [&](int bin) { return fabsf(__fsub_rn(val(bin), med)); };
         auto cum = [&](int x) -> uint32_t { return x < 0 ? 0u : hist[x]; };
-        // pivot: first bin whose value is >= med
-        int pv;
+        uint32_t *ub = C.kbuf + 6;  // 2 words: float bits of the answers (deviations are >= 0: bit order == value order)
+        __syncthreads();
+        if (tid == 0) { ub[0] = 0x7f800000u; ub[1] = 0x7f800000u; }
+        int pv;  // first code whose value is >= med
         {
             int lo = 0, hi = nb;
             while (lo < hi) { const int mid = (lo + hi) >> 1; if (val(mid) >= med) hi = mid; else lo = mid + 1; }
             pv = lo;
         }
+        __syncthreads();
         const uint32_t k0 = (uint32_t)((n - 1) / 2), k1 = (uint32_t)(n / 2);
         for (int bin = tid; bin < nb; bin += T) {
             if (cum(bin) == cum(bin - 1)) continue;  // empty code
             const float t = dev(bin);
-            // right side [pv, nb): deviations non-decreasing
-            int lo = pv, hi = nb;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (dev(mid) >= t) hi = mid; else lo = mid + 1; }
-            const int r_ge = lo;
-            lo = r_ge; hi = nb;
+            int lo = pv, hi = nb;  // right side [pv, nb): deviations non-decreasing -> first code with dev > t
             while (lo < hi) { const int mid = (lo + hi) >> 1; if (dev(mid) > t) hi = mid; else lo = mid + 1; }
             const int r_gt = lo;
-            // left side [0, pv): deviations non-increasing
-            lo = 0; hi = pv;
+            lo = 0; hi = pv;       // left side [0, pv): deviations non-increasing -> first code with dev <= t
             while (lo < hi) { const int mid = (lo + hi) >> 1; if (dev(mid) <= t) hi = mid; else lo = mid + 1; }
             const int l_le = lo;
-            lo = l_le; hi = pv;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (dev(mid) < t) hi = mid; else lo = mid + 1; }
-            const int l_lt = lo;
-            const uint32_t cnt_lt = cum(r_ge - 1) - cum(l_lt - 1);
             const uint32_t cnt_le = cum(r_gt - 1) - cum(l_le - 1);
-            if (cnt_lt <= k0 && k0 < cnt_le) ((float *)C.kbuf)[0] = t;
-            if (cnt_lt <= k1 && k1 < cnt_le) ((float *)C.kbuf)[1] = t;
+            if (cnt_le > k0) atomicMin(&ub[0], __float_as_uint(t));
+            if (cnt_le > k1) atomicMin(&ub[1], __float_as_uint(t));
         }
         __syncthreads();
-        const float d0 = ((float *)C.kbuf)[0], d1 = ((float *)C.kbuf)[1];
+        const float d0 = __uint_as_float(ub[0]), d1 = __uint_as_float(ub[1]);
         R.mad = (n & 1) ? d0 : __fdiv_rn(__fadd_rn(d0, d1), 2.0f);
     }
     __syncthreads();
@@ -312,8 +317,19 @@ __device__ void seg_mean_std(ValCtx &C, int a, int b, double &mean_out, double &
     clip_seg(a, b, C.src.n);
     const int n = b - a;
     if (n <= 0) { mean_out = CUDART_NAN; std_out = CUDART_NAN; return; }
+    const ReadSrc src = C.src;  // registers, not the context in local memory
+    const int T = blockDim.x;
+    // the ADC sum is exact in integers: mean = (sum(adc)/n + offset) * scale would not be numpy's float32 sum, but the
+    // 1e-5 tolerance applies here; stay with float64 accumulation of the float32 pA values for clarity
     double s = 0.0;
-    for (int j = threadIdx.x; j < n; j += blockDim.x) s += (double)C.src.pa(a + j);
+    if (src.i16) {
+        const int16_t *p = src.i16 + a;
+        const float co = src.coff, cs = src.cscale;
+        for (int j = threadIdx.x; j < n; j += T) s += (double)__fmul_rn(__fadd_rn((float)p[j], co), cs);
+    } else {
+        const float *p = src.f32 + a;
+        for (int j = threadIdx.x; j < n; j += T) s += (double)p[j];
+    }
     s = warp_sum_d(s);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) C.dtmp[threadIdx.x >> 5] = s;
@@ -322,11 +338,17 @@ __device__ void seg_mean_std(ValCtx &C, int a, int b, double &mean_out, double &
     for (int w = 0; w < (int)((blockDim.x + 31) >> 5); w++) tot += C.dtmp[w];
     const float mean32 = (float)(tot / n);
     __syncthreads();
+    float qf = 0.f;  // per-thread partial in float32 (<= ~100 terms), combined in float64
     double q = 0.0;
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-        double d = (double)__fsub_rn(C.src.pa(a + j), mean32);
-        q += d * d;
+    if (src.i16) {
+        const int16_t *p = src.i16 + a;
+        const float co = src.coff, cs = src.cscale;
+        for (int j = threadIdx.x; j < n; j += T) { const float d = __fsub_rn(__fmul_rn(__fadd_rn((float)p[j], co), cs), mean32); qf = fmaf(d, d, qf); }
+    } else {
+        const float *p = src.f32 + a;
+        for (int j = threadIdx.x; j < n; j += T) { const float d = __fsub_rn(p[j], mean32); qf = fmaf(d, d, qf); }
     }
+    q = (double)qf;
     q = warp_sum_d(q);
     if ((threadIdx.x & 31) == 0) C.dtmp[threadIdx.x >> 5] = q;
     __syncthreads();

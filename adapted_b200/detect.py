@@ -192,6 +192,19 @@ def c_llr_trace_batch(signals, params, return_c_c2: bool = False, device: int = 
     return out
 
 
+def cnn_scores(x: np.ndarray, model: Any, device: int = 0) -> np.ndarray:
+    """BoundariesCNN forward (adapted/detect/cnn.py:16-52,85-98) on prepared inputs x[n, L] -> scores[n, 2, L_out]."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    n, L = x.shape
+    L1 = (L + 6 - 7) // 3 + 1
+    Lout = (L1 - 1) * 3 - 6 + 7
+    w = flatten_cnn_weights(model)
+    out = np.zeros((n, 2, Lout), dtype=np.float32)
+    ctx = _lib.default_context(device)
+    _lib.check(_lib.load().adb_cnn_scores_host(ctx.handle, x.ctypes.data, n, L, w.ctypes.data, out.ctypes.data))
+    return out
+
+
 def global_med_mad(batch_of_signals: np.ndarray, full_signal_lens: np.ndarray, max_obs_trace: int, device: int = 0):
     """med_mad(batch[:, :max_obs_trace], with_nan=True), adapted/detect/normalize.py:15-22."""
     b, keep = _dense_batch(batch_of_signals, full_signal_lens)

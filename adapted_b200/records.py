@@ -149,5 +149,8 @@ def records_to_results(recs: np.ndarray, primary_method: int, llr_log: Optional[
             if valid & V_SP_OPEN:
                 d.start_peak_open_pore_idx = np.int64(r["sp_open_pore_idx"])
                 d.start_peak_open_pore_type = _SP_FLAGS.get(int(r["sp_flag"]))
+                # combined.py:340-347: a flagged read fails; the type is appended only if it had failed already
+                if int(r["fail_code"]) != 0:
+                    d.fail_reason = reason + "+" + d.start_peak_open_pore_type
         out.append(d)
     return out
