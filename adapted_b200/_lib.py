@@ -103,6 +103,10 @@ def load() -> C.CDLL:
     L.adb_ctx_destroy.restype = None
     L.adb_ctx_launch_count.argtypes = [vp]
     L.adb_ctx_launch_count.restype = C.c_int64
+    L.adb_ctx_set_option.argtypes = [vp, C.c_char_p, ip]
+    L.adb_ctx_set_option.restype = ip
+    L.adb_ctx_query.argtypes = [vp, C.c_char_p]
+    L.adb_ctx_query.restype = C.c_int64
     L.adb_detect_host.argtypes = [vp, C.POINTER(AdbBatch), C.POINTER(AdbConfig), vp, vp, vp]
     L.adb_detect_dev.argtypes = [vp, C.POINTER(AdbBatch), C.POINTER(AdbConfig), vp, vp, vp, vp]
     L.adb_detect_pipelined_host.argtypes = [vp, C.POINTER(AdbBatch), C.POINTER(AdbConfig), vp, vp, vp, C.c_int32]
@@ -155,6 +159,12 @@ class Context:
     @property
     def launches(self) -> int:
         return int(load().adb_ctx_launch_count(self._h))
+
+    def set_option(self, name: str, value: int) -> None:
+        check(load().adb_ctx_set_option(self._h, name.encode(), int(value)))
+
+    def query(self, name: str) -> int:
+        return int(load().adb_ctx_query(self._h, name.encode()))
 
     def close(self) -> None:
         if getattr(self, "_h", None):

@@ -13,6 +13,7 @@
 #include "adb_common.cuh"
 #include "adb_ctx.cuh"
 #include "adb_global.cuh"
+#include "adb_gsample.cuh"
 #include "adb_llr.cuh"
 #include "adb_read_kernel.cuh"
 #include "adb_cnn.cuh"
@@ -66,7 +67,8 @@ extern "C" void adb_ctx_destroy(adb_ctx *c) {
     cudaSetDevice(c->device);
     DevBuf *all[] = {&c->states, &c->hist, &c->series, &c->given, &c->status, &c->cnn_x, &c->cnn_act0,
                      &c->cnn_act1, &c->cnn_scores, &c->cnn_w, &c->cnn_aux, &c->cnn_post, &c->sp_rows, &c->h_signal, &c->h_offsets,
-                     &c->h_lens, &c->h_coff, &c->h_cscale, &c->h_records, &c->h_misc, &c->h_misc2, &c->h_misc3};
+                     &c->h_lens, &c->h_coff, &c->h_cscale, &c->h_records, &c->h_misc, &c->h_misc2, &c->h_misc3,
+                     &c->gsb_plan, &c->gsb_hist, &c->gsb_tab, &c->gsb_bases, &c->gsb_active};
     for (DevBuf *b : all) b->release();
     for (int k = 0; k < 2; k++) {
         DevBuf *pb[] = {&c->p_signal[k], &c->p_offsets[k], &c->p_lens[k], &c->p_coff[k], &c->p_cscale[k], &c->p_records[k], &c->p_status[k]};
@@ -81,6 +83,29 @@ extern "C" void adb_ctx_destroy(adb_ctx *c) {
 }
 
 extern "C" int64_t adb_ctx_launch_count(const adb_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int adb_ctx_set_option(adb_ctx *c, const char *name, int value) {
+    if (!c || !name) return ADB_ERR_ARG;
+    if (!strcmp(name, "exact_global_select")) { c->opt_exact_gsel = value; return ADB_OK; }
+    set_err(std::string("unknown option: ") + name);
+    return ADB_ERR_ARG;
+}
+
+// diagnostics of the most recent call on this context (synchronises the context's stream)
+extern "C" int64_t adb_ctx_query(adb_ctx *c, const char *name) {
+    if (!c || !name) return -1;
+    if (!strcmp(name, "global_select_fallbacks")) {
+        // minibatches of the last LLR call that the sampled select handed to the exact multi-pass select
+        if (!c->gsb_last_batches || !c->gsb_active.p) return 0;
+        std::vector<int> h(c->gsb_last_batches);
+        if (cudaSetDevice(c->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
+            cudaMemcpy(h.data(), c->gsb_active.p, sizeof(int) * h.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        int64_t n = 0;
+        for (int v : h) n += (v != 0);
+        return n;
+    }
+    return -1;
+}
 
 extern "C" int adb_ctx_set_timing(adb_ctx *c, int on) {
     if (!c) return ADB_ERR_ARG;
@@ -165,23 +190,60 @@ static int check_config(const adb_config *cfg) {
 }
 
 // ---- global median / MAD -------------------------------------------------------------------------------------
+// int16 sources: sampled one-pass select (adb_gsample.cuh); whatever it cannot settle -- and every float32 source --
+// goes through the exact multi-pass radix select (adb_global.cuh), whose kernels skip the settled minibatches.
 static int run_global_med_mad(adb_ctx *ctx, const BatchDev &B, int n_batches, int max_obs_trace, cudaStream_t st) {
     if (ctx->states.ensure(sizeof(GselState) * (size_t)n_batches)) { set_err("cudaMalloc states"); return ADB_ERR_CUDA; }
     if (ctx->hist.ensure(sizeof(unsigned) * 2 * GSEL_BINS * (size_t)n_batches)) { set_err("cudaMalloc hist"); return ADB_ERR_CUDA; }
     CUDA_TRY(cudaMemsetAsync(ctx->states.p, 0, sizeof(GselState) * (size_t)n_batches, st));
     CUDA_TRY(cudaMemsetAsync(ctx->hist.p, 0, sizeof(unsigned) * 2 * GSEL_BINS * (size_t)n_batches, st));
-    int gx = std::max(1, std::min(B.batch_size, (ctx->sm_count * 8 + n_batches - 1) / n_batches));
+    const int gx = std::max(1, std::min(B.batch_size, (ctx->sm_count * 8 + n_batches - 1) / n_batches));
+    const int *active = nullptr;
+    ctx->gsb_last_batches = 0;
+    if (B.sig_type == ADB_SIG_I16 && !ctx->opt_exact_gsel) {
+        if (ctx->gsb_plan.ensure(sizeof(GsbPlan) * (size_t)n_batches) || ctx->gsb_hist.ensure(sizeof(unsigned) * GSB_BINS * (size_t)n_batches) ||
+            ctx->gsb_tab.ensure(sizeof(unsigned) * GSB_TAB * (size_t)B.n_reads) || ctx->gsb_bases.ensure(sizeof(GsbRead) * (size_t)B.n_reads) ||
+            ctx->gsb_active.ensure(sizeof(int) * (size_t)n_batches)) { set_err("cudaMalloc sampled select"); return ADB_ERR_CUDA; }
+        CUDA_TRY(cudaMemsetAsync(ctx->gsb_hist.p, 0, sizeof(unsigned) * GSB_BINS * (size_t)n_batches, st));
+        CUDA_TRY(cudaMemsetAsync(ctx->gsb_tab.p, 0, sizeof(unsigned) * GSB_TAB * (size_t)B.n_reads, st));
+        const size_t sm = sizeof(unsigned) * GSB_BINS;
+        CUDA_TRY(cudaFuncSetAttribute(gsb_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        CUDA_TRY(cudaFuncSetAttribute(gsb_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        const int gs = std::max(1, std::min(B.batch_size, (ctx->sm_count * 3 + n_batches - 1) / n_batches));
+        {
+            KernelTimer t(ctx, 1, st);
+            // about GSB_TARGET_SAMPLE samples per minibatch, never denser than every 4th sample
+            const long long per_mb = (long long)std::min(B.batch_size, B.n_reads) * std::max(1, std::min(max_obs_trace, B.m));
+            const int stride = (int)std::max<long long>(4, std::min<long long>(GSB_STRIDE, per_mb / GSB_TARGET_SAMPLE));
+            gsb_sample_kernel<<<dim3(gs, n_batches), 256, sm, st>>>(B, max_obs_trace, stride, (unsigned *)ctx->gsb_hist.p);
+            gsb_plan_kernel<<<n_batches, 256, sm, st>>>((const unsigned *)ctx->gsb_hist.p, (GsbPlan *)ctx->gsb_plan.p);
+        }
+        {
+            KernelTimer t(ctx, 0, st);
+            gsb_pass_kernel<<<dim3(gx, n_batches), 256, 0, st>>>(B, max_obs_trace, (GsbPlan *)ctx->gsb_plan.p,
+                                                                 (unsigned *)ctx->gsb_tab.p, (GsbRead *)ctx->gsb_bases.p);
+        }
+        {
+            KernelTimer t(ctx, 1, st);
+            gsb_finish_kernel<<<n_batches, 256, 0, st>>>(B, (GsbPlan *)ctx->gsb_plan.p, (const unsigned *)ctx->gsb_tab.p,
+                                                         (const GsbRead *)ctx->gsb_bases.p, (GselState *)ctx->states.p,
+                                                         (int *)ctx->gsb_active.p);
+        }
+        ctx->launches += 4;
+        ctx->gsb_last_batches = n_batches;
+        active = (const int *)ctx->gsb_active.p;
+    }
     dim3 grid(gx, n_batches);
     for (int stage = 0; stage < 2; stage++) {
         for (int pass = 0; pass < 3; pass++) {
             {
-                KernelTimer t(ctx, 0, st);
+                KernelTimer t(ctx, active ? 7 : 0, st);
                 gsel_hist_kernel<<<grid, 256, 0, st>>>(B, max_obs_trace, stage, pass, (const GselState *)ctx->states.p,
-                                                       (unsigned *)ctx->hist.p);
+                                                       (unsigned *)ctx->hist.p, active);
             }
             {
-                KernelTimer t(ctx, 1, st);
-                gsel_scan_kernel<<<n_batches, 256, 0, st>>>(stage, pass, (GselState *)ctx->states.p, (unsigned *)ctx->hist.p);
+                KernelTimer t(ctx, active ? 7 : 1, st);
+                gsel_scan_kernel<<<n_batches, 256, 0, st>>>(stage, pass, (GselState *)ctx->states.p, (unsigned *)ctx->hist.p, active);
             }
             ctx->launches += 2;
         }

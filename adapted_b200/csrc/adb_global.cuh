@@ -28,9 +28,10 @@ __device__ __forceinline__ uint32_t gsel_mask(int pass) { return pass == 2 ? 102
 // stage: 0 = median of x, 1 = median of |x - med|
 // hist layout: [minibatch][2 targets][GSEL_BINS]
 __global__ void __launch_bounds__(256) gsel_hist_kernel(BatchDev B, int max_obs_trace, int stage, int pass,
-                                                        const GselState *states, unsigned int *hist) {
+                                                        const GselState *states, unsigned int *hist, const int *active) {
     __shared__ unsigned int sh[2][GSEL_BINS];
     const int mb = blockIdx.y;
+    if (active && !active[mb]) return;  // this minibatch was settled by the sampled one-pass select (adb_gsample.cuh)
     const int r0 = mb * B.batch_size, r1 = min(r0 + B.batch_size, B.n_reads);
     const GselState st = states[mb];
     for (int b = threadIdx.x; b < 2 * GSEL_BINS; b += blockDim.x) (&sh[0][0])[b] = 0;
@@ -107,11 +108,13 @@ __global__ void __launch_bounds__(256) gsel_hist_kernel(BatchDev B, int max_obs_
 }
 
 // one CTA (256 threads) per minibatch
-__global__ void __launch_bounds__(256) gsel_scan_kernel(int stage, int pass, GselState *states, unsigned int *hist) {
+__global__ void __launch_bounds__(256) gsel_scan_kernel(int stage, int pass, GselState *states, unsigned int *hist,
+                                                        const int *active) {
     __shared__ unsigned long long part[256];
     __shared__ int found_bin[2];
     __shared__ unsigned long long found_before[2];
     const int mb = blockIdx.x, tid = threadIdx.x;
+    if (active && !active[mb]) return;
     GselState *st = &states[mb];
     unsigned int *gh = hist + (size_t)mb * 2 * GSEL_BINS;
     const bool same = (pass == 0) || (st->prefix[0] == st->prefix[1]);

@@ -215,6 +215,33 @@ def global_med_mad(batch_of_signals: np.ndarray, full_signal_lens: np.ndarray, m
     return float(out[0]), float(out[1])
 
 
+def global_med_mad_i16(adc: np.ndarray, offsets: np.ndarray, full_lens: np.ndarray, calib_offset: np.ndarray,
+                       calib_scale: np.ndarray, m: int, max_obs_trace: int, minibatch_size: int, device: int = 0,
+                       exact: bool = False):
+    """Same statistic on ragged int16 reads, one (med, mad) per minibatch.  Returns (med_mad [n_batches, 2],
+    number of minibatches the sampled one-pass select handed to the exact multi-pass select).  ``exact=True``
+    forces the multi-pass select."""
+    adc = np.ascontiguousarray(adc, dtype=np.int16)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    lens = np.ascontiguousarray(full_lens, dtype=np.int32)
+    coff = np.ascontiguousarray(calib_offset, dtype=np.float32)
+    cscale = np.ascontiguousarray(calib_scale, dtype=np.float32)
+    n = lens.size
+    b = _lib.AdbBatch(signal=adc.ctypes.data, sig_type=_lib.SIG_I16, n_reads=n, m=int(m), batch_size=int(minibatch_size),
+                      offsets=offsets.ctypes.data, full_lens=lens.ctypes.data, calib_offset=coff.ctypes.data,
+                      calib_scale=cscale.ctypes.data)
+    n_batches = (n + minibatch_size - 1) // minibatch_size
+    out = np.zeros((n_batches, 2), dtype=np.float32)
+    ctx = _lib.default_context(device)
+    ctx.set_option("exact_global_select", 1 if exact else 0)
+    try:
+        _lib.check(_lib.load().adb_global_med_mad_host(ctx.handle, C.byref(b), int(max_obs_trace), out.ctypes.data))
+        fallbacks = 0 if exact else ctx.query("global_select_fallbacks")
+    finally:
+        ctx.set_option("exact_global_select", 0)
+    return out, fallbacks
+
+
 def downscale_signal(batch_of_signals: np.ndarray, full_signal_lens: np.ndarray, factor: int, col0: int = 0,
                      device: int = 0) -> np.ndarray:
     """downscale_signal(batch[:, col0:], factor), adapted/detect/downscale.py:37-41."""

@@ -122,6 +122,50 @@ def test_global_med_mad_even_odd_and_ties():
         assert mad == float(np.nanmedian(np.abs(x - want_med)))
 
 
+@pytest.mark.parametrize("chem,n,mbs,seed", [("rna002", 400, 200, 11), ("rna004", 300, 300, 12), ("rna002", 64, 64, 13)])
+def test_global_med_mad_sampled_one_pass_select(chem, n, mbs, seed):
+    """int16 ingest: the sampled one-pass select must settle these minibatches itself (no hand-over to the exact
+    multi-pass select) and return numpy's order statistics bit for bit; the multi-pass select agrees."""
+    from adapted_b200.config import get_chemistry_specific_config
+    from adapted_b200.detect import global_med_mad_i16
+    from adapted_b200.synth import make_reads
+
+    spc = get_chemistry_specific_config(chem)
+    b = make_reads(n, chem, spc.sig_preload_size, seed=seed, short_frac=0.1)
+    tm = spc.core.max_obs_trace
+    got, fallbacks = global_med_mad_i16(b.adc, b.offsets, b.full_lens, b.calib_offset, b.calib_scale, b.m, tm, mbs)
+    exact, _ = global_med_mad_i16(b.adc, b.offsets, b.full_lens, b.calib_offset, b.calib_scale, b.m, tm, mbs, exact=True)
+    assert fallbacks == 0
+    x = b.to_dense_pa()
+    for i in range(got.shape[0]):
+        sub = x[i * mbs:(i + 1) * mbs, :tm]
+        med = np.float32(np.nanmedian(sub))
+        mad = np.float32(np.nanmedian(np.abs(sub - med)))
+        assert (got[i, 0], got[i, 1]) == (med, mad), (i, got[i], med, mad)
+        assert (exact[i, 0], exact[i, 1]) == (med, mad)
+
+
+def test_global_med_mad_sampled_select_hands_over_when_it_cannot_decide():
+    """heavy ties / tiny minibatches / degenerate calibration: the sampled select must hand over, results stay exact"""
+    from adapted_b200.detect import global_med_mad_i16
+
+    rng = np.random.default_rng(21)
+    n, m = 40, 3000
+    lens = rng.integers(500, m, size=n).astype(np.int32)
+    offs = np.zeros(n + 1, np.int64)
+    np.cumsum(lens, out=offs[1:])
+    # two-level signal: the median sits on a huge tie, MAD has few distinct values
+    adc = np.where(rng.random(offs[-1]) < 0.5, 500, 520).astype(np.int16) + rng.integers(0, 2, size=offs[-1]).astype(np.int16)
+    coff = np.full(n, -10.0, np.float32)
+    cscale = np.full(n, 0.1755, np.float32)
+    got, fallbacks = global_med_mad_i16(adc, offs, lens, coff, cscale, m, m, 20)
+    for i in range(2):
+        vals = np.concatenate([(adc[offs[r]:offs[r + 1]].astype(np.float32) + coff[r]) * cscale[r] for r in range(i * 20, (i + 1) * 20)])
+        med = np.float32(np.median(vals))
+        mad = np.float32(np.median(np.abs(vals - med)))
+        assert (got[i, 0], got[i, 1]) == (med, mad)
+
+
 @pytest.mark.parametrize("factor,col0", [(10, 1000), (20, 2000), (10, 0), (7, 3)])
 def test_downscale_bit_exact(factor, col0):
     from adapted_b200.detect import downscale_signal
