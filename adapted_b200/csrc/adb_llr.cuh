@@ -106,23 +106,25 @@ __device__ void cta_trace_support(const double *g, int n, int &start, int &end, 
     __syncthreads();
 }
 
-// np.nanstd over g[lo:hi) (numpy/lib/_nanfunctions_impl.py _nanvar): NaN -> 0, pairwise sums; one thread.
-__device__ double lane_nanstd(const double *g, int lo, int hi) {
-    int n = hi - lo;
+// np.nanstd over g[lo:hi) (numpy/lib/_nanfunctions_impl.py _nanvar): NaN -> 0 in the sums, divided by the non-NaN
+// count.  Warp-wide tree sums in float64: the result can differ from numpy's pairwise order in the last bits, which
+// is far below the difference the two `log` implementations already put into every gain (it only scales the
+// prominence threshold of adapter_end_from_trace, llr.py:221).  Returns the value to every lane.
+__device__ double warp_nanstd(const double *g, int lo, int hi) {
+    const int lane = threadIdx.x & 31;
+    const int n = hi - lo;
     if (n <= 0) return CUDART_NAN;
     int cnt = 0;
-    for (int i = lo; i < hi; i++) cnt += (g[i] == g[i]);
+    double s = 0.0;
+    for (int i = lo + lane; i < hi; i += 32) { const double v = g[i]; if (v == v) { cnt++; s += v; } }
+    cnt = warp_sum_i(cnt);
+    s = warp_sum_d(s);
     if (cnt == 0) return CUDART_NAN;
-    double avg = __ddiv_rn(np_sum_f64([&](int k) { double v = g[lo + k]; return v == v ? v : 0.0; }, n), (double)cnt);
-    double ss = np_sum_f64(
-        [&](int k) {
-            double v = g[lo + k];
-            if (!(v == v)) return 0.0;
-            double d = __dsub_rn(v, avg);
-            return __dmul_rn(d, d);
-        },
-        n);
-    return sqrt(__ddiv_rn(ss, (double)cnt));
+    const double avg = s / (double)cnt;
+    double ss = 0.0;
+    for (int i = lo + lane; i < hi; i += 32) { const double v = g[i]; if (v == v) { const double d = v - avg; ss += d * d; } }
+    ss = warp_sum_d(ss);
+    return sqrt(ss / (double)cnt);
 }
 
 // correct_for_plateau (llr.py:145-177), warp-wide.  Returns the corrected absolute index.

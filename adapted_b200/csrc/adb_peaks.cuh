@@ -69,46 +69,50 @@ __device__ PeakProps warp_prominence(const TraceView &V, int peak) {
     const int lane = threadIdx.x & 31;
     const double xp = V.at(peak);
     PeakProps P;
-    // left walk: i = peak, peak-1, ... while i >= 0 and x[i] <= xp; strict '<' keeps the first minimum met
+    // left walk: i = peak, peak-1, ... while i >= 0 and x[i] <= xp; strict '<' keeps the first minimum met.
+    // Every lane keeps the minimum of the positions it visits (its own sub-sequence is in walk order, so a strict
+    // '<' keeps the first one met); ONE warp reduction at the end of the walk merges the 32 candidates.
+    double best = CUDART_INF;
+    int bidx = -1;
+    for (int cur = peak; cur >= 0; cur -= 32) {
+        const int i = cur - lane;
+        const double v = (i >= 0) ? V.at(i) : 0.0;
+        const bool stop = (i < 0) || !(v <= xp);
+        const unsigned sm = __ballot_sync(ADB_FULL, stop);
+        const int nvalid = sm ? (__ffs(sm) - 1) : 32;
+        if (lane < nvalid && v < best) { best = v; bidx = i; }
+        if (sm) break;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(ADB_FULL, best, o);
+        const int oi = __shfl_xor_sync(ADB_FULL, bidx, o);
+        // smaller value wins; on ties the element met first in walk order (larger index on the left walk)
+        if (ov < best || (ov == best && oi > bidx)) { best = ov; bidx = oi; }
+    }
     double lmin = xp;
     int lbase = peak;
-    for (int cur = peak; cur >= 0; cur -= 32) {
-        int i = cur - lane;
-        double v = (i >= 0) ? V.at(i) : 0.0;
-        bool stop = (i < 0) || !(v <= xp);
-        unsigned sm = __ballot_sync(ADB_FULL, stop);
-        int nvalid = sm ? (__ffs(sm) - 1) : 32;
-        double cand = (lane < nvalid) ? v : CUDART_INF;
-        int cidx = i;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            double ov = __shfl_xor_sync(ADB_FULL, cand, o);
-            int oi = __shfl_xor_sync(ADB_FULL, cidx, o);
-            // smaller value wins; on ties the element met first in walk order (larger index on the left walk)
-            if (ov < cand || (ov == cand && oi > cidx)) { cand = ov; cidx = oi; }
-        }
-        if (cand < lmin) { lmin = cand; lbase = cidx; }
+    if (best < lmin) { lmin = best; lbase = bidx; }
+    best = CUDART_INF;
+    bidx = 0x7fffffff;
+    for (int cur = peak; cur < V.n; cur += 32) {
+        const int i = cur + lane;
+        const double v = (i < V.n) ? V.at(i) : 0.0;
+        const bool stop = (i >= V.n) || !(v <= xp);
+        const unsigned sm = __ballot_sync(ADB_FULL, stop);
+        const int nvalid = sm ? (__ffs(sm) - 1) : 32;
+        if (lane < nvalid && v < best) { best = v; bidx = i; }
         if (sm) break;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(ADB_FULL, best, o);
+        const int oi = __shfl_xor_sync(ADB_FULL, bidx, o);
+        if (ov < best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
     }
     double rmin = xp;
     int rbase = peak;
-    for (int cur = peak; cur < V.n; cur += 32) {
-        int i = cur + lane;
-        double v = (i < V.n) ? V.at(i) : 0.0;
-        bool stop = (i >= V.n) || !(v <= xp);
-        unsigned sm = __ballot_sync(ADB_FULL, stop);
-        int nvalid = sm ? (__ffs(sm) - 1) : 32;
-        double cand = (lane < nvalid) ? v : CUDART_INF;
-        int cidx = i;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            double ov = __shfl_xor_sync(ADB_FULL, cand, o);
-            int oi = __shfl_xor_sync(ADB_FULL, cidx, o);
-            if (ov < cand || (ov == cand && oi < cidx)) { cand = ov; cidx = oi; }
-        }
-        if (cand < rmin) { rmin = cand; rbase = cidx; }
-        if (sm) break;
-    }
+    if (best < rmin) { rmin = best; rbase = bidx; }
     P.prominence = __dsub_rn(xp, fmax(lmin, rmin));
     P.left_base = lbase;
     P.right_base = rbase;

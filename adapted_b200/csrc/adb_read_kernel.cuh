@@ -4,7 +4,8 @@
 //                        clip / normalise with the minibatch-global med/MAD -> float32 mean-pool downscale in numpy's
 //                        pairwise order -> sequential float64 prefix sums -> adapter LLR trace -> first surviving peak
 //                        (+ plateau / split fixes) -> poly(A) LLR trace -> spike rule.  Small shared-memory footprint
-//                        (3 x nds doubles), many CTAs per SM to hide the sequential prefix sums.
+//                        (3 x nds doubles); one WARP per read (CTAs of 32 threads), so that the strictly sequential
+//                        pieces (prefix sums, peak walks) of one read overlap the parallel pieces of the others.
 //   validate_kernel      validate_boundaries + partition statistics (combined.py:358-631) for boundaries taken from
 //                        a device array (LLR / CNN / start-peak primaries alike), plus the CNN path's "hail mary"
 //                        LLR fallback (combined.py:251-301).  The read's preload window is staged ONCE in shared
@@ -20,7 +21,7 @@
 #include "adb_select.cuh"
 #include "adb_validate.cuh"
 
-#define ADB_TRACE_THREADS 128
+#define ADB_TRACE_THREADS 32   // one warp per read: every phase of the LLR primary path is at most warp-wide
 #define ADB_VAL_THREADS 256
 
 // float32 mean of one downscale block in numpy's pairwise order.  f(k) = k-th sample of the block.
@@ -71,15 +72,28 @@ __device__ __forceinline__ TraceScratch trace_scratch_from(unsigned char *base, 
 __device__ void llr_boundaries_cta(const float *ds, int nds, const TraceScratch &T, const adb_config &cfg,
                                    bool adapter_stage, int &ae_ds, int &pe_ds) {
     double *trace = T.trace, *c = T.c, *c2 = T.c2;
-    // sequential float64 prefix sums (_c_llr.pyx:216-217): two independent chains on two warps
-    if (threadIdx.x == 0) {
+    // sequential float64 prefix sums (_c_llr.pyx:216-217): the two chains run in lockstep on lanes 0 (x) and 1 (x*x)
+    // of the first warp; loads are hoisted four elements ahead so that only the dependent adds remain on the chain
+    if (threadIdx.x < 2) {
+        const bool sq = threadIdx.x == 1;
+        double *dst = sq ? c2 : c;
         double s = 0.0;
-#pragma unroll 4
-        for (int i = 0; i < nds; i++) { s = __dadd_rn(s, (double)ds[i]); c[i] = s; }
-    } else if (threadIdx.x == 32) {
-        double s2 = 0.0;
-#pragma unroll 4
-        for (int i = 0; i < nds; i++) { double x = (double)ds[i]; s2 = __dadd_rn(s2, __dmul_rn(x, x)); c2[i] = s2; }
+        int i = 0;
+        for (; i + 4 <= nds; i += 4) {
+            const float4 v = *reinterpret_cast<const float4 *>(ds + i);  // ds is 16-byte aligned (start of the trace buffer)
+            double x0 = (double)v.x, x1 = (double)v.y, x2 = (double)v.z, x3 = (double)v.w;
+            if (sq) { x0 = __dmul_rn(x0, x0); x1 = __dmul_rn(x1, x1); x2 = __dmul_rn(x2, x2); x3 = __dmul_rn(x3, x3); }
+            s = __dadd_rn(s, x0); dst[i] = s;
+            s = __dadd_rn(s, x1); dst[i + 1] = s;
+            s = __dadd_rn(s, x2); dst[i + 2] = s;
+            s = __dadd_rn(s, x3); dst[i + 3] = s;
+        }
+        for (; i < nds; i++) {
+            double x = (double)ds[i];
+            if (sq) x = __dmul_rn(x, x);
+            s = __dadd_rn(s, x);
+            dst[i] = s;
+        }
     }
     __syncthreads();
     ae_ds = 0;
@@ -89,7 +103,7 @@ __device__ void llr_boundaries_cta(const float *ds, int nds, const TraceScratch 
         cta_llr_gains(c, c2, nds, 0, nds - 1, 5, 5, 1, trace);
         int s0, e0;
         cta_trace_support(trace, nds, s0, e0, T.itmp);
-        if (threadIdx.x == 0) T.dtmp[0] = lane_nanstd(trace, s0, e0);
+        if (threadIdx.x < 32) { const double sd = warp_nanstd(trace, s0, e0); if (threadIdx.x == 0) T.dtmp[0] = sd; }
         __syncthreads();
         const double pmin = __dmul_rn(cfg.adapter_peak_prominence, T.dtmp[0]);
         const double wmin = (double)(cfg.adapter_peak_width / cfg.downscale_factor);
