@@ -68,7 +68,7 @@ extern "C" void adb_ctx_destroy(adb_ctx *c) {
     DevBuf *all[] = {&c->states, &c->hist, &c->series, &c->given, &c->status, &c->cnn_x, &c->cnn_act0,
                      &c->cnn_act1, &c->cnn_scores, &c->cnn_w, &c->cnn_aux, &c->cnn_post, &c->sp_rows, &c->h_signal, &c->h_offsets,
                      &c->h_lens, &c->h_coff, &c->h_cscale, &c->h_records, &c->h_misc, &c->h_misc2, &c->h_misc3,
-                     &c->gsb_plan, &c->gsb_hist, &c->gsb_tab, &c->gsb_bases, &c->gsb_active};
+                     &c->gsb_plan, &c->gsb_hist, &c->gsb_tab, &c->gsb_bases, &c->gsb_active, &c->vf_done};
     for (DevBuf *b : all) b->release();
     for (int k = 0; k < 2; k++) {
         DevBuf *pb[] = {&c->p_signal[k], &c->p_offsets[k], &c->p_lens[k], &c->p_coff[k], &c->p_cscale[k], &c->p_records[k], &c->p_status[k]};
@@ -87,6 +87,7 @@ extern "C" int64_t adb_ctx_launch_count(const adb_ctx *c) { return c ? c->launch
 extern "C" int adb_ctx_set_option(adb_ctx *c, const char *name, int value) {
     if (!c || !name) return ADB_ERR_ARG;
     if (!strcmp(name, "exact_global_select")) { c->opt_exact_gsel = value; return ADB_OK; }
+    if (!strcmp(name, "no_fast_validate")) { c->opt_no_fast_validate = value; return ADB_OK; }
     set_err(std::string("unknown option: ") + name);
     return ADB_ERR_ARG;
 }
@@ -362,9 +363,34 @@ static int launch_validate(adb_ctx *ctx, const BatchDev &B, const adb_config &cf
         A.pre_off = M.row_off;
         A.pre_meta = M.meta;
     }
+    A.done = nullptr;
+    if (B.sig_type == ADB_SIG_I16 && !ctx->opt_no_fast_validate) {
+        // int16 sources: counting-based validation (adb_vfast.cuh); what it leaves is picked up by validate_kernel
+        const size_t fsm = vfast_smem_bytes(A.win_bytes);
+        if ((int)fsm <= ctx->max_smem_optin) {
+            if (ctx->vf_done.ensure((size_t)B.n_reads + 16)) { set_err("cudaMalloc done flags"); return ADB_ERR_CUDA; }
+            CUDA_TRY(cudaMemsetAsync(ctx->vf_done.p, 0, (size_t)B.n_reads, st));
+            VfastArgs F;
+            F.B = B; F.given = given; F.given_stride = given_stride; F.given_ntopk = given_ntopk; F.ntopk_per_read = ntopk_per_read;
+            F.mode = mode; F.win_bytes = A.win_bytes; F.out = out; F.batch_status = batch_status;
+            F.pre_var = A.pre_var; F.pre_mean = A.pre_mean; F.pre_off = A.pre_off; F.pre_meta = A.pre_meta;
+            F.done = (unsigned char *)ctx->vf_done.p;
+            CUDA_TRY(cudaFuncSetAttribute(validate_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+            int focc = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&focc, validate_fast_kernel, VF_THREADS, fsm));
+            if (focc < 1) focc = 1;
+            const int fgrid = std::max(1, std::min(B.n_reads, ctx->sm_count * focc));
+            {
+                KernelTimer t(ctx, 2, st);
+                validate_fast_kernel<<<fgrid, VF_THREADS, fsm, st>>>(F, cfg);
+            }
+            ctx->launches += 1;
+            A.done = F.done;
+        }
+    }
     {
         int grid = std::max(1, std::min(B.n_reads, grid_max));
-        KernelTimer t(ctx, 2, st);
+        KernelTimer t(ctx, A.done ? 7 : 2, st);
         validate_kernel<<<grid, ADB_VAL_THREADS, smem, st>>>(A, cfg);
     }
     ctx->launches += 1;

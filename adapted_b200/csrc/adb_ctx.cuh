@@ -64,6 +64,8 @@ struct adb_ctx {
     // scratch (device)
     DevBuf states, hist, series, given, status;
     DevBuf gsb_plan, gsb_hist, gsb_tab, gsb_bases, gsb_active;  // sampled one-pass global select
+    DevBuf vf_done;            // per-read flags of validate_fast_kernel
+    int opt_no_fast_validate = 0;
     int gsb_last_batches = 0;
     int opt_exact_gsel = 0;  // adb_ctx_set_option("exact_global_select"): always use the multi-pass select
     DevBuf cnn_x, cnn_act0, cnn_act1, cnn_scores, cnn_w, cnn_aux, cnn_post, sp_rows;

@@ -20,6 +20,7 @@
 #include "adb_llr.cuh"
 #include "adb_select.cuh"
 #include "adb_validate.cuh"
+#include "adb_vfast.cuh"
 
 #define ADB_TRACE_THREADS 32   // one warp per read: every phase of the LLR primary path is at most warp-wide
 #define ADB_VAL_THREADS 256
@@ -218,6 +219,7 @@ struct ValidateArgs {
     const float *pre_var, *pre_mean;  // compact pools of precomputed moving statistics (mvs_series_kernel)
     const long long *pre_off;         // [n_reads] row offset into the pools, -1: none
     const int *pre_meta;              // [n_reads][2] = (adapter_end, polya_end) of the row
+    const unsigned char *done;        // optional [n_reads]: 1 = already written by validate_fast_kernel
 };
 
 __host__ __device__ inline size_t validate_smem_bytes(int win_bytes, int nds_max, int peak_cap) {
@@ -264,6 +266,7 @@ __global__ void __launch_bounds__(ADB_VAL_THREADS, 3) validate_kernel(ValidateAr
         const int mb = r / A.B.batch_size;
         adb_record *rec = A.out + r;
         __syncthreads();
+        if (A.done && A.done[r]) continue;
         {
             const long long po = A.pre_off ? A.pre_off[r] : -1;
             C.pre_var = (po >= 0) ? A.pre_var + po : nullptr;

@@ -514,14 +514,15 @@ struct MvsSeriesArgs {
     int *meta;                // [n_reads][2] = ae, pe the row belongs to
 };
 
-#define MVS_LANES 128   // reads per CTA (one lane each)
+#define MVS_LANES 128   // reads per CTA (one lane each; every warp works on its own 32 reads, no CTA-wide sync)
 #define MVS_C 32        // samples staged per step
-#define MVS_RING 256    // circular input columns per read (>= window + MVS_C), power of two
+#define MVS_RING 256    // circular input columns per read (>= window + 2 * MVS_C), power of two
 #define MVS_RING_STRIDE 258  // int16 units: 516 B = 129 words, odd -> lanes walking their own row hit distinct banks
 #define MVS_OUT_STRIDE 33    // float units
+#define MVS_MAX_WINDOW (MVS_RING - 2 * MVS_C)
 
 __host__ __device__ inline size_t mvs_smem_bytes() {
-    return (size_t)MVS_LANES * MVS_RING_STRIDE * 2 + 2 * (size_t)MVS_LANES * MVS_OUT_STRIDE * 4 + MVS_LANES * 24 + 64;
+    return (size_t)MVS_LANES * MVS_RING_STRIDE * 2 + 2 * (size_t)MVS_LANES * MVS_OUT_STRIDE * 4 + 64;
 }
 
 // eligibility of a read for the precomputed series (mirrors the early exits of mvs.py:76-107)
@@ -540,100 +541,87 @@ __device__ __forceinline__ bool mvs_plan(const adb_config &cfg, const ReadSrc &s
     return true;
 }
 
-// int16 sources: 128 reads per CTA, one lane per read.  The input is staged through shared memory in chunks of
-// MVS_C samples per read (coalesced row loads, circular history for a[i - window]) and the outputs leave through
-// a shared tile (coalesced row stores), so neither side pays 32 L1 wavefronts per access.
+// int16 sources: one lane per read, 32 reads per warp, warps independent of each other.  Per step of MVS_C samples a
+// warp (1) issues the coalesced row loads of the NEXT step into registers, (2) lets every lane advance its two
+// recurrences over the current step from its own row of a shared-memory ring (circular history for a[i - window]),
+// (3) writes the step's outputs row by row (coalesced) from a shared tile, (4) parks the prefetched samples in the
+// ring.  The global-load latency of (1) is covered by the ~25 dependent float operations per sample of (2).
 __global__ void __launch_bounds__(MVS_LANES) mvs_series_kernel(MvsSeriesArgs A, adb_config cfg) {
     extern __shared__ __align__(16) unsigned char smem[];
-    int16_t *ring = (int16_t *)smem;
-    float *ov = (float *)(smem + (size_t)MVS_LANES * MVS_RING_STRIDE * 2);
-    float *om = ov + MVS_LANES * MVS_OUT_STRIDE;
-    const int16_t **rptr = (const int16_t **)(om + MVS_LANES * MVS_OUT_STRIDE);
-    int *rlen = (int *)(rptr + MVS_LANES);
-    int *rflag = rlen + MVS_LANES;
-    __shared__ int lmax_sh;
-    __shared__ long long base_sh;
-    __shared__ int wsum_sh[MVS_LANES / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int16_t *ring = (int16_t *)smem + (size_t)warp * 32 * MVS_RING_STRIDE;
+    float *ov = (float *)(smem + (size_t)MVS_LANES * MVS_RING_STRIDE * 2) + warp * 32 * MVS_OUT_STRIDE;
+    float *om = ov + MVS_LANES * MVS_OUT_STRIDE;
     const int q = blockIdx.x * MVS_LANES + tid;
     const int wv = cfg.pA_var_window, wm = cfg.pA_mean_window;
     bool active = false, win_var = false, win_mean = false;
     int a = 0, L = 0, ae = 0, pe = 0;
     float coff = 0.f, cscale = 1.f;
-    if (tid == 0) lmax_sh = 0;
-    __syncthreads();
+    const int16_t *rp = nullptr;
     if (q < A.n_reads) {
-        const int r = q;
-        const int *g = A.given + (size_t)r * A.given_stride;
+        const int *g = A.given + (size_t)q * A.given_stride;
         ae = g[0]; pe = g[1];
-        const ReadSrc src = make_src(A.B, r);
-        active = (src.i16 != nullptr) && mvs_plan(cfg, src, ae, pe, a, L, win_var, win_mean) &&
-                 isfinite(src.coff) && isfinite(src.cscale);
+        const ReadSrc src = make_src(A.B, q);
+        active = (src.i16 != nullptr) && wv <= MVS_MAX_WINDOW && wm <= MVS_MAX_WINDOW &&
+                 mvs_plan(cfg, src, ae, pe, a, L, win_var, win_mean) && isfinite(src.coff) && isfinite(src.cscale);
         coff = src.coff; cscale = src.cscale;
-        rptr[tid] = active ? src.i16 + a : nullptr;
-    } else {
-        rptr[tid] = nullptr;
+        if (active) rp = src.i16 + a;
     }
-    // compact row allocation: in-CTA exclusive scan of the (4-float aligned) row lengths + one atomic per CTA
+    // compact row allocation: warp-level exclusive scan of the (4-float aligned) row lengths + one atomic per warp
     const int need = active ? ((L + 3) & ~3) : 0;
     int incl = need;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        int v = __shfl_up_sync(ADB_FULL, incl, o);
+        const int v = __shfl_up_sync(ADB_FULL, incl, o);
         if (lane >= o) incl += v;
     }
-    if (lane == 31) wsum_sh[warp] = incl;
-    __syncthreads();
-    int wbase = 0, total = 0;
-    for (int w = 0; w < MVS_LANES / 32; w++) { if (w < warp) wbase += wsum_sh[w]; total += wsum_sh[w]; }
-    if (tid == 0) base_sh = (long long)atomicAdd(A.cursor, (unsigned long long)total);
-    __syncthreads();
-    long long myoff = base_sh + wbase + incl - need;
+    const int total = __shfl_sync(ADB_FULL, incl, 31);
+    long long base = 0;
+    if (lane == 0 && total > 0) base = (long long)atomicAdd(A.cursor, (unsigned long long)total);
+    base = __shfl_sync(ADB_FULL, base, 0);
+    const long long myoff = base + incl - need;
     if (active && myoff + need > A.pool_cap) active = false;  // pool exhausted: the validate kernel falls back
     if (q < A.n_reads) {
         A.row_off[q] = active ? myoff : -1;
         A.meta[2 * (size_t)q] = active ? ae : -1;
         A.meta[2 * (size_t)q + 1] = active ? pe : -1;
     }
-    if (!active) rptr[tid] = nullptr;
-    rlen[tid] = active ? L : 0;
-    rflag[tid] = (win_var ? 1 : 0) | (win_mean ? 2 : 0);
-    long long *roff_sh = (long long *)(rflag + MVS_LANES);
-    roff_sh[tid] = myoff;
-    if (active) atomicMax(&lmax_sh, L);
-    __syncthreads();
-    const int Lmax = lmax_sh;
+    if (!active) { L = 0; rp = nullptr; }
+    int Lmax = L;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) Lmax = max(Lmax, __shfl_xor_sync(ADB_FULL, Lmax, o));
+    if (Lmax == 0) return;
+    const int flag = (win_var ? 1 : 0) | (win_mean ? 2 : 0);
     float amean = 0.f, assqdm = 0.f, asum = 0.f;
     const float cinv_v = (float)(1.0 / (double)wv), cinv_m = (float)(1.0 / (double)wm);
-    const int16_t *myrow = ring + (size_t)tid * MVS_RING_STRIDE;
-    float *myov = ov + tid * MVS_OUT_STRIDE, *myom = om + tid * MVS_OUT_STRIDE;
+    const int16_t *myrow = ring + (size_t)lane * MVS_RING_STRIDE;
+    float *myov = ov + lane * MVS_OUT_STRIDE, *myom = om + lane * MVS_OUT_STRIDE;
     float *gv = A.var_pool, *gm = A.mean_pool;
-    for (int base = 0; base < Lmax; base += MVS_C) {
-        // ---- stage MVS_C samples of every row (warp w loads rows w, w+4, ...; 8 loads in flight) ----
-        {
-            const int i = base + lane;
-            for (int row0 = warp; row0 < MVS_LANES; row0 += 8 * (MVS_LANES / 32)) {
-                int16_t v[8];
-                bool ok[8];
+    // prefetch registers: sample (base + lane) of every row
+    int16_t pf[32];
+    auto prefetch = [&](int step_base) {
+        const int i = step_base + lane;
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int row = row0 + u * (MVS_LANES / 32);
-                    const int16_t *p = (row < MVS_LANES) ? rptr[row] : nullptr;
-                    ok[u] = (p != nullptr) && (i < rlen[row]);
-                    v[u] = ok[u] ? p[i] : (int16_t)0;
-                }
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int row = row0 + u * (MVS_LANES / 32);
-                    if (ok[u]) ring[(size_t)row * MVS_RING_STRIDE + (i & (MVS_RING - 1))] = v[u];
-                }
-            }
+        for (int row = 0; row < 32; row++) {
+            const int16_t *p = (const int16_t *)__shfl_sync(ADB_FULL, (unsigned long long)rp, row);
+            const int Lr = __shfl_sync(ADB_FULL, L, row);
+            pf[row] = (i < Lr) ? __ldg(p + i) : (int16_t)0;
         }
-        __syncthreads();
-        // ---- each lane advances its own recurrences ----
-        if (active) {
-            const int iend = min(base + MVS_C, L);
-            for (int i = base; i < iend; i++) {
+    };
+    auto park = [&](int step_base) {
+        const int col = (step_base + lane) & (MVS_RING - 1);
+#pragma unroll
+        for (int row = 0; row < 32; row++) ring[(size_t)row * MVS_RING_STRIDE + col] = pf[row];
+    };
+    prefetch(0);
+    park(0);
+    __syncwarp();
+    for (int base_i = 0; base_i < Lmax; base_i += MVS_C) {
+        const bool more = base_i + MVS_C < Lmax;
+        if (more) prefetch(base_i + MVS_C);  // loads in flight while the recurrences run
+        if (base_i < L) {
+            const int iend = min(base_i + MVS_C, L);
+            for (int i = base_i; i < iend; i++) {
                 const float x = __fmul_rn(__fadd_rn((float)myrow[i & (MVS_RING - 1)], coff), cscale);
                 if (win_var) {
                     if (i < wv) {
@@ -642,7 +630,7 @@ __global__ void __launch_bounds__(MVS_LANES) mvs_series_kernel(MvsSeriesArgs A, 
                         assqdm = __fadd_rn(assqdm, __fmul_rn(delta, __fsub_rn(x, amean)));
                         if (i == wv - 1) {
                             if (assqdm < 0) assqdm = 0;
-                            myov[i - base] = __fdiv_rn(assqdm, (float)wv);
+                            myov[i - base_i] = __fdiv_rn(assqdm, (float)wv);
                         }
                     } else {
                         float ai = x;
@@ -653,34 +641,38 @@ __global__ void __launch_bounds__(MVS_LANES) mvs_series_kernel(MvsSeriesArgs A, 
                         ai = __fsub_rn(ai, amean);
                         assqdm = __fadd_rn(assqdm, __fmul_rn(__fadd_rn(ai, aold), delta));
                         if (assqdm < 0) assqdm = 0;
-                        myov[i - base] = __fmul_rn(assqdm, cinv_v);
+                        myov[i - base_i] = __fmul_rn(assqdm, cinv_v);
                     }
                 }
                 if (win_mean) {
                     if (i < wm) {
                         asum = __fadd_rn(asum, x);
-                        if (i == wm - 1) myom[i - base] = __fdiv_rn(asum, (float)wm);
+                        if (i == wm - 1) myom[i - base_i] = __fdiv_rn(asum, (float)wm);
                     } else {
                         const float aold = __fmul_rn(__fadd_rn((float)myrow[(i - wm) & (MVS_RING - 1)], coff), cscale);
                         asum = __fadd_rn(asum, __fsub_rn(x, aold));
-                        myom[i - base] = __fmul_rn(asum, cinv_m);
+                        myom[i - base_i] = __fmul_rn(asum, cinv_m);
                     }
                 }
             }
         }
-        __syncthreads();
+        __syncwarp();
         // ---- coalesced row stores of the valid entries ----
-        for (int row = warp; row < MVS_LANES; row += MVS_LANES / 32) {
-            const int Lr = rlen[row];
-            const int i = base + lane;
-            if (i < Lr) {
-                const long long rowoff = roff_sh[row];
-                const int fl = rflag[row];
-                if ((fl & 1) && i >= wv - 1) gv[rowoff + i - (wv - 1)] = ov[row * MVS_OUT_STRIDE + lane];
-                if ((fl & 2) && i >= wm - 1) gm[rowoff + i - (wm - 1)] = om[row * MVS_OUT_STRIDE + lane];
+        {
+            const int i = base_i + lane;
+#pragma unroll 4
+            for (int row = 0; row < 32; row++) {
+                const int Lr = __shfl_sync(ADB_FULL, L, row);
+                const long long ro = __shfl_sync(ADB_FULL, myoff, row);
+                const int fl = __shfl_sync(ADB_FULL, flag, row);
+                if (i < Lr) {
+                    if ((fl & 1) && i >= wv - 1) gv[ro + i - (wv - 1)] = ov[row * MVS_OUT_STRIDE + lane];
+                    if ((fl & 2) && i >= wm - 1) gm[ro + i - (wm - 1)] = om[row * MVS_OUT_STRIDE + lane];
+                }
             }
         }
-        __syncthreads();
+        if (more) park(base_i + MVS_C);
+        __syncwarp();
     }
 }
 

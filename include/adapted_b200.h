@@ -138,7 +138,8 @@ void adb_ctx_destroy(adb_ctx *ctx);
 /* number of kernels this context has launched so far (bench.py: gpu_launches) */
 int64_t adb_ctx_launch_count(const adb_ctx *ctx);
 /* Tuning switches that never change results.  "exact_global_select" = 1: always take the multi-pass radix select
- * for the minibatch-global median / MAD (normalize.py:15-22) instead of the sampled one-pass select. */
+ * for the minibatch-global median / MAD (normalize.py:15-22) instead of the sampled one-pass select.
+ * "no_fast_validate" = 1: int16 reads go through the histogram-based validate kernel only (A/B testing). */
 int adb_ctx_set_option(adb_ctx *ctx, const char *name, int value);
 /* Diagnostics of the most recent call (synchronises the device).  "global_select_fallbacks": minibatches the sampled
  * select handed to the exact multi-pass select.  -1: unknown name / error. */
