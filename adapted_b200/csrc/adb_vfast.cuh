@@ -39,13 +39,19 @@ struct VfTask {
     int pA, pB;    // probes of the running pass: count the codes in [pA, pB]
     int mid;
     int active;
-    int rot;       // rotation of the vector -> thread assignment (load balance across tasks)
+    // scan geometry, fixed per task: full 16-byte vectors [v0, v1) of W16, `voff` = offset of v0 in the flattened
+    // vector space of all tasks of the round, boundary elements [hb, he) and [tb, te) (W16 indices, < 8 each)
+    int v0, v1, voff;
+    int hb, he, tb, te;
 };
 
 struct VfScratch {  // shared memory
     VfTask task[VF_MAX_TASKS];
     unsigned cnt[VF_MAX_TASKS];
     int ntask;
+    int vtotal;    // vectors of all tasks of the round
+    int4 items[VF_THREADS / 32][VF_MAX_TASKS];  // per warp: (task, first vector, end vector, owns the boundary elements)
+    int nitems[VF_THREADS / 32];
     int itmp[16];
     unsigned wtot[8];
     long long ltmp[8];
@@ -77,27 +83,24 @@ __device__ __forceinline__ __half2 vf_h2(unsigned code) {
     return *reinterpret_cast<const __half2 *>(&w);
 }
 
-// per-thread partial of: number of window samples j in [a, b) whose code lies in [pA, pB]
-__device__ __forceinline__ int vf_count_thread(const VfRead &R, int a, int b, int pA, int pB, int rot) {
-    if (pB < pA || b <= a) return 0;
-    const int tid = threadIdx.x;
+// scan geometry of the window range [a, b) (a < b)
+__device__ __forceinline__ void vf_geometry(const VfRead &R, VfTask &t, int a, int b, int voff) {
     const int i0 = R.s0 + a, i1 = R.s0 + b;
-    const int v0 = (i0 + 7) >> 3, v1 = i1 >> 3;
-    const int head_end = min(i1, v0 << 3), tail_beg = max(v1 << 3, head_end);
-    int cnt = 0;
-    if (tid < 8) {
-        const int i = i0 + tid;
-        if (i < head_end) { const int c = R.W16[i]; cnt += (c >= pA && c <= pB); }
-    } else if (tid < 16) {
-        const int i = tail_beg + tid - 8;
-        if (i < i1) { const int c = R.W16[i]; cnt += (c >= pA && c <= pB); }
-    }
+    const int v0 = (i0 + 7) >> 3, v1 = max(i1 >> 3, v0);
+    t.v0 = v0; t.v1 = v1; t.voff = voff;
+    t.hb = i0; t.he = min(i1, v0 << 3);
+    t.tb = max(v1 << 3, t.he); t.te = i1;
+}
+
+// per-lane partial of: number of samples in the full vectors [vb, ve) of W16 whose code lies in [pA, pB] (pA <= pB)
+__device__ __forceinline__ int vf_count_vectors(const VfRead &R, int vb, int ve, int pA, int pB) {
+    const int lane = threadIdx.x & 31;
     const uint4 *V = reinterpret_cast<const uint4 *>(R.W16);
     const __half2 hB = vf_h2((unsigned)pB);
     unsigned sB = 0, sA = 0;
     if (pA > 0) {
         const __half2 hA = vf_h2((unsigned)(pA - 1));
-        for (int v = v0 + ((tid - rot) & (VF_THREADS - 1)); v < v1; v += VF_THREADS) {
+        for (int v = vb + lane; v < ve; v += 32) {
             const uint4 q = V[v];
             const unsigned w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
@@ -107,17 +110,15 @@ __device__ __forceinline__ int vf_count_thread(const VfRead &R, int a, int b, in
                 sA += __hle2_mask(h, hA);
             }
         }
-        cnt += (int)vf_decode(sB) - (int)vf_decode(sA);
-    } else {
-        for (int v = v0 + ((tid - rot) & (VF_THREADS - 1)); v < v1; v += VF_THREADS) {
-            const uint4 q = V[v];
-            const unsigned w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int t = 0; t < 4; t++) sB += __hle2_mask(*reinterpret_cast<const __half2 *>(&w[t]), hB);
-        }
-        cnt += (int)vf_decode(sB);
+        return (int)vf_decode(sB) - (int)vf_decode(sA);
     }
-    return cnt;
+    for (int v = vb + lane; v < ve; v += 32) {
+        const uint4 q = V[v];
+        const unsigned w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int t = 0; t < 4; t++) sB += __hle2_mask(*reinterpret_cast<const __half2 *>(&w[t]), hB);
+    }
+    return (int)vf_decode(sB);
 }
 
 // float32 deviation of a code from the median, as the reference computes it on the pA values
@@ -143,24 +144,52 @@ __device__ void vf_probes(const VfRead &R, VfTask &t, int mid) {
     t.pA = c; t.pB = lo - 1;
 }
 
-// run every task of S to convergence.  CTA-wide.
+// run every task of S to convergence.  CTA-wide.  The full vectors of all tasks form one flattened index space that
+// is cut into equal contiguous shares, one per warp, so a pass costs every warp the same number of vector loads
+// whatever the sizes of the individual segments; the (< 16) boundary elements of task q go to warp q % 8.  Every
+// warp lists its (task, vector range) items once per round and only walks that list in the passes.
 __device__ void vf_run(const VfRead &R, VfScratch &S) {
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __syncthreads();
     const int ntask = S.ntask;
+    const int nw = VF_THREADS / 32;
+    if (lane == 0) {
+        const int wbeg = (int)(((long long)S.vtotal * warp) / nw), wend = (int)(((long long)S.vtotal * (warp + 1)) / nw);
+        int n = 0;
+        for (int q = 0; q < ntask; q++) {
+            const VfTask &t = S.task[q];
+            if (!(t.lo < t.hi)) continue;
+            const int fb = max(t.voff, wbeg), fe = min(t.voff + (t.v1 - t.v0), wend);
+            const int edge = (warp == (q & (nw - 1))) && (t.hb < t.he || t.tb < t.te);
+            if (fb < fe) S.items[warp][n++] = make_int4(q, t.v0 + (fb - t.voff), t.v0 + (fe - t.voff), edge);
+            else if (edge) S.items[warp][n++] = make_int4(q, 0, 0, 1);
+        }
+        S.nitems[warp] = n;
+    }
     bool mine = false;
     if (tid < ntask) {
         VfTask &t = S.task[tid];
         S.cnt[tid] = 0;
         if (t.lo < t.hi) { t.active = 1; vf_probes(R, t, (t.lo + t.hi) >> 1); mine = true; } else t.active = 0;
     }
+    __syncwarp();
+    const int nit = S.nitems[warp];
     while (__syncthreads_or(mine)) {
-        for (int q = 0; q < ntask; q++) {
-            const VfTask &t = S.task[q];
+        for (int it = 0; it < nit; it++) {
+            const int4 item = S.items[warp][it];
+            const VfTask &t = S.task[item.x];
             if (!t.active) continue;
-            int c = vf_count_thread(R, t.a, t.b, t.pA, t.pB, t.rot);
+            const int pA = t.pA, pB = t.pB;
+            if (pB < pA) continue;
+            int c = 0;
+            if (item.y < item.z) c = vf_count_vectors(R, item.y, item.z, pA, pB);
+            if (item.w && lane < 16) {
+                const int i = (lane < 8) ? t.hb + lane : t.tb + (lane - 8);
+                const int iend = (lane < 8) ? t.he : t.te;
+                if (i < iend) { const int code = R.W16[i]; c += (code >= pA && code <= pB); }
+            }
             c = __reduce_add_sync(ADB_FULL, c);
-            if ((tid & 31) == 0 && c) atomicAdd(&S.cnt[q], (unsigned)c);
+            if (lane == 0 && c) atomicAdd(&S.cnt[item.x], (unsigned)c);
         }
         __syncthreads();
         mine = false;
@@ -417,19 +446,28 @@ __device__ void vf_series_medians(VfScratch &S, const float *g0, int n0, const f
         atomicMax(&S.utmp[2], mx[0]); atomicMax(&S.utmp[3], mx[1]);
     }
     __syncthreads();
-    // search state in registers (identical in every thread): smallest key with count(<= key) > rank
+    // search state in registers (identical in every thread): smallest key with count(<= key) > rank.  The probe
+    // alternates between the linear interpolation of the empirical CDF over the bracket (the series are smooth,
+    // unimodal samples: this homes in within a few passes) and plain bisection (guaranteed progress).
     uint32_t lo[2] = {S.utmp[0], S.utmp[1]}, hi[2] = {S.utmp[2], S.utmp[3]};
     const int nn[2] = {n0, n1};
     const uint32_t *kk[2] = {k0, k1};
     unsigned rank[2] = {n0 > 0 ? (unsigned)(n0 - 1) / 2 : 0u, n1 > 0 ? (unsigned)(n1 - 1) / 2 : 0u};
-    unsigned cnt_hi[2] = {(unsigned)n0, (unsigned)n1};
+    unsigned cnt_hi[2] = {(unsigned)n0, (unsigned)n1}, cnt_lo[2] = {0u, 0u};
+    if (tid < 6) S.cnt[tid] = 0;
     __syncthreads();
+    int pass = 0;
     while ((n0 > 0 && lo[0] < hi[0]) || (n1 > 0 && lo[1] < hi[1])) {
-        if (tid < 2) S.cnt[tid] = 0;
-        __syncthreads();
         uint32_t mid[2];
         for (int q = 0; q < 2; q++) {
-            mid[q] = lo[q] + ((hi[q] - lo[q]) >> 1);
+            const uint32_t span = hi[q] - lo[q];
+            mid[q] = lo[q] + (span >> 1);
+            if (!(pass & 1) && cnt_hi[q] > cnt_lo[q]) {
+                const double frac = ((double)rank[q] + 0.5 - (double)cnt_lo[q]) / (double)(cnt_hi[q] - cnt_lo[q]);
+                double off = frac * (double)span;
+                off = fmin(fmax(off, 0.0), (double)span - 1.0);
+                mid[q] = lo[q] + (uint32_t)off;
+            }
             if (nn[q] <= 0 || !(lo[q] < hi[q])) continue;
             int c = 0;
             const uint4 *V = reinterpret_cast<const uint4 *>(kk[q]);
@@ -441,16 +479,22 @@ __device__ void vf_series_medians(VfScratch &S, const float *g0, int n0, const f
             const int j = (nv << 2) + tid;
             if (j < nn[q]) c += (kk[q][j] <= mid[q]);
             c = __reduce_add_sync(ADB_FULL, c);
-            if ((tid & 31) == 0 && c) atomicAdd(&S.cnt[q], (unsigned)c);
+            if ((tid & 31) == 0 && c) atomicAdd(&S.cnt[q + 2 * (pass % 3)], (unsigned)c);
         }
         __syncthreads();
         for (int q = 0; q < 2; q++) {
             if (nn[q] <= 0 || !(lo[q] < hi[q])) continue;
-            const unsigned c = S.cnt[q];
-            if (c > rank[q]) { hi[q] = mid[q]; cnt_hi[q] = c; } else lo[q] = mid[q] + 1;
+            const unsigned c = S.cnt[q + 2 * (pass % 3)];
+            if (c > rank[q]) { hi[q] = mid[q]; cnt_hi[q] = c; } else { lo[q] = mid[q] + 1; cnt_lo[q] = c; }
         }
-        __syncthreads();
+        // three rotating counter sets: the set of the previous pass has been read by everybody (this pass's barrier
+        // lies in between) and is not used again before the pass after next
+        if (tid < 2) S.cnt[tid + 2 * ((pass + 2) % 3)] = 0;
+        pass++;
     }
+    __syncthreads();
+    if (tid < 6) S.cnt[tid] = 0;
+    __syncthreads();
     for (int q = 0; q < 2; q++) {
         if (nn[q] <= 0) { out[q] = CUDART_NAN_F; continue; }
         const float a = key_f32(hi[q]);
@@ -492,7 +536,7 @@ struct VfastArgs {
 };
 
 __host__ __device__ inline size_t vfast_smem_bytes(int win_bytes) {
-    return (((size_t)win_bytes + 48 + 15) & ~(size_t)15) + ((sizeof(VfScratch) + 15) & ~(size_t)15) + 16;
+    return (((size_t)win_bytes + 48 + 15) & ~(size_t)15);  // dynamic part: the window; the scratch is static
 }
 
 // one rank task over the window range [a, b) (clipped); returns the task index or -1 if the range is empty
@@ -501,12 +545,14 @@ __device__ __forceinline__ int vf_add_rank(VfScratch &S, const VfRead &R, int &n
     const int n = b - a;
     if (n <= 0) return -1;
     const int q = nt++;
+    const int nvec = max(((R.s0 + b) >> 3) - ((R.s0 + a + 7) >> 3), 0);
     if (threadIdx.x == 0) {
         VfTask &t = S.task[q];
         t.a = a; t.b = b; t.kind = 0; t.k = k; t.lo = R.kmin; t.hi = R.kmax; t.cnt_hi = n; t.pv = 0; t.med = 0.f;
-        t.rot = rot & (VF_THREADS - 1); t.active = 0;
+        t.active = 0;
+        vf_geometry(R, t, a, b, rot);
     }
-    rot += (n + 7) >> 3;
+    rot += nvec;
     return q;
 }
 
@@ -542,16 +588,18 @@ __device__ __forceinline__ int vf_add_mad(VfScratch &S, const VfRead &R, int &nt
     int ok = 1;
     int pv = gsb_code_at(med, false, R.coff, R.cscale, &ok);
     pv = min(max(pv, R.kmin), R.kmax + 1);
+    const int nvec = max(((R.s0 + b) >> 3) - ((R.s0 + a + 7) >> 3), 0);
     if (threadIdx.x == 0) {
         VfTask &t = S.task[q];
         t.a = a; t.b = b; t.kind = 1; t.k = (n - 1) / 2; t.lo = pv; t.hi = R.kmax + 1; t.cnt_hi = -1; t.pv = pv; t.med = med;
-        t.rot = rot & (VF_THREADS - 1); t.active = 0;
+        t.active = 0;
+        vf_geometry(R, t, a, b, rot);
         VfTask &u = S.task[q + 1];
         u = t;
         u.kind = 2; u.lo = 0; u.hi = pv - R.kmin;
-        u.rot = (rot + ((n + 7) >> 3)) & (VF_THREADS - 1);
+        u.voff = rot + nvec;
     }
-    rot += 2 * ((n + 7) >> 3);
+    rot += 2 * nvec;
     return q;
 }
 
@@ -589,8 +637,9 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_fast_kernel(VfastArgs 
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *winbuf = smem;
     const size_t win_cap = (((size_t)A.win_bytes + 48 + 15) & ~(size_t)15);
-    VfScratch &S = *reinterpret_cast<VfScratch *>(smem + win_cap);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + win_cap + ((sizeof(VfScratch) + 15) & ~(size_t)15));
+    __shared__ VfScratch S;
+    __shared__ uint64_t bar_storage;
+    uint64_t *bar = &bar_storage;
     const int tid = threadIdx.x;
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
@@ -686,7 +735,7 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_fast_kernel(VfastArgs 
             VfTask &t = S.task[tid];
             if (tid != tL15 && tid != tL85 && tid != tP15 && tid != tP85) t.k = (t.b - t.a - 1) / 2;
         }
-        if (tid == 0) S.ntask = nt;
+        if (tid == 0) { S.ntask = nt; S.vtotal = rot; }
         vf_run(R, S);
         const float medA0 = vf_median_of(R, S, tA0), medA1 = vf_median_of(R, S, tA1);
         const float medP = vf_median_of(R, S, tP), medR = vf_median_of(R, S, tR);
@@ -713,7 +762,7 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_fast_kernel(VfastArgs 
         const int dP = (tP >= 0) ? vf_add_mad(S, R, nt, rot, a_end, pe_best, medP) : -1;
         const int dR = (tR >= 0) ? vf_add_mad(S, R, nt, rot, pe_best, size, medR) : -1;
         __syncthreads();
-        if (tid == 0) S.ntask = nt;
+        if (tid == 0) { S.ntask = nt; S.vtotal = rot; }
         vf_run(R, S);
         const float madA0 = vf_mad_of(R, S, dA0), madA1 = vf_mad_of(R, S, dA1);
         const float madP = vf_mad_of(R, S, dP), madR = vf_mad_of(R, S, dR);
