@@ -68,7 +68,7 @@ extern "C" void adb_ctx_destroy(adb_ctx *c) {
     DevBuf *all[] = {&c->states, &c->hist, &c->series, &c->given, &c->status, &c->cnn_x, &c->cnn_act0,
                      &c->cnn_act1, &c->cnn_scores, &c->cnn_w, &c->cnn_aux, &c->cnn_post, &c->sp_rows, &c->h_signal, &c->h_offsets,
                      &c->h_lens, &c->h_coff, &c->h_cscale, &c->h_records, &c->h_misc, &c->h_misc2, &c->h_misc3,
-                     &c->gsb_plan, &c->gsb_hist, &c->gsb_tab, &c->gsb_bases, &c->gsb_active, &c->vf_done};
+                     &c->gsb_plan, &c->gsb_hist, &c->gsb_tab, &c->gsb_bases, &c->gsb_active, &c->vf_done, &c->mvs_perm};
     for (DevBuf *b : all) b->release();
     for (int k = 0; k < 2; k++) {
         DevBuf *pb[] = {&c->p_signal[k], &c->p_offsets[k], &c->p_lens[k], &c->p_coff[k], &c->p_cscale[k], &c->p_records[k], &c->p_status[k]};
@@ -348,9 +348,20 @@ static int launch_validate(adb_ctx *ctx, const BatchDev &B, const adb_config &cf
         M.row_off = lbase + 2;
         M.meta = (int *)(lbase + 2 + B.n_reads);
         CUDA_TRY(cudaMemsetAsync(M.cursor, 0, 16, st));
+        M.perm = nullptr;
         {
             KernelTimer t(ctx, 4, st);
             if (B.sig_type == ADB_SIG_I16) {
+                // reads of similar segment length share a warp (counting sort by length, three tiny kernels)
+                if (ctx->mvs_perm.ensure(sizeof(int) * ((size_t)B.n_reads + MVS_NBUCKET))) { set_err("cudaMalloc mvs perm"); return ADB_ERR_CUDA; }
+                int *bucket = (int *)ctx->mvs_perm.p, *perm = bucket + MVS_NBUCKET;
+                CUDA_TRY(cudaMemsetAsync(bucket, 0, sizeof(int) * MVS_NBUCKET, st));
+                const int sgrid = std::max(1, std::min((B.n_reads + 255) / 256, ctx->sm_count * 4));
+                mvs_len_hist_kernel<<<sgrid, 256, 0, st>>>(M, cfg, bucket);
+                mvs_len_scan_kernel<<<1, MVS_NBUCKET, 0, st>>>(bucket);
+                mvs_len_scatter_kernel<<<sgrid, 256, 0, st>>>(M, cfg, bucket, perm);
+                ctx->launches += 3;
+                M.perm = perm;
                 CUDA_TRY(cudaFuncSetAttribute(mvs_series_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mvs_smem_bytes()));
                 mvs_series_kernel<<<(B.n_reads + MVS_LANES - 1) / MVS_LANES, MVS_LANES, mvs_smem_bytes(), st>>>(M, cfg);
             } else {

@@ -64,6 +64,7 @@ struct adb_ctx {
     // scratch (device)
     DevBuf states, hist, series, given, status;
     DevBuf gsb_plan, gsb_hist, gsb_tab, gsb_bases, gsb_active;  // sampled one-pass global select
+    DevBuf mvs_perm;           // length-sorted read order of mvs_series_kernel
     DevBuf vf_done;            // per-read flags of validate_fast_kernel
     int opt_no_fast_validate = 0;
     int gsb_last_batches = 0;

@@ -180,14 +180,51 @@ __device__ int warp_adapter_end(const double *g, int n, int start, int end, doub
 
 // detect_full_polya_trace_peak_with_spike (llr.py:406-479) on the full-length trace g[0..n).  Warp-wide.
 // Returns the downscaled index (0 = none).
-__device__ int warp_polya_end(const double *g, int n, const PeakScratch &PS) {
+__device__ int warp_polya_end(double *g, int n, const PeakScratch &PS) {
     const int lane = threadIdx.x & 31;
     TraceView W;
     W.x = g;
     W.n = n;
-    W.nan2num = 1;
+    // np.nan_to_num(trace, nan=0) (llr.py:445): non-finite gains are rare (a one-sample head segment has variance
+    // "zero" up to rounding, so its log is -inf or NaN).  Up to four of them are replaced in place for the peak
+    // search and restored afterwards, so that the search reads plain doubles; more than four keep the trace as it
+    // is and convert on every access.
+    int nf_idx[4] = {-1, -1, -1, -1};
+    double nf_val[4] = {0, 0, 0, 0};
+    int nnf = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const double v = (i < n) ? g[i] : 0.0;
+        unsigned m = __ballot_sync(ADB_FULL, !(fabs(v) <= DBL_MAX));
+        while (m) {
+            const int l = __ffs(m) - 1;
+            m &= m - 1;
+            const double bv = __shfl_sync(ADB_FULL, v, l);
+#pragma unroll
+            for (int q = 0; q < 4; q++) if (nnf == q) { nf_idx[q] = base + l; nf_val[q] = bv; }
+            nnf++;
+        }
+    }
+    const bool patched = nnf <= 4;
+    if (patched) {
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (q < nnf) { const double v = nf_val[q]; g[nf_idx[q]] = (v != v) ? 0.0 : (v > 0 ? DBL_MAX : -DBL_MAX); }
+        }
+        __syncwarp();
+    }
+    W.nan2num = patched ? 0 : 1;
     int pk[2];
     int k = warp_find_first_peaks(W, 10, 1.0, 10.0, 0.5, 2, pk, PS);
+    if (patched && nnf > 0) {
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) if (q < nnf) g[nf_idx[q]] = nf_val[q];
+        }
+        __syncwarp();
+    }
     if (k == 0) return 0;
     if (k == 1) return pk[0];
     const double h0 = g[pk[0]], h1 = g[pk[1]];  // raw trace, not nan_to_num (llr.py:459)

@@ -152,11 +152,18 @@ __device__ double warp_width(const TraceView &V, int peak, const PeakProps &P, d
 }
 
 // ---- 2. budgeted classification, one lane per peak -----------------------------------------------------------
-// returns true if the peak is certainly rejected by `pmin <= prominence` (an upper bound of the prominence,
-// obtained from a side whose walk finished within the budget, is already below pmin; a NaN pmin rejects all).
-__device__ __forceinline__ bool lane_quick_reject(const TraceView &V, int peak, double pmin, int budget) {
+// returns true if the peak is certainly rejected by `pmin <= prominence` or by `wmin <= width`:
+//   * a side whose walk finished within the budget bounds the prominence from above (prom <= x[peak] - min of that
+//     side); if that bound is already below pmin the peak is out (a NaN pmin rejects all);
+//   * the width is measured at height x[peak] - prominence * rel_height, and a lower evaluation height can only widen
+//     it (the bases only stop the walk earlier): with the prominence bound the lowest possible height is known, and
+//     if the samples at or below it are found within the budget on both sides and are no more than wmin apart, the
+//     true width is below wmin.
+__device__ __forceinline__ bool lane_quick_reject(const TraceView &V, int peak, double pmin, double wmin,
+                                                  double rel_height, int budget) {
     if (!(pmin == pmin)) return true;
     const double xp = V.at(peak);
+    double prom_ub = CUDART_INF;
     double m = xp;
     int i = peak - 1, steps = 0;
     bool done = false;
@@ -167,7 +174,10 @@ __device__ __forceinline__ bool lane_quick_reject(const TraceView &V, int peak, 
         m = fmin(m, v);
         i--; steps++;
     }
-    if (done && !(pmin <= __dsub_rn(xp, m))) return true;
+    if (done) {
+        prom_ub = __dsub_rn(xp, m);
+        if (!(pmin <= prom_ub)) return true;
+    }
     m = xp; i = peak + 1; steps = 0; done = false;
     while (steps < budget) {
         if (i >= V.n) { done = true; break; }
@@ -176,7 +186,31 @@ __device__ __forceinline__ bool lane_quick_reject(const TraceView &V, int peak, 
         m = fmin(m, v);
         i++; steps++;
     }
-    if (done && !(pmin <= __dsub_rn(xp, m))) return true;
+    if (done) {
+        const double pr = __dsub_rn(xp, m);
+        if (!(pmin <= pr)) return true;
+        prom_ub = fmin(prom_ub, pr);
+    }
+    if (prom_ub < CUDART_INF && wmin > 0.0) {
+        // lowest possible evaluation height; a NaN / inf height never rejects
+        const double h = __dsub_rn(xp, __dmul_rn(prom_ub, rel_height));
+        if (h == h && h > -CUDART_INF) {
+            int il = -1, ir = -1;
+            for (int k = 1; k <= budget; k++) {
+                const int j = peak - k;
+                if (j < 0) break;
+                if (!(h < V.at(j))) { il = j; break; }
+            }
+            for (int k = 1; k <= budget; k++) {
+                const int j = peak + k;
+                if (j >= V.n) break;
+                if (!(h < V.at(j))) { ir = j; break; }
+            }
+            // the walks of _peak_widths stop at il / ir at the latest: width <= ir - il (strictly less unless both
+            // samples sit exactly at h, in which case it is equal) -- reject only with one sample to spare
+            if (il >= 0 && ir >= 0 && (double)(ir - il) < wmin) return true;
+        }
+    }
     return false;
 }
 
@@ -236,7 +270,7 @@ __device__ int warp_find_first_peaks(const TraceView &V, int dist, double pmin, 
     const int npk = warp_local_maxima(V, S.pk, S.cap);
     __syncwarp();
     for (int j = lane; j < npk; j += 32) {
-        S.flags[j] = lane_quick_reject(V, S.pk[j], pmin, 12) ? 0 : 1;
+        S.flags[j] = lane_quick_reject(V, S.pk[j], pmin, wmin, rel_height, 12) ? 0 : 1;
         S.status[j] = 0;
     }
     __syncwarp();

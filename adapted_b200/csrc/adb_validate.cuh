@@ -512,6 +512,7 @@ struct MvsSeriesArgs {
     unsigned long long *cursor;  // allocation cursor (zeroed before the launch)
     long long *row_off;       // [n_reads] offset of the read's row in the pools, or -1 (not precomputed)
     int *meta;                // [n_reads][2] = ae, pe the row belongs to
+    const int *perm;          // optional [n_reads]: lane q works on read perm[q] (reads sorted by segment length)
 };
 
 #define MVS_LANES 128   // reads per CTA (one lane each; every warp works on its own 32 reads, no CTA-wide sync)
@@ -552,7 +553,8 @@ __global__ void __launch_bounds__(MVS_LANES) mvs_series_kernel(MvsSeriesArgs A, 
     int16_t *ring = (int16_t *)smem + (size_t)warp * 32 * MVS_RING_STRIDE;
     float *ov = (float *)(smem + (size_t)MVS_LANES * MVS_RING_STRIDE * 2) + warp * 32 * MVS_OUT_STRIDE;
     float *om = ov + MVS_LANES * MVS_OUT_STRIDE;
-    const int q = blockIdx.x * MVS_LANES + tid;
+    const int qi = blockIdx.x * MVS_LANES + tid;
+    const int q = (qi < A.n_reads) ? (A.perm ? A.perm[qi] : qi) : A.n_reads;
     const int wv = cfg.pA_var_window, wm = cfg.pA_mean_window;
     bool active = false, win_var = false, win_mean = false;
     int a = 0, L = 0, ae = 0, pe = 0;
@@ -674,6 +676,45 @@ __global__ void __launch_bounds__(MVS_LANES) mvs_series_kernel(MvsSeriesArgs A, 
         if (more) park(base_i + MVS_C);
         __syncwarp();
     }
+}
+
+// ---- reads sorted by the length of their moving-statistics segment -------------------------------------------------
+// A warp of mvs_series_kernel runs as long as its longest read, so reads of similar length are put into the same
+// warp: counting sort by length bucket (64 samples), longest first; reads without a segment come last.
+#define MVS_NBUCKET 512
+__device__ __forceinline__ int mvs_len_bucket(const MvsSeriesArgs &A, const adb_config &cfg, int r) {
+    const int *g = A.given + (size_t)r * A.given_stride;
+    const ReadSrc src = make_src(A.B, r);
+    int a, L;
+    bool wv_, wm_;
+    if (src.i16 == nullptr || !mvs_plan(cfg, src, g[0], g[1], a, L, wv_, wm_)) return MVS_NBUCKET - 1;
+    return max(MVS_NBUCKET - 2 - min(L >> 6, MVS_NBUCKET - 2), 0);  // longest first
+}
+__global__ void mvs_len_hist_kernel(MvsSeriesArgs A, adb_config cfg, int *bucket_cnt) {
+    __shared__ int sh[MVS_NBUCKET];
+    for (int b = threadIdx.x; b < MVS_NBUCKET; b += blockDim.x) sh[b] = 0;
+    __syncthreads();
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < A.n_reads; r += gridDim.x * blockDim.x)
+        atomicAdd(&sh[mvs_len_bucket(A, cfg, r)], 1);
+    __syncthreads();
+    for (int b = threadIdx.x; b < MVS_NBUCKET; b += blockDim.x) if (sh[b]) atomicAdd(&bucket_cnt[b], sh[b]);
+}
+__global__ void mvs_len_scan_kernel(int *bucket_cnt /* in: counts, out: running cursors = start offsets */) {
+    __shared__ int sh[MVS_NBUCKET];
+    const int t = threadIdx.x;  // MVS_NBUCKET threads
+    sh[t] = bucket_cnt[t];
+    __syncthreads();
+    for (int o = 1; o < MVS_NBUCKET; o <<= 1) {
+        const int v = (t >= o) ? sh[t - o] : 0;
+        __syncthreads();
+        sh[t] += v;
+        __syncthreads();
+    }
+    bucket_cnt[t] = sh[t] - bucket_cnt[t];  // exclusive prefix
+}
+__global__ void mvs_len_scatter_kernel(MvsSeriesArgs A, adb_config cfg, int *bucket_cursor, int *perm) {
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < A.n_reads; r += gridDim.x * blockDim.x)
+        perm[atomicAdd(&bucket_cursor[mvs_len_bucket(A, cfg, r)], 1)] = r;
 }
 
 // float32 sources (the reference seam): one thread per read straight from global memory.  This path is PCIe-bound
