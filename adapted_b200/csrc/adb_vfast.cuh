@@ -36,6 +36,8 @@ struct VfTask {
     int cnt_hi;    // count at hi
     int pv;        // deviation search: first code whose value is >= med
     float med;
+    int sent;      // sentinel: hi == sent means "no index of this task satisfies the predicate"
+    int smin, smax;  // code bounds of the samples of the segment
     int pA, pB;    // probes of the running pass: count the codes in [pA, pB]
     int mid;
     int active;
@@ -52,6 +54,7 @@ struct VfScratch {  // shared memory
     int vtotal;    // vectors of all tasks of the round
     int4 items[VF_THREADS / 32][VF_MAX_TASKS];  // per warp: (task, first vector, end vector, owns the boundary elements)
     int nitems[VF_THREADS / 32];
+    unsigned tmin[VF_MAX_TASKS], tmax[VF_MAX_TASKS];  // per-task code bounds (vf_task_bounds)
     int itmp[16];
     unsigned wtot[8];
     long long ltmp[8];
@@ -131,7 +134,7 @@ __device__ void vf_probes(const VfRead &R, VfTask &t, int mid) {
     if (t.kind == 1) {
         // right side: code c = mid >= pv; left end = smallest code in [kmin, pv) with dev <= dev(c)
         const float d = vf_dev(R, mid, t.med);
-        int lo = R.kmin, hi = t.pv;  // first code in [lo, hi) with dev <= d (dev is non-increasing there), hi if none
+        int lo = min(t.smin, t.pv), hi = t.pv;  // first code in [lo, hi) with dev <= d (dev is non-increasing there), hi if none
         while (lo < hi) { const int m = (lo + hi) >> 1; if (vf_dev(R, m, t.med) <= d) hi = m; else lo = m + 1; }
         t.pA = lo; t.pB = mid;
         return;
@@ -139,7 +142,7 @@ __device__ void vf_probes(const VfRead &R, VfTask &t, int mid) {
     // left side: index i <-> code c = pv - 1 - i; right end = largest code in [pv, kmax] with dev <= dev(c)
     const int c = t.pv - 1 - mid;
     const float d = vf_dev(R, c, t.med);
-    int lo = t.pv, hi = R.kmax + 1;  // first code in [lo, hi) with dev > d (dev is non-decreasing there)
+    int lo = t.pv, hi = max(t.smax + 1, t.pv);  // first code in [lo, hi) with dev > d (dev is non-decreasing there)
     while (lo < hi) { const int m = (lo + hi) >> 1; if (vf_dev(R, m, t.med) > d) hi = m; else lo = m + 1; }
     t.pA = c; t.pB = lo - 1;
 }
@@ -148,9 +151,8 @@ __device__ void vf_probes(const VfRead &R, VfTask &t, int mid) {
 // is cut into equal contiguous shares, one per warp, so a pass costs every warp the same number of vector loads
 // whatever the sizes of the individual segments; the (< 16) boundary elements of task q go to warp q % 8.  Every
 // warp lists its (task, vector range) items once per round and only walks that list in the passes.
-__device__ void vf_run(const VfRead &R, VfScratch &S) {
+__device__ void vf_build_items(VfScratch &S, bool all_tasks) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    __syncthreads();
     const int ntask = S.ntask;
     const int nw = VF_THREADS / 32;
     if (lane == 0) {
@@ -158,7 +160,7 @@ __device__ void vf_run(const VfRead &R, VfScratch &S) {
         int n = 0;
         for (int q = 0; q < ntask; q++) {
             const VfTask &t = S.task[q];
-            if (!(t.lo < t.hi)) continue;
+            if (!all_tasks && !(t.lo < t.hi)) continue;
             const int fb = max(t.voff, wbeg), fe = min(t.voff + (t.v1 - t.v0), wend);
             const int edge = (warp == (q & (nw - 1))) && (t.hb < t.he || t.tb < t.te);
             if (fb < fe) S.items[warp][n++] = make_int4(q, t.v0 + (fb - t.voff), t.v0 + (fe - t.voff), edge);
@@ -166,13 +168,59 @@ __device__ void vf_run(const VfRead &R, VfScratch &S) {
         }
         S.nitems[warp] = n;
     }
+    __syncwarp();
+}
+
+// code bounds of the samples of every (rank) task: the bisections then start from the segment's own range instead of
+// the window's (an open-pore stretch or a spike elsewhere in the read would cost every task three more passes).
+// CTA-wide; sets lo / hi / smin / smax of every task.
+__device__ void vf_task_bounds(const VfRead &R, VfScratch &S) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __syncthreads();
+    const int ntask = S.ntask;
+    if (tid < ntask) { S.tmin[tid] = 0xffffu; S.tmax[tid] = 0u; }
+    vf_build_items(S, true);
+    __syncthreads();
+    const uint4 *V = reinterpret_cast<const uint4 *>(R.W16);
+    const int nit = S.nitems[warp];
+    for (int it = 0; it < nit; it++) {
+        const int4 item = S.items[warp][it];
+        const VfTask &t = S.task[item.x];
+        unsigned mn = 0xffffffffu, mx = 0u;
+        for (int v = item.y + lane; v < item.z; v += 32) {
+            const uint4 q = V[v];
+            mn = __vminu2(__vminu2(mn, q.x), __vminu2(q.y, __vminu2(q.z, q.w)));
+            mx = __vmaxu2(__vmaxu2(mx, q.x), __vmaxu2(q.y, __vmaxu2(q.z, q.w)));
+        }
+        unsigned lo = min(mn & 0xffffu, mn >> 16), hi = max(mx & 0xffffu, mx >> 16);
+        if (item.w && lane < 16) {
+            const int i = (lane < 8) ? t.hb + lane : t.tb + (lane - 8);
+            const int iend = (lane < 8) ? t.he : t.te;
+            if (i < iend) { const unsigned code = R.W16[i]; lo = min(lo, code); hi = max(hi, code); }
+        }
+        lo = __reduce_min_sync(ADB_FULL, lo);
+        hi = __reduce_max_sync(ADB_FULL, hi);
+        if (lane == 0) { atomicMin(&S.tmin[item.x], lo); atomicMax(&S.tmax[item.x], hi); }
+    }
+    __syncthreads();
+    if (tid < ntask) {
+        VfTask &t = S.task[tid];
+        t.smin = (int)S.tmin[tid]; t.smax = (int)S.tmax[tid];
+        t.lo = t.smin; t.hi = t.smax; t.sent = t.smax + 1;
+    }
+}
+
+__device__ void vf_run(const VfRead &R, VfScratch &S) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __syncthreads();
+    const int ntask = S.ntask;
+    vf_build_items(S, false);
     bool mine = false;
     if (tid < ntask) {
         VfTask &t = S.task[tid];
         S.cnt[tid] = 0;
         if (t.lo < t.hi) { t.active = 1; vf_probes(R, t, (t.lo + t.hi) >> 1); mine = true; } else t.active = 0;
     }
-    __syncwarp();
     const int nit = S.nitems[warp];
     while (__syncthreads_or(mine)) {
         for (int it = 0; it < nit; it++) {
@@ -549,7 +597,7 @@ __device__ __forceinline__ int vf_add_rank(VfScratch &S, const VfRead &R, int &n
     if (threadIdx.x == 0) {
         VfTask &t = S.task[q];
         t.a = a; t.b = b; t.kind = 0; t.k = k; t.lo = R.kmin; t.hi = R.kmax; t.cnt_hi = n; t.pv = 0; t.med = 0.f;
-        t.active = 0;
+        t.active = 0; t.sent = R.kmax + 1; t.smin = R.kmin; t.smax = R.kmax;
         vf_geometry(R, t, a, b, rot);
     }
     rot += nvec;
@@ -578,8 +626,10 @@ __device__ float vf_median_of(const VfRead &R, VfScratch &S, int q) {
 
 struct VfDevOut { float mad; };
 
-// add the two deviation-search tasks of a segment (median known); returns the index of the first or -1
-__device__ __forceinline__ int vf_add_mad(VfScratch &S, const VfRead &R, int &nt, int &rot, int a, int b, float med) {
+// add the two deviation-search tasks of a segment (median known, code bounds [smin, smax] of its samples); returns the
+// index of the first or -1
+__device__ __forceinline__ int vf_add_mad(VfScratch &S, const VfRead &R, int &nt, int &rot, int a, int b, float med,
+                                          int smin, int smax) {
     clip_seg(a, b, R.n);
     const int n = b - a;
     if (n <= 0 || !(med == med)) return -1;
@@ -587,16 +637,18 @@ __device__ __forceinline__ int vf_add_mad(VfScratch &S, const VfRead &R, int &nt
     nt += 2;
     int ok = 1;
     int pv = gsb_code_at(med, false, R.coff, R.cscale, &ok);
-    pv = min(max(pv, R.kmin), R.kmax + 1);
+    pv = min(max(pv, smin), smax + 1);
     const int nvec = max(((R.s0 + b) >> 3) - ((R.s0 + a + 7) >> 3), 0);
     if (threadIdx.x == 0) {
         VfTask &t = S.task[q];
-        t.a = a; t.b = b; t.kind = 1; t.k = (n - 1) / 2; t.lo = pv; t.hi = R.kmax + 1; t.cnt_hi = -1; t.pv = pv; t.med = med;
+        t.a = a; t.b = b; t.kind = 1; t.k = (n - 1) / 2; t.cnt_hi = -1; t.pv = pv; t.med = med;
+        t.smin = smin; t.smax = smax;
+        t.lo = pv; t.hi = smax + 1; t.sent = smax + 1;  // codes pv .. smax
         t.active = 0;
         vf_geometry(R, t, a, b, rot);
         VfTask &u = S.task[q + 1];
         u = t;
-        u.kind = 2; u.lo = 0; u.hi = pv - R.kmin;
+        u.kind = 2; u.lo = 0; u.hi = pv - smin; u.sent = pv - smin;  // codes pv - 1 down to smin
         u.voff = rot + nvec;
     }
     rot += 2 * nvec;
@@ -609,7 +661,7 @@ __device__ float vf_mad_of(const VfRead &R, VfScratch &S, int q) {
     const VfTask tr = S.task[q], tl = S.task[q + 1];
     const int n = tr.b - tr.a, k = tr.k, pv = tr.pv;
     const float med = tr.med;
-    const bool hasR = tr.hi <= R.kmax, hasL = tl.hi < pv - R.kmin;
+    const bool hasR = tr.hi < tr.sent, hasL = tl.hi < tl.sent;
     const float dR = hasR ? vf_dev(R, tr.hi, med) : CUDART_INF_F;
     const float dL = hasL ? vf_dev(R, pv - 1 - tl.hi, med) : CUDART_INF_F;
     const float d0 = fminf(dR, dL);
@@ -736,6 +788,7 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_fast_kernel(VfastArgs 
             if (tid != tL15 && tid != tL85 && tid != tP15 && tid != tP85) t.k = (t.b - t.a - 1) / 2;
         }
         if (tid == 0) { S.ntask = nt; S.vtotal = rot; }
+        vf_task_bounds(R, S);
         vf_run(R, S);
         const float medA0 = vf_median_of(R, S, tA0), medA1 = vf_median_of(R, S, tA1);
         const float medP = vf_median_of(R, S, tP), medR = vf_median_of(R, S, tR);
@@ -755,12 +808,17 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_fast_kernel(VfastArgs 
         const double lrP = local_range(tP15, tP85, nP, vP15, vP85);
 
         // ---- round B: every MAD ----
+        int bmin[4] = {0, 0, 0, 0}, bmax[4] = {0, 0, 0, 0};
+        {
+            const int src[4] = {tA0, tA1, tP, tR};
+            for (int q = 0; q < 4; q++) if (src[q] >= 0) { bmin[q] = S.task[src[q]].smin; bmax[q] = S.task[src[q]].smax; }
+        }
         nt = 0; rot = 0;
         __syncthreads();
-        const int dA0 = (tA0 >= 0) ? vf_add_mad(S, R, nt, rot, 0, a_end, medA0) : -1;
-        const int dA1 = (tA1 >= 0) ? vf_add_mad(S, R, nt, rot, a_start1, a_end, medA1) : -1;
-        const int dP = (tP >= 0) ? vf_add_mad(S, R, nt, rot, a_end, pe_best, medP) : -1;
-        const int dR = (tR >= 0) ? vf_add_mad(S, R, nt, rot, pe_best, size, medR) : -1;
+        const int dA0 = (tA0 >= 0) ? vf_add_mad(S, R, nt, rot, 0, a_end, medA0, bmin[0], bmax[0]) : -1;
+        const int dA1 = (tA1 >= 0) ? vf_add_mad(S, R, nt, rot, a_start1, a_end, medA1, bmin[1], bmax[1]) : -1;
+        const int dP = (tP >= 0) ? vf_add_mad(S, R, nt, rot, a_end, pe_best, medP, bmin[2], bmax[2]) : -1;
+        const int dR = (tR >= 0) ? vf_add_mad(S, R, nt, rot, pe_best, size, medR, bmin[3], bmax[3]) : -1;
         __syncthreads();
         if (tid == 0) { S.ntask = nt; S.vtotal = rot; }
         vf_run(R, S);
