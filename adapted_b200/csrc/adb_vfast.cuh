@@ -55,6 +55,8 @@ struct VfScratch {  // shared memory
     int4 items[VF_THREADS / 32][VF_MAX_TASKS];  // per warp: (task, first vector, end vector, owns the boundary elements)
     int nitems[VF_THREADS / 32];
     unsigned tmin[VF_MAX_TASKS], tmax[VF_MAX_TASKS];  // per-task code bounds (vf_task_bounds)
+    uint32_t cand[2][64];  // keys left inside the brackets of vf_series_medians
+    int ncand[2];
     int itmp[16];
     unsigned wtot[8];
     long long ltmp[8];
@@ -477,10 +479,13 @@ __device__ void vf_mean_std3(const VfRead &R, VfScratch &S, const int sa[3], con
     __syncthreads();
 }
 
-// np.nanmedian of up to two NaN-free float32 series (global memory) staged as ordered keys in `buf` (shared memory,
-// capacity cap words): bisection on the key value, both series advancing in the same passes.  CTA-wide.
+// np.nanmedian of up to two NaN-free float32 series (global memory) staged as ordered keys in `buf` (shared memory):
+// bisection on the key value, both series advancing in the same passes, until at most VF_NCAND keys are left inside
+// the bracket; those are gathered and ranked directly (float keys are nearly all distinct, so isolating a single key
+// by bisection would take ~22 passes; isolating 64 of ~3000 takes ~6).  CTA-wide.
+#define VF_NCAND 64
 __device__ void vf_series_medians(VfScratch &S, const float *g0, int n0, const float *g1, int n1, uint32_t *buf, float out[2]) {
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t *k0 = buf, *k1 = buf + ((n0 + 3) & ~3);
     __syncthreads();
     uint32_t mn[2] = {0xffffffffu, 0xffffffffu}, mx[2] = {0u, 0u};
@@ -488,35 +493,27 @@ __device__ void vf_series_medians(VfScratch &S, const float *g0, int n0, const f
     for (int j = tid; j < n1; j += VF_THREADS) { const uint32_t k = f32_key(g1[j]); k1[j] = k; mn[1] = min(mn[1], k); mx[1] = max(mx[1], k); }
     for (int q = 0; q < 2; q++) { mn[q] = warp_min_u(mn[q]); mx[q] = warp_max_u(mx[q]); }
     if (tid < 4) S.utmp[tid] = (tid < 2) ? 0xffffffffu : 0u;
+    if (tid < 6) S.cnt[tid] = 0;
+    if (tid < 2) S.ncand[tid] = 0;
     __syncthreads();
-    if ((tid & 31) == 0) {
+    if (lane == 0) {
         atomicMin(&S.utmp[0], mn[0]); atomicMin(&S.utmp[1], mn[1]);
         atomicMax(&S.utmp[2], mx[0]); atomicMax(&S.utmp[3], mx[1]);
     }
     __syncthreads();
-    // search state in registers (identical in every thread): smallest key with count(<= key) > rank.  The probe
-    // alternates between the linear interpolation of the empirical CDF over the bracket (the series are smooth,
-    // unimodal samples: this homes in within a few passes) and plain bisection (guaranteed progress).
+    // search state in registers (identical in every thread): keys in [lo, hi] hold the ranks cnt_lo .. cnt_hi - 1
     uint32_t lo[2] = {S.utmp[0], S.utmp[1]}, hi[2] = {S.utmp[2], S.utmp[3]};
     const int nn[2] = {n0, n1};
     const uint32_t *kk[2] = {k0, k1};
-    unsigned rank[2] = {n0 > 0 ? (unsigned)(n0 - 1) / 2 : 0u, n1 > 0 ? (unsigned)(n1 - 1) / 2 : 0u};
+    const unsigned rank[2] = {n0 > 0 ? (unsigned)(n0 - 1) / 2 : 0u, n1 > 0 ? (unsigned)(n1 - 1) / 2 : 0u};
     unsigned cnt_hi[2] = {(unsigned)n0, (unsigned)n1}, cnt_lo[2] = {0u, 0u};
-    if (tid < 6) S.cnt[tid] = 0;
-    __syncthreads();
+    auto open = [&](int q) { return nn[q] > 0 && lo[q] < hi[q] && cnt_hi[q] - cnt_lo[q] > VF_NCAND; };
     int pass = 0;
-    while ((n0 > 0 && lo[0] < hi[0]) || (n1 > 0 && lo[1] < hi[1])) {
+    while (open(0) || open(1)) {
         uint32_t mid[2];
         for (int q = 0; q < 2; q++) {
-            const uint32_t span = hi[q] - lo[q];
-            mid[q] = lo[q] + (span >> 1);
-            if (!(pass & 1) && cnt_hi[q] > cnt_lo[q]) {
-                const double frac = ((double)rank[q] + 0.5 - (double)cnt_lo[q]) / (double)(cnt_hi[q] - cnt_lo[q]);
-                double off = frac * (double)span;
-                off = fmin(fmax(off, 0.0), (double)span - 1.0);
-                mid[q] = lo[q] + (uint32_t)off;
-            }
-            if (nn[q] <= 0 || !(lo[q] < hi[q])) continue;
+            mid[q] = lo[q] + ((hi[q] - lo[q]) >> 1);
+            if (!open(q)) continue;
             int c = 0;
             const uint4 *V = reinterpret_cast<const uint4 *>(kk[q]);
             const int nv = nn[q] >> 2;
@@ -527,11 +524,11 @@ __device__ void vf_series_medians(VfScratch &S, const float *g0, int n0, const f
             const int j = (nv << 2) + tid;
             if (j < nn[q]) c += (kk[q][j] <= mid[q]);
             c = __reduce_add_sync(ADB_FULL, c);
-            if ((tid & 31) == 0 && c) atomicAdd(&S.cnt[q + 2 * (pass % 3)], (unsigned)c);
+            if (lane == 0 && c) atomicAdd(&S.cnt[q + 2 * (pass % 3)], (unsigned)c);
         }
         __syncthreads();
         for (int q = 0; q < 2; q++) {
-            if (nn[q] <= 0 || !(lo[q] < hi[q])) continue;
+            if (!open(q)) continue;
             const unsigned c = S.cnt[q + 2 * (pass % 3)];
             if (c > rank[q]) { hi[q] = mid[q]; cnt_hi[q] = c; } else { lo[q] = mid[q] + 1; cnt_lo[q] = c; }
         }
@@ -540,29 +537,65 @@ __device__ void vf_series_medians(VfScratch &S, const float *g0, int n0, const f
         if (tid < 2) S.cnt[tid + 2 * ((pass + 2) % 3)] = 0;
         pass++;
     }
+    // gather the keys left in the brackets (cnt_hi - cnt_lo of them, or all equal keys when lo == hi)
+    for (int q = 0; q < 2; q++) {
+        if (nn[q] <= 0 || lo[q] == hi[q]) continue;
+        for (int j = tid; j < nn[q]; j += VF_THREADS) {
+            const uint32_t k = kk[q][j];
+            if (k >= lo[q] && k <= hi[q]) { const int p = atomicAdd(&S.ncand[q], 1); if (p < VF_NCAND) S.cand[q][p] = k; }
+        }
+    }
     __syncthreads();
-    if (tid < 6) S.cnt[tid] = 0;
+    // warp q ranks the candidates of series q: the keys at ranks r and r + 1 inside the bracket
+    if (warp < 2) {
+        const int q = warp;
+        if (nn[q] > 0) {
+            uint32_t a = hi[q], b = 0xffffffffu;  // lower / upper middle key; b unknown yet
+            bool have_b = false;
+            if (lo[q] == hi[q]) {
+                have_b = cnt_hi[q] > rank[q] + 1;
+                b = hi[q];
+            } else {
+                const int m = min((int)(cnt_hi[q] - cnt_lo[q]), VF_NCAND);
+                const int r = (int)(rank[q] - cnt_lo[q]);
+                for (int i = lane; i < m; i += 32) {
+                    const uint32_t ki = S.cand[q][i];
+                    int pos = 0;
+                    for (int j = 0; j < m; j++) { const uint32_t kj = S.cand[q][j]; pos += (kj < ki) || (kj == ki && j < i); }
+                    if (pos == r) S.utmp[4 + 2 * q] = ki;
+                    if (pos == r + 1) S.utmp[5 + 2 * q] = ki;
+                }
+                __syncwarp();
+                a = S.utmp[4 + 2 * q];
+                have_b = (r + 1 < m);
+                if (have_b) b = S.utmp[5 + 2 * q];
+            }
+            if (lane == 0) { S.utmp[4 + 2 * q] = a; S.utmp[5 + 2 * q] = b; S.itmp[q] = have_b ? 1 : 0; }
+        }
+    }
     __syncthreads();
     for (int q = 0; q < 2; q++) {
         if (nn[q] <= 0) { out[q] = CUDART_NAN_F; continue; }
-        const float a = key_f32(hi[q]);
+        const float a = key_f32(S.utmp[4 + 2 * q]);
         if (nn[q] & 1) { out[q] = a; continue; }
-        // even count: the upper middle element is the same key unless the count at it stops exactly at the rank
-        uint32_t up = hi[q];
-        if (!(cnt_hi[q] > rank[q] + 1)) {
+        uint32_t up = S.utmp[5 + 2 * q];
+        if (!S.itmp[q]) {
+            // the upper middle element lies beyond the bracket: smallest key above hi (rare)
             __syncthreads();
-            if (tid == 0) S.utmp[4] = 0xffffffffu;
+            if (tid == 0) S.utmp[3] = 0xffffffffu;
             __syncthreads();
             uint32_t best = 0xffffffffu;
             for (int j = tid; j < nn[q]; j += VF_THREADS) { const uint32_t k = kk[q][j]; if (k > hi[q]) best = min(best, k); }
             best = warp_min_u(best);
-            if ((tid & 31) == 0) atomicMin(&S.utmp[4], best);
+            if (lane == 0) atomicMin(&S.utmp[3], best);
             __syncthreads();
-            up = S.utmp[4];
+            up = S.utmp[3];
             __syncthreads();
         }
         out[q] = __fdiv_rn(__fadd_rn(a, key_f32(up)), 2.0f);
     }
+    __syncthreads();
+    if (tid < 6) S.cnt[tid] = 0;
     __syncthreads();
 }
 

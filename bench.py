@@ -225,6 +225,7 @@ def main():
     L.adb_ctx_set_timing(ctx.handle, 0)
     n_pass = int(torch.frombuffer(records.cpu().numpy(), dtype=torch.int32).reshape(n, 128)[:, 0].sum().item())
     lost = int((status != 0).sum().item())
+    gsel_fallbacks = ctx.query("global_select_fallbacks")
 
     # ---------------- e2e: pinned host -> H2D -> kernels -> D2H ----------------
     host = {k: data[k].cpu().pin_memory() for k in ("adc", "offsets", "full_lens", "calib_offset", "calib_scale")}
@@ -273,13 +274,16 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    cls_names = ["global_select_hist", "global_select_scan", "validate_kernel", "llr_primary_kernel",
-                 "mvs_series_kernel", "cnn", "start_peak", "other"]
+    # timing classes of adb_ctx_get_timing: 0 the streaming pass of the minibatch-global median/MAD (gsb_pass_kernel),
+    # 1 its small sample / plan / finish kernels, 2 validate_fast_kernel, 3 llr_primary_kernel, 4 the length sort +
+    # mvs_series_kernel, 5 CNN, 6 start-peak, 7 hand-over kernels (exact multi-pass select, histogram validate kernel)
+    cls_names = ["global_select_pass", "global_select_small", "validate_fast_kernel", "llr_primary_kernel",
+                 "mvs_series_kernel", "cnn", "start_peak", "handover_kernels"]
     per_cls = {cls_names[i]: {"ms": tim[2 * i], "launches": int(tim[2 * i + 1])} for i in range(8) if tim[2 * i + 1] > 0}
     dom = max(range(8), key=lambda i: tim[2 * i])
     alg_bytes_per_step = 2.0 * samples + (8 + 4 + 512) * n
     if dom in (0, 3):  # these kernels stream the first max_obs_trace samples of every read once per launch
-        launches_dom = max(per_cls[cls_names[0]]["launches"], 1)
+        launches_dom = max(per_cls[cls_names[dom]]["launches"], 1)
         alg_launch = 2.0 * float(torch.clamp(data["offsets"][1:] - data["offsets"][:-1], max=flat["max_obs_trace"]).sum().item())
     else:
         launches_dom = max(per_cls[cls_names[dom]]["launches"], 1)
@@ -305,7 +309,8 @@ def main():
                         "steps": e2e_steps, "records_identical_to_device_run": same,
                         "api": "adb_detect_pipelined_host (pinned host int16 -> H2D -> kernels -> D2H records)"},
                 "gpu_launches": int(tot[2]), "roofline": roofline, "clocks": sampler.summary(),
-                "pass_fraction": float(tot[3]) / tot_reads, "lost_minibatches": int(tot[4])}
+                "pass_fraction": float(tot[3]) / tot_reads, "lost_minibatches": int(tot[4]),
+                "global_select_handovers_rank0": int(gsel_fallbacks)}
         if world == 1 and not args.no_cpu_baseline:
             rpw = args.cpu_reads_per_worker or 256
             rps, sps, sec_step, reads_step = cpu_arm(args.chemistry, 1, 1, rpw, cores)

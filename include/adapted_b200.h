@@ -188,8 +188,10 @@ int adb_detect_pipelined_host(adb_ctx *ctx, const adb_batch *batch, const adb_co
                               adb_record *out_records, int32_t *batch_status, int32_t chunk_batches);
 
 /* Per-kernel-class device timing (CUDA events around every launch; used by bench.py for the roofline):
- * class 0 global-select histogram passes, 1 global-select scans, 2 validate kernel, 3 LLR-primary kernel,
- * 4 moving-statistics kernel, 5 CNN kernels, 6 start-peak kernels, 7 other.
+ * class 0 streaming pass of the minibatch-global median / MAD (multi-pass histogram kernels when forced),
+ * 1 its sample / plan / finish kernels (scan kernels of the multi-pass select when forced), 2 validate kernel
+ * (counting-based for int16 reads, histogram-based otherwise), 3 LLR-primary kernel, 4 moving-statistics kernels,
+ * 5 CNN kernels, 6 start-peak kernels, 7 hand-over kernels (what the fast paths pass on to the general kernels).
  * adb_ctx_get_timing fills out[16] = {ms, launches} x 8; call it after synchronising the stream. */
 int adb_ctx_set_timing(adb_ctx *ctx, int on);
 int adb_ctx_get_timing(adb_ctx *ctx, double *out);
