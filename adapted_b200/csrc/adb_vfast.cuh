@@ -9,9 +9,9 @@
 // and the 0xffff / 0 lane masks are summed with plain integer adds.  All statistics of a read advance together:
 //   round A  bisection on the code value for every rank needed (medians, p15 / p85 of numpy's linear percentile),
 //   round B  bisection for the k-th smallest |pA(code) - med| (MAD): deviations are monotone on either side of the
-//            median, so "how many samples deviate at most dev(c)" is the count of one code interval whose other end
-//            is found by evaluating the float32 deviation exactly; the two sides are searched independently and the
-//            smaller answer is the order statistic.
+//            median, so "how many samples deviate at most t" is the count of one code interval whose ends are found
+//            by evaluating the float32 deviations exactly; the candidates of both sides are halved together by
+//            probing the middle candidate of the longer side.
 // Sums for mean / std are exact integer sums of the codes.  The float32 moving-statistics series (bottleneck
 // recurrences, mvs_series_kernel) are staged in shared memory and their medians found by bisection on the ordered
 // float bits.  Anything outside this path (float32 sources, codes outside [0, 0x7c00), no precomputed series, further
@@ -30,7 +30,7 @@
 
 struct VfTask {
     int a, b;      // sample range [a, b) of the window
-    int kind;      // 0: rank (count of codes <= idx); 1 / 2: deviation search over the codes >= pv / < pv
+    int kind;      // 0: rank (count of codes <= idx); 1: k-th smallest deviation from the median (MAD)
     int k;         // 0-based rank looked for
     int lo, hi;    // search interval over the index; hi = first index whose count exceeds k (or the sentinel)
     int cnt_hi;    // count at hi
@@ -38,6 +38,13 @@ struct VfTask {
     float med;
     int sent;      // sentinel: hi == sent means "no index of this task satisfies the predicate"
     int smin, smax;  // code bounds of the samples of the segment
+    // deviation search: candidates still undecided on the right side (codes pv + i, i in [rlo, rhi)) and on the left
+    // side (codes pv - 1 - i, i in [llo, lhi)); candidates below the lows fail the predicate, from the his on they pass
+    int rlo, rhi, llo, lhi;
+    int jL, jR;    // codes pv - jL .. pv + jR - 1 deviate at most t_probe
+    float t_probe; // deviation probed in the running pass
+    float t_best;  // smallest deviation found so far that passes, and the count of samples deviating at most that much
+    int c_best;
     int pA, pB;    // probes of the running pass: count the codes in [pA, pB]
     int mid;
     int active;
@@ -52,7 +59,7 @@ struct VfScratch {  // shared memory
     unsigned cnt[VF_MAX_TASKS];
     int ntask;
     int vtotal;    // vectors of all tasks of the round
-    int4 items[VF_THREADS / 32][VF_MAX_TASKS];  // per warp: (task, first vector, end vector, owns the boundary elements)
+    ushort4 items[VF_THREADS / 32][VF_MAX_TASKS];  // per warp: (task, first vector, end vector, owns the boundary elements)
     int nitems[VF_THREADS / 32];
     unsigned tmin[VF_MAX_TASKS], tmax[VF_MAX_TASKS];  // per-task code bounds (vf_task_bounds)
     uint32_t cand[2][64];  // keys left inside the brackets of vf_series_medians
@@ -129,30 +136,73 @@ __device__ __forceinline__ int vf_count_vectors(const VfRead &R, int vb, int ve,
 // float32 deviation of a code from the median, as the reference computes it on the pA values
 __device__ __forceinline__ float vf_dev(const VfRead &R, int code, float med) { return fabsf(__fsub_rn(vf_pa(R, code), med)); }
 
-// probes of a task for the index `mid` (one thread)
-__device__ void vf_probes(const VfRead &R, VfTask &t, int mid) {
-    t.mid = mid;
-    if (t.kind == 0) { t.pA = 0; t.pB = mid; return; }
-    if (t.kind == 1) {
-        // right side: code c = mid >= pv; left end = smallest code in [kmin, pv) with dev <= dev(c)
-        const float d = vf_dev(R, mid, t.med);
-        int lo = min(t.smin, t.pv), hi = t.pv;  // first code in [lo, hi) with dev <= d (dev is non-increasing there), hi if none
-        while (lo < hi) { const int m = (lo + hi) >> 1; if (vf_dev(R, m, t.med) <= d) hi = m; else lo = m + 1; }
-        t.pA = lo; t.pB = mid;
-        return;
-    }
-    // left side: index i <-> code c = pv - 1 - i; right end = largest code in [pv, kmax] with dev <= dev(c)
-    const int c = t.pv - 1 - mid;
-    const float d = vf_dev(R, c, t.med);
-    int lo = t.pv, hi = max(t.smax + 1, t.pv);  // first code in [lo, hi) with dev > d (dev is non-decreasing there)
-    while (lo < hi) { const int m = (lo + hi) >> 1; if (vf_dev(R, m, t.med) > d) hi = m; else lo = m + 1; }
-    t.pA = c; t.pB = lo - 1;
+// deviation of the i-th candidate of a side (right: code pv + i, left: code pv - 1 - i); non-decreasing in i
+__device__ __forceinline__ float vf_side_dev(const VfRead &R, const VfTask &t, bool right, int i) {
+    return vf_dev(R, right ? t.pv + i : t.pv - 1 - i, t.med);
 }
 
-// run every task of S to convergence.  CTA-wide.  The full vectors of all tasks form one flattened index space that
-// is cut into equal contiguous shares, one per warp, so a pass costs every warp the same number of vector loads
-// whatever the sizes of the individual segments; the (< 16) boundary elements of task q go to warp q % 8.  Every
-// warp lists its (task, vector range) items once per round and only walks that list in the passes.
+// first index of a side (n candidates) whose deviation is > t (strict) or >= t: the calibration is nearly linear, so
+// t / scale is within a step or two of the answer; the guess is corrected by exact float32 evaluations
+__device__ int vf_side_first(const VfRead &R, const VfTask &t, bool right, int n, float thr, bool strict) {
+    float gf = thr / R.cscale;
+    int g = (gf == gf && gf < 1e9f) ? (int)gf : n;
+    g = min(max(g, 0), n);
+    int guard = 0;
+    while (g > 0 && guard++ < 100000) {
+        const float d = vf_side_dev(R, t, right, g - 1);
+        if (strict ? (d > thr) : (d >= thr)) g--; else break;
+    }
+    while (g < n && guard++ < 100000) {
+        const float d = vf_side_dev(R, t, right, g);
+        if (strict ? !(d > thr) : !(d >= thr)) g++; else break;
+    }
+    return g;
+}
+
+__device__ __forceinline__ bool vf_pending(const VfTask &t) {
+    return t.kind == 0 ? (t.lo < t.hi) : (t.rlo < t.rhi || t.llo < t.lhi);
+}
+
+// choose the probe of the next pass (one thread); false when the task has converged
+__device__ bool vf_prepare(const VfRead &R, VfTask &t) {
+    if (!vf_pending(t)) { t.active = 0; return false; }
+    t.active = 1;
+    if (t.kind == 0) { t.mid = (t.lo + t.hi) >> 1; t.pA = 0; t.pB = t.mid; return true; }
+    // the middle candidate of the longer side: by symmetry of the two sides it halves the other one as well
+    const int nR = t.smax + 1 - t.pv, nL = t.pv - t.smin;
+    const bool right = (t.rhi - t.rlo) >= (t.lhi - t.llo);
+    const int i = right ? (t.rlo + t.rhi) >> 1 : (t.llo + t.lhi) >> 1;
+    const float thr = vf_side_dev(R, t, right, i);
+    t.t_probe = thr;
+    t.jR = vf_side_first(R, t, true, nR, thr, true);
+    t.jL = vf_side_first(R, t, false, nL, thr, true);
+    t.pA = t.pv - t.jL;
+    t.pB = t.pv + t.jR - 1;
+    return true;
+}
+
+// take the count of the pass (one thread)
+__device__ void vf_update(const VfRead &R, VfTask &t, int c) {
+    if (t.kind == 0) {
+        if (c > t.k) { t.hi = t.mid; t.cnt_hi = c; } else t.lo = t.mid + 1;
+        return;
+    }
+    if (c > t.k) {
+        // every candidate deviating at least t_probe passes
+        const int nR = t.smax + 1 - t.pv, nL = t.pv - t.smin;
+        t.rhi = min(t.rhi, vf_side_first(R, t, true, nR, t.t_probe, false));
+        t.lhi = min(t.lhi, vf_side_first(R, t, false, nL, t.t_probe, false));
+        t.rlo = min(t.rlo, t.rhi);
+        t.llo = min(t.llo, t.lhi);
+        t.t_best = t.t_probe;
+        t.c_best = c;
+    } else {
+        // every candidate deviating at most t_probe fails
+        t.rlo = min(max(t.rlo, t.jR), t.rhi);
+        t.llo = min(max(t.llo, t.jL), t.lhi);
+    }
+}
+
 __device__ void vf_build_items(VfScratch &S, bool all_tasks) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ntask = S.ntask;
@@ -162,11 +212,11 @@ __device__ void vf_build_items(VfScratch &S, bool all_tasks) {
         int n = 0;
         for (int q = 0; q < ntask; q++) {
             const VfTask &t = S.task[q];
-            if (!all_tasks && !(t.lo < t.hi)) continue;
+            if (!all_tasks && !vf_pending(t)) continue;
             const int fb = max(t.voff, wbeg), fe = min(t.voff + (t.v1 - t.v0), wend);
             const int edge = (warp == (q & (nw - 1))) && (t.hb < t.he || t.tb < t.te);
-            if (fb < fe) S.items[warp][n++] = make_int4(q, t.v0 + (fb - t.voff), t.v0 + (fe - t.voff), edge);
-            else if (edge) S.items[warp][n++] = make_int4(q, 0, 0, 1);
+            if (fb < fe) S.items[warp][n++] = make_ushort4((unsigned short)q, (unsigned short)(t.v0 + (fb - t.voff)), (unsigned short)(t.v0 + (fe - t.voff)), (unsigned short)edge);
+            else if (edge) S.items[warp][n++] = make_ushort4((unsigned short)q, 0, 0, 1);
         }
         S.nitems[warp] = n;
     }
@@ -186,7 +236,7 @@ __device__ void vf_task_bounds(const VfRead &R, VfScratch &S) {
     const uint4 *V = reinterpret_cast<const uint4 *>(R.W16);
     const int nit = S.nitems[warp];
     for (int it = 0; it < nit; it++) {
-        const int4 item = S.items[warp][it];
+        const ushort4 item = S.items[warp][it];
         const VfTask &t = S.task[item.x];
         unsigned mn = 0xffffffffu, mx = 0u;
         for (int v = item.y + lane; v < item.z; v += 32) {
@@ -221,12 +271,12 @@ __device__ void vf_run(const VfRead &R, VfScratch &S) {
     if (tid < ntask) {
         VfTask &t = S.task[tid];
         S.cnt[tid] = 0;
-        if (t.lo < t.hi) { t.active = 1; vf_probes(R, t, (t.lo + t.hi) >> 1); mine = true; } else t.active = 0;
+        mine = vf_prepare(R, t);
     }
     const int nit = S.nitems[warp];
     while (__syncthreads_or(mine)) {
         for (int it = 0; it < nit; it++) {
-            const int4 item = S.items[warp][it];
+            const ushort4 item = S.items[warp][it];
             const VfTask &t = S.task[item.x];
             if (!t.active) continue;
             const int pA = t.pA, pB = t.pB;
@@ -248,8 +298,8 @@ __device__ void vf_run(const VfRead &R, VfScratch &S) {
             if (t.active) {
                 const int c = (int)S.cnt[tid];
                 S.cnt[tid] = 0;
-                if (c > t.k) { t.hi = t.mid; t.cnt_hi = c; } else t.lo = t.mid + 1;
-                if (t.lo < t.hi) { vf_probes(R, t, (t.lo + t.hi) >> 1); mine = true; } else t.active = 0;
+                vf_update(R, t, c);
+                mine = vf_prepare(R, t);
             }
         }
     }
@@ -659,15 +709,14 @@ __device__ float vf_median_of(const VfRead &R, VfScratch &S, int q) {
 
 struct VfDevOut { float mad; };
 
-// add the two deviation-search tasks of a segment (median known, code bounds [smin, smax] of its samples); returns the
-// index of the first or -1
+// add the deviation-search task of a segment (median known, code bounds [smin, smax] of its samples); returns its
+// index or -1
 __device__ __forceinline__ int vf_add_mad(VfScratch &S, const VfRead &R, int &nt, int &rot, int a, int b, float med,
                                           int smin, int smax) {
     clip_seg(a, b, R.n);
     const int n = b - a;
     if (n <= 0 || !(med == med)) return -1;
-    const int q = nt;
-    nt += 2;
+    const int q = nt++;
     int ok = 1;
     int pv = gsb_code_at(med, false, R.coff, R.cscale, &ok);
     pv = min(max(pv, smin), smax + 1);
@@ -676,32 +725,26 @@ __device__ __forceinline__ int vf_add_mad(VfScratch &S, const VfRead &R, int &nt
         VfTask &t = S.task[q];
         t.a = a; t.b = b; t.kind = 1; t.k = (n - 1) / 2; t.cnt_hi = -1; t.pv = pv; t.med = med;
         t.smin = smin; t.smax = smax;
-        t.lo = pv; t.hi = smax + 1; t.sent = smax + 1;  // codes pv .. smax
+        t.lo = 0; t.hi = 0; t.sent = 0;
+        t.rlo = 0; t.rhi = smax + 1 - pv; t.llo = 0; t.lhi = pv - smin;
+        t.t_best = CUDART_INF_F; t.c_best = -1;
         t.active = 0;
         vf_geometry(R, t, a, b, rot);
-        VfTask &u = S.task[q + 1];
-        u = t;
-        u.kind = 2; u.lo = 0; u.hi = pv - smin; u.sent = pv - smin;  // codes pv - 1 down to smin
-        u.voff = rot + nvec;
     }
-    rot += 2 * nvec;
+    rot += nvec;
     return q;
 }
 
-// median of |x - med| from the two finished deviation tasks q (right side) and q + 1 (left side).  CTA-wide (uniform).
+// median of |x - med| from the finished deviation task q.  CTA-wide (uniform).
 __device__ float vf_mad_of(const VfRead &R, VfScratch &S, int q) {
     if (q < 0) return CUDART_NAN_F;
-    const VfTask tr = S.task[q], tl = S.task[q + 1];
-    const int n = tr.b - tr.a, k = tr.k, pv = tr.pv;
-    const float med = tr.med;
-    const bool hasR = tr.hi < tr.sent, hasL = tl.hi < tl.sent;
-    const float dR = hasR ? vf_dev(R, tr.hi, med) : CUDART_INF_F;
-    const float dL = hasL ? vf_dev(R, pv - 1 - tl.hi, med) : CUDART_INF_F;
-    const float d0 = fminf(dR, dL);
+    const VfTask t = S.task[q];
+    const int n = t.b - t.a, k = t.k, pv = t.pv;
+    const float med = t.med;
+    const float d0 = t.t_best;  // the last probe that passed is the smallest passing candidate (see vf_update)
     if (n & 1) return d0;
-    const int cnt0 = (dR <= dL) ? tr.cnt_hi : tl.cnt_hi;
     float d1 = d0;
-    if (!(cnt0 > k + 1)) {
+    if (!(t.c_best > k + 1)) {
         // the next larger deviation: first occupied code beyond the interval [l, r] of the codes deviating <= d0
         int lo = R.kmin, hi = pv;
         while (lo < hi) { const int m = (lo + hi) >> 1; if (vf_dev(R, m, med) <= d0) hi = m; else lo = m + 1; }
@@ -709,8 +752,8 @@ __device__ float vf_mad_of(const VfRead &R, VfScratch &S, int q) {
         lo = pv; hi = R.kmax + 1;
         while (lo < hi) { const int m = (lo + hi) >> 1; if (vf_dev(R, m, med) > d0) hi = m; else lo = m + 1; }
         const int r = lo - 1;  // == pv - 1 if no right code deviates <= d0
-        const int up = vf_neighbour(R, S, tr.a, tr.b, r, true);
-        const int dn = vf_neighbour(R, S, tr.a, tr.b, l, false);
+        const int up = vf_neighbour(R, S, t.a, t.b, r, true);
+        const int dn = vf_neighbour(R, S, t.a, t.b, l, false);
         d1 = CUDART_INF_F;
         if (up >= 0) d1 = fminf(d1, vf_dev(R, up, med));
         if (dn >= 0) d1 = fminf(d1, vf_dev(R, dn, med));

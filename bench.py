@@ -123,7 +123,7 @@ def main():
     ap.add_argument("--reads", type=int, default=100000, help="reads per GPU")
     ap.add_argument("--chemistry", default="rna002")
     ap.add_argument("--minibatch", type=int, default=1000)
-    ap.add_argument("--chunk-batches", type=int, default=8, help="minibatches per H2D chunk of the pipelined ingest")
+    ap.add_argument("--chunk-batches", type=int, default=16, help="minibatches per H2D chunk of the pipelined ingest")
     ap.add_argument("--cpu-reads-per-worker", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -140,6 +140,9 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
+        from adapted_b200.config import flatten_config as _fc, get_chemistry_specific_config as _gc
+
+        config["preload_window"] = _fc(_gc(args.chemistry))["sig_preload_size"]
         rpw = args.cpu_reads_per_worker or 128
         rps, sps, sec_per_step, reads_step = cpu_arm(args.chemistry, args.steps, args.warmup, rpw, cores)
         line = {"impl": "reference", "metric": METRIC, "value": rps, "unit": "reads/s", "n_gpus": args.gpus,
