@@ -12,7 +12,8 @@ from typing import Any, Dict
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "csrc", "libadapted_b200.so")
+# ADB_LIB_PATH: load another build of the same library (A/B runs of kernel variants)
+SO_PATH = os.environ.get("ADB_LIB_PATH") or os.path.join(HERE, "csrc", "libadapted_b200.so")
 
 ADB_MAX_CAND = 16
 ADB_MAX_OPEN_PORES = 20

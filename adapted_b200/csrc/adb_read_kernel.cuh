@@ -22,7 +22,7 @@
 #include "adb_validate.cuh"
 #include "adb_vfast.cuh"
 
-#define ADB_TRACE_THREADS 32   // one warp per read: every phase of the LLR primary path is at most warp-wide
+#define ADB_TRACE_THREADS 128   // one warp per read: every phase of the LLR primary path is at most warp-wide
 #define ADB_VAL_THREADS 256
 
 // float32 mean of one downscale block in numpy's pairwise order.  f(k) = k-th sample of the block.
@@ -147,7 +147,7 @@ struct PrimaryArgs {
     int *batch_status;
 };
 
-__global__ void __launch_bounds__(ADB_TRACE_THREADS) llr_primary_kernel(PrimaryArgs A, adb_config cfg) {
+__global__ void __launch_bounds__(ADB_TRACE_THREADS, 7) llr_primary_kernel(PrimaryArgs A, adb_config cfg) {
     extern __shared__ __align__(16) unsigned char smem[];
     const TraceScratch T = trace_scratch_from(smem, A.nds_max, A.peak_cap);
     float *ds = (float *)T.trace;
@@ -159,6 +159,17 @@ __global__ void __launch_bounds__(ADB_TRACE_THREADS) llr_primary_kernel(PrimaryA
         const GselState gs = A.gstates[mb];
         if (gs.status != ADB_OK) continue;  // minibatch lost (host raises)
         const ReadSrc src = make_src(A.B, r);
+        // pull the trace window of the NEXT read of this warp into L2 while this one is processed (one warp per read
+        // at low occupancy: the loads of the downscale step would otherwise wait on HBM)
+        if (r + (int)gridDim.x < A.B.n_reads && A.B.sig_type == ADB_SIG_I16) {
+            const int rn = r + gridDim.x;
+            const int64_t o0 = A.B.offsets[rn], o1 = A.B.offsets[rn + 1];
+            const int nn = (int)min((int64_t)Tm, o1 - o0);
+            const char *p = (const char *)((const int16_t *)A.B.signal + o0 + A0);
+            const int bytes = max(nn - A0, 0) * 2;
+            for (int b = threadIdx.x * 128; b < bytes; b += blockDim.x * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p + b));
+        }
         // number of non-NaN downscaled bins (combined.py:133-154)
         int nds;
         {
