@@ -264,7 +264,7 @@ __global__ void merge_status_kernel(const GselState *states, int *batch_status, 
 // ---- the detect entry point (device pointers) -----------------------------------------------------------------
 static int trace_dims(const adb_config &cfg, int span, int *nds_max, int *peak_cap) {
     *nds_max = std::max(64, (std::max(span, 0) + cfg.downscale_factor - 1) / cfg.downscale_factor + 2);
-    *peak_cap = *nds_max / 2 + 8;
+    *peak_cap = *nds_max / 2 + 24;  // >= 16 slots per 32-position chunk of cta_peaks_prepare
     return 0;
 }
 

@@ -149,82 +149,49 @@ __device__ int warp_plateau_fix(const double *g, int n, int peak) {
     return plateau_end > 0 ? peak + plateau_end : peak;
 }
 
-// correct_for_split_peak (llr.py:180-201), warp-wide.
-__device__ int warp_split_fix(const double *g, int n, int peak, const PeakScratch &PS) {
-    TraceView W;
-    W.x = g + peak;
-    W.n = min(peak + 500, n) - peak;
-    W.nan2num = 0;
-    int out[2];
-    int k = warp_find_first_peaks(W, 0, 1.0, 10.0, 0.5, 1, out, PS);
-    if (k > 0 && g[out[0] + peak] >= __dmul_rn(0.9, g[peak])) return out[0] + peak;
-    return peak;
-}
-
-// adapter_end_from_trace (llr.py:204-259) -> cands[0] or -1 if there is no candidate.  Warp-wide
-// (support [start, end) and the nanstd threshold are computed by the caller).
-__device__ int warp_adapter_end(const double *g, int n, int start, int end, double pmin, double wmin,
-                                double rel_height, const PeakScratch &PS) {
+// adapter_end_from_trace (llr.py:204-259) -> cands[0] or -1 if there is no candidate: first peak of
+// find_peaks(width, prominence, rel_height) on the support [start, end) of the trace, moved by correct_for_plateau
+// (llr.py:145-177) and correct_for_split_peak (llr.py:180-201).  The candidate preparation of the two peak searches
+// runs on every warp of the CTA, the selection walks on warp 0.  CTA-wide; `itmp` = 2 ints of shared memory.
+__device__ int cta_adapter_end(const double *g, int n, int start, int end, double pmin, double wmin, double rel_height,
+                               const PeakScratch &PS, int *itmp) {
     TraceView W;
     W.x = g + start;
     W.n = end - start;
     W.nan2num = 0;
-    int out[2];
-    int k = warp_find_first_peaks(W, 0, pmin, wmin, rel_height, 1, out, PS);
-    if (k == 0) return -1;
-    int peak = out[0] + start;
-    peak = warp_plateau_fix(g, n, peak);
-    peak = warp_split_fix(g, n, peak, PS);
+    const int npk = cta_peaks_prepare(W, pmin, wmin, rel_height, PS, &itmp[0]);
+    if (threadIdx.x < 32) {
+        int out[2];
+        int peak = -1;
+        if (warp_peaks_select(W, npk, 0, pmin, wmin, rel_height, 1, out, PS) > 0) peak = warp_plateau_fix(g, n, out[0] + start);
+        if (threadIdx.x == 0) itmp[1] = peak;
+    }
+    __syncthreads();
+    int peak = itmp[1];
+    if (peak < 0) return -1;
+    // split-peak correction: first peak of find_peaks(trace[peak : peak + 500], width=10, prominence=1.0)
+    TraceView W2;
+    W2.x = g + peak;
+    W2.n = min(peak + 500, n) - peak;
+    W2.nan2num = 0;
+    const int npk2 = cta_peaks_prepare(W2, 1.0, 10.0, 0.5, PS, &itmp[0]);
+    if (threadIdx.x < 32) {
+        int out[2];
+        int res = peak;
+        if (warp_peaks_select(W2, npk2, 0, 1.0, 10.0, 0.5, 1, out, PS) > 0 && g[out[0] + peak] >= __dmul_rn(0.9, g[peak]))
+            res = out[0] + peak;
+        if (threadIdx.x == 0) itmp[1] = res;
+    }
+    __syncthreads();
+    peak = itmp[1];
+    __syncthreads();
     return peak;
 }
 
-// detect_full_polya_trace_peak_with_spike (llr.py:406-479) on the full-length trace g[0..n).  Warp-wide.
-// Returns the downscaled index (0 = none).
-__device__ int warp_polya_end(double *g, int n, const PeakScratch &PS) {
+// the two-peak rule of detect_full_polya_trace_peak_with_spike (llr.py:452-477) given the first k (<= 2) peaks of the
+// poly(A) trace g (raw values, not nan_to_num).  Warp-wide.  Returns the downscaled index (0 = none).
+__device__ int warp_polya_spike(const double *g, int k, const int pk[2]) {
     const int lane = threadIdx.x & 31;
-    TraceView W;
-    W.x = g;
-    W.n = n;
-    // np.nan_to_num(trace, nan=0) (llr.py:445): non-finite gains are rare (a one-sample head segment has variance
-    // "zero" up to rounding, so its log is -inf or NaN).  Up to four of them are replaced in place for the peak
-    // search and restored afterwards, so that the search reads plain doubles; more than four keep the trace as it
-    // is and convert on every access.
-    int nf_idx[4] = {-1, -1, -1, -1};
-    double nf_val[4] = {0, 0, 0, 0};
-    int nnf = 0;
-    for (int base = 0; base < n; base += 32) {
-        const int i = base + lane;
-        const double v = (i < n) ? g[i] : 0.0;
-        unsigned m = __ballot_sync(ADB_FULL, !(fabs(v) <= DBL_MAX));
-        while (m) {
-            const int l = __ffs(m) - 1;
-            m &= m - 1;
-            const double bv = __shfl_sync(ADB_FULL, v, l);
-#pragma unroll
-            for (int q = 0; q < 4; q++) if (nnf == q) { nf_idx[q] = base + l; nf_val[q] = bv; }
-            nnf++;
-        }
-    }
-    const bool patched = nnf <= 4;
-    if (patched) {
-        if (lane == 0) {
-#pragma unroll
-            for (int q = 0; q < 4; q++)
-                if (q < nnf) { const double v = nf_val[q]; g[nf_idx[q]] = (v != v) ? 0.0 : (v > 0 ? DBL_MAX : -DBL_MAX); }
-        }
-        __syncwarp();
-    }
-    W.nan2num = patched ? 0 : 1;
-    int pk[2];
-    int k = warp_find_first_peaks(W, 10, 1.0, 10.0, 0.5, 2, pk, PS);
-    if (patched && nnf > 0) {
-        __syncwarp();
-        if (lane == 0) {
-#pragma unroll
-            for (int q = 0; q < 4; q++) if (q < nnf) g[nf_idx[q]] = nf_val[q];
-        }
-        __syncwarp();
-    }
     if (k == 0) return 0;
     if (k == 1) return pk[0];
     const double h0 = g[pk[0]], h1 = g[pk[1]];  // raw trace, not nan_to_num (llr.py:459)
@@ -266,4 +233,65 @@ __device__ int warp_polya_end(double *g, int n, const PeakScratch &PS) {
         if (r > 1.0) r = 1.0; else if (r < -1.0) r = -1.0;
     }
     return (r * r >= 0.99) ? pk[1] : 0;
+}
+
+// detect_full_polya_trace_peak_with_spike (llr.py:406-479) on the full-length trace g[0..n).  CTA-wide (candidate
+// preparation on every warp, selection and the two-peak rule on warp 0); `itmp` = 2 ints of shared memory.  Returns
+// the downscaled index (0 = none) to every thread.
+__device__ int cta_polya_end(double *g, int n, const PeakScratch &PS, int *itmp) {
+    const int lane = threadIdx.x & 31;
+    // np.nan_to_num(trace, nan=0) (llr.py:445): non-finite gains are rare (a one-sample head segment has variance
+    // "zero" up to rounding, so its log is -inf or NaN).  Up to four of them are replaced in place for the peak
+    // search and restored afterwards, so that the search reads plain doubles; more than four keep the trace as it
+    // is and convert on every access.  Warp 0 owns the side list.
+    int nf_idx[4] = {-1, -1, -1, -1};
+    double nf_val[4] = {0, 0, 0, 0};
+    int nnf = 0;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            const double v = (i < n) ? g[i] : 0.0;
+            unsigned m = __ballot_sync(ADB_FULL, !(fabs(v) <= DBL_MAX));
+            while (m) {
+                const int l = __ffs(m) - 1;
+                m &= m - 1;
+                const double bv = __shfl_sync(ADB_FULL, v, l);
+#pragma unroll
+                for (int q = 0; q < 4; q++) if (nnf == q) { nf_idx[q] = base + l; nf_val[q] = bv; }
+                nnf++;
+            }
+        }
+        if (nnf <= 4 && lane == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (q < nnf) { const double v = nf_val[q]; g[nf_idx[q]] = (v != v) ? 0.0 : (v > 0 ? DBL_MAX : -DBL_MAX); }
+        }
+        if (threadIdx.x == 0) itmp[1] = (nnf <= 4) ? 1 : 0;
+    }
+    __syncthreads();
+    const bool patched = itmp[1] != 0;
+    TraceView W;
+    W.x = g;
+    W.n = n;
+    W.nan2num = patched ? 0 : 1;
+    const int npk = cta_peaks_prepare(W, 1.0, 10.0, 0.5, PS, &itmp[0]);
+    if (threadIdx.x < 32) {
+        int pk[2] = {0, 0};
+        const int k = warp_peaks_select(W, npk, 10, 1.0, 10.0, 0.5, 2, pk, PS);
+        if (patched && nnf > 0) {
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) if (q < nnf) g[nf_idx[q]] = nf_val[q];
+            }
+            __syncwarp();
+        }
+        const int res = warp_polya_spike(g, k, pk);
+        if (lane == 0) itmp[1] = res;
+    }
+    __syncthreads();
+    const int res = itmp[1];
+    __syncthreads();
+    return res;
 }

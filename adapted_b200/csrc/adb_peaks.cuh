@@ -263,17 +263,10 @@ struct PeakScratch {
     int cap;
 };
 
-__device__ int warp_find_first_peaks(const TraceView &V, int dist, double pmin, double wmin, double rel_height,
-                                     int want, int *out, const PeakScratch &S) {
+// phase 3: the first `want` peaks among the prepared candidates (S.pk[0..npk), S.flags).  Warp-wide.
+__device__ int warp_peaks_select(const TraceView &V, int npk, int dist, double pmin, double wmin, double rel_height,
+                                 int want, int *out, const PeakScratch &S) {
     const int lane = threadIdx.x & 31;
-    if (V.n < 3) return 0;
-    const int npk = warp_local_maxima(V, S.pk, S.cap);
-    __syncwarp();
-    for (int j = lane; j < npk; j += 32) {
-        S.flags[j] = lane_quick_reject(V, S.pk[j], pmin, wmin, rel_height, 12) ? 0 : 1;
-        S.status[j] = 0;
-    }
-    __syncwarp();
     int found = 0;
     for (int base = 0; base < npk && found < want; base += 32) {
         int j = base + lane;
@@ -296,4 +289,72 @@ __device__ int warp_find_first_peaks(const TraceView &V, int dist, double pmin, 
         }
     }
     return found;
+}
+
+__device__ int warp_find_first_peaks(const TraceView &V, int dist, double pmin, double wmin, double rel_height,
+                                     int want, int *out, const PeakScratch &S) {
+    const int lane = threadIdx.x & 31;
+    if (V.n < 3) return 0;
+    const int npk = warp_local_maxima(V, S.pk, S.cap);
+    __syncwarp();
+    for (int j = lane; j < npk; j += 32) {
+        S.flags[j] = lane_quick_reject(V, S.pk[j], pmin, wmin, rel_height, 12) ? 0 : 1;
+        S.status[j] = 0;
+    }
+    __syncwarp();
+    return warp_peaks_select(V, npk, dist, pmin, wmin, rel_height, want, out, S);
+}
+
+// phases 1 + 2 with every warp of the CTA: local maxima chunk by chunk (32 positions per chunk, warps take chunks
+// round robin; the at most 16 maxima of a chunk go to a fixed slot of `stack`, the counts to `status`), compaction in
+// position order into S.pk, quick classification one thread per maximum.  `tmp` = one int of shared memory.
+// CTA-wide; returns the number of maxima (uniform).  The view must not exceed (cap / 16 - 1) * 32 positions.
+__device__ int cta_peaks_prepare(const TraceView &V, double pmin, double wmin, double rel_height, const PeakScratch &S,
+                                 int *tmp) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (V.n < 3) return 0;
+    const int imax = V.n - 1;
+    const int nch = (imax - 1 + 31) >> 5;  // positions 1 .. imax - 1
+    for (int ch = warp; ch < nch; ch += nw) {
+        const int i = 1 + (ch << 5) + lane;
+        int mid = -1;
+        if (i < imax) {
+            const double xi = V.at(i);
+            if (V.at(i - 1) < xi) {
+                int ia = i + 1;
+                while (ia < imax && V.at(ia) == xi) ia++;
+                if (V.at(ia) < xi) mid = (i + ia - 1) / 2;
+            }
+        }
+        const unsigned m = __ballot_sync(ADB_FULL, mid >= 0);
+        if (mid >= 0) S.stack[(ch << 4) + __popc(m & ((1u << lane) - 1u))] = (unsigned short)mid;
+        if (lane == 0) S.status[ch] = (unsigned char)__popc(m);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int total = 0;
+        for (int base = 0; base < nch; base += 32) {
+            const int ch = base + lane;
+            const int cnt = (ch < nch) ? S.status[ch] : 0;
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(ADB_FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int off = total + incl - cnt;
+            for (int k = 0; k < cnt; k++) if (off + k < S.cap) S.pk[off + k] = S.stack[(ch << 4) + k];
+            total += __shfl_sync(ADB_FULL, incl, 31);
+        }
+        if (lane == 0) *tmp = min(total, S.cap);
+    }
+    __syncthreads();
+    const int npk = *tmp;
+    for (int j = threadIdx.x; j < npk; j += blockDim.x) {
+        S.flags[j] = lane_quick_reject(V, S.pk[j], pmin, wmin, rel_height, 12) ? 0 : 1;
+        S.status[j] = 0;
+    }
+    __syncthreads();
+    return npk;
 }

@@ -108,13 +108,7 @@ __device__ void llr_boundaries_cta(const float *ds, int nds, const TraceScratch 
         __syncthreads();
         const double pmin = __dmul_rn(cfg.adapter_peak_prominence, T.dtmp[0]);
         const double wmin = (double)(cfg.adapter_peak_width / cfg.downscale_factor);
-        if (threadIdx.x < 32) {
-            int r = warp_adapter_end(trace, nds, s0, e0, pmin, wmin, cfg.adapter_peak_rel_height, T.PS);
-            if (threadIdx.x == 0) T.itmp[4] = r;
-        }
-        __syncthreads();
-        ae_ds = T.itmp[4];
-        __syncthreads();
+        ae_ds = cta_adapter_end(trace, nds, s0, e0, pmin, wmin, cfg.adapter_peak_rel_height, T.PS, T.itmp + 4);
         if (ae_ds < 0) return;
         // poly(A) trace: start = adapter_end, head 1, tail 1, same prefix sums (combined.py:189-204)
         cta_llr_gains(c, c2, nds, ae_ds, nds - 1, 1, 1, 1, trace);
@@ -122,13 +116,7 @@ __device__ void llr_boundaries_cta(const float *ds, int nds, const TraceScratch 
         // hail-mary variant: a single trace (head 5, tail 5) feeds the spike rule directly (combined.py:277-292)
         cta_llr_gains(c, c2, nds, 0, nds - 1, 5, 5, 1, trace);
     }
-    if (threadIdx.x < 32) {
-        int r = warp_polya_end(trace, nds, T.PS);
-        if (threadIdx.x == 0) T.itmp[5] = r;
-    }
-    __syncthreads();
-    pe_ds = T.itmp[5];
-    __syncthreads();
+    pe_ds = cta_polya_end(trace, nds, T.PS, T.itmp + 4);
 }
 
 // normalised, clipped sample j of the read (normalize.py:25-28,61-63), float32 steps
