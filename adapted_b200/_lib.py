@@ -114,6 +114,8 @@ def load() -> C.CDLL:
     L.adb_ctx_set_timing.argtypes = [vp, ip]
     L.adb_ctx_get_timing.argtypes = [vp, vp]
     L.adb_llr_trace_host.argtypes = [vp, vp, vp, C.c_int32, vp, vp, vp, vp]
+    L.adb_llr_detect_host.argtypes = [vp, vp, vp, C.c_int32, vp, vp]
+    L.adb_llr_detect_host.restype = ip
     L.adb_global_med_mad_host.argtypes = [vp, C.POINTER(AdbBatch), C.c_int32, vp]
     L.adb_downscale_host.argtypes = [vp, C.POINTER(AdbBatch), C.c_int32, C.c_int32, vp]
     L.adb_cnn_scores_host.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, vp]

@@ -18,6 +18,7 @@
 #include "adb_read_kernel.cuh"
 #include "adb_cnn.cuh"
 #include "adb_start_peak.cuh"
+#include "adb_legacy.cuh"
 
 extern "C" int adb_abi_version(void) { return ADB_ABI_VERSION; }
 extern "C" const char *adb_last_error(void) { return adb_err_string().c_str(); }
@@ -689,6 +690,36 @@ extern "C" int adb_llr_trace_host(adb_ctx *ctx, const double *signals, const int
     CUDA_TRY(cudaMemcpyAsync(gains, dg.p, total * 8, cudaMemcpyDeviceToHost, st));
     if (c) CUDA_TRY(cudaMemcpyAsync(c, dc.p, total * 8, cudaMemcpyDeviceToHost, st));
     if (c2) CUDA_TRY(cudaMemcpyAsync(c2, dc2.p, total * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return ADB_OK;
+}
+
+// ---- legacy three-split detectors -----------------------------------------------------------------------------------
+extern "C" int adb_llr_detect_host(adb_ctx *ctx, const double *signals, const int64_t *sig_offsets, int32_t n_signals,
+                                   const int64_t *params, int64_t *out) {
+    if (!ctx || !signals || !sig_offsets || !params || !out || n_signals < 0) { set_err("null argument"); return ADB_ERR_ARG; }
+    if (n_signals == 0) return ADB_OK;
+    for (int t = 0; t < n_signals; t++)
+        if (params[3 * (size_t)t] < 0 || params[3 * (size_t)t + 1] < 0) { set_err("negative min_obs_adapter / border_trim"); return ADB_ERR_ARG; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t total = (size_t)sig_offsets[n_signals];
+    DevBuf &dx = ctx->h_signal, &dc = ctx->h_misc2, &dc2 = ctx->h_misc3, &doff = ctx->h_offsets, &dp = ctx->h_misc, &dout = ctx->h_records;
+    if (dx.ensure(total * 8 + 8) || dc.ensure(total * 8 + 8) || dc2.ensure(total * 8 + 8) ||
+        doff.ensure(sizeof(int64_t) * ((size_t)n_signals + 1)) || dp.ensure(sizeof(int64_t) * 3 * (size_t)n_signals) ||
+        dout.ensure(sizeof(int64_t) * 4 * (size_t)n_signals)) {
+        set_err("cudaMalloc llr detect buffers");
+        return ADB_ERR_CUDA;
+    }
+    CUDA_TRY(cudaMemcpyAsync(dx.p, signals, total * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(doff.p, sig_offsets, sizeof(int64_t) * ((size_t)n_signals + 1), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dp.p, params, sizeof(int64_t) * 3 * (size_t)n_signals, cudaMemcpyHostToDevice, st));
+    llr_legacy_detect_kernel<<<n_signals, ADB_LEGACY_THREADS, 0, st>>>((const double *)dx.p, (const int64_t *)doff.p,
+                                                                       (const int64_t *)dp.p, (double *)dc.p, (double *)dc2.p,
+                                                                       (int64_t *)dout.p);
+    ctx->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, dout.p, sizeof(int64_t) * 4 * (size_t)n_signals, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return ADB_OK;
 }

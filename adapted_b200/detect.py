@@ -192,6 +192,64 @@ def c_llr_trace_batch(signals, params, return_c_c2: bool = False, device: int = 
     return out
 
 
+def c_llr_detect_batch(signals, min_obs_adapter, border_trim, min_obs_polya=None, device: int = 0) -> np.ndarray:
+    """The legacy three-split detectors for many signals: int64 [n, 4] = adapter_start, adapter_end, polya_end and
+    the length of the tuple the reference function returns (see include/adapted_b200.h)."""
+    sigs = [np.ascontiguousarray(s, dtype=np.float64) for s in signals]
+    n = len(sigs)
+    offs = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum([s.size for s in sigs], out=offs[1:])
+    blob = np.concatenate(sigs) if sigs else np.zeros(0)
+    p = np.empty((n, 3), dtype=np.int64)
+    p[:, 0], p[:, 1] = min_obs_adapter, border_trim
+    p[:, 2] = -1 if min_obs_polya is None else min_obs_polya
+    out = np.zeros((n, 4), dtype=np.int64)
+    ctx = _lib.default_context(device)
+    _lib.check(_lib.load().adb_llr_detect_host(ctx.handle, blob.ctypes.data, offs.ctypes.data, n, p.ctypes.data,
+                                               out.ctypes.data))
+    return out
+
+
+def c_llr_detect_adapter(raw_signal, min_obs_adapter, border_trim, device: int = 0):
+    """_c_llr.pyx:239-288 on the GPU -> (adapter_start, adapter_end)"""
+    r = c_llr_detect_batch([raw_signal], min_obs_adapter, border_trim, None, device)[0]
+    return int(r[0]), int(r[1])
+
+
+def c_llr_detect_adapter_polya(raw_signal, min_obs_adapter, border_trim, min_obs_polya, device: int = 0):
+    """_c_llr.pyx:290-363 on the GPU -> (adapter_start, adapter_end, polya_end), or (0, 0) for an empty signal"""
+    r = c_llr_detect_batch([raw_signal], min_obs_adapter, border_trim, min_obs_polya, device)[0]
+    return (0, 0) if r[3] == 2 else (int(r[0]), int(r[1]), int(r[2]))
+
+
+def c_llr_boundary_traces(raw_signal, min_obs_adapter, border_trim, device: int = 0):
+    """c_llr_detect_adapter_trace / c_llr_boundary_traces (_c_llr.pyx:368-388, 415-434): the gains of the three
+    splits; the traces come from the GPU gain kernel, the arg-max between them from numpy like in the reference."""
+    return _legacy_traces(raw_signal, min_obs_adapter, border_trim, None, device)
+
+
+c_llr_detect_adapter_trace = c_llr_boundary_traces
+
+
+def c_llr_detect_adapter_polya_trace(raw_signal, min_obs_adapter, border_trim, min_obs_polya, device: int = 0):
+    """_c_llr.pyx:390-413"""
+    return _legacy_traces(raw_signal, min_obs_adapter, border_trim, min_obs_polya, device)
+
+
+def _legacy_traces(raw_signal, moa, bt, mop, device):
+    x = np.ascontiguousarray(raw_signal, dtype=np.float64)
+    length = x.size - 1
+    g_first = c_llr_trace(x, 0, length, moa + bt, bt, device=device)
+    x_first = int(np.argmax(g_first))
+    g_head, g_tail = c_llr_trace_batch([x, x], [(0, x_first, bt, moa, 1, 0, 0, 0, 0, 0, 0),
+                                                (x_first, length, moa, bt, 1, 0, 0, 0, 0, 0, 0)], device=device)
+    if mop is None:
+        return g_first, g_head, g_tail
+    x_last = int(np.argmax(g_tail))
+    g_polya = c_llr_trace(x, x_last, length, mop, bt, device=device)
+    return g_first, g_head, g_tail, g_polya
+
+
 def cnn_scores(x: np.ndarray, model: Any, device: int = 0) -> np.ndarray:
     """BoundariesCNN forward (adapted/detect/cnn.py:16-52,85-98) on prepared inputs x[n, L] -> scores[n, 2, L_out]."""
     x = np.ascontiguousarray(x, dtype=np.float32)

@@ -208,6 +208,18 @@ int adb_ctx_get_timing(adb_ctx *ctx, double *out);
 int adb_llr_trace_host(adb_ctx *ctx, const double *signals, const int64_t *sig_offsets, int32_t n_traces,
                        const int64_t *params, double *gains, double *c, double *c2);
 
+/*
+ * Drop-in for the legacy three-split detectors (no caller inside the reference; library-level operators)
+ *   c_llr_detect_adapter(raw_signal, min_obs_adapter, border_trim)                      adapted/detect/_c_llr.pyx:239-288
+ *   c_llr_detect_adapter_polya(raw_signal, min_obs_adapter, border_trim, min_obs_polya) adapted/detect/_c_llr.pyx:290-363
+ * (both on _best_split, _c_llr.pyx:40-64) for `n_signals` float64 signals at once (HOST buffers, offsets as above).
+ * params[i*3 .. i*3+3) = min_obs_adapter, border_trim, min_obs_polya (< 0: adapter only, polya_end stays 0).
+ * out[i*4 .. i*4+4) = adapter_start, adapter_end, polya_end, length of the tuple the reference returns (2: the
+ * "empty signal" early return of either function, else 3).
+ */
+int adb_llr_detect_host(adb_ctx *ctx, const double *signals, const int64_t *sig_offsets, int32_t n_signals,
+                        const int64_t *params, int64_t *out);
+
 /* Minibatch-global median / MAD of normalize_signal (adapted/detect/normalize.py:15-22,54), HOST buffers. */
 int adb_global_med_mad_host(adb_ctx *ctx, const adb_batch *batch, int32_t max_obs_trace, float *med_mad /*[n_batches*2]*/);
 

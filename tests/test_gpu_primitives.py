@@ -177,3 +177,37 @@ def test_downscale_bit_exact(factor, col0):
     want = detect_ref.mean_pool(x[:, col0:], factor)
     assert got.shape == want.shape
     assert np.array_equal(got, want, equal_nan=True)
+
+
+def _four_level(rng, n):
+    k = sorted(rng.integers(5, n - 5, size=3))
+    lv, sd = rng.normal(0, 1.5, size=4), rng.uniform(0.2, 1.5, size=4)
+    parts = [k[0], k[1] - k[0], k[2] - k[1], n - k[2]]
+    x = np.concatenate([rng.normal(lv[i], sd[i], m) for i, m in enumerate(parts)])
+    return x.astype(np.float32).astype(np.float64)
+
+
+def test_legacy_three_split_detectors_match_oracle():
+    """c_llr_detect_adapter / c_llr_detect_adapter_polya (_c_llr.pyx:239-363, the arg-max-of-LLR detectors) on the
+    GPU against the oracle (itself pinned bit for bit against the reference's compiled kernel)"""
+    from adapted_b200.detect import (c_llr_detect_adapter, c_llr_detect_adapter_polya, c_llr_detect_adapter_polya_trace,
+                                     c_llr_detect_batch)
+
+    rng = np.random.default_rng(41)
+    sigs = [_four_level(rng, int(rng.integers(40, 1700))) for _ in range(120)]
+    sigs.append(_four_level(rng, 30))       # too short for any split
+    sigs.append(np.round(_four_level(rng, 600)))  # heavy ties in the medians
+    for moa, bt, mop in ((20, 5, 10), (8, 2, 4), (50, 1, 30)):
+        got = c_llr_detect_batch(sigs, moa, bt, mop)
+        got2 = c_llr_detect_batch(sigs, moa, bt, None)
+        for x, g, g2 in zip(sigs, got, got2):
+            want = detect_ref.llr_detect_adapter_polya(x, moa, bt, mop)
+            have = (0, 0) if g[3] == 2 else (int(g[0]), int(g[1]), int(g[2]))
+            assert have == want, (x.size, moa, bt, mop)
+            assert (int(g2[0]), int(g2[1])) == detect_ref.llr_detect_adapter(x, moa, bt)
+    x = sigs[3]
+    assert c_llr_detect_adapter(x, 20, 5) == detect_ref.llr_detect_adapter(x, 20, 5)
+    assert c_llr_detect_adapter_polya(x, 20, 5, 10) == detect_ref.llr_detect_adapter_polya(x, 20, 5, 10)
+    for g, w in zip(c_llr_detect_adapter_polya_trace(x, 20, 5, 10), detect_ref.llr_boundary_traces(x, 20, 5, 10)):
+        assert np.array_equal(g == 0, w == 0)
+        assert np.allclose(g, w, rtol=0, atol=1e-8, equal_nan=True)

@@ -80,3 +80,34 @@ def test_pairwise_sum_matches_numpy():
         a = rng.normal(size=n) * 10 ** rng.uniform(-3, 3, size=n)
         got = lib().adb_oracle_pairwise_sum_f64(a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), n)
         assert got == (np.add.reduce(a) if n else 0.0)
+
+
+def _four_level(rng, n):
+    k = sorted(rng.integers(5, n - 5, size=3))
+    lv, sd = rng.normal(0, 1.5, size=4), rng.uniform(0.2, 1.5, size=4)
+    parts = [k[0], k[1] - k[0], k[2] - k[1], n - k[2]]
+    x = np.concatenate([rng.normal(lv[i], sd[i], m) for i, m in enumerate(parts)])
+    return x.astype(np.float32).astype(np.float64)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_legacy_three_split_detectors_match_reference_kernel(seed):
+    """_best_split / c_llr_detect_adapter[_polya] / the *_trace variants (_c_llr.pyx:40-64, 239-434): the oracle's
+    restatement against the reference's compiled Cython module, tuples and traces bit for bit"""
+    ref = _load_ref()
+    rng = np.random.default_rng(300 + seed)
+    for _ in range(40):
+        n = int(rng.integers(40, 1500))
+        x = _four_level(rng, n)
+        moa, bt, mop = int(rng.integers(3, 40)), int(rng.integers(1, 8)), int(rng.integers(2, 20))
+        assert tuple(int(v) for v in ref.c_llr_detect_adapter(x, moa, bt)) == detect_ref.llr_detect_adapter(x, moa, bt)
+        assert tuple(int(v) for v in ref.c_llr_detect_adapter_polya(x, moa, bt, mop)) == \
+            detect_ref.llr_detect_adapter_polya(x, moa, bt, mop)
+        for got, want in zip(detect_ref.llr_boundary_traces(x, moa, bt, mop), ref.c_llr_detect_adapter_polya_trace(x, moa, bt, mop)):
+            assert np.array_equal(got, want, equal_nan=True)
+        for got, want in zip(detect_ref.llr_boundary_traces(x, moa, bt), ref.c_llr_boundary_traces(x, moa, bt)):
+            assert np.array_equal(got, want, equal_nan=True)
+    # degenerate inputs: too short for any split -> (0, 0) from both functions
+    x = _four_level(rng, 30)
+    assert tuple(int(v) for v in ref.c_llr_detect_adapter(x, 40, 5)) == detect_ref.llr_detect_adapter(x, 40, 5) == (0, 0)
+    assert tuple(int(v) for v in ref.c_llr_detect_adapter_polya(x, 40, 5, 3)) == detect_ref.llr_detect_adapter_polya(x, 40, 5, 3)
