@@ -410,6 +410,13 @@ static int launch_validate(adb_ctx *ctx, const BatchDev &B, const adb_config &cf
     return ADB_OK;
 }
 
+// minibatches processed by one set of launches: bounds the scratch arena (moving-statistics pools, tallies, CNN
+// activations) for calls of any size; larger calls are cut at minibatch boundaries, which never changes a record
+#define ADB_MAX_BATCHES_PER_PASS 256
+
+static int detect_dev_pass(adb_ctx *ctx, const adb_batch *batch, const adb_config *cfg, const float *cnn_weights,
+                           adb_record *out_records, int32_t *batch_status, cudaStream_t st);
+
 extern "C" int adb_detect_dev(adb_ctx *ctx, const adb_batch *batch, const adb_config *cfg, const float *cnn_weights,
                               adb_record *out_records, int32_t *batch_status, void *cuda_stream) {
     if (!ctx || !out_records) { set_err("null argument"); return ADB_ERR_ARG; }
@@ -420,6 +427,29 @@ extern "C" int adb_detect_dev(adb_ctx *ctx, const adb_batch *batch, const adb_co
     CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
     if (batch->n_reads == 0) return ADB_OK;
+    const int n_batches = (batch->n_reads + batch->batch_size - 1) / batch->batch_size;
+    for (int b0 = 0; b0 < n_batches; b0 += ADB_MAX_BATCHES_PER_PASS) {
+        const int r0 = b0 * batch->batch_size;
+        const int r1 = (int)std::min<long long>((long long)(b0 + ADB_MAX_BATCHES_PER_PASS) * batch->batch_size, batch->n_reads);
+        adb_batch sub = *batch;
+        sub.n_reads = r1 - r0;
+        sub.full_lens = batch->full_lens + r0;
+        if (batch->sig_type == ADB_SIG_F32) {
+            sub.signal = (const float *)batch->signal + (size_t)r0 * batch->m;
+        } else {  // offsets stay absolute: the blob pointer does not move
+            sub.offsets = batch->offsets + r0;
+            sub.calib_offset = batch->calib_offset + r0;
+            sub.calib_scale = batch->calib_scale + r0;
+        }
+        rc = detect_dev_pass(ctx, &sub, cfg, cnn_weights, out_records + r0, batch_status ? batch_status + b0 : nullptr, st);
+        if (rc) return rc;
+    }
+    return ADB_OK;
+}
+
+static int detect_dev_pass(adb_ctx *ctx, const adb_batch *batch, const adb_config *cfg, const float *cnn_weights,
+                           adb_record *out_records, int32_t *batch_status, cudaStream_t st) {
+    int rc = ADB_OK;
     const int n_batches = (batch->n_reads + batch->batch_size - 1) / batch->batch_size;
     BatchDev B = to_dev_view(*batch);
     int *status = batch_status;
