@@ -106,6 +106,16 @@ extern "C" int64_t adb_ctx_query(adb_ctx *c, const char *name) {
         for (int v : h) n += (v != 0);
         return n;
     }
+    if (!strcmp(name, "validate_handovers")) {
+        // reads of the last pass that validate_fast_kernel left to validate_kernel
+        if (!c->vf_last_reads || !c->vf_done.p) return 0;
+        std::vector<unsigned char> h(c->vf_last_reads);
+        if (cudaSetDevice(c->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
+            cudaMemcpy(h.data(), c->vf_done.p, h.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        int64_t n = 0;
+        for (unsigned char v : h) n += (v == 0);
+        return n;
+    }
     return -1;
 }
 
@@ -376,6 +386,7 @@ static int launch_validate(adb_ctx *ctx, const BatchDev &B, const adb_config &cf
         A.pre_meta = M.meta;
     }
     A.done = nullptr;
+    ctx->vf_last_reads = 0;
     if (B.sig_type == ADB_SIG_I16 && !ctx->opt_no_fast_validate) {
         // int16 sources: counting-based validation (adb_vfast.cuh); what it leaves is picked up by validate_kernel
         const size_t fsm = vfast_smem_bytes(A.win_bytes);
@@ -398,6 +409,7 @@ static int launch_validate(adb_ctx *ctx, const BatchDev &B, const adb_config &cf
             }
             ctx->launches += 1;
             A.done = F.done;
+            ctx->vf_last_reads = B.n_reads;
         }
     }
     {

@@ -67,6 +67,7 @@ struct adb_ctx {
     DevBuf mvs_perm;           // length-sorted read order of mvs_series_kernel
     DevBuf vf_done;            // per-read flags of validate_fast_kernel
     int opt_no_fast_validate = 0;
+    int vf_last_reads = 0;
     int gsb_last_batches = 0;
     int opt_exact_gsel = 0;  // adb_ctx_set_option("exact_global_select"): always use the multi-pass select
     DevBuf cnn_x, cnn_act0, cnn_act1, cnn_scores, cnn_w, cnn_aux, cnn_post, sp_rows;

@@ -1038,19 +1038,35 @@ __device__ void validate_boundaries_cta(ValCtx &C, const PrimaryBounds &B, int f
             }
             if (!exception && B.n_topk < 0) { exception = true; fail = ADB_FAIL_EXC_TOPK_NONE; }
             if (!exception) {
-                for (int t = 0; t < B.n_topk; t++) {
-                    const int pe = B.topk[t];
-                    if (pe == 0) break;
-                    MvsOut R = mvs_check(C, a_end, pe, mlo, mhi);
-                    for (int i = 0; i < 5; i++) mvs_v[i] = R.v[i];
+                // combined.py:464-566.  `success` is never set back to True, so once the first candidate fails the
+                // reference evaluates EVERY remaining non-zero candidate and ends with: the values of the LAST
+                // candidate, the fail reason of the last candidate that failed, polya_end = the first candidate.
+                // The checks are pure functions of (adapter_end, candidate), so the same final state follows from
+                // candidate 0, then the last candidate, then -- only while those pass -- the ones before it.
+                int n_eval = 0;
+                while (n_eval < B.n_topk && B.topk[n_eval] != 0) n_eval++;
+                auto take_fail = [&](const MvsOut &R) {
+                    if (R.v[0] == 0.0) { fail = ADB_FAIL_MVS_NOT_ENOUGH; fail_mask = 0; }
+                    else { fail = ADB_FAIL_MVS_CHECKS; fail_mask = R.fail_mask; }
+                };
+                if (n_eval > 0) {
+                    const int pe0 = B.topk[0];
+                    const MvsOut R0 = mvs_check(C, a_end, pe0, mlo, mhi);
+                    for (int i = 0; i < 5; i++) mvs_v[i] = R0.v[i];
                     valid |= ADB_V_MVS;
-                    if (R.ok || R.v[0] != 0.0) { polya_med_cache = (float)R.v[2]; polya_mad_cache = R.polya_mad; polya_med_cache_pe = pe; }
-                    if (!R.ok) {
+                    if (R0.ok || R0.v[0] != 0.0) { polya_med_cache = (float)R0.v[2]; polya_mad_cache = R0.polya_mad; polya_med_cache_pe = pe0; }
+                    if (R0.ok) {
+                        pe_best = pe0;
+                    } else {
                         success = false;
-                        if (R.v[0] == 0.0) { fail = ADB_FAIL_MVS_NOT_ENOUGH; fail_mask = 0; }
-                        else { fail = ADB_FAIL_MVS_CHECKS; fail_mask = R.fail_mask; }
+                        take_fail(R0);
+                        bool fail_known = false;  // fail reason of the last failing candidate found?
+                        for (int t = n_eval - 1; t >= 1 && !fail_known; t--) {
+                            const MvsOut R = mvs_check(C, a_end, B.topk[t], mlo, mhi);
+                            if (t == n_eval - 1) for (int i = 0; i < 5; i++) mvs_v[i] = R.v[i];
+                            if (!R.ok) { take_fail(R); fail_known = true; }
+                        }
                     }
-                    if (success) { pe_best = pe; break; }
                 }
             }
         }

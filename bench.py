@@ -27,7 +27,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "reads_per_sec"
-WORKLOAD = "RNA002 rna002_70bps, LLR primary path, synthetic squiggles, minibatches of 1000 reads"
+WORKLOADS = {
+    "rna002": "RNA002 rna002_70bps, LLR primary path, synthetic squiggles, minibatches of 1000 reads",
+    "rna004": "RNA004 rna004_130bps, CNN primary path (+ hail-mary LLR fallback), synthetic squiggles, minibatches of 1000 reads",
+}
 
 
 def _env_int(name, default):
@@ -52,11 +55,22 @@ def _cpu_worker(args):
     spc = get_chemistry_specific_config(chem)
     b = make_reads(n, chem, spc.sig_preload_size, seed=seed)
     x = b.to_dense_pa()
+    weights = _cnn_weights() if spc.primary_method == "cnn" else None
     t0 = time.perf_counter()
-    res = detect_ref.detect_llr2(x, b.full_lens, spc)
+    if weights is not None:
+        res = detect_ref.detect_cnn(x, b.full_lens, weights, spc)
+        res = res if isinstance(res, list) else [res]
+    else:
+        res = detect_ref.detect_llr2(x, b.full_lens, spc)
     dt = time.perf_counter() - t0
     samples = int(np.minimum(b.full_lens, spc.sig_preload_size).sum())
     return n, samples, dt, sum(bool(r["success"]) for r in res)
+
+
+def _cnn_weights():
+    """the shipped model's weights (adapted/models/rna004_130bps@v0.2.4.pth) as committed fixture"""
+    with np.load(os.path.join(ROOT, "tests", "golden", "cnn_weights_rna004_130bps_v0.2.4.npz")) as z:
+        return {k: z[k] for k in z.files}
 
 
 def cpu_arm(chem: str, steps: int, warmup: int, reads_per_worker: int, cores: int):
@@ -132,7 +146,7 @@ def main():
     rank, world = _env_int("RANK", 0), _env_int("WORLD_SIZE", 1)
     local_rank = _env_int("LOCAL_RANK", 0)
     cores = os.cpu_count() or 1
-    config = {"workload": WORKLOAD, "chemistry": args.chemistry, "reads_per_gpu": args.reads,
+    config = {"workload": WORKLOADS.get(args.chemistry.lower(), args.chemistry), "chemistry": args.chemistry, "reads_per_gpu": args.reads,
               "minibatch": args.minibatch, "preload_window": None, "l2": "inputs (>= 5 GB per GPU) exceed the 126 MB L2",
               "parallelism": f"minibatches sharded over {world} GPU(s), no collective"}
 
@@ -188,6 +202,12 @@ def main():
     L = _lib.load()
     ctx = _lib.Context(local_rank)
     cfg = _lib.fill_config(flat)
+    w_host = w_dev = None
+    if flat["primary_method"] == 1:
+        from adapted_b200.detect import flatten_cnn_weights
+
+        w_host = torch.from_numpy(flatten_cnn_weights(_cnn_weights()))
+        w_dev = w_host.to(dev)
     records = torch.zeros(n * 512, dtype=torch.uint8, device=dev)
     n_batches = (n + args.minibatch - 1) // args.minibatch
     status = torch.zeros(n_batches, dtype=torch.int32, device=dev)
@@ -202,8 +222,8 @@ def main():
     assert stream != 0
 
     def step():
-        _lib.check(L.adb_detect_dev(ctx.handle, C.byref(batch), C.byref(cfg), None, records.data_ptr(),
-                                    status.data_ptr(), C.c_void_p(stream)))
+        _lib.check(L.adb_detect_dev(ctx.handle, C.byref(batch), C.byref(cfg), w_dev.data_ptr() if w_dev is not None else None,
+                                    records.data_ptr(), status.data_ptr(), C.c_void_p(stream)))
 
     for _ in range(args.warmup):
         step()
@@ -228,7 +248,8 @@ def main():
     L.adb_ctx_set_timing(ctx.handle, 0)
     n_pass = int(torch.frombuffer(records.cpu().numpy(), dtype=torch.int32).reshape(n, 128)[:, 0].sum().item())
     lost = int((status != 0).sum().item())
-    gsel_fallbacks = ctx.query("global_select_fallbacks")
+    gsel_fallbacks = ctx.query("global_select_fallbacks") if flat["primary_method"] == 0 else 0
+    val_handovers = ctx.query("validate_handovers")
 
     # ---------------- e2e: pinned host -> H2D -> kernels -> D2H ----------------
     host = {k: data[k].cpu().pin_memory() for k in ("adc", "offsets", "full_lens", "calib_offset", "calib_scale")}
@@ -240,7 +261,8 @@ def main():
                            calib_scale=host["calib_scale"].data_ptr())
 
     def e2e_step():
-        _lib.check(L.adb_detect_pipelined_host(ctx.handle, C.byref(hbatch), C.byref(cfg), None, rec_host.data_ptr(),
+        _lib.check(L.adb_detect_pipelined_host(ctx.handle, C.byref(hbatch), C.byref(cfg),
+                                               w_host.data_ptr() if w_host is not None else None, rec_host.data_ptr(),
                                                st_host.data_ptr(), args.chunk_batches))
 
     e2e_steps = max(1, min(args.steps, 3))
@@ -313,7 +335,7 @@ def main():
                         "api": "adb_detect_pipelined_host (pinned host int16 -> H2D -> kernels -> D2H records)"},
                 "gpu_launches": int(tot[2]), "roofline": roofline, "clocks": sampler.summary(),
                 "pass_fraction": float(tot[3]) / tot_reads, "lost_minibatches": int(tot[4]),
-                "global_select_handovers_rank0": int(gsel_fallbacks)}
+                "global_select_handovers_rank0": int(gsel_fallbacks), "validate_handovers_rank0": int(val_handovers)}
         if world == 1 and not args.no_cpu_baseline:
             rpw = args.cpu_reads_per_worker or 256
             rps, sps, sec_step, reads_step = cpu_arm(args.chemistry, 1, 1, rpw, cores)

@@ -142,7 +142,8 @@ int64_t adb_ctx_launch_count(const adb_ctx *ctx);
  * "no_fast_validate" = 1: int16 reads go through the histogram-based validate kernel only (A/B testing). */
 int adb_ctx_set_option(adb_ctx *ctx, const char *name, int value);
 /* Diagnostics of the most recent call (synchronises the device).  "global_select_fallbacks": minibatches the sampled
- * select handed to the exact multi-pass select.  -1: unknown name / error. */
+ * select handed to the exact multi-pass select; "validate_handovers": reads the counting-based validate kernel left
+ * to the histogram-based one (both for the last pass of at most 256 minibatches).  -1: unknown name / error. */
 int64_t adb_ctx_query(adb_ctx *ctx, const char *name);
 
 /* ---- minibatch detection ---------------------------------------------------------------------------- */
