@@ -17,6 +17,7 @@
 #include "adb_llr.cuh"
 #include "adb_read_kernel.cuh"
 #include "adb_cnn.cuh"
+#include "adb_cnn_tc.cuh"
 #include "adb_start_peak.cuh"
 #include "adb_legacy.cuh"
 
@@ -89,6 +90,7 @@ extern "C" int adb_ctx_set_option(adb_ctx *c, const char *name, int value) {
     if (!c || !name) return ADB_ERR_ARG;
     if (!strcmp(name, "exact_global_select")) { c->opt_exact_gsel = value; return ADB_OK; }
     if (!strcmp(name, "no_fast_validate")) { c->opt_no_fast_validate = value; return ADB_OK; }
+    if (!strcmp(name, "cnn_fp32_pipe")) { c->opt_cnn_fp32 = value; return ADB_OK; }
     set_err(std::string("unknown option: ") + name);
     return ADB_ERR_ARG;
 }

@@ -492,6 +492,12 @@ static CnnDims cnn_dims(int m, int A0, int f) {
 }
 
 // x [n][Lx] (device) -> scores [n][2][Lout] (device); chunked over reads to bound the activation buffers
+// tensor-core version of the two 64 -> 64 convolutions (adb_cnn_tc.cuh)
+__global__ void cnn_tc_pack_weights_kernel(const float *w, float *packed);
+static int cnn_tc_launch_setup();
+static void cnn_tc_launch(bool fuse_l1, const float *in, float *out, const float *wp, const float *bias, const float *w1,
+                          const float *b1, int n_reads, int Lx, int L1, int LP, int sm_count, cudaStream_t st);
+
 static int cnn_forward_dev(adb_ctx *ctx, const float *x, int n, const CnnDims &D, const float *w_dev, float *scores,
                            cudaStream_t st) {
     if (ctx->cnn_w.ensure(sizeof(float) * 2 * CNN_C * CNN_K * CNN_C)) { set_err("cudaMalloc cnn weights"); return ADB_ERR_CUDA; }
@@ -511,10 +517,29 @@ static int cnn_forward_dev(adb_ctx *ctx, const float *x, int n, const CnnDims &D
     CUDA_TRY(cudaFuncSetAttribute(cnn_conv64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(cudaFuncSetAttribute(cnn_conv64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     float *a0 = (float *)ctx->cnn_act0.p, *a1 = (float *)ctx->cnn_act1.p;
+    const bool use_tc = !ctx->opt_cnn_fp32;
+    float *wtc = nullptr;
+    if (use_tc) {
+        if (ctx->cnn_wtc.ensure(sizeof(float) * 2 * CNN_K * 2 * 4096)) { set_err("cudaMalloc cnn tc weights"); return ADB_ERR_CUDA; }
+        wtc = (float *)ctx->cnn_wtc.p;
+        {
+            KernelTimer t(ctx, 5, st);
+            cnn_tc_pack_weights_kernel<<<(2 * CNN_K * 4096 + 255) / 256, 256, 0, st>>>(w_dev, wtc);
+        }
+        ctx->launches += 1;
+        if (cnn_tc_launch_setup()) { set_err("cudaFuncSetAttribute cnn tc"); return ADB_ERR_CUDA; }
+    }
     for (int r0 = 0; r0 < n; r0 += chunk) {
         const int nc = std::min(chunk, n - r0);
         const int tiles = nc * ((D.L1 + CNN_TILE - 1) / CNN_TILE);
         const int grid = std::max(1, std::min(tiles, ctx->sm_count));
+        if (use_tc) {
+            KernelTimer t(ctx, 5, st);
+            cnn_tc_launch(true, x + (size_t)r0 * D.Lx, a0, wtc, w_dev + CNN_B2, w_dev + CNN_W1, w_dev + CNN_B1, nc, D.Lx, D.L1, D.LP,
+                          ctx->sm_count, st);
+            cnn_tc_launch(false, a0, a1, wtc + (size_t)CNN_K * 2 * 4096, w_dev + CNN_B3, nullptr, nullptr, nc, D.Lx, D.L1, D.LP,
+                          ctx->sm_count, st);
+        } else {
         {
             KernelTimer t(ctx, 5, st);
             cnn_conv64_kernel<true><<<grid, CNN_THREADS, smem, st>>>(x + (size_t)r0 * D.Lx, a0, packed, w_dev + CNN_B2,
@@ -524,6 +549,7 @@ static int cnn_forward_dev(adb_ctx *ctx, const float *x, int n, const CnnDims &D
             KernelTimer t(ctx, 5, st);
             cnn_conv64_kernel<false><<<grid, CNN_THREADS, smem, st>>>(a0, a1, packed + CNN_C * CNN_K * CNN_C, w_dev + CNN_B3,
                                                                        nullptr, nullptr, nc, D.Lx, D.L1, D.LP);
+        }
         }
         {
             KernelTimer t(ctx, 5, st);

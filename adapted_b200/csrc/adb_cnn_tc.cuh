@@ -1,0 +1,257 @@
+// Conv1d(64 -> 64, k = 7, pad 3) + ReLU of BoundariesCNN (adapted/detect/cnn.py:16-52, layers 2 and 3: 98 % of the
+// 64.6 MFLOP per read) on the 5th-generation tensor cores: tcgen05.mma kind::tf32, accumulators in TMEM.
+//
+// Implicit GEMM: out[t][co] = sum_k sum_ci in[ci][t + k - 3] * W[co][ci][k]  ->  for each of the 7 taps one
+// [M = positions][K = 64 ci] x [K][N = 64 co] product accumulated into the same TMEM tile.  The activation tile of a
+// job (up to 256 positions + 3 halo rows on each side) is kept in shared memory in the canonical K-major
+// "interleaved" (no-swizzle) UMMA layout with the rows of consecutive 8-row groups contiguous:
+//     element (position row q, channel ci)  at  ((ci / 4) * R + q) * 16 B + (ci % 4) * 4 B
+// so that tap k is simply the same tile with its start address advanced by k rows (k * 16 B) -- no im2col copy.
+// The weights of one tap are a K-major [64 co][64 ci] tile in the same layout, streamed from L2 by the TMA bulk
+// engine through a ring of 16 KB stages.
+//
+// Precision: the reference is float32 (torch CPU) and the boundary contract is +-1 downscaled step on arg-maxima of
+// fairly flat score curves, which plain TF32 (10-bit mantissa) does not keep.  3xTF32: every operand is split into
+// hi = its top 19 bits and lo = x - hi (exact); the products hi*hi + lo*hi + hi*lo are accumulated in float32 in TMEM
+// (the dropped lo*lo term is 2^-22 relative).  Layer 1 (1 -> 64, 0.8 % of the flops) is fused into the tile build of
+// layer 2 on the FP32 pipe, the transposed convolution (64 -> 2) stays in cnn_convT_kernel.
+#pragma once
+#include "adb_cnn.cuh"
+
+#define TC_THREADS 256
+#define TC_ROWS 256                 // output positions per job (two M = 128 tiles)
+#define TC_R (TC_ROWS + 8)          // rows of the activation tile (6 halo rows, rounded to a multiple of 8)
+#define TC_PLANE (16 * TC_R * 16)   // bytes of one activation plane (hi or lo): 16 channel quads x R rows x 16 B
+#define TC_WBLOCK (16 * 64 * 16)    // bytes of one weight block: 16 channel quads x 64 co x 16 B
+#define TC_STAGES 3
+#define TC_NBLOCKS 14               // 7 taps x (hi, lo)
+#define TC_IDESC ((1u << 4) | (2u << 7) | (2u << 10) | (8u << 17) | (8u << 24))  // f32 accum, tf32 x tf32, K-major, N = 64, M = 128
+
+__host__ __device__ inline size_t cnn_tc_smem_bytes() {
+    return 2 * (size_t)TC_PLANE + (size_t)TC_STAGES * TC_WBLOCK + 3 * (TC_ROWS + 6) * 4 + 64 + 64 * 8 * 4 + 256 + 1024;
+}
+
+// weights: torch layout w[co][ci][k] -> [layer][tap][hi, lo][ci / 4][co][ci % 4]
+__global__ void cnn_tc_pack_weights_kernel(const float *w, float *packed) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * CNN_K * 4096) return;
+    const int layer = i / (CNN_K * 4096), rem = i % (CNN_K * 4096);
+    const int k = rem / 4096, e = rem % 4096;
+    const int kc = e / 256, co = (e / 4) % 64, j = e % 4;
+    const int ci = kc * 4 + j;
+    const float v = (w + (layer == 0 ? CNN_W2 : CNN_W3))[(co * CNN_C + ci) * CNN_K + k];
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    float *dst = packed + ((size_t)(layer * CNN_K + k) * 2) * 4096;
+    dst[e] = hi;
+    dst[4096 + e] = __fsub_rn(v, hi);
+}
+
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    // SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start >> 4 [0,14), LBO >> 4 [16,30), SBO >> 4 [32,46), version 1
+    // [46,48), base offset 0, layout type SWIZZLE_NONE (0) [61,64)
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(TC_IDESC), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t v[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// in  : FUSE_L1 ? x [N][Lx] : act [N][64][LP]        out : act [N][64][LP]
+// wp  : packed weights of this layer, [7][2][4096] floats (cnn_tc_pack_weights_kernel)
+template <bool FUSE_L1>
+__global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const float *in, float *out, const float *wp,
+                                                                     const float *bias, const float *w1, const float *b1,
+                                                                     int n_reads, int Lx, int L1, int LP) {
+    extern __shared__ __align__(1024) unsigned char tsm[];
+    unsigned char *A_hi = tsm, *A_lo = tsm + TC_PLANE;
+    unsigned char *Wst = tsm + 2 * TC_PLANE;
+    float *Xs = (float *)(Wst + TC_STAGES * TC_WBLOCK);   // FUSE_L1: x window, 3 * (TC_ROWS + 6) + 6 floats
+    float *W1s = Xs + 3 * (TC_ROWS + 6) + 16;              // [64][7] + [64]
+    uint64_t *bars = (uint64_t *)(((uintptr_t)(W1s + 64 * 8) + 15) & ~(uintptr_t)15);  // full[S], empty[S], acc
+    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * TC_STAGES + 1);
+    uint64_t *full = bars, *empty = bars + TC_STAGES, *accb = bars + 2 * TC_STAGES;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(accb, 1);
+    }
+    if (FUSE_L1) {
+        for (int i = tid; i < CNN_C * CNN_K; i += blockDim.x) W1s[i] = w1[i];
+        for (int i = tid; i < CNN_C; i += blockDim.x) W1s[CNN_C * CNN_K + i] = b1[i];
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    const int jobs_per_read = (L1 + TC_ROWS - 1) / TC_ROWS;
+    const int n_jobs = n_reads * jobs_per_read;
+    uint32_t full_phase = 0, empty_phase = 0, acc_phase = 0;  // one bit per stage (thread 0) / for the accumulator barrier
+    float bv_lo[32], bv_hi[32];
+#pragma unroll
+    for (int c = 0; c < 32; c++) { bv_lo[c] = bias[c]; bv_hi[c] = bias[32 + c]; }
+
+    for (int job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+        const int r = job / jobs_per_read, t0 = (job % jobs_per_read) * TC_ROWS;
+        const int rows = min(TC_ROWS, L1 - t0);
+        const int n_mt = (rows + 127) / 128;
+        // ---- 1. activation tile (hi / lo planes), rows q <-> positions t0 - 3 + q ----
+        if (FUSE_L1) {
+            const float *xr = in + (size_t)r * Lx;
+            const int x0 = 3 * (t0 - 3) - 3, nx = 3 * (TC_ROWS + 6) + 6;
+            for (int i = tid; i < nx; i += blockDim.x) {
+                const int j = x0 + i;
+                Xs[i] = (j >= 0 && j < Lx) ? xr[j] : 0.0f;
+            }
+            __syncthreads();
+        }
+        const int nq = n_mt * 128 + 6;
+        for (int i = tid; i < 16 * nq; i += blockDim.x) {
+            const int kc = i / nq, q = i % nq;
+            const int p = t0 - 3 + q;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (p >= 0 && p < L1) {
+                if (FUSE_L1) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int ci = kc * 4 + j;
+                        float a = W1s[CNN_C * CNN_K + ci];
+#pragma unroll
+                        for (int k = 0; k < CNN_K; k++) a = fmaf(W1s[ci * CNN_K + k], Xs[3 * q + k], a);
+                        v[j] = fmaxf(a, 0.0f);
+                    }
+                } else {
+                    const float *ar = in + (size_t)r * CNN_C * LP + (size_t)(kc * 4) * LP + p;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) v[j] = ar[(size_t)j * LP];
+                }
+            }
+            float4 h, l;
+            h.x = __uint_as_float(__float_as_uint(v[0]) & 0xffffe000u); l.x = __fsub_rn(v[0], h.x);
+            h.y = __uint_as_float(__float_as_uint(v[1]) & 0xffffe000u); l.y = __fsub_rn(v[1], h.y);
+            h.z = __uint_as_float(__float_as_uint(v[2]) & 0xffffe000u); l.z = __fsub_rn(v[2], h.z);
+            h.w = __uint_as_float(__float_as_uint(v[3]) & 0xffffe000u); l.w = __fsub_rn(v[3], h.w);
+            *reinterpret_cast<float4 *>(A_hi + ((size_t)kc * TC_R + q) * 16) = h;
+            *reinterpret_cast<float4 *>(A_lo + ((size_t)kc * TC_R + q) * 16) = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to the tensor core
+        __syncthreads();
+        // ---- 2. one thread streams the 14 weight blocks and issues the MMAs ----
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = smem_u32(A_hi), a_lo = smem_u32(A_lo);
+            auto load_block = [&](int b) {
+                const int s = b % TC_STAGES;
+                mbar_expect_tx(&full[s], TC_WBLOCK);
+                tma_bulk_g2s(Wst + (size_t)s * TC_WBLOCK, wp + (size_t)b * 4096, TC_WBLOCK, &full[s]);
+            };
+            for (int b = 0; b < TC_STAGES && b < TC_NBLOCKS; b++) load_block(b);
+            for (int b = 0; b < TC_NBLOCKS; b++) {
+                const int s = b % TC_STAGES, k = b >> 1;
+                const bool w_lo = b & 1;
+                mbar_wait(&full[s], (full_phase >> s) & 1u);
+                full_phase ^= 1u << s;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t wb = smem_u32(Wst + (size_t)s * TC_WBLOCK);
+                for (int mt = 0; mt < n_mt; mt++) {
+                    const uint32_t d = tmem + (uint32_t)(mt * 64);
+#pragma unroll
+                    for (int kp = 0; kp < 8; kp++) {
+                        const uint32_t a_off = (uint32_t)(((2 * kp) * TC_R + mt * 128 + k) * 16);
+                        const uint64_t bd = tc_smem_desc(wb + (uint32_t)(2 * kp * 64 * 16), 64 * 16, 128);
+                        const uint64_t ad_hi = tc_smem_desc(a_hi + a_off, TC_R * 16, 128);
+                        tc_mma_tf32(d, ad_hi, bd, (b > 0 || kp > 0) ? 1u : 0u);
+                        if (!w_lo) {
+                            const uint64_t ad_lo = tc_smem_desc(a_lo + a_off, TC_R * 16, 128);
+                            tc_mma_tf32(d, ad_lo, bd, 1u);
+                        }
+                    }
+                }
+                tc_commit(&empty[s]);  // arrives when the MMAs issued so far have read their operands
+                if (b + TC_STAGES < TC_NBLOCKS) {
+                    mbar_wait(&empty[s], (empty_phase >> s) & 1u);
+                    empty_phase ^= 1u << s;
+                    load_block(b + TC_STAGES);
+                } else {
+                    // keep the phase bookkeeping of the empty barriers in step for the next job
+                    mbar_wait(&empty[s], (empty_phase >> s) & 1u);
+                    empty_phase ^= 1u << s;
+                }
+            }
+            tc_commit(accb);
+        }
+        // ---- 3. epilogue: TMEM -> registers -> bias + ReLU -> global [co][p] ----
+        mbar_wait(accb, acc_phase);
+        acc_phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {
+            const int mt = warp >> 2;  // warps 0-3: tile 0, warps 4-7: tile 1
+            const int q = (warp & 3) * 32 + lane;
+            const int p = t0 + mt * 128 + q;
+            if (mt < n_mt) {
+                const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mt * 64);
+                float *orow = out + (size_t)r * CNN_C * LP + p;
+                uint32_t v[32];
+                tc_ld32(taddr, v);
+                if (p < L1) {
+#pragma unroll
+                    for (int c = 0; c < 32; c++) orow[(size_t)c * LP] = fmaxf(__fadd_rn(__uint_as_float(v[c]), bv_lo[c]), 0.0f);
+                }
+                tc_ld32(taddr + 32, v);
+                if (p < L1) {
+#pragma unroll
+                    for (int c = 0; c < 32; c++) orow[(size_t)(32 + c) * LP] = fmaxf(__fadd_rn(__uint_as_float(v[c]), bv_hi[c]), 0.0f);
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+    }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+}
+
+static int cnn_tc_launch_setup() {
+    const int smem = (int)cnn_tc_smem_bytes();
+    if (cudaFuncSetAttribute(cnn_conv64_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(cnn_conv64_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
+    return 0;
+}
+
+static void cnn_tc_launch(bool fuse_l1, const float *in, float *out, const float *wp, const float *bias, const float *w1,
+                          const float *b1, int n_reads, int Lx, int L1, int LP, int sm_count, cudaStream_t st) {
+    const int jobs = n_reads * ((L1 + TC_ROWS - 1) / TC_ROWS);
+    const int grid = std::max(1, std::min(jobs, sm_count));
+    const size_t smem = cnn_tc_smem_bytes();
+    if (fuse_l1) cnn_conv64_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(in, out, wp, bias, w1, b1, n_reads, Lx, L1, LP);
+    else cnn_conv64_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(in, out, wp, bias, w1, b1, n_reads, Lx, L1, LP);
+}
