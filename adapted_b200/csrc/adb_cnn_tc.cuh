@@ -23,7 +23,7 @@
 #define TC_R (TC_ROWS + 8)          // rows of the activation tile (6 halo rows, rounded to a multiple of 8)
 #define TC_PLANE (16 * TC_R * 16)   // bytes of one activation plane (hi or lo): 16 channel quads x R rows x 16 B
 #define TC_WBLOCK (16 * 64 * 16)    // bytes of one weight block: 16 channel quads x 64 co x 16 B
-#define TC_STAGES 3
+#define TC_STAGES 4
 #define TC_NBLOCKS 14               // 7 taps x (hi, lo)
 #define TC_IDESC ((1u << 4) | (2u << 7) | (2u << 10) | (8u << 17) | (8u << 24))  // f32 accum, tf32 x tf32, K-major, N = 64, M = 128
 
@@ -136,12 +136,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const floa
             __syncthreads();
         }
         const int nq = n_mt * 128 + 6;
-        for (int i = tid; i < 16 * nq; i += blockDim.x) {
-            const int kc = i / nq, q = i % nq;
-            const int p = t0 - 3 + q;
-            float v[4] = {0.f, 0.f, 0.f, 0.f};
-            if (p >= 0 && p < L1) {
-                if (FUSE_L1) {
+        auto split_store = [&](int kc, int q, const float v[4]) {
+            float4 h, l;
+            h.x = __uint_as_float(__float_as_uint(v[0]) & 0xffffe000u); l.x = __fsub_rn(v[0], h.x);
+            h.y = __uint_as_float(__float_as_uint(v[1]) & 0xffffe000u); l.y = __fsub_rn(v[1], h.y);
+            h.z = __uint_as_float(__float_as_uint(v[2]) & 0xffffe000u); l.z = __fsub_rn(v[2], h.z);
+            h.w = __uint_as_float(__float_as_uint(v[3]) & 0xffffe000u); l.w = __fsub_rn(v[3], h.w);
+            *reinterpret_cast<float4 *>(A_hi + ((size_t)kc * TC_R + q) * 16) = h;
+            *reinterpret_cast<float4 *>(A_lo + ((size_t)kc * TC_R + q) * 16) = l;
+        };
+        if (FUSE_L1) {
+            for (int i = tid; i < 16 * nq; i += blockDim.x) {
+                const int kc = i / nq, q = i % nq;
+                const int p = t0 - 3 + q;
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                if (p >= 0 && p < L1) {
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         const int ci = kc * 4 + j;
@@ -150,19 +159,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const floa
                         for (int k = 0; k < CNN_K; k++) a = fmaf(W1s[ci * CNN_K + k], Xs[3 * q + k], a);
                         v[j] = fmaxf(a, 0.0f);
                     }
-                } else {
-                    const float *ar = in + (size_t)r * CNN_C * LP + (size_t)(kc * 4) * LP + p;
+                }
+                split_store(kc, q, v);
+            }
+        } else {
+            // four items per thread and iteration, all sixteen global loads issued before the first use
+            const float *ar = in + (size_t)r * CNN_C * LP;
+            const int total = 16 * nq;
+            for (int i0 = tid; i0 < total; i0 += 4 * blockDim.x) {
+                float v[4][4];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) v[j] = ar[(size_t)j * LP];
+                for (int u = 0; u < 4; u++) {
+                    const int i = i0 + u * blockDim.x;
+                    const int kc = i / nq, q = i % nq;
+                    const int p = t0 - 3 + q;
+                    const bool ok = (i < total) && p >= 0 && p < L1;
+                    const float *src = ar + (size_t)(kc * 4) * LP + p;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) v[u][j] = ok ? src[(size_t)j * LP] : 0.0f;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int i = i0 + u * blockDim.x;
+                    if (i < total) split_store(i / nq, i % nq, v[u]);
                 }
             }
-            float4 h, l;
-            h.x = __uint_as_float(__float_as_uint(v[0]) & 0xffffe000u); l.x = __fsub_rn(v[0], h.x);
-            h.y = __uint_as_float(__float_as_uint(v[1]) & 0xffffe000u); l.y = __fsub_rn(v[1], h.y);
-            h.z = __uint_as_float(__float_as_uint(v[2]) & 0xffffe000u); l.z = __fsub_rn(v[2], h.z);
-            h.w = __uint_as_float(__float_as_uint(v[3]) & 0xffffe000u); l.w = __fsub_rn(v[3], h.w);
-            *reinterpret_cast<float4 *>(A_hi + ((size_t)kc * TC_R + q) * 16) = h;
-            *reinterpret_cast<float4 *>(A_lo + ((size_t)kc * TC_R + q) * 16) = l;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to the tensor core
         __syncthreads();
@@ -198,15 +219,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const floa
                     }
                 }
                 tc_commit(&empty[s]);  // arrives when the MMAs issued so far have read their operands
-                if (b + TC_STAGES < TC_NBLOCKS) {
-                    mbar_wait(&empty[s], (empty_phase >> s) & 1u);
-                    empty_phase ^= 1u << s;
-                    load_block(b + TC_STAGES);
-                } else {
-                    // keep the phase bookkeeping of the empty barriers in step for the next job
-                    mbar_wait(&empty[s], (empty_phase >> s) & 1u);
-                    empty_phase ^= 1u << s;
+                // refill the stage of the PREVIOUS block (its MMAs are done or about to be, this block's are queued
+                // behind them: the tensor pipe never waits for this thread)
+                if (b >= 1) {
+                    const int pb = b - 1, ps = pb % TC_STAGES;
+                    mbar_wait(&empty[ps], (empty_phase >> ps) & 1u);
+                    empty_phase ^= 1u << ps;
+                    if (pb + TC_STAGES < TC_NBLOCKS) load_block(pb + TC_STAGES);
                 }
+            }
+            {
+                const int ps = (TC_NBLOCKS - 1) % TC_STAGES;
+                mbar_wait(&empty[ps], (empty_phase >> ps) & 1u);
+                empty_phase ^= 1u << ps;
             }
             tc_commit(accb);
         }
