@@ -183,8 +183,13 @@ static int check_batch(const adb_batch *b) {
 static int check_config(const adb_config *cfg) {
     if (!cfg) return ADB_ERR_ARG;
     if (cfg->mvs_detect_check && cfg->mvs_detect_overwrite) {
-        set_err("mvs_detect_overwrite=true (mean_var_shift_polyA_detect_at_loc) is outside the built scope");
-        return ADB_ERR_UNSUPPORTED;
+        // mean_var_shift_polyA_detect_at_loc reads moving_*[2 * offset] (mvs.py:289-290): an IndexError in the
+        // reference when the search window is not longer than the larger moving window
+        const int offset = cfg->pA_mean_window > cfg->pA_var_window ? cfg->pA_mean_window : cfg->pA_var_window;
+        if (cfg->search_window <= offset || cfg->search_window < 1) {
+            set_err("mvs_detect_overwrite needs search_window > max(pA_mean_window, pA_var_window)");
+            return ADB_ERR_UNSUPPORTED;
+        }
     }
     if (cfg->downscale_factor < 1 || cfg->downscale_factor > 128 || cfg->sp_downscale_factor < 1 ||
         cfg->sp_downscale_factor > 128) {
@@ -333,7 +338,8 @@ static int launch_validate(adb_ctx *ctx, const BatchDev &B, const adb_config &cf
     if (occ < 1) occ = 1;
     // moving statistics of the first poly(A) candidate are precomputed thread-per-read into compact pools sized for
     // an average poly(A) share of 1/4 of the window; reads that do not fit fall back to the in-CTA path (same result)
-    const bool pre = cfg.mvs_detect_check != 0;
+    const bool overwrite = cfg.mvs_detect_check && cfg.mvs_detect_overwrite;  // general kernel only (row f3)
+    const bool pre = cfg.mvs_detect_check != 0 && !overwrite;
     const long long pool_cap = std::max<long long>(1 << 20, (long long)B.n_reads * B.m / 4);
     if (pre && (ctx->cnn_aux.ensure((size_t)pool_cap * sizeof(float) * 2) ||
                 ctx->h_misc3.ensure(sizeof(int) * 2 * (size_t)B.n_reads + sizeof(long long) * ((size_t)B.n_reads + 2)))) {
@@ -389,7 +395,7 @@ static int launch_validate(adb_ctx *ctx, const BatchDev &B, const adb_config &cf
     }
     A.done = nullptr;
     ctx->vf_last_reads = 0;
-    if (B.sig_type == ADB_SIG_I16 && !ctx->opt_no_fast_validate) {
+    if (B.sig_type == ADB_SIG_I16 && !ctx->opt_no_fast_validate && !overwrite) {
         // int16 sources: counting-based validation (adb_vfast.cuh); what it leaves is picked up by validate_kernel
         const size_t fsm = vfast_smem_bytes(A.win_bytes);
         if ((int)fsm <= ctx->max_smem_optin) {

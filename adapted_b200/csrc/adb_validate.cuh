@@ -870,6 +870,64 @@ __device__ MvsOut mvs_check(ValCtx &C, int ae, int pe, double mean_lo, double me
     return R;
 }
 
+// ---- mean_var_shift_polyA_detect_at_loc (mvs.py:181-338, less_signal_ok=False) -------------------------------
+// The poly(A) start is looked for in [loc, loc + search_window): bottleneck move_mean / move_var over
+// signal[loc - offset : loc + search_window) (offset = the larger window), first position where both are in range.
+struct MvsLocOut {
+    bool ok;
+    int idx;      // mvs_adapter_end (0: nothing found)
+    double v[5];  // mean, var at the found position (or at loc + offset), polya med, local range, med shift
+};
+
+__device__ MvsLocOut mvs_detect_at_loc(ValCtx &C, int loc, double mean_lo, double mean_hi, bool mean_bounds_f64) {
+    const adb_config &cfg = *C.cfg;
+    MvsLocOut R;
+    R.ok = false; R.idx = 0;
+    for (int i = 0; i < 5; i++) R.v[i] = 0.0;
+    const int size = C.src.n;
+    const int wm = cfg.pA_mean_window, wv = cfg.pA_var_window, sw = cfg.search_window;
+    if (size < loc + sw + max(cfg.median_shift_window, cfg.polyA_window)) return R;  // mvs.py:238-254
+    const int offset = max(wm, wv);
+    if (loc < offset) return R;                                                     // mvs.py:257-269
+    const int a = loc - offset, L = offset + sw;
+    seg_moving_stats(C, a, L, wv, wm, true, true);
+    // series_a[j] = move_var[j + wv - 1], series_b[j] = move_mean[j + wm - 1]; the first offset-1 entries of at
+    // least one series are NaN (never in range).  in_range on a float32 array (utils.py:16-28) compares in float32
+    // against python-float bounds (numpy casts the weak scalar) and in float64 against np.float64 bounds, which is
+    // what pA_mean_range holds once it is derived from the adapter median (combined.py:447-458).
+    const float vlo = (float)cfg.pA_var_range[0], vhi = (float)cfg.pA_var_range[1];
+    const float mlo32 = (float)mean_lo, mhi32 = (float)mean_hi;
+    __syncthreads();
+    if (threadIdx.x == 0) C.itmp[7] = 0x7fffffff;
+    __syncthreads();
+    for (int i = offset - 1 + (int)threadIdx.x; i < L; i += blockDim.x) {
+        const float mm = C.series_b[i - (wm - 1)], mv = C.series_a[i - (wv - 1)];
+        const bool mean_ok = mean_bounds_f64 ? (mean_lo <= (double)mm && (double)mm <= mean_hi) : (mlo32 <= mm && mm <= mhi32);
+        if (mean_ok && vlo <= mv && mv <= vhi) { atomicMin(&C.itmp[7], i); break; }
+    }
+    __syncthreads();
+    int idx = C.itmp[7];
+    if (idx == 0x7fffffff) idx = 0;  // np.argmax of an all-False mask
+    float mean32, var32;
+    if (idx > 0) {
+        mean32 = C.series_b[idx - (wm - 1)]; var32 = C.series_a[idx - (wv - 1)];
+        idx += loc - offset;
+    } else {  // mvs.py:288-291: the features at loc (running-window lag = offset)
+        mean32 = C.series_b[2 * offset - (wm - 1)]; var32 = C.series_a[2 * offset - (wv - 1)];
+    }
+    __syncthreads();
+    const int loc_ = max(loc, idx);
+    const SegStats P = seg_stats(C, loc_, min(loc_ + cfg.polyA_window, size), SS_MED | SS_LR);
+    const float m_after = seg_stats(C, loc_, min(loc_ + cfg.median_shift_window, size), SS_MED).med;
+    const float m_before = seg_stats(C, 0, loc_, SS_MED).med;
+    R.idx = idx;
+    R.v[0] = (double)mean32; R.v[1] = (double)var32; R.v[2] = (double)P.med; R.v[3] = P.lr;
+    R.v[4] = (double)__fsub_rn(m_after, m_before);
+    R.ok = idx > 0 && in_range_d(R.v[2], cfg.polyA_med_range) && in_range_d(R.v[3], cfg.polyA_local_range) &&
+           in_range_d(R.v[4], cfg.median_shift_range);
+    return R;
+}
+
 // ---- find_open_pores (anomalies.py:15-35) on signal[a:b), absolute indices ------------------------------------
 // Returns the number of reported positions; *last = open_pores[-1]; the first ADB_MAX_OPEN_PORES go to rec.
 __device__ int open_pores_scan(ValCtx &C, int a, int b, adb_record *rec, int *last) {
@@ -974,6 +1032,9 @@ __device__ void validate_boundaries_cta(ValCtx &C, const PrimaryBounds &B, int f
     double real_v[3] = {0, 0, 0};
     double med_shift = 0.0;
     int n_open = 0;
+    int mvs_a_end = 0;
+    bool polya_none = false;
+    const int a_end0 = B.adapter_end;
     float polya_med_cache = 0.f, polya_mad_cache = 0.f; int polya_med_cache_pe = -1;
     bool lr0_ok = false; double lr0 = 0.0;
 
@@ -1037,6 +1098,32 @@ __device__ void validate_boundaries_cta(ValCtx &C, const PrimaryBounds &B, int f
                 exception = true; fail = ADB_FAIL_EXC_PA_MEAN_RANGE;
             }
             if (!exception && B.n_topk < 0) { exception = true; fail = ADB_FAIL_EXC_TOPK_NONE; }
+            if (!exception && cfg.mvs_detect_overwrite) {
+                // combined.py:517-566.  The detection only depends on adapter_end, which changes on success only,
+                // and success ends the loop: every further candidate after a failure repeats the same evaluation.
+                if (B.n_topk > 0 && B.topk[0] != 0) {
+                    const bool f64_bounds = cfg.pA_mean_range_empty != 0;
+                    const MvsLocOut R = mvs_detect_at_loc(C, a_end, mlo, mhi, f64_bounds);
+                    for (int i = 0; i < 5; i++) mvs_v[i] = R.v[i];
+                    mvs_a_end = R.idx;
+                    valid |= ADB_V_MVS | ADB_V_MVS_ADAPTER_END;
+                    if (!R.ok) {
+                        success = false; fail = ADB_FAIL_MVS_NO_ADAPTER;
+                    } else {
+                        int pe = B.topk[0];
+                        if (R.idx - a_end > 0) {
+                            a_end = R.idx;
+                            if (a_end > pe) {
+                                // polya_end_adjust and polya_truncated are None in v0.2.4, so polya_end becomes
+                                // trace_early_stop_pos -- None as well (combined.py:560-562)
+                                polya_none = true;
+                                valid |= ADB_V_TO_EARLY_STOP | ADB_V_POLYA_NONE;
+                            }
+                        }
+                        pe_best = pe;
+                    }
+                }
+            } else
             if (!exception) {
                 // combined.py:464-566.  `success` is never set back to True, so once the first candidate fails the
                 // reference evaluates EVERY remaining non-zero candidate and ends with: the values of the LAST
@@ -1094,14 +1181,15 @@ __device__ void validate_boundaries_cta(ValCtx &C, const PrimaryBounds &B, int f
     if (a_end > a_start) {
         seg_mean_std(C, a_start, a_end, st[0][0], st[0][1]);
         float med = a_med, mad = a_mad;
-        if (!(have_amed && a_start == a_start0)) {
+        if (!(have_amed && a_start == a_start0 && a_end == a_end0)) {
             const SegStats Q = seg_stats(C, a_start, a_end, SS_MED | SS_MAD);
             med = Q.med; mad = Q.mad;
         }
         st[0][2] = (double)med; st[0][3] = (double)mad;
         valid |= ADB_V_ADAPTER_STATS;
     }
-    if (pe_best > a_end) {
+    if (polya_none) pe_best = 0;  // calc_partition_stats(…, None): no polya and no rna partition
+    if (!polya_none && pe_best > a_end) {
         seg_mean_std(C, a_end, pe_best, st[1][0], st[1][1]);
         float med = polya_med_cache, mad = polya_mad_cache;
         if (polya_med_cache_pe != pe_best) {
@@ -1111,7 +1199,7 @@ __device__ void validate_boundaries_cta(ValCtx &C, const PrimaryBounds &B, int f
         st[1][2] = (double)med; st[1][3] = (double)mad;
         valid |= ADB_V_POLYA_STATS;
     }
-    if (size > pe_best) {
+    if (!polya_none && size > pe_best) {
         seg_mean_std(C, pe_best, size, st[2][0], st[2][1]);
         const SegStats Q = seg_stats(C, pe_best, size, SS_MED | SS_MAD);
         const float med = Q.med, mad = Q.mad;
@@ -1130,7 +1218,7 @@ __device__ void validate_boundaries_cta(ValCtx &C, const PrimaryBounds &B, int f
         rec->polya_end = pe_best;
         rec->primary_adapter_end = B.adapter_end;
         rec->primary_polya_end = B.polya_end;
-        rec->mvs_adapter_end = 0;
+        rec->mvs_adapter_end = mvs_a_end;
         rec->n_cand = max(B.n_topk, 0);
         for (int t = 0; t < ADB_MAX_CAND; t++) rec->cand[t] = (t < B.n_topk) ? B.topk[t] : 0;
         rec->n_open_pores = n_open;

@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libadapted_b200.so")
-SOURCES = ["adb_api.cu"]
+SOURCES = ["adb_api.cu", "adb_csv.cpp"]
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false",  # the arithmetic contract: no silent FMA contraction; explicit fmaf() only
@@ -19,7 +19,7 @@ def needs_build() -> bool:
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    deps = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".cu", ".cuh"))]
+    deps = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".cu", ".cuh", ".cpp"))]
     deps.append(os.path.join(HERE, "..", "..", "include", "adapted_b200.h"))
     return any(os.path.getmtime(d) > t for d in deps)
 

@@ -60,8 +60,8 @@ ReadResult = make_dataclass(
 )
 
 # valid bits (include/adapted_b200.h)
-V_ADAPTER, V_POLYA, V_RNA, V_MVS, V_REAL_MEANS, V_REAL_RANGE, V_OPEN, V_MEDSHIFT, V_CAND, V_SP, V_SP_OPEN, V_FIELDS = (
-    1 << i for i in range(12))
+(V_ADAPTER, V_POLYA, V_RNA, V_MVS, V_REAL_MEANS, V_REAL_RANGE, V_OPEN, V_MEDSHIFT, V_CAND, V_SP, V_SP_OPEN, V_FIELDS,
+ V_MVS_ADAPTER_END, V_TO_EARLY_STOP, V_POLYA_NONE) = (1 << i for i in range(15))
 
 _FAIL_TEXT = {
     1: "No adapter detected (primary)",
@@ -70,6 +70,7 @@ _FAIL_TEXT = {
     4: "Real signal check failed",
     5: "No polya detected (primary)",
     6: "MVS polya check failed: not enough signal",
+    8: "No adapter detected in range (mvs_detect)",
     9: "Median shift check failed",
     20: "pA_mean_range is not specified",
     21: "'NoneType' object is not iterable",
@@ -106,16 +107,20 @@ def records_to_results(recs: np.ndarray, primary_method: int, llr_log: Optional[
         d.signal_len = np.int32(r["signal_len"])
         d.preloaded = size
         d.adapter_end = np.int64(a_end)
-        d.polya_end = np.int64(p_end)
+        # mvs_detect_overwrite can leave polya_end = trace_early_stop_pos = None (combined.py:560-562)
+        polya_none = bool(valid & V_POLYA_NONE)
+        d.polya_end = None if polya_none else np.int64(p_end)
         d.fail_reason = reason
         d.llr_detect_log = llr_log
         d.mvs_llr_polya_end_adjust_ignored = False
-        d.mvs_llr_polya_end_to_early_stop = False
+        d.mvs_llr_polya_end_to_early_stop = bool(valid & V_TO_EARLY_STOP)
+        if valid & V_MVS_ADAPTER_END:
+            d.mvs_adapter_end = int(r["mvs_adapter_end"])
         # partitions (signal_partitions.py:65-96)
         for idx, (name, s0, s1, bit) in enumerate((("adapter", a_start, a_end, V_ADAPTER),
                                                     ("polya", a_end, p_end, V_POLYA),
                                                     ("rna_preloaded", p_end, size, V_RNA))):
-            setattr(d, f"{name}_start", s0)
+            setattr(d, f"{name}_start", None if (polya_none and name == "rna_preloaded") else s0)
             if valid & bit:
                 setattr(d, f"{name}_len", s1 - s0)
                 for q, key in enumerate(("mean", "std", "med", "mad")):

@@ -81,7 +81,9 @@ def cpu_arm(chem: str, steps: int, warmup: int, reads_per_worker: int, cores: in
     from oracle._clib import build as build_oracle
 
     build_oracle()
-    with ProcessPoolExecutor(max_workers=cores) as ex:
+    import multiprocessing as mp
+
+    with ProcessPoolExecutor(max_workers=cores, mp_context=mp.get_context("spawn")) as ex:
         for w in range(max(warmup, 1)):
             list(ex.map(_cpu_worker, [(1000 + i, 16, chem) for i in range(cores)]))
         reads = samples = 0
@@ -337,12 +339,20 @@ def main():
                 "pass_fraction": float(tot[3]) / tot_reads, "lost_minibatches": int(tot[4]),
                 "global_select_handovers_rank0": int(gsel_fallbacks), "validate_handovers_rank0": int(val_handovers)}
         if world == 1 and not args.no_cpu_baseline:
-            rpw = args.cpu_reads_per_worker or 256
-            rps, sps, sec_step, reads_step = cpu_arm(args.chemistry, 1, 1, rpw, cores)
-            line["cpu_baseline"] = {"value": rps, "unit": "reads/s", "cores": cores, "kind": "port",
-                                    "samples_per_sec": sps,
-                                    "sample": f"{reads_step} reads = {cores} minibatches of {rpw} reads, one per worker process "
-                                              f"(oracle/detect_ref.py, {sec_step:.1f} s)"}
+            # the CPU arm runs in a fresh interpreter: forking pool workers out of a process that has initialised CUDA
+            # and torch's thread pools deadlocks the torch-CPU convolutions of the CNN oracle
+            rpw = args.cpu_reads_per_worker or (256 if flat["primary_method"] == 1 else 4096)
+            try:
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--chemistry",
+                                      args.chemistry, "--steps", "1", "--warmup", "1", "--cpu-reads-per-worker", str(rpw)],
+                                     capture_output=True, text=True, timeout=420).stdout
+                ref = json.loads(out.strip().splitlines()[-1])
+                line["cpu_baseline"] = {"value": ref["value"], "unit": "reads/s", "cores": ref["cpu_baseline"]["cores"],
+                                        "kind": "port", "samples_per_sec": ref["samples_per_sec"],
+                                        "sample": ref["cpu_baseline"]["sample"] + f" (oracle/detect_ref.py, {ref['ms_per_step'] / 1e3:.1f} s)"}
+            except Exception as e:  # noqa: BLE001 -- the GPU line must still be printed
+                line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": cores, "kind": "port",
+                                        "sample": f"failed: {type(e).__name__}: {e}"}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -33,7 +33,7 @@ typedef enum adb_status {
     ADB_ERR_MAD_ZERO = -3,      /* global MAD == 0: the reference raises ValueError (normalize.py:56-59)        */
     ADB_ERR_EMPTY_TRACE = -4,   /* a read has no downscaled sample: the reference raises ValueError (llr.py:136)
                                    outside any try and loses the minibatch (combined.py:145-211)              */
-    ADB_ERR_UNSUPPORTED = -5    /* configuration outside the built scope (e.g. mvs_detect_overwrite)            */
+    ADB_ERR_UNSUPPORTED = -5    /* configuration outside the built scope (e.g. windows larger than the build caps)  */
 } adb_status;
 
 /* signal element types */
@@ -83,6 +83,7 @@ enum adb_fail_code {
     ADB_FAIL_NO_POLYA = 5,          /* "No polya detected (primary)"                       combined.py:444 */
     ADB_FAIL_MVS_NOT_ENOUGH = 6,    /* "MVS polya check failed: not enough signal"         combined.py:495 */
     ADB_FAIL_MVS_CHECKS = 7,        /* "MVS polya check failed: <names from mvs_fail_mask>" combined.py:515 */
+    ADB_FAIL_MVS_NO_ADAPTER = 8,    /* "No adapter detected in range (mvs_detect)"         combined.py:542 */
     ADB_FAIL_MED_SHIFT = 9,         /* "Median shift check failed"                         combined.py:580 */
     ADB_FAIL_EXC_PA_MEAN_RANGE = 20,/* ValueError("pA_mean_range is not specified")        combined.py:462 */
     ADB_FAIL_EXC_TOPK_NONE = 21,    /* TypeError: 'NoneType' object is not iterable         combined.py:464 */
@@ -104,6 +105,10 @@ enum adb_fail_code {
 #define ADB_V_START_PEAK (1u << 9)
 #define ADB_V_SP_OPEN_PORE (1u << 10)
 #define ADB_V_FIELDS (1u << 11) /* cleared for reads that died on an exception: every field but fail is None */
+/* mvs_detect_overwrite branch (combined.py:517-562, mean_var_shift_polyA_detect_at_loc mvs.py:181-338) */
+#define ADB_V_MVS_ADAPTER_END (1u << 12) /* mvs_adapter_end is set                                              */
+#define ADB_V_TO_EARLY_STOP (1u << 13)   /* mvs_llr_polya_end_to_early_stop = True                              */
+#define ADB_V_POLYA_NONE (1u << 14)      /* polya_end became trace_early_stop_pos, which v0.2.4 never sets: None */
 
 /* Fixed-layout result record, one per read (container_types.py:22-94 DetectResults). 512 bytes. */
 typedef struct adb_record {
@@ -230,6 +235,20 @@ int adb_downscale_host(adb_ctx *ctx, const adb_batch *batch, int32_t col0, int32
 
 /* CNN scores of BoundariesCNN (adapted/detect/cnn.py:16-52,85-98) on prepared inputs x[n, L] -> scores[n, 2, L_out] */
 int adb_cnn_scores_host(adb_ctx *ctx, const float *x, int32_t n, int32_t L, const float *cnn_weights, float *scores);
+
+/* ---- result tables ---------------------------------------------------------------------- */
+/*
+ * Drop-in for save_detected_boundaries(processing_results, filename, save_fail_reasons)   adapted/output.py:26-51
+ * (with ReadResult.to_summary_dict, adapted/container_types.py:112-120): the CSV text pandas writes for the reads
+ * `sel[0..n_sel)` of `recs` (sel == NULL: the first n_sel records), byte for byte -- column order, per-column type
+ * inference (an int column holding a None prints as float), round(3), numpy's str() of the candidate / open-pore
+ * arrays, empty cells for None, `fail_reason` last and only if save_fail_reasons.  Pure host code, no device needed.
+ * read_ids[i] belongs to recs[i].  Returns the number of bytes of the table; when that exceeds `cap` nothing useful
+ * is in `out` and the call is to be repeated with a larger buffer (cap = 0, out = NULL sizes the table).
+ */
+int64_t adb_format_csv(const adb_record *recs, const int32_t *sel, int32_t n_sel, const char *const *read_ids,
+                       int32_t primary_method, const char *llr_detect_log, int32_t save_fail_reasons, char *out,
+                       int64_t cap);
 
 #ifdef __cplusplus
 }

@@ -40,7 +40,41 @@ CASES = [
     ("cnn_rna004_stress", "cnn", "rna004", 32, 23, {"stress": True}),
     ("start_peak_rna004_basic", "start_peak", "rna004", 48, 31, {}),
     ("start_peak_rna004_poisoned", "start_peak", "rna004", 8, 32, {"short_frac": 0.5}),
+    # mvs_detect_overwrite = true: mean_var_shift_polyA_detect_at_loc moves adapter_end
+    ("llr_rna002_overwrite", "llr2", "rna002", 48, 41, {}, "overwrite"),
+    ("llr_rna002_overwrite_stress", "llr2", "rna002", 32, 42, {"stress": True}, "overwrite"),
+    ("cnn_rna004_overwrite", "cnn", "rna004", 48, 43, {}, "overwrite"),
+    ("cnn_rna004_overwrite_short", "cnn", "rna004", 32, 44, {"short_frac": 0.3}, "overwrite"),
 ]
+
+
+def read_ids_for(name: str, n: int):
+    """deterministic uuid-shaped read ids (what pod5 gives the reference, file_proc.py:175)"""
+    import uuid
+
+    h = int.from_bytes(hashlib.sha256(name.encode()).digest()[:8], "little")
+    return [str(uuid.UUID(int=(h << 64) | i)) for i in range(n)]
+
+
+def reference_csvs(res, read_ids):
+    """What worker_detect_on_preloaded_signals + the saver threads write for one minibatch (file_proc.py:246-266,
+    418-457; output.py:26-51): the pass table and the fail table as text."""
+    import tempfile
+
+    from adapted.container_types import ReadResult
+    from adapted.output import save_detected_boundaries
+
+    rr = [ReadResult(read_id=i, success=r.success, fail_reason=r.fail_reason, detect_results=r)
+          for r, i in zip(res, read_ids)]
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        for key, sel, with_reason in (("csv_pass", [r for r in rr if r.success], False),
+                                      ("csv_fail", [r for r in rr if not r.success], True)):
+            fn = os.path.join(d, key + ".csv")
+            save_detected_boundaries(sel, fn, save_fail_reasons=with_reason)
+            with open(fn, newline="") as f:
+                out[key] = f.read()
+    return out
 
 
 def _jsonable(v):
@@ -77,6 +111,12 @@ def reference_configs():
         sp.update_primary_method()
         sp.update_sig_preload_size()
         out[("start_peak", chem)] = sp
+        d = config_name_to_dict({"rna002": "rna002_70bps@v0.2.4", "rna004": "rna004_130bps@v0.2.4"}[chem])
+        d["mvs_polya"]["mvs_detect_overwrite"] = True
+        ow = nested_config_from_dict(d, SigProcConfig)
+        ow.update_primary_method()
+        ow.update_sig_preload_size()
+        out[("overwrite", chem)] = ow
     return out
 
 
@@ -102,8 +142,8 @@ def main():
     versions = dict(numpy=np.__version__, scipy=scipy.__version__, torch=torch.__version__,
                     pandas=pandas.__version__, reference="KleistLab/ADAPTed v0.2.4",
                     bottleneck="oracle.bn_restate stand-in (unpinned)")
-    for name, seam, chem, n, seed, kw in CASES:
-        spc = cfgs[("start_peak" if seam == "start_peak" else "plain", chem)]
+    for name, seam, chem, n, seed, kw, *variant in CASES:
+        spc = cfgs[(variant[0] if variant else "start_peak" if seam == "start_peak" else "plain", chem)]
         batch = make_reads(n, chem, spc.sig_preload_size, seed=seed, **kw)
         x = batch.to_dense_pa()
         rec = dict(name=name, seam=seam, chemistry=chem, n=n, seed=seed, gen_kwargs=kw,
@@ -116,7 +156,11 @@ def main():
                 res = combined_detect_cnn(x, batch.full_lens, model, spc)
             else:
                 res = combined_detect_start_peak(x, batch.full_lens, spc)
+            if not isinstance(res, list):
+                res = [res]
             rec["results"] = [{k: _jsonable(v) for k, v in r.to_dict().items()} for r in res]
+            rec["read_ids"] = read_ids_for(name, n)
+            rec.update(reference_csvs(res, rec["read_ids"]))
             n_pass = sum(bool(r.success) for r in res)
         except Exception as e:  # whole-minibatch failure
             rec["raises"] = dict(type=type(e).__name__, message=str(e))

@@ -15,8 +15,10 @@ from adapted_b200.synth import make_reads
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 SEAM_CASES = {
-    "llr2": ["llr_rna002_basic", "llr_rna002_stress", "llr_rna002_lost_minibatch"],
-    "cnn": ["cnn_rna004_basic", "cnn_rna004_short", "cnn_rna004_stress"],
+    "llr2": ["llr_rna002_basic", "llr_rna002_stress", "llr_rna002_lost_minibatch", "llr_rna002_overwrite",
+             "llr_rna002_overwrite_stress"],
+    "cnn": ["cnn_rna004_basic", "cnn_rna004_short", "cnn_rna004_stress", "cnn_rna004_overwrite",
+            "cnn_rna004_overwrite_short"],
     "start_peak": ["start_peak_rna004_basic", "start_peak_rna004_poisoned"],
 }
 

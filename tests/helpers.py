@@ -63,3 +63,85 @@ def diff_results(got: Iterable, want: Iterable, exact_floats: bool = False, limi
                 if len(out) >= limit:
                     return out
     return out
+
+
+def results_to_records(results, primary_method: int):
+    """Inverse of adapted_b200.records.records_to_results: reference-style result dicts -> adb_record array.
+    Lets the CPU tests feed the native table writer with exactly what the executed reference returned."""
+    from adapted_b200 import _lib
+    from adapted_b200 import records as R
+
+    codes = {v: k for k, v in R._FAIL_TEXT.items()}
+    sp_flags = {v: k for k, v in R._SP_FLAGS.items()}
+    method = R._METHOD[primary_method]
+    recs = np.zeros(len(results), dtype=_lib.RECORD_DTYPE)
+    for rec, r in zip(recs, results):
+        r = as_dict(r)
+        reason = r.get("fail_reason")
+        sp_type = r.get("start_peak_open_pore_type")
+        base = reason
+        if reason is not None and sp_type is not None and reason.endswith("+" + sp_type):
+            base = reason[: -len(sp_type) - 1]
+        if base is None:
+            rec["fail_code"] = 0
+        elif base.startswith("MVS polya check failed: ") and base not in codes:
+            rec["fail_code"] = 7
+            names = base[len("MVS polya check failed: "):].split()
+            rec["mvs_fail_mask"] = sum(1 << i for i, n in enumerate(("mean", "var", "med", "range", "shift")) if n in names)
+        else:
+            rec["fail_code"] = codes[base]
+        rec["success"] = int(bool(r["success"]))
+        if r.get("signal_len") is None:  # DetectResults(success=False, fail_reason=str(e))
+            continue
+        valid = R.V_FIELDS
+        rec["signal_len"], rec["preloaded"] = r["signal_len"], r["preloaded"]
+        rec["adapter_start"], rec["adapter_end"] = r["adapter_start"], r["adapter_end"]
+        if r["polya_end"] is None:
+            valid |= R.V_POLYA_NONE
+        else:
+            rec["polya_end"] = r["polya_end"]
+        for idx, (name, bit) in enumerate((("adapter", R.V_ADAPTER), ("polya", R.V_POLYA), ("rna_preloaded", R.V_RNA))):
+            if r.get(f"{name}_len") is not None:
+                valid |= bit
+                for q, key in enumerate(("mean", "std", "med", "mad")):
+                    v = r[f"{name}_{key}"]
+                    rec["stats"][idx][q] = np.nan if v is None else v
+        if r.get("polya_candidates") is not None:
+            valid |= R.V_CAND
+            c = np.asarray(r["polya_candidates"])
+            rec["n_cand"] = c.size
+            rec["cand"][: c.size] = c
+        rec["primary_adapter_end"] = r[f"{method}_adapter_end"]
+        rec["primary_polya_end"] = r[f"{method}_polya_end"]
+        if r.get("mvs_detect_mean_at_loc") is not None:
+            valid |= R.V_MVS
+            rec["mvs"][:] = [r[f"mvs_detect_{k}"] for k in ("mean_at_loc", "var_at_loc", "polya_med", "polya_local_range", "med_shift")]
+        if r.get("mvs_adapter_end") is not None:
+            valid |= R.V_MVS_ADAPTER_END
+            rec["mvs_adapter_end"] = r["mvs_adapter_end"]
+        if r.get("mvs_llr_polya_end_to_early_stop"):
+            valid |= R.V_TO_EARLY_STOP
+        if r.get("real_adapter_mean_start") is not None:
+            valid |= R.V_REAL_MEANS
+            rec["real"][0], rec["real"][1] = r["real_adapter_mean_start"], r["real_adapter_mean_end"]
+        if r.get("real_adapter_local_range") is not None:
+            valid |= R.V_REAL_RANGE
+            rec["real"][2] = r["real_adapter_local_range"]
+        if r.get("open_pores") is not None:
+            valid |= R.V_OPEN
+            op = np.asarray(r["open_pores"])
+            rec["n_open_pores"] = op.size
+            rec["open_pores"][: min(op.size, rec["open_pores"].size)] = op[: rec["open_pores"].size]
+        if r.get("adapter_rna_median_shift") is not None:
+            valid |= R.V_MEDSHIFT
+            rec["med_shift"] = r["adapter_rna_median_shift"]
+        if r.get("start_peak_idx") is not None:
+            valid |= R.V_SP
+            rec["sp_idx"], rec["sp_pa"] = r["start_peak_idx"], r["start_peak_pa"]
+            rec["sp_next_idx"], rec["sp_next_pa"] = r["start_peak_next_max_idx"], r["start_peak_next_max_pa"]
+            if r.get("start_peak_open_pore_idx") is not None:
+                valid |= R.V_SP_OPEN
+                rec["sp_open_pore_idx"] = r["start_peak_open_pore_idx"]
+                rec["sp_flag"] = sp_flags.get(sp_type, 0)
+        rec["valid"] = valid
+    return recs

@@ -1,0 +1,132 @@
+"""the native table writer (adb_format_csv) against the CSV text the executed reference wrote
+(save_detected_boundaries through pandas; captured in tests/golden by oracle/make_golden.py).  Runs without a GPU:
+the golden results are packed into adb_record arrays (tests/helpers.results_to_records) and formatted natively."""
+import os
+
+import numpy as np
+import pytest
+
+from adapted_b200 import _lib
+from adapted_b200.output import BoundaryTableWriter, format_detected_boundaries
+from tests.golden_io import SEAM_CASES, load_case
+from tests.helpers import results_to_records
+
+METHOD = {"llr2": 0, "cnn": 1, "start_peak": 2}
+CASES = [(s, n) for s, names in SEAM_CASES.items() for n in names]
+
+
+@pytest.mark.parametrize("seam,name", CASES)
+def test_native_csv_equals_reference_csv(seam, name):
+    rec = load_case(name)
+    if "raises" in rec:
+        pytest.skip("minibatch lost by the reference: nothing is written")
+    recs = results_to_records(rec["results"], METHOD[seam])
+    ok = recs["success"] != 0
+    log = rec["results"][0].get("llr_detect_log") if rec["results"] else None
+    got_pass = format_detected_boundaries(recs, rec["read_ids"], METHOD[seam], False, np.flatnonzero(ok), log)
+    got_fail = format_detected_boundaries(recs, rec["read_ids"], METHOD[seam], True, np.flatnonzero(~ok), log)
+    assert got_pass.decode() == rec["csv_pass"]
+    assert got_fail.decode() == rec["csv_fail"]
+
+
+def test_int_columns_turn_float_when_a_read_died(tmp_path):
+    """pandas infers float64 for an int column holding a None: one exception record changes every int cell."""
+    rec = load_case("llr_rna002_stress")
+    recs = results_to_records(rec["results"], 0)
+    fail = np.flatnonzero(recs["success"] == 0)
+    dead = recs[fail[:1]].copy()
+    dead["valid"] = 0
+    dead["fail_code"] = 21
+    both = np.concatenate([recs[fail], dead])
+    txt = format_detected_boundaries(both, [f"r{i}" for i in range(both.size)], 0, True).decode().splitlines()
+    hdr = txt[0].split(",")
+    first = txt[1].split(",")
+    assert first[hdr.index("signal_len")].endswith(".0") and first[hdr.index("adapter_end")].endswith(".0")
+    assert txt[-1].split(",")[-1] == "'NoneType' object is not iterable"
+    assert txt[-1].split(",")[1:-1] == [""] * (len(hdr) - 2)
+
+
+def test_table_writer_file_layout(tmp_path):
+    """4000-reads-per-file batching, file names and index continuation of the saver threads (file_proc.py:312-457)."""
+    rec = load_case("cnn_rna004_short")
+    recs = results_to_records(rec["results"], 1)
+    ids = rec["read_ids"]
+    out = str(tmp_path)
+    with BoundaryTableWriter(os.path.join(out, "boundaries"), os.path.join(out, "failed_reads"), 1,
+                             batch_size_output=16) as w:
+        for s in range(0, recs.size, 10):
+            w.add(recs[s: s + 10], ids[s: s + 10])
+    n_pass = int((recs["success"] != 0).sum())
+    files = sorted(os.listdir(os.path.join(out, "boundaries")))
+    assert files == [f"detected_boundaries_{i}.csv" for i in range((n_pass + 15) // 16)]
+    rows = []
+    for i in range(len(files)):
+        with open(os.path.join(out, "boundaries", f"detected_boundaries_{i}.csv")) as f:
+            lines = f.read().splitlines()
+        assert len(lines) - 1 == (16 if i < len(files) - 1 or n_pass % 16 == 0 else n_pass % 16)
+        rows += [l.split(",")[0] for l in lines[1:]]
+    assert rows == [i for i, r in zip(ids, recs) if r["success"]]
+    w2 = BoundaryTableWriter.continue_from(out, 1)
+    assert w2.bidx["pass"] == len(files)
+    assert w2.bidx["fail"] == len(os.listdir(os.path.join(out, "failed_reads")))
+
+
+def test_empty_selection():
+    assert format_detected_boundaries(np.zeros(0, _lib.RECORD_DTYPE), [], 0) == b"\n"
+
+
+def _pandas_csv(results, read_ids, save_fail_reasons):
+    """The reference's writer restated (adapted/output.py:26-51 + container_types.py:112-120): the checker."""
+    import io
+
+    import pandas as pd
+
+    rows = []
+    for r, i in zip(results, read_ids):
+        d = r.to_dict()
+        reason = d.pop("fail_reason", None)
+        rows.append({"read_id": i, **d, "fail_reason": reason})
+    df = pd.DataFrame(rows)
+    if not df.empty:
+        drop = ["success", "llr_trace"] + ([] if save_fail_reasons else ["fail_reason"])
+        df = df.drop(columns=[c for c in drop if c in df.columns])
+    buf = io.StringIO()
+    df.round(3).to_csv(buf, index=False)
+    return buf.getvalue()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_native_csv_equals_pandas_on_random_records(seed):
+    """Randomised records (rounding ties at the third decimal, float32 columns, long open-pore lists that numpy
+    wraps, dead reads) through records_to_results -> pandas versus the native writer."""
+    from adapted_b200.records import records_to_results
+
+    rng = np.random.default_rng(seed)
+    case = ["llr_rna002_stress", "cnn_rna004_short", "start_peak_rna004_basic", "cnn_rna004_overwrite_short"][seed % 4]
+    seam = [s for s, names in SEAM_CASES.items() if case in names][0]
+    base = results_to_records(load_case(case)["results"], METHOD[seam])
+    recs = base[rng.integers(0, base.size, size=200)].copy()
+    for name in ("stats", "mvs", "real", "med_shift"):
+        v = recs[name]
+        kind = rng.integers(0, 3, size=v.shape)
+        ties = (rng.integers(-200000, 200000, size=v.shape) + 0.5) / 1000.0          # x.xxx5 in float64
+        f32 = rng.normal(90, 40, size=v.shape).astype(np.float32).astype(np.float64)  # float32-born values
+        recs[name] = np.where(kind == 0, ties, np.where(kind == 1, f32, np.round(f32, 1)))
+    recs["real"][:, :2] = recs["real"][:, :2].astype(np.float32)
+    recs["med_shift"] = recs["med_shift"].astype(np.float32)
+    n_op = rng.integers(0, 21, size=recs.size)
+    recs["n_open_pores"] = n_op
+    recs["open_pores"] = rng.integers(0, 30000, size=recs["open_pores"].shape)
+    if seed % 2:
+        dead = rng.random(recs.size) < 0.05
+        recs["valid"][dead] = 0
+        recs["success"][dead] = 0
+        recs["fail_code"][dead] = 21
+    ids = [f"read-{i}" for i in range(recs.size)]
+    res = records_to_results(recs, METHOD[seam], "" if seam == "llr2" else None)
+    ok = recs["success"] != 0
+    for mask, with_reason in ((ok, False), (~ok, True)):
+        sel = np.flatnonzero(mask)
+        got = format_detected_boundaries(recs, ids, METHOD[seam], with_reason, sel, "" if seam == "llr2" else None)
+        want = _pandas_csv([res[i] for i in sel], [ids[i] for i in sel], with_reason)
+        assert got.decode() == want

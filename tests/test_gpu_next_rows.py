@@ -1,0 +1,113 @@
+"""SURVEY rows f2 / f3 on the GPU: the mvs_detect_overwrite branch of validate_boundaries (combined.py:517-562,
+mean_var_shift_polyA_detect_at_loc mvs.py:181-338) and the native result tables written from GPU records."""
+import csv
+import io
+
+import numpy as np
+import pytest
+
+from adapted_b200.config import config_as_dict, config_from_dict, get_chemistry_specific_config
+from adapted_b200.synth import make_reads
+from oracle import detect_ref
+from tests.golden_io import load_case, load_cnn_weights
+from tests.helpers import FLOAT_FIELDS, diff_results
+from tests.test_gpu_cnn_path import _cnn_compare
+
+pytestmark = pytest.mark.gpu
+
+
+def _overwrite_config(chem):
+    d = config_as_dict(get_chemistry_specific_config(chem))
+    d["mvs_polya"]["mvs_detect_overwrite"] = True
+    return config_from_dict(d)
+
+
+@pytest.mark.parametrize("name", ["llr_rna002_overwrite", "llr_rna002_overwrite_stress"])
+def test_llr2_overwrite_golden(name):
+    from adapted_b200.detect import combined_detect_llr2
+
+    rec = load_case(name)
+    got = combined_detect_llr2(rec["batch"].to_dense_pa(), rec["batch"].full_lens, rec["spc"])
+    assert diff_results(got, rec["results"]) == []
+
+
+@pytest.mark.parametrize("name", ["cnn_rna004_overwrite", "cnn_rna004_overwrite_short"])
+def test_cnn_overwrite_golden(name):
+    from adapted_b200.detect import combined_detect_cnn
+
+    rec = load_case(name)
+    got = combined_detect_cnn(rec["batch"].to_dense_pa(), rec["batch"].full_lens, load_cnn_weights(), rec["spc"])
+    _cnn_compare(got, rec["results"], rec["spc"].core.downscale_factor)
+
+
+@pytest.mark.parametrize("seed,kw", [(701, {}), (702, {"stress": True}), (703, {"short_frac": 0.3})])
+def test_llr2_overwrite_i16_matches_oracle(seed, kw):
+    """int16 ingest with mvs_detect_overwrite: every read goes through the general validate kernel"""
+    from adapted_b200.detect import detect_reads
+
+    spc = _overwrite_config("rna002")
+    b = make_reads(192, "rna002", spc.sig_preload_size, seed=seed, **kw)
+    x = b.to_dense_pa()
+    try:
+        want = detect_ref.detect_llr2(x, b.full_lens, spc)
+    except ValueError:
+        pytest.skip("the reference loses this minibatch")
+    got, status = detect_reads(b.adc, b.offsets, b.full_lens, b.calib_offset, b.calib_scale, spc, minibatch_size=192)
+    assert not status.any()
+    assert diff_results(got, want) == []
+    assert any(r["mvs_adapter_end"] for r in want)
+
+
+def test_overwrite_bounded_mean_range_f32_compare():
+    """an explicit pA_mean_range is compared in float32 against the moving mean (numpy weak-scalar rule)"""
+    from adapted_b200.detect import combined_detect_llr2
+
+    d = config_as_dict(_overwrite_config("rna002"))
+    d["mvs_polya"]["pA_mean_range"] = (104.3, 111.7)
+    d["mvs_polya"]["pA_var_range"] = (0.1, 17.3)
+    spc = config_from_dict(d)
+    b = make_reads(128, "rna002", spc.sig_preload_size, seed=704)
+    x = b.to_dense_pa()
+    want = detect_ref.detect_llr2(x, b.full_lens, spc)
+    got = combined_detect_llr2(x, b.full_lens, spc)
+    assert diff_results(got, want) == []
+
+
+def _cells(text):
+    rows = list(csv.reader(io.StringIO(text)))
+    return rows[0], rows[1:]
+
+
+@pytest.mark.parametrize("name,method", [("llr_rna002_basic", 0), ("llr_rna002_stress", 0),
+                                         ("llr_rna002_overwrite_stress", 0), ("start_peak_rna004_basic", 2)])
+def test_gpu_records_to_reference_csv(name, method):
+    """GPU records -> native writer == the CSV files the executed reference wrote (configs[0]: CSV-for-CSV).
+    Integer, boolean, text and array cells are identical; float cells may differ by the 1e-5 contract before
+    rounding, i.e. by at most one unit of the third decimal."""
+    from adapted_b200 import _lib
+    from adapted_b200.config import flatten_config
+    from adapted_b200.detect import _dense_batch, _run_flat
+    from adapted_b200.output import format_detected_boundaries
+
+    rec = load_case(name)
+    x = rec["batch"].to_dense_pa()
+    b, keep = _dense_batch(x, rec["batch"].full_lens)
+    flat = flatten_config(rec["spc"])
+    flat["primary_method"] = method
+    recs, status, _ = _run_flat(b, flat, None, 0, keep)
+    assert not status.any()
+    ok = recs["success"] != 0
+    log = rec["results"][0].get("llr_detect_log")
+    for sel, with_reason, key in ((np.flatnonzero(ok), False, "csv_pass"), (np.flatnonzero(~ok), True, "csv_fail")):
+        got = format_detected_boundaries(recs, rec["read_ids"], method, with_reason, sel, log).decode()
+        if got == rec[key]:
+            continue
+        gh, grows = _cells(got)
+        wh, wrows = _cells(rec[key])
+        assert gh == wh and len(grows) == len(wrows)
+        for gr, wr in zip(grows, wrows):
+            for col, g, w in zip(gh, gr, wr):
+                if g == w:
+                    continue
+                assert col in FLOAT_FIELDS, (col, g, w)
+                assert abs(float(g) - float(w)) <= 0.0011 + 1e-5 * abs(float(w)), (col, g, w)
