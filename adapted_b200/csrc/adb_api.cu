@@ -368,6 +368,7 @@ static int launch_validate(adb_ctx *ctx, const BatchDev &B, const adb_config &cf
         M.meta = (int *)(lbase + 2 + B.n_reads);
         CUDA_TRY(cudaMemsetAsync(M.cursor, 0, 16, st));
         M.perm = nullptr;
+        M.n_active = nullptr; M.all_cands = 0; M.n_cand = given_ntopk; M.ntopk_per_read = ntopk_per_read;
         {
             KernelTimer t(ctx, 4, st);
             if (B.sig_type == ADB_SIG_I16) {
@@ -418,6 +419,26 @@ static int launch_validate(adb_ctx *ctx, const BatchDev &B, const adb_config &cf
             ctx->launches += 1;
             A.done = F.done;
             ctx->vf_last_reads = B.n_reads;
+            if (pre && mode == ADB_METHOD_CNN && (ntopk_per_read || given_ntopk > 1)) {
+                // what is left mostly failed its first poly(A) candidate: the general kernel walks further candidates
+                // (and the hail-mary end), each needing the two moving-statistics series.  One thread-per-read pass
+                // up to the largest candidate serves them all as prefixes (the pools of the first pass are free now).
+                MvsSeriesArgs M;
+                M.B = B; M.given = given; M.given_stride = given_stride; M.n_reads = B.n_reads;
+                M.var_pool = (float *)A.pre_var; M.mean_pool = (float *)A.pre_mean; M.pool_cap = pool_cap;
+                long long *lbase = (long long *)ctx->h_misc3.p;
+                M.cursor = (unsigned long long *)lbase;
+                M.row_off = lbase + 2;
+                M.meta = (int *)(lbase + 2 + B.n_reads);
+                int *cnt = (int *)ctx->mvs_perm.p, *list = cnt + MVS_NBUCKET;  // counting-sort scratch of the first pass
+                CUDA_TRY(cudaMemsetAsync(M.cursor, 0, 16, st));
+                CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(int), st));
+                M.perm = list; M.n_active = cnt; M.all_cands = 1; M.n_cand = given_ntopk; M.ntopk_per_read = ntopk_per_read;
+                KernelTimer t(ctx, 7, st);
+                mvs_pending_kernel<<<(B.n_reads + 255) / 256, 256, 0, st>>>(F.done, B.n_reads, list, cnt);
+                mvs_series_kernel<<<(B.n_reads + MVS_LANES - 1) / MVS_LANES, MVS_LANES, mvs_smem_bytes(), st>>>(M, cfg);
+                ctx->launches += 2;
+            }
         }
     }
     {

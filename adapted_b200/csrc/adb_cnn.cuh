@@ -16,6 +16,7 @@
 // "boundaries within +-1 downscaled step" (north_star).  The convolutions are ~64.6 MFLOP per read and compute bound
 // (SURVEY.md section 8d); a tcgen05 (3xTF32) version of cnn_conv64_kernel is the planned next step, see DESIGN.md.
 #pragma once
+#include <cuda_fp16.h>
 #include <float.h>
 
 #include "adb_common.cuh"
@@ -120,10 +121,18 @@ __global__ void cnn_pack_weights_kernel(const float *w, float *packed /* 2 x [64
 // ---- Conv1d(64 -> 64, k = 7, pad 3) + ReLU ------------------------------------------------------------------------------
 // in  : FUSE_L1 ? x [N][Lx] : act [N][64][LP]        out : act [N][64][LP]   (LP = padded row length, multiple of 4)
 // Persistent CTAs; the 114.7 KB of packed weights stay in shared memory for the CTA's whole life.
+// `only` (optional, [n_reads]): process just the reads flagged there (the reads the tensor-core kernel could not
+// represent in its fp16 split, adb_cnn_tc.cuh).
 template <bool FUSE_L1>
 __global__ void __launch_bounds__(CNN_THREADS, 1) cnn_conv64_kernel(const float *in, float *out, const float *packed_w,
                                                                    const float *bias, const float *w1, const float *b1,
-                                                                   int n_reads, int Lx, int L1, int LP) {
+                                                                   int n_reads, int Lx, int L1, int LP, const int *only) {
+    if (only) {  // nothing flagged for this CTA: leave before the 114.7 KB of weights are loaded
+        const int tiles_per_read = (L1 + CNN_TILE - 1) / CNN_TILE, n_tiles = n_reads * tiles_per_read;
+        bool mine = false;
+        for (int tile = blockIdx.x; tile < n_tiles && !mine; tile += gridDim.x) mine = only[tile / tiles_per_read] != 0;
+        if (!__syncthreads_or(mine)) return;
+    }
     extern __shared__ __align__(16) float sm[];
     float *Ws = sm;                                   // [64][7][64]
     float *Is = Ws + CNN_C * CNN_K * CNN_C;           // [64][CNN_TILE_IN]
@@ -144,6 +153,7 @@ __global__ void __launch_bounds__(CNN_THREADS, 1) cnn_conv64_kernel(const float 
     for (int c = 0; c < 8; c++) bv[c] = bias[co0 + c];
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int r = tile / tiles_per_read, t0 = (tile % tiles_per_read) * CNN_TILE;
+        if (only && !only[r]) continue;
         __syncthreads();
         if (FUSE_L1) {
             // x window needed by act1 positions [t0-3, t0+CNN_TILE+3): x[3p-3 .. 3p+3]
@@ -493,10 +503,10 @@ static CnnDims cnn_dims(int m, int A0, int f) {
 
 // x [n][Lx] (device) -> scores [n][2][Lout] (device); chunked over reads to bound the activation buffers
 // tensor-core version of the two 64 -> 64 convolutions (adb_cnn_tc.cuh)
-__global__ void cnn_tc_pack_weights_kernel(const float *w, float *packed);
+__global__ void cnn_tc_pack_weights_kernel(const float *w, __half *packed);
 static int cnn_tc_launch_setup();
-static void cnn_tc_launch(bool fuse_l1, const float *in, float *out, const float *wp, const float *bias, const float *w1,
-                          const float *b1, int n_reads, int Lx, int L1, int LP, int sm_count, cudaStream_t st);
+static void cnn_tc_launch(bool fuse_l1, const float *in, float *out, const __half *wp, const float *bias, const float *w1,
+                          const float *b1, int n_reads, int Lx, int L1, int LP, int *redo, int sm_count, cudaStream_t st);
 
 static int cnn_forward_dev(adb_ctx *ctx, const float *x, int n, const CnnDims &D, const float *w_dev, float *scores,
                            cudaStream_t st) {
@@ -518,10 +528,14 @@ static int cnn_forward_dev(adb_ctx *ctx, const float *x, int n, const CnnDims &D
     CUDA_TRY(cudaFuncSetAttribute(cnn_conv64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     float *a0 = (float *)ctx->cnn_act0.p, *a1 = (float *)ctx->cnn_act1.p;
     const bool use_tc = !ctx->opt_cnn_fp32;
-    float *wtc = nullptr;
+    __half *wtc = nullptr;
+    int *redo = nullptr;
     if (use_tc) {
-        if (ctx->cnn_wtc.ensure(sizeof(float) * 2 * CNN_K * 2 * 4096)) { set_err("cudaMalloc cnn tc weights"); return ADB_ERR_CUDA; }
-        wtc = (float *)ctx->cnn_wtc.p;
+        // split fp16 weights of both layers, then the per-read "outside the fp16 range" flags of one chunk
+        const size_t wbytes = sizeof(__half) * 2 * CNN_K * 2 * 4096;
+        if (ctx->cnn_wtc.ensure(wbytes + sizeof(int) * (size_t)chunk)) { set_err("cudaMalloc cnn tc weights"); return ADB_ERR_CUDA; }
+        wtc = (__half *)ctx->cnn_wtc.p;
+        redo = (int *)((unsigned char *)ctx->cnn_wtc.p + wbytes);
         {
             KernelTimer t(ctx, 5, st);
             cnn_tc_pack_weights_kernel<<<(2 * CNN_K * 4096 + 255) / 256, 256, 0, st>>>(w_dev, wtc);
@@ -534,21 +548,36 @@ static int cnn_forward_dev(adb_ctx *ctx, const float *x, int n, const CnnDims &D
         const int tiles = nc * ((D.L1 + CNN_TILE - 1) / CNN_TILE);
         const int grid = std::max(1, std::min(tiles, ctx->sm_count));
         if (use_tc) {
-            KernelTimer t(ctx, 5, st);
-            cnn_tc_launch(true, x + (size_t)r0 * D.Lx, a0, wtc, w_dev + CNN_B2, w_dev + CNN_W1, w_dev + CNN_B1, nc, D.Lx, D.L1, D.LP,
-                          ctx->sm_count, st);
-            cnn_tc_launch(false, a0, a1, wtc + (size_t)CNN_K * 2 * 4096, w_dev + CNN_B3, nullptr, nullptr, nc, D.Lx, D.L1, D.LP,
-                          ctx->sm_count, st);
+            CUDA_TRY(cudaMemsetAsync(redo, 0, sizeof(int) * (size_t)nc, st));
+            {
+                KernelTimer t(ctx, 5, st);
+                cnn_tc_launch(true, x + (size_t)r0 * D.Lx, a0, wtc, w_dev + CNN_B2, w_dev + CNN_W1, w_dev + CNN_B1, nc, D.Lx, D.L1,
+                              D.LP, redo, ctx->sm_count, st);
+            }
+            {
+                KernelTimer t(ctx, 5, st);
+                cnn_tc_launch(false, a0, a1, wtc + (size_t)CNN_K * 2 * 4096, w_dev + CNN_B3, nullptr, nullptr, nc, D.Lx, D.L1, D.LP,
+                              redo, ctx->sm_count, st);
+            }
+            {
+                // reads with a value outside the fp16 range (flagged by either layer): both layers again on the FP32 pipe
+                KernelTimer t(ctx, 5, st);
+                cnn_conv64_kernel<true><<<grid, CNN_THREADS, smem, st>>>(x + (size_t)r0 * D.Lx, a0, packed, w_dev + CNN_B2,
+                                                                          w_dev + CNN_W1, w_dev + CNN_B1, nc, D.Lx, D.L1, D.LP, redo);
+                cnn_conv64_kernel<false><<<grid, CNN_THREADS, smem, st>>>(a0, a1, packed + CNN_C * CNN_K * CNN_C, w_dev + CNN_B3,
+                                                                           nullptr, nullptr, nc, D.Lx, D.L1, D.LP, redo);
+            }
+            ctx->launches += 2;
         } else {
         {
             KernelTimer t(ctx, 5, st);
             cnn_conv64_kernel<true><<<grid, CNN_THREADS, smem, st>>>(x + (size_t)r0 * D.Lx, a0, packed, w_dev + CNN_B2,
-                                                                      w_dev + CNN_W1, w_dev + CNN_B1, nc, D.Lx, D.L1, D.LP);
+                                                                      w_dev + CNN_W1, w_dev + CNN_B1, nc, D.Lx, D.L1, D.LP, nullptr);
         }
         {
             KernelTimer t(ctx, 5, st);
             cnn_conv64_kernel<false><<<grid, CNN_THREADS, smem, st>>>(a0, a1, packed + CNN_C * CNN_K * CNN_C, w_dev + CNN_B3,
-                                                                       nullptr, nullptr, nc, D.Lx, D.L1, D.LP);
+                                                                       nullptr, nullptr, nc, D.Lx, D.L1, D.LP, nullptr);
         }
         }
         {

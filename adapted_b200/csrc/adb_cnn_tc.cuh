@@ -1,66 +1,88 @@
 // Conv1d(64 -> 64, k = 7, pad 3) + ReLU of BoundariesCNN (adapted/detect/cnn.py:16-52, layers 2 and 3: 98 % of the
-// 64.6 MFLOP per read) on the 5th-generation tensor cores: tcgen05.mma kind::tf32, accumulators in TMEM.
+// 64.6 MFLOP per read) on the 5th-generation tensor cores: tcgen05.mma kind::f16, accumulators in TMEM.
 //
 // Implicit GEMM: out[t][co] = sum_k sum_ci in[ci][t + k - 3] * W[co][ci][k]  ->  for each of the 7 taps one
-// [M = positions][K = 64 ci] x [K][N = 64 co] product accumulated into the same TMEM tile.  The activation tile of a
-// job (up to 256 positions + 3 halo rows on each side) is kept in shared memory in the canonical K-major
-// "interleaved" (no-swizzle) UMMA layout with the rows of consecutive 8-row groups contiguous:
-//     element (position row q, channel ci)  at  ((ci / 4) * R + q) * 16 B + (ci % 4) * 4 B
+// [M = 128 positions][K = 64 ci] x [K][N = 64 co] product accumulated into the same TMEM tile.  The activation tile of
+// a job (128 positions + 3 halo rows on each side) is kept in shared memory in the canonical K-major "interleaved"
+// (no-swizzle) UMMA layout with the rows of consecutive 8-row groups contiguous:
+//     element (position row q, channel ci)  at  ((ci / 8) * RA + q) * 16 B + (ci % 8) * 2 B
 // so that tap k is simply the same tile with its start address advanced by k rows (k * 16 B) -- no im2col copy.
-// The weights of one tap are a K-major [64 co][64 ci] tile in the same layout, streamed from L2 by the TMA bulk
-// engine through a ring of 16 KB stages.
 //
 // Precision: the reference is float32 (torch CPU) and the boundary contract is +-1 downscaled step on arg-maxima of
-// fairly flat score curves, which plain TF32 (10-bit mantissa) does not keep.  3xTF32: every operand is split into
-// hi = its top 19 bits and lo = x - hi (exact); the products hi*hi + lo*hi + hi*lo are accumulated in float32 in TMEM
-// (the dropped lo*lo term is 2^-22 relative).  Layer 1 (1 -> 64, 0.8 % of the flops) is fused into the tile build of
-// layer 2 on the FP32 pipe, the transposed convolution (64 -> 2) stays in cnn_convT_kernel.
+// fairly flat score curves, which a single 11-bit operand does not keep.  Split arithmetic: every operand is
+// x = hi + lo with hi = fp16(x) (11 significant bits) and lo = fp16(x - hi) (the next 11 bits; x - hi is exact in
+// float32); the products hi*hi + lo*hi + hi*lo are exact in the tensor core and accumulate in float32 in TMEM (the
+// dropped lo*lo term is 2^-22 relative) -- the same error budget as 3xTF32 at half the operand bytes and twice the
+// MMA rate.  With 2-byte operands the split weights of a whole layer (7 taps x (hi, lo) x 8 KB = 112 KB) stay
+// RESIDENT in shared memory for the CTA's life: nothing is streamed per tile.  Values outside the fp16 range
+// (|x| >= 65504: pathological reads only) set a per-read flag; flagged reads are recomputed by the FP32-pipe kernel
+// (cnn_conv64_kernel with a read filter), so the result never depends on the range.
+//
+// Pipeline (one persistent CTA per SM, 256 threads, tiles double-buffered in shared memory and in TMEM):
+//   iteration i:  (a) global loads of tile i+1 into registers           -- latency covered by (b)-(c)
+//                 (b) one thread issues the 84 MMAs of tile i            -- the tensor pipe works on them during (c)-(d)
+//                 (c) epilogue of tile i-1: TMEM -> registers -> bias + ReLU -> global
+//                 (d) split the prefetched registers into the hi / lo planes of the other tile buffer
+// Layer 1 (1 -> 64, 0.8 % of the flops) is fused into (d) of layer 2 on the FP32 pipe, the transposed convolution
+// (64 -> 2) stays in cnn_convT_kernel.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "adb_cnn.cuh"
 
 #define TC_THREADS 256
-#define TC_ROWS 256                 // output positions per job (two M = 128 tiles)
-#define TC_R (TC_ROWS + 8)          // rows of the activation tile (6 halo rows, rounded to a multiple of 8)
-#define TC_PLANE (16 * TC_R * 16)   // bytes of one activation plane (hi or lo): 16 channel quads x R rows x 16 B
-#define TC_WBLOCK (16 * 64 * 16)    // bytes of one weight block: 16 channel quads x 64 co x 16 B
-#define TC_STAGES 4
-#define TC_NBLOCKS 14               // 7 taps x (hi, lo)
-#define TC_IDESC ((1u << 4) | (2u << 7) | (2u << 10) | (8u << 17) | (8u << 24))  // f32 accum, tf32 x tf32, K-major, N = 64, M = 128
+#define TC_ROWS 128                      // output positions per job (one M = 128 tile)
+#define TC_RA (TC_ROWS + 8)              // rows of the activation tile (6 halo rows, rounded to a multiple of 8)
+#define TC_NQ (TC_ROWS + 6)              // rows actually filled
+#define TC_PLANE (8 * TC_RA * 16)        // bytes of one activation plane (hi or lo): 8 channel octets x RA rows x 16 B
+#define TC_WPART (8 * 64 * 16)           // bytes of one weight part of one tap: 8 channel octets x 64 co x 16 B
+#define TC_WBYTES (CNN_K * 2 * TC_WPART) // resident weights of one layer: 114 688 B
+#define TC_NX (3 * TC_NQ + 6)            // x samples under one tile of layer 1 (FUSE_L1)
+#define TC_ITEMS (8 * TC_NQ)             // (octet, row) items of a tile: 8 channels each
+#define TC_ROUNDS ((TC_ITEMS + TC_THREADS - 1) / TC_THREADS)
+// instruction descriptor (cute/arch/mma_sm100_desc.hpp): D = f32 [4,6) = 1, A = B = f16 (0), both K-major,
+// N >> 3 at [17,23), M >> 4 at [24,29)
+#define TC_IDESC ((1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24))
 
 __host__ __device__ inline size_t cnn_tc_smem_bytes() {
-    return 2 * (size_t)TC_PLANE + (size_t)TC_STAGES * TC_WBLOCK + 3 * (TC_ROWS + 6) * 4 + 64 + 64 * 8 * 4 + 256 + 1024;
+    return (size_t)TC_WBYTES + 4 * (size_t)TC_PLANE + (size_t)(TC_NX + 10) * 4 + 64 * 8 * 4 + 64 * 4 + 64 + 1024;
 }
 
-// weights: torch layout w[co][ci][k] -> [layer][tap][hi, lo][ci / 4][co][ci % 4]
-__global__ void cnn_tc_pack_weights_kernel(const float *w, float *packed) {
+// weights: torch layout w[co][ci][k] -> [layer][tap][hi, lo][ci / 8][co][ci % 8] fp16
+__global__ void cnn_tc_pack_weights_kernel(const float *w, __half *packed) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 2 * CNN_K * 4096) return;
     const int layer = i / (CNN_K * 4096), rem = i % (CNN_K * 4096);
     const int k = rem / 4096, e = rem % 4096;
-    const int kc = e / 256, co = (e / 4) % 64, j = e % 4;
-    const int ci = kc * 4 + j;
+    const int kc = e / 512, co = (e / 8) % 64, j = e % 8;
+    const int ci = kc * 8 + j;
     const float v = (w + (layer == 0 ? CNN_W2 : CNN_W3))[(co * CNN_C + ci) * CNN_K + k];
-    const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-    float *dst = packed + ((size_t)(layer * CNN_K + k) * 2) * 4096;
+    const __half hi = __float2half_rn(v);
+    __half *dst = packed + ((size_t)(layer * CNN_K + k) * 2) * 4096;
     dst[e] = hi;
-    dst[4096 + e] = __fsub_rn(v, hi);
+    dst[4096 + e] = __float2half_rn(__fsub_rn(v, __half2float(hi)));
 }
 
-__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    // SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start >> 4 [0,14), LBO >> 4 [16,30), SBO >> 4 [32,46), version 1
-    // [46,48), base offset 0, layout type SWIZZLE_NONE (0) [61,64)
-    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
+// SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start >> 4 [0,14), LBO >> 4 [16,30), SBO >> 4 [32,46), version 1
+// [46,48), base offset 0, layout type SWIZZLE_NONE (0) [61,64).  Kept as two 32-bit halves: moving the start address
+// is one 32-bit add on the low word (the tile never crosses the 14-bit field).
+__device__ __forceinline__ uint32_t tc_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+    return ((saddr >> 4) & 0x3fffu) | (((lbo_bytes >> 4) & 0x3fffu) << 16);
 }
+__device__ __forceinline__ uint32_t tc_desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3fffu) | (1u << 14); }
 
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                           uint32_t accumulate) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
         "}\n" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(TC_IDESC), "r"(accumulate)
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(TC_IDESC), "r"(accumulate)
         : "memory");
 }
 
@@ -81,30 +103,50 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t v[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 8 channels of one row -> 16 B of the hi plane + 16 B of the lo plane; returns true if a value left the fp16 range
+__device__ __forceinline__ bool tc_split_store(unsigned char *hi_plane, unsigned char *lo_plane, int kc, int q,
+                                               const float v[8]) {
+    __half2 h[4], l[4];
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const __half h0 = __float2half_rn(v[2 * j]), h1 = __float2half_rn(v[2 * j + 1]);
+        const float f0 = __half2float(h0), f1 = __half2float(h1);
+        bad |= !(fabsf(f0) <= 65504.0f) || !(fabsf(f1) <= 65504.0f);
+        h[j] = __halves2half2(h0, h1);
+        l[j] = __halves2half2(__float2half_rn(__fsub_rn(v[2 * j], f0)), __float2half_rn(__fsub_rn(v[2 * j + 1], f1)));
+    }
+    const size_t off = ((size_t)kc * TC_RA + q) * 16;
+    *reinterpret_cast<uint4 *>(hi_plane + off) = *reinterpret_cast<const uint4 *>(h);
+    *reinterpret_cast<uint4 *>(lo_plane + off) = *reinterpret_cast<const uint4 *>(l);
+    return bad;
+}
+
 // in  : FUSE_L1 ? x [N][Lx] : act [N][64][LP]        out : act [N][64][LP]
-// wp  : packed weights of this layer, [7][2][4096] floats (cnn_tc_pack_weights_kernel)
+// wp  : packed weights of this layer, [7][2][4096] fp16 (cnn_tc_pack_weights_kernel)
+// redo: [N] set to 1 for reads with a value outside the fp16 range (recomputed on the FP32 pipe afterwards)
 template <bool FUSE_L1>
-__global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const float *in, float *out, const float *wp,
+__global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const float *in, float *out, const __half *wp,
                                                                      const float *bias, const float *w1, const float *b1,
-                                                                     int n_reads, int Lx, int L1, int LP) {
+                                                                     int n_reads, int Lx, int L1, int LP, int *redo) {
     extern __shared__ __align__(1024) unsigned char tsm[];
-    unsigned char *A_hi = tsm, *A_lo = tsm + TC_PLANE;
-    unsigned char *Wst = tsm + 2 * TC_PLANE;
-    float *Xs = (float *)(Wst + TC_STAGES * TC_WBLOCK);   // FUSE_L1: x window, 3 * (TC_ROWS + 6) + 6 floats
-    float *W1s = Xs + 3 * (TC_ROWS + 6) + 16;              // [64][7] + [64]
-    uint64_t *bars = (uint64_t *)(((uintptr_t)(W1s + 64 * 8) + 15) & ~(uintptr_t)15);  // full[S], empty[S], acc
-    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * TC_STAGES + 1);
-    uint64_t *full = bars, *empty = bars + TC_STAGES, *accb = bars + 2 * TC_STAGES;
+    unsigned char *Wsm = tsm;                                   // resident weights [7][hi, lo][8][64][8] fp16
+    unsigned char *Abuf = tsm + TC_WBYTES;                      // 2 buffers x (hi plane, lo plane)
+    float *Xs = (float *)(Abuf + 4 * TC_PLANE);                 // FUSE_L1: x window of the tile being built
+    float *W1s = Xs + TC_NX + 10;                               // [64][7] + [64]
+    float *Bs = W1s + 64 * 8;                                   // bias [64]
+    uint64_t *accb = (uint64_t *)(((uintptr_t)(Bs + 64) + 15) & ~(uintptr_t)15);  // accumulator barriers [2]
+    uint32_t *tmem_slot = (uint32_t *)(accb + 2);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    if (tid == 0) {
-        for (int s = 0; s < TC_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(accb, 1);
-    }
+    if (tid == 0) { mbar_init(&accb[0], 1); mbar_init(&accb[1], 1); }
+    for (int i = tid; i < TC_WBYTES / 16; i += blockDim.x)
+        reinterpret_cast<uint4 *>(Wsm)[i] = reinterpret_cast<const uint4 *>(wp)[i];
     if (FUSE_L1) {
         for (int i = tid; i < CNN_C * CNN_K; i += blockDim.x) W1s[i] = w1[i];
         for (int i = tid; i < CNN_C; i += blockDim.x) W1s[CNN_C * CNN_K + i] = b1[i];
     }
+    if (tid < CNN_C) Bs[tid] = bias[tid];
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -116,152 +158,135 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const floa
 
     const int jobs_per_read = (L1 + TC_ROWS - 1) / TC_ROWS;
     const int n_jobs = n_reads * jobs_per_read;
-    uint32_t full_phase = 0, empty_phase = 0, acc_phase = 0;  // one bit per stage (thread 0) / for the accumulator barrier
-    float bv_lo[32], bv_hi[32];
-#pragma unroll
-    for (int c = 0; c < 32; c++) { bv_lo[c] = bias[c]; bv_hi[c] = bias[32 + c]; }
 
-    for (int job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+    // ---- tile building: (a) loads into registers, (d) split into the planes of buffer `b` ----
+    float pf[TC_ROUNDS][8];   // !FUSE_L1: 8 channels of TC_ROUNDS (octet, row) items
+    float px[2];              // FUSE_L1: two samples of the x window
+    auto prefetch = [&](int job) {
         const int r = job / jobs_per_read, t0 = (job % jobs_per_read) * TC_ROWS;
-        const int rows = min(TC_ROWS, L1 - t0);
-        const int n_mt = (rows + 127) / 128;
-        // ---- 1. activation tile (hi / lo planes), rows q <-> positions t0 - 3 + q ----
         if (FUSE_L1) {
             const float *xr = in + (size_t)r * Lx;
-            const int x0 = 3 * (t0 - 3) - 3, nx = 3 * (TC_ROWS + 6) + 6;
-            for (int i = tid; i < nx; i += blockDim.x) {
-                const int j = x0 + i;
-                Xs[i] = (j >= 0 && j < Lx) ? xr[j] : 0.0f;
+            const int x0 = 3 * (t0 - 3) - 3;
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int i = tid + u * TC_THREADS, j = x0 + i;
+                px[u] = (i < TC_NX && j >= 0 && j < Lx) ? xr[j] : 0.0f;
+            }
+        } else {
+            const float *ar = in + (size_t)r * CNN_C * LP;
+#pragma unroll
+            for (int u = 0; u < TC_ROUNDS; u++) {
+                const int i = tid + u * TC_THREADS;
+                const int kc = i / TC_NQ, q = i % TC_NQ;
+                const int p = t0 - 3 + q;
+                const bool ok = (i < TC_ITEMS) && p >= 0 && p < L1;
+                const float *src = ar + (size_t)(kc * 8) * LP + p;
+#pragma unroll
+                for (int j = 0; j < 8; j++) pf[u][j] = ok ? src[(size_t)j * LP] : 0.0f;
+            }
+        }
+    };
+    auto build = [&](int job, int b) {
+        const int r = job / jobs_per_read, t0 = (job % jobs_per_read) * TC_ROWS;
+        unsigned char *hi_plane = Abuf + (size_t)b * 2 * TC_PLANE, *lo_plane = hi_plane + TC_PLANE;
+        bool bad = false;
+        if (FUSE_L1) {
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int i = tid + u * TC_THREADS;
+                if (i < TC_NX) Xs[i] = px[u];
             }
             __syncthreads();
-        }
-        const int nq = n_mt * 128 + 6;
-        auto split_store = [&](int kc, int q, const float v[4]) {
-            float4 h, l;
-            h.x = __uint_as_float(__float_as_uint(v[0]) & 0xffffe000u); l.x = __fsub_rn(v[0], h.x);
-            h.y = __uint_as_float(__float_as_uint(v[1]) & 0xffffe000u); l.y = __fsub_rn(v[1], h.y);
-            h.z = __uint_as_float(__float_as_uint(v[2]) & 0xffffe000u); l.z = __fsub_rn(v[2], h.z);
-            h.w = __uint_as_float(__float_as_uint(v[3]) & 0xffffe000u); l.w = __fsub_rn(v[3], h.w);
-            *reinterpret_cast<float4 *>(A_hi + ((size_t)kc * TC_R + q) * 16) = h;
-            *reinterpret_cast<float4 *>(A_lo + ((size_t)kc * TC_R + q) * 16) = l;
-        };
-        if (FUSE_L1) {
-            for (int i = tid; i < 16 * nq; i += blockDim.x) {
-                const int kc = i / nq, q = i % nq;
+            for (int i = tid; i < TC_ITEMS; i += TC_THREADS) {
+                const int kc = i / TC_NQ, q = i % TC_NQ;
                 const int p = t0 - 3 + q;
-                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // zero padding of layer 2's input outside [0, L1)
                 if (p >= 0 && p < L1) {
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int ci = kc * 4 + j;
+                    for (int j = 0; j < 8; j++) {
+                        const int ci = kc * 8 + j;
                         float a = W1s[CNN_C * CNN_K + ci];
 #pragma unroll
                         for (int k = 0; k < CNN_K; k++) a = fmaf(W1s[ci * CNN_K + k], Xs[3 * q + k], a);
                         v[j] = fmaxf(a, 0.0f);
                     }
                 }
-                split_store(kc, q, v);
+                bad |= tc_split_store(hi_plane, lo_plane, kc, q, v);
             }
         } else {
-            // four items per thread and iteration, all sixteen global loads issued before the first use
-            const float *ar = in + (size_t)r * CNN_C * LP;
-            const int total = 16 * nq;
-            for (int i0 = tid; i0 < total; i0 += 4 * blockDim.x) {
-                float v[4][4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int i = i0 + u * blockDim.x;
-                    const int kc = i / nq, q = i % nq;
-                    const int p = t0 - 3 + q;
-                    const bool ok = (i < total) && p >= 0 && p < L1;
-                    const float *src = ar + (size_t)(kc * 4) * LP + p;
-#pragma unroll
-                    for (int j = 0; j < 4; j++) v[u][j] = ok ? src[(size_t)j * LP] : 0.0f;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int i = i0 + u * blockDim.x;
-                    if (i < total) split_store(i / nq, i % nq, v[u]);
-                }
+            for (int u = 0; u < TC_ROUNDS; u++) {
+                const int i = tid + u * TC_THREADS;
+                if (i < TC_ITEMS) bad |= tc_split_store(hi_plane, lo_plane, i / TC_NQ, i % TC_NQ, pf[u]);
             }
         }
+        if (bad) redo[r] = 1;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to the tensor core
-        __syncthreads();
-        // ---- 2. one thread streams the 14 weight blocks and issues the MMAs ----
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_hi = smem_u32(A_hi), a_lo = smem_u32(A_lo);
-            auto load_block = [&](int b) {
-                const int s = b % TC_STAGES;
-                mbar_expect_tx(&full[s], TC_WBLOCK);
-                tma_bulk_g2s(Wst + (size_t)s * TC_WBLOCK, wp + (size_t)b * 4096, TC_WBLOCK, &full[s]);
-            };
-            for (int b = 0; b < TC_STAGES && b < TC_NBLOCKS; b++) load_block(b);
-            for (int b = 0; b < TC_NBLOCKS; b++) {
-                const int s = b % TC_STAGES, k = b >> 1;
-                const bool w_lo = b & 1;
-                mbar_wait(&full[s], (full_phase >> s) & 1u);
-                full_phase ^= 1u << s;
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t wb = smem_u32(Wst + (size_t)s * TC_WBLOCK);
-                for (int mt = 0; mt < n_mt; mt++) {
-                    const uint32_t d = tmem + (uint32_t)(mt * 64);
+    };
+    // ---- (b) the 84 MMAs of one tile: 7 taps x 4 K-steps of 16 channels x (hi*hi, lo*hi, hi*lo) ----
+    const uint32_t w_lo0 = tc_desc_lo(smem_u32(Wsm), 64 * 16), w_hi = tc_desc_hi(128);
+    const uint32_t a_hi_word = tc_desc_hi(128);
+    auto issue = [&](int b) {
+        const uint32_t ah0 = tc_desc_lo(smem_u32(Abuf + (size_t)b * 2 * TC_PLANE), TC_RA * 16);
+        const uint32_t al0 = ah0 + (TC_PLANE >> 4);
+        const uint32_t d = tmem + (uint32_t)(b * 64);
 #pragma unroll
-                    for (int kp = 0; kp < 8; kp++) {
-                        const uint32_t a_off = (uint32_t)(((2 * kp) * TC_R + mt * 128 + k) * 16);
-                        const uint64_t bd = tc_smem_desc(wb + (uint32_t)(2 * kp * 64 * 16), 64 * 16, 128);
-                        const uint64_t ad_hi = tc_smem_desc(a_hi + a_off, TC_R * 16, 128);
-                        tc_mma_tf32(d, ad_hi, bd, (b > 0 || kp > 0) ? 1u : 0u);
-                        if (!w_lo) {
-                            const uint64_t ad_lo = tc_smem_desc(a_lo + a_off, TC_R * 16, 128);
-                            tc_mma_tf32(d, ad_lo, bd, 1u);
-                        }
-                    }
-                }
-                tc_commit(&empty[s]);  // arrives when the MMAs issued so far have read their operands
-                // refill the stage of the PREVIOUS block (its MMAs are done or about to be, this block's are queued
-                // behind them: the tensor pipe never waits for this thread)
-                if (b >= 1) {
-                    const int pb = b - 1, ps = pb % TC_STAGES;
-                    mbar_wait(&empty[ps], (empty_phase >> ps) & 1u);
-                    empty_phase ^= 1u << ps;
-                    if (pb + TC_STAGES < TC_NBLOCKS) load_block(pb + TC_STAGES);
-                }
+        for (int k = 0; k < CNN_K; k++) {
+#pragma unroll
+            for (int kp = 0; kp < 4; kp++) {
+                const uint32_t a_off = (uint32_t)((2 * kp) * TC_RA + k);              // 16-byte units
+                const uint32_t w_off = (uint32_t)(((k * 2) * TC_WPART + 2 * kp * 64 * 16) >> 4);
+                tc_mma_f16(d, ah0 + a_off, a_hi_word, w_lo0 + w_off, w_hi, (k > 0 || kp > 0) ? 1u : 0u);
+                tc_mma_f16(d, al0 + a_off, a_hi_word, w_lo0 + w_off, w_hi, 1u);
+                tc_mma_f16(d, ah0 + a_off, a_hi_word, w_lo0 + w_off + (TC_WPART >> 4), w_hi, 1u);
             }
-            {
-                const int ps = (TC_NBLOCKS - 1) % TC_STAGES;
-                mbar_wait(&empty[ps], (empty_phase >> ps) & 1u);
-                empty_phase ^= 1u << ps;
-            }
-            tc_commit(accb);
         }
-        // ---- 3. epilogue: TMEM -> registers -> bias + ReLU -> global [co][p] ----
-        mbar_wait(accb, acc_phase);
-        acc_phase ^= 1u;
+        tc_commit(&accb[b]);
+    };
+    // ---- (c) epilogue of one tile: warp w reads TMEM lanes (w % 4) * 32.., columns (w / 4) * 32.. of buffer b ----
+    auto epilogue = [&](int job, int b, uint32_t phase) {
+        const int r = job / jobs_per_read, t0 = (job % jobs_per_read) * TC_ROWS;
+        mbar_wait(&accb[b], phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        {
-            const int mt = warp >> 2;  // warps 0-3: tile 0, warps 4-7: tile 1
-            const int q = (warp & 3) * 32 + lane;
-            const int p = t0 + mt * 128 + q;
-            if (mt < n_mt) {
-                const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mt * 64);
-                float *orow = out + (size_t)r * CNN_C * LP + p;
-                uint32_t v[32];
-                tc_ld32(taddr, v);
-                if (p < L1) {
+        const int q = (warp & 3) * 32 + lane, ch0 = (warp >> 2) * 32;
+        const int p = t0 + q;
+        const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(b * 64 + ch0);
+        uint32_t v[32];
+        tc_ld32(taddr, v);
+        if (p < L1) {
+            float *orow = out + (size_t)r * CNN_C * LP + (size_t)ch0 * LP + p;
 #pragma unroll
-                    for (int c = 0; c < 32; c++) orow[(size_t)c * LP] = fmaxf(__fadd_rn(__uint_as_float(v[c]), bv_lo[c]), 0.0f);
-                }
-                tc_ld32(taddr + 32, v);
-                if (p < L1) {
-#pragma unroll
-                    for (int c = 0; c < 32; c++) orow[(size_t)(32 + c) * LP] = fmaxf(__fadd_rn(__uint_as_float(v[c]), bv_hi[c]), 0.0f);
-                }
-            }
+            for (int c = 0; c < 32; c++) orow[(size_t)c * LP] = fmaxf(__fadd_rn(__uint_as_float(v[c]), Bs[ch0 + c]), 0.0f);
         }
+    };
+
+    int job = blockIdx.x;
+    if (job < n_jobs) {
+        prefetch(job);
+        build(job, 0);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    int prev_job = -1;
+    uint32_t it = 0;
+    for (; job < n_jobs; job += gridDim.x, it++) {
+        const int b = (int)(it & 1u);
+        const int next = job + (int)gridDim.x;
+        const bool has_next = next < n_jobs;
+        if (has_next) prefetch(next);                                   // (a)
+        if (tid == 0) {                                                 // (b)
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            issue(b);
+        }
+        if (prev_job >= 0) epilogue(prev_job, b ^ 1, ((it - 1) >> 1) & 1u);  // (c): also proves buffer b^1 is free
+        if (has_next) build(next, b ^ 1);                               // (d)
+        prev_job = job;
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
     }
+    if (prev_job >= 0) epilogue(prev_job, (int)((it - 1) & 1u), ((it - 1) >> 1) & 1u);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
 }
 
@@ -272,11 +297,11 @@ static int cnn_tc_launch_setup() {
     return 0;
 }
 
-static void cnn_tc_launch(bool fuse_l1, const float *in, float *out, const float *wp, const float *bias, const float *w1,
-                          const float *b1, int n_reads, int Lx, int L1, int LP, int sm_count, cudaStream_t st) {
+static void cnn_tc_launch(bool fuse_l1, const float *in, float *out, const __half *wp, const float *bias, const float *w1,
+                          const float *b1, int n_reads, int Lx, int L1, int LP, int *redo, int sm_count, cudaStream_t st) {
     const int jobs = n_reads * ((L1 + TC_ROWS - 1) / TC_ROWS);
     const int grid = std::max(1, std::min(jobs, sm_count));
     const size_t smem = cnn_tc_smem_bytes();
-    if (fuse_l1) cnn_conv64_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(in, out, wp, bias, w1, b1, n_reads, Lx, L1, LP);
-    else cnn_conv64_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(in, out, wp, bias, w1, b1, n_reads, Lx, L1, LP);
+    if (fuse_l1) cnn_conv64_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(in, out, wp, bias, w1, b1, n_reads, Lx, L1, LP, redo);
+    else cnn_conv64_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(in, out, wp, bias, w1, b1, n_reads, Lx, L1, LP, redo);
 }

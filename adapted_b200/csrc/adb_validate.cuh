@@ -513,7 +513,27 @@ struct MvsSeriesArgs {
     long long *row_off;       // [n_reads] offset of the read's row in the pools, or -1 (not precomputed)
     int *meta;                // [n_reads][2] = ae, pe the row belongs to
     const int *perm;          // optional [n_reads]: lane q works on read perm[q] (reads sorted by segment length)
+    // second pass (reads the counting-based validate kernel handed over): only the first *n_active entries of perm are
+    // reads, and the series run up to the LARGEST poly(A) candidate -- the recurrences start at adapter_end, so the
+    // series of every smaller candidate (and of the hail-mary poly(A) end) is a prefix of that row
+    const int *n_active;      // optional device counter
+    int all_cands;            // 1: polya_end = max over the read's non-zero candidates
+    int n_cand;               // candidates per read in `given` (after adapter_end) when ntopk_per_read == nullptr
+    const int *ntopk_per_read;
 };
+
+// reads still to be validated after validate_fast_kernel -> compact list (order irrelevant: rows are independent)
+__global__ void mvs_pending_kernel(const unsigned char *done, int n_reads, int *list, int *count) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool p = r < n_reads && !done[r];
+    const unsigned m = __ballot_sync(ADB_FULL, p);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(ADB_FULL, base, 0);
+    if (p) list[base + __popc(m & ((1u << lane) - 1))] = r;
+}
 
 #define MVS_LANES 128   // reads per CTA (one lane each; every warp works on its own 32 reads, no CTA-wide sync)
 #define MVS_C 32        // samples staged per step
@@ -554,7 +574,8 @@ __global__ void __launch_bounds__(MVS_LANES) mvs_series_kernel(MvsSeriesArgs A, 
     float *ov = (float *)(smem + (size_t)MVS_LANES * MVS_RING_STRIDE * 2) + warp * 32 * MVS_OUT_STRIDE;
     float *om = ov + MVS_LANES * MVS_OUT_STRIDE;
     const int qi = blockIdx.x * MVS_LANES + tid;
-    const int q = (qi < A.n_reads) ? (A.perm ? A.perm[qi] : qi) : A.n_reads;
+    const int n_lim = A.n_active ? min(*A.n_active, A.n_reads) : A.n_reads;
+    const int q = (qi < n_lim) ? (A.perm ? A.perm[qi] : qi) : A.n_reads;
     const int wv = cfg.pA_var_window, wm = cfg.pA_mean_window;
     bool active = false, win_var = false, win_mean = false;
     int a = 0, L = 0, ae = 0, pe = 0;
@@ -563,6 +584,10 @@ __global__ void __launch_bounds__(MVS_LANES) mvs_series_kernel(MvsSeriesArgs A, 
     if (q < A.n_reads) {
         const int *g = A.given + (size_t)q * A.given_stride;
         ae = g[0]; pe = g[1];
+        if (A.all_cands) {  // the candidates the reference's loop can reach (combined.py:464-466: stops at the first 0)
+            const int nt = A.ntopk_per_read ? A.ntopk_per_read[q] : A.n_cand;
+            for (int t = 0; t < nt && g[1 + t] != 0; t++) pe = max(pe, g[1 + t]);
+        }
         const ReadSrc src = make_src(A.B, q);
         active = (src.i16 != nullptr) && wv <= MVS_MAX_WINDOW && wm <= MVS_MAX_WINDOW &&
                  mvs_plan(cfg, src, ae, pe, a, L, win_var, win_mean) && isfinite(src.coff) && isfinite(src.cscale);
@@ -843,7 +868,8 @@ __device__ MvsOut mvs_check(ValCtx &C, int ae, int pe, double mean_lo, double me
     float var32, mean32;
     const bool win_var = !(pe - ae <= cfg.pA_var_window + 2);
     const bool win_mean = !(pe - ae <= cfg.pA_mean_window + 2);
-    const bool pre = (C.pre_var != nullptr) && C.pre_ae == ae && C.pre_pe == pe;
+    // a precomputed row serves every poly(A) end up to its own: the series of [ae, pe) is a prefix of the row
+    const bool pre = (C.pre_var != nullptr) && C.pre_ae == ae && pe <= C.pre_pe;
     if (!pre && (win_var || win_mean))
         seg_moving_stats(C, a, L, cfg.pA_var_window, cfg.pA_mean_window, win_var, win_mean);
     if (win_var) var32 = series_nanmedian(C, pre ? C.pre_var : C.series_a, L - (cfg.pA_var_window - 1));

@@ -126,3 +126,22 @@ def test_start_peak_with_mvs_enabled_raises_per_read_like_reference():
     want = detect_ref.detect_start_peak(x, b.full_lens, spc)
     assert diff_results(got, want) == []
     assert any(r.fail_reason == "'NoneType' object is not iterable" for r in got)
+
+
+def test_cnn_scores_outside_fp16_range_take_the_fp32_pipe():
+    """reads whose activations leave the fp16 range of the tensor-core split are recomputed on the FP32 pipe:
+    scores stay within the float32 tolerance for them and for their neighbours"""
+    from adapted_b200.detect import cnn_scores
+
+    rng = np.random.default_rng(1)
+    w = load_cnn_weights()
+    x = rng.normal(0, 1.5, size=(12, 1650)).astype(np.float32)
+    x[2, 700:720] = 3.0e6      # layer-1 outputs far above 65504
+    x[7, 100] = -4.0e7
+    x[9, :] *= 1.0e-6          # deep in the fp16 subnormal range: absolute accuracy must hold
+    got = cnn_scores(x, w)
+    want = detect_ref.cnn_forward(x, w)
+    assert np.isfinite(got).all()
+    for r in range(x.shape[0]):
+        scale = np.abs(want[r]).max()
+        assert np.abs(got[r] - want[r]).max() <= 2e-5 * scale + 1e-4, r
