@@ -51,6 +51,16 @@ class AdbConfig(C.Structure):
     ]
 
 
+class AdbStreamConfig(C.Structure):
+    _fields_ = [
+        ("min_obs_adapter", C.c_int32), ("min_obs_post_loc", C.c_int32), ("search_increment_step", C.c_int32),
+        ("pA_mean_window", C.c_int32), ("pA_var_window", C.c_int32), ("median_shift_window", C.c_int32),
+        ("polyA_window", C.c_int32), ("_pad", C.c_int32),
+        ("pA_mean_range", D2), ("pA_var_range", D2), ("median_shift_range", D2), ("polyA_med_range", D2),
+        ("polyA_local_range", D2),
+    ]
+
+
 class AdbBatch(C.Structure):
     _fields_ = [
         ("signal", C.c_void_p), ("sig_type", C.c_int32), ("n_reads", C.c_int32), ("m", C.c_int32),
@@ -119,6 +129,8 @@ def load() -> C.CDLL:
     L.adb_global_med_mad_host.argtypes = [vp, C.POINTER(AdbBatch), C.c_int32, vp]
     L.adb_downscale_host.argtypes = [vp, C.POINTER(AdbBatch), C.c_int32, C.c_int32, vp]
     L.adb_cnn_scores_host.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, vp]
+    L.adb_mvs_stream_detect_host.argtypes = [vp, C.POINTER(AdbBatch), C.POINTER(AdbStreamConfig), vp]
+    L.adb_mvs_stream_detect_host.restype = ip
     L.adb_format_csv.argtypes = [vp, vp, C.c_int32, vp, C.c_int32, C.c_char_p, C.c_int32, vp, C.c_int64]
     L.adb_format_csv.restype = C.c_int64
     for f in ("adb_detect_pipelined_host", "adb_ctx_set_timing", "adb_ctx_get_timing", "adb_ctx_create", "adb_detect_host", "adb_detect_dev", "adb_llr_trace_host",
@@ -145,6 +157,16 @@ def fill_config(flat: Dict[str, Any]) -> AdbConfig:
             setattr(cfg, name, D2(float(v[0]), float(v[1])))
         else:
             setattr(cfg, name, v)
+    return cfg
+
+
+def fill_stream_config(flat: Dict[str, Any]) -> AdbStreamConfig:
+    cfg = AdbStreamConfig()
+    for name, _ in AdbStreamConfig._fields_:
+        if name == "_pad":
+            continue
+        v = flat[name]
+        setattr(cfg, name, D2(float(v[0]), float(v[1])) if isinstance(v, tuple) else v)
     return cfg
 
 

@@ -67,6 +67,23 @@ class MVSPolyAConfig:
 
 
 @dataclass
+class StreamingConfig:
+    """adapted/config/sig_proc.py:140-158 (defaults: RNA002 live data) -- parameters of mean_var_shift_polyA_detect."""
+    min_obs_adapter: int = 2500
+    min_obs_post_loc: int = 300
+    search_increment_step: int = 100
+    pA_mean_window: int = 20
+    pA_mean_range: Range = (90.0, 130.0)
+    pA_var_window: int = 100
+    pA_var_range: Range = (None, 20.0)
+    median_shift_window: int = 2000
+    median_shift_range: Range = (20.0, None)
+    polyA_window: int = 300
+    polyA_med_range: Range = (90.0, 130.0)
+    polyA_local_range: Range = (0.0, 10.0)
+
+
+@dataclass
 class RNAStartPeakConfig:
     detect_rna_start_peak: bool = False
     downscale_factor: int = 10
@@ -250,6 +267,15 @@ def range_is_empty(rng) -> bool:
     if rng is None:
         return True
     return (rng[0] == -INF and rng[1] == INF) or (rng[0] is None and rng[1] is None)
+
+
+def flatten_streaming_config(p: Any) -> Dict[str, Any]:
+    """StreamingConfig (local or the reference's) -> the scalar dict that fills ``adb_stream_config``."""
+    d = {k: int(getattr(p, k)) for k in ("min_obs_adapter", "min_obs_post_loc", "search_increment_step", "pA_mean_window",
+                                         "pA_var_window", "median_shift_window", "polyA_window")}
+    for k in ("pA_mean_range", "pA_var_range", "median_shift_range", "polyA_med_range", "polyA_local_range"):
+        d[k] = _lo_hi(getattr(p, k))
+    return d
 
 
 _METHOD_CODE = {"llr": 0, "cnn": 1, "start_peak": 2}

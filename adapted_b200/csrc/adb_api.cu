@@ -17,6 +17,7 @@
 #include "adb_llr.cuh"
 #include "adb_read_kernel.cuh"
 #include "adb_cnn.cuh"
+#include "adb_stream.cuh"
 #include "adb_cnn_tc.cuh"
 #include "adb_start_peak.cuh"
 #include "adb_legacy.cuh"
@@ -676,6 +677,46 @@ extern "C" int adb_global_med_mad_host(adb_ctx *ctx, const adb_batch *batch, int
     CUDA_TRY(cudaMemcpyAsync(hs.data(), ctx->states.p, sizeof(GselState) * (size_t)n_batches, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     for (int i = 0; i < n_batches; i++) { med_mad[2 * i] = hs[i].med; med_mad[2 * i + 1] = hs[i].mad; }
+    return ADB_OK;
+}
+
+// ---- streaming poly(A) detector (row f4) ----------------------------------------------------------------------------
+extern "C" int adb_mvs_stream_detect_host(adb_ctx *ctx, const adb_batch *batch, const adb_stream_config *cfg,
+                                          int32_t *polya_start) {
+    if (!ctx || !cfg || !polya_start) { set_err("null argument"); return ADB_ERR_ARG; }
+    int rc = check_batch(batch);
+    if (rc) return rc;
+    if (cfg->pA_mean_window < 1 || cfg->pA_var_window < 1 || cfg->pA_mean_window > ADB_MAX_MOVE_WINDOW ||
+        cfg->pA_var_window > ADB_MAX_MOVE_WINDOW || cfg->min_obs_adapter < 0 || cfg->search_increment_step < 1 ||
+        cfg->polyA_window < 1 || cfg->median_shift_window < 1) {
+        set_err("streaming config outside the supported range");
+        return ADB_ERR_UNSUPPORTED;
+    }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (batch->n_reads == 0) return ADB_OK;
+    cudaStream_t st = ctx->stream;
+    StagedBatch sb;
+    rc = stage_batch(ctx, batch, &sb, st);
+    if (rc) return rc;
+    StreamArgs A;
+    A.B = to_dev_view(sb.dev);
+    A.win_bytes = A.B.m * (A.B.sig_type == ADB_SIG_F32 ? 4 : 2);
+    const size_t smem = (((size_t)A.win_bytes + 48 + 15) & ~(size_t)15) + (((size_t)ADB_SEL_SMEM_BYTES + 64 + 15) & ~(size_t)15) + 256;
+    if ((int)smem > ctx->max_smem_optin) { set_err("signal window does not fit in shared memory"); return ADB_ERR_UNSUPPORTED; }
+    CUDA_TRY(cudaFuncSetAttribute(mvs_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mvs_stream_kernel, ADB_VAL_THREADS, smem));
+    if (occ < 1) occ = 1;
+    const int grid = std::max(1, std::min(A.B.n_reads, ctx->sm_count * occ));
+    if (ctx->series.ensure((size_t)grid * 2 * (size_t)A.B.m * sizeof(float)) ||
+        ctx->h_misc.ensure(sizeof(int32_t) * (size_t)A.B.n_reads + 16)) { set_err("cudaMalloc stream scratch"); return ADB_ERR_CUDA; }
+    A.series = (float *)ctx->series.p;
+    A.out = (int32_t *)ctx->h_misc.p;
+    mvs_stream_kernel<<<grid, ADB_VAL_THREADS, smem, st>>>(A, *cfg);
+    ctx->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(polya_start, A.out, sizeof(int32_t) * (size_t)A.B.n_reads, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return ADB_OK;
 }
 

@@ -232,34 +232,48 @@ __host__ __device__ inline size_t cnn_conv_smem_bytes() {
 
 // ---- ConvTranspose1d(64 -> 2, k = 7, stride 3, pad 3) ---------------------------------------------------------------------
 // out[co][j] = b[co] + sum_ci sum_{k = j%3 (+3, +6)} in[ci][(j + 3 - k) / 3] * w[ci][co][k]
+// One thread per input position u produces the three outputs j = 3u, 3u+1, 3u+2 of both channels from in[ci][u-1],
+// in[ci][u], in[ci][u+1]:  out[3u] = x[u+1] w0 + x[u] w3 + x[u-1] w6,  out[3u+1] = x[u+1] w1 + x[u] w4,
+// out[3u+2] = x[u+1] w2 + x[u] w5  (three coalesced loads and 14 FMAs per input channel; the per-output summation
+// order -- channels ascending, taps ascending -- is unchanged).
 __global__ void __launch_bounds__(256) cnn_convT_kernel(const float *act, const float *w4, const float *b4, int L1, int LP,
                                                         int Lout, float *scores) {
-    __shared__ float ws[CNN_C * 2 * CNN_K];
-    for (int i = threadIdx.x; i < CNN_C * 2 * CNN_K; i += blockDim.x) ws[i] = w4[i];
+    __shared__ __align__(16) float ws[CNN_C * 16];  // per ci: co0 k0..6, pad, co1 k0..6, pad
+    for (int i = threadIdx.x; i < CNN_C * 16; i += blockDim.x) {
+        const int ci = i >> 4, e = i & 15, co = e >> 3, k = e & 7;
+        ws[i] = (k < CNN_K) ? w4[(ci * 2 + co) * CNN_K + k] : 0.0f;
+    }
     __syncthreads();
     const int r = blockIdx.y;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= Lout) return;
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (3 * u >= Lout) return;
     const float *ar = act + (size_t)r * CNN_C * LP;
-    float a0 = b4[0], a1 = b4[1];
-    const int k0 = j % 3;
+    const float bias0 = b4[0], bias1 = b4[1];
+    float o[2][3] = {{bias0, bias0, bias0}, {bias1, bias1, bias1}};
+    const bool has_m = (u - 1 >= 0) && (u - 1 < L1), has_c = u < L1, has_p = u + 1 < L1;
+#pragma unroll 4
     for (int ci = 0; ci < CNN_C; ci++) {
         const float *ap = ar + (size_t)ci * LP;
+        const float xm = has_m ? ap[u - 1] : 0.0f, xc = has_c ? ap[u] : 0.0f, xp = has_p ? ap[u + 1] : 0.0f;
+        const float4 wa = *reinterpret_cast<const float4 *>(ws + ci * 16), wb = *reinterpret_cast<const float4 *>(ws + ci * 16 + 4);
+        const float4 wc = *reinterpret_cast<const float4 *>(ws + ci * 16 + 8), wd = *reinterpret_cast<const float4 *>(ws + ci * 16 + 12);
+        // taps in ascending k: k = j%3 pairs with x[u+1], k+3 with x[u], k+6 with x[u-1]
+        if (has_p) { o[0][0] = fmaf(xp, wa.x, o[0][0]); o[1][0] = fmaf(xp, wc.x, o[1][0]); }
+        if (has_c) { o[0][0] = fmaf(xc, wa.w, o[0][0]); o[1][0] = fmaf(xc, wc.w, o[1][0]); }
+        if (has_m) { o[0][0] = fmaf(xm, wb.z, o[0][0]); o[1][0] = fmaf(xm, wd.z, o[1][0]); }
+        if (has_p) { o[0][1] = fmaf(xp, wa.y, o[0][1]); o[1][1] = fmaf(xp, wc.y, o[1][1]); }
+        if (has_c) { o[0][1] = fmaf(xc, wb.x, o[0][1]); o[1][1] = fmaf(xc, wd.x, o[1][1]); }
+        if (has_p) { o[0][2] = fmaf(xp, wa.z, o[0][2]); o[1][2] = fmaf(xp, wc.z, o[1][2]); }
+        if (has_c) { o[0][2] = fmaf(xc, wb.y, o[0][2]); o[1][2] = fmaf(xc, wd.y, o[1][2]); }
+    }
 #pragma unroll
-        for (int kk = 0; kk < 3; kk++) {
-            const int k = k0 + 3 * kk;
-            if (k < CNN_K) {
-                const int t = (j + 3 - k) / 3;
-                if (t >= 0 && t < L1) {
-                    const float v = ap[t];
-                    a0 = fmaf(v, ws[(ci * 2 + 0) * CNN_K + k], a0);
-                    a1 = fmaf(v, ws[(ci * 2 + 1) * CNN_K + k], a1);
-                }
-            }
+    for (int c = 0; c < 3; c++) {
+        const int j = 3 * u + c;
+        if (j < Lout) {
+            scores[((size_t)r * 2 + 0) * Lout + j] = o[0][c];
+            scores[((size_t)r * 2 + 1) * Lout + j] = o[1][c];
         }
     }
-    scores[((size_t)r * 2 + 0) * Lout + j] = a0;
-    scores[((size_t)r * 2 + 1) * Lout + j] = a1;
 }
 
 // ---- post-processing (cnn.py:117-160) ---------------------------------------------------------------------------------
@@ -582,7 +596,7 @@ static int cnn_forward_dev(adb_ctx *ctx, const float *x, int n, const CnnDims &D
         }
         {
             KernelTimer t(ctx, 5, st);
-            dim3 g((D.Lout + 255) / 256, nc);
+            dim3 g(((D.Lout + 2) / 3 + 255) / 256, nc);
             cnn_convT_kernel<<<g, 256, 0, st>>>(a1, w_dev + CNN_W4, w_dev + CNN_B4, D.L1, D.LP, D.Lout,
                                                 scores + (size_t)r0 * 2 * D.Lout);
         }

@@ -535,15 +535,21 @@ __global__ void mvs_pending_kernel(const unsigned char *done, int n_reads, int *
     if (p) list[base + __popc(m & ((1u << lane) - 1))] = r;
 }
 
+struct __align__(16) MvsRow {  // per-read constants of the transposing phases, read as shared-memory broadcasts
+    const int16_t *rp;        // first sample of the segment
+    float *gvp, *gmp;         // output rows, pre-shifted: entry i of the series lives at gvp[i] / gmp[i]
+    int L, iminv, iminm, pad; // segment length; first valid index of either series (INT_MAX: series not wanted)
+};
 #define MVS_LANES 128   // reads per CTA (one lane each; every warp works on its own 32 reads, no CTA-wide sync)
 #define MVS_C 32        // samples staged per step
 #define MVS_RING 256    // circular input columns per read (>= window + 2 * MVS_C), power of two
-#define MVS_RING_STRIDE 258  // int16 units: 516 B = 129 words, odd -> lanes walking their own row hit distinct banks
+#define MVS_RING_STRIDE 257  // float units, odd -> lanes walking their own row hit distinct banks
 #define MVS_OUT_STRIDE 33    // float units
 #define MVS_MAX_WINDOW (MVS_RING - 2 * MVS_C)
 
 __host__ __device__ inline size_t mvs_smem_bytes() {
-    return (size_t)MVS_LANES * MVS_RING_STRIDE * 2 + 2 * (size_t)MVS_LANES * MVS_OUT_STRIDE * 4 + 64;
+    return (size_t)MVS_LANES * MVS_RING_STRIDE * 4 + 2 * (size_t)MVS_LANES * MVS_OUT_STRIDE * 4 + (size_t)MVS_LANES * 8 +
+           (size_t)MVS_LANES * sizeof(MvsRow) + 64;
 }
 
 // eligibility of a read for the precomputed series (mirrors the early exits of mvs.py:76-107)
@@ -564,15 +570,21 @@ __device__ __forceinline__ bool mvs_plan(const adb_config &cfg, const ReadSrc &s
 
 // int16 sources: one lane per read, 32 reads per warp, warps independent of each other.  Per step of MVS_C samples a
 // warp (1) issues the coalesced row loads of the NEXT step into registers, (2) lets every lane advance its two
-// recurrences over the current step from its own row of a shared-memory ring (circular history for a[i - window]),
-// (3) writes the step's outputs row by row (coalesced) from a shared tile, (4) parks the prefetched samples in the
-// ring.  The global-load latency of (1) is covered by the ~25 dependent float operations per sample of (2).
+// recurrences over the current step from its own row of a shared-memory ring of CALIBRATED samples (circular history
+// for a[i - window]), (3) writes the step's outputs row by row (coalesced) from a shared tile, (4) calibrates and
+// parks the prefetched samples in the ring.  A read's time is its segment length times the cycles per sample of (2)
+// -- the kernel's duration is that of its longest read -- so the steady state of (2) is branch-free and unrolled:
+// the loads and the differences a[i] - a[i - window] of eight samples are independent of the recurrences, what stays
+// loop-carried is one addition per sample for each running mean and an add + clamp for the sum of squares.
 __global__ void __launch_bounds__(MVS_LANES) mvs_series_kernel(MvsSeriesArgs A, adb_config cfg) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int16_t *ring = (int16_t *)smem + (size_t)warp * 32 * MVS_RING_STRIDE;
-    float *ov = (float *)(smem + (size_t)MVS_LANES * MVS_RING_STRIDE * 2) + warp * 32 * MVS_OUT_STRIDE;
+    float *ring = (float *)smem + (size_t)warp * 32 * MVS_RING_STRIDE;
+    float *ov = (float *)smem + (size_t)MVS_LANES * MVS_RING_STRIDE + warp * 32 * MVS_OUT_STRIDE;
     float *om = ov + MVS_LANES * MVS_OUT_STRIDE;
+    float2 *cal_all = (float2 *)((float *)smem + (size_t)MVS_LANES * MVS_RING_STRIDE + 2 * MVS_LANES * MVS_OUT_STRIDE);
+    float2 *cal = cal_all + warp * 32;
+    MvsRow *tab = (MvsRow *)(cal_all + MVS_LANES) + warp * 32;
     const int qi = blockIdx.x * MVS_LANES + tid;
     const int n_lim = A.n_active ? min(*A.n_active, A.n_reads) : A.n_reads;
     const int q = (qi < n_lim) ? (A.perm ? A.perm[qi] : qi) : A.n_reads;
@@ -618,38 +630,90 @@ __global__ void __launch_bounds__(MVS_LANES) mvs_series_kernel(MvsSeriesArgs A, 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) Lmax = max(Lmax, __shfl_xor_sync(ADB_FULL, Lmax, o));
     if (Lmax == 0) return;
+    cal[lane] = make_float2(coff, cscale);
     const int flag = (win_var ? 1 : 0) | (win_mean ? 2 : 0);
     float amean = 0.f, assqdm = 0.f, asum = 0.f;
     const float cinv_v = (float)(1.0 / (double)wv), cinv_m = (float)(1.0 / (double)wm);
-    const int16_t *myrow = ring + (size_t)lane * MVS_RING_STRIDE;
+    const float *myrow = ring + (size_t)lane * MVS_RING_STRIDE;
     float *myov = ov + lane * MVS_OUT_STRIDE, *myom = om + lane * MVS_OUT_STRIDE;
-    float *gv = A.var_pool, *gm = A.mean_pool;
+    const int wmax = max(wv, wm);
+    {
+        MvsRow t;
+        t.rp = rp;
+        t.gvp = A.var_pool + myoff - (wv - 1);
+        t.gmp = A.mean_pool + myoff - (wm - 1);
+        t.L = L;
+        t.iminv = (flag & 1) ? wv - 1 : 0x7fffffff;
+        t.iminm = (flag & 2) ? wm - 1 : 0x7fffffff;
+        t.pad = 0;
+        tab[lane] = t;
+    }
+    // steps inside [wmax, Lmin) need no per-row tests when every row wants both series
+    int Lmin = L;
+    bool both = flag == 3;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) Lmin = min(Lmin, __shfl_xor_sync(ADB_FULL, Lmin, o));
+    both = __all_sync(ADB_FULL, both);
+    if (!both) Lmin = 0;
     // prefetch registers: sample (base + lane) of every row
     int16_t pf[32];
     auto prefetch = [&](int step_base) {
         const int i = step_base + lane;
+        if (step_base + MVS_C <= Lmin) {
 #pragma unroll
-        for (int row = 0; row < 32; row++) {
-            const int16_t *p = (const int16_t *)__shfl_sync(ADB_FULL, (unsigned long long)rp, row);
-            const int Lr = __shfl_sync(ADB_FULL, L, row);
-            pf[row] = (i < Lr) ? __ldg(p + i) : (int16_t)0;
+            for (int row = 0; row < 32; row++) pf[row] = __ldg(tab[row].rp + i);
+        } else {
+#pragma unroll
+            for (int row = 0; row < 32; row++) {
+                const int16_t *p = tab[row].rp;
+                pf[row] = (i < tab[row].L) ? __ldg(p + i) : (int16_t)0;
+            }
         }
     };
-    auto park = [&](int step_base) {
+    auto park = [&](int step_base) {  // pA = (adc + offset) * scale, each step rounded to float32
         const int col = (step_base + lane) & (MVS_RING - 1);
 #pragma unroll
-        for (int row = 0; row < 32; row++) ring[(size_t)row * MVS_RING_STRIDE + col] = pf[row];
+        for (int row = 0; row < 32; row++) {
+            const float2 c = cal[row];
+            ring[(size_t)row * MVS_RING_STRIDE + col] = __fmul_rn(__fadd_rn((float)pf[row], c.x), c.y);
+        }
     };
+    __syncwarp();
     prefetch(0);
     park(0);
     __syncwarp();
     for (int base_i = 0; base_i < Lmax; base_i += MVS_C) {
         const bool more = base_i + MVS_C < Lmax;
         if (more) prefetch(base_i + MVS_C);  // loads in flight while the recurrences run
-        if (base_i < L) {
+        if (base_i >= wmax) {
+            // steady state (every window is full); lanes past their own end compute on zeros, nothing of it is stored
+#pragma unroll
+            for (int g = 0; g < MVS_C; g += 8) {
+                float x[8], xv[8], xm[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int i = base_i + g + u;
+                    x[u] = myrow[i & (MVS_RING - 1)];
+                    xv[u] = myrow[(i - wv) & (MVS_RING - 1)];
+                    xm[u] = myrow[(i - wm) & (MVS_RING - 1)];
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    asum = __fadd_rn(asum, __fsub_rn(x[u], xm[u]));
+                    myom[g + u] = __fmul_rn(asum, cinv_m);
+                    const float delta = __fsub_rn(x[u], xv[u]);
+                    const float ao = __fsub_rn(xv[u], amean);
+                    amean = __fadd_rn(amean, __fmul_rn(delta, cinv_v));
+                    const float ai = __fsub_rn(x[u], amean);
+                    assqdm = __fadd_rn(assqdm, __fmul_rn(__fadd_rn(ai, ao), delta));
+                    assqdm = (assqdm < 0.f) ? 0.f : assqdm;
+                    myov[g + u] = __fmul_rn(assqdm, cinv_v);
+                }
+            }
+        } else if (base_i < L) {
             const int iend = min(base_i + MVS_C, L);
             for (int i = base_i; i < iend; i++) {
-                const float x = __fmul_rn(__fadd_rn((float)myrow[i & (MVS_RING - 1)], coff), cscale);
+                const float x = myrow[i & (MVS_RING - 1)];
                 if (win_var) {
                     if (i < wv) {
                         const float delta = __fsub_rn(x, amean);
@@ -661,7 +725,7 @@ __global__ void __launch_bounds__(MVS_LANES) mvs_series_kernel(MvsSeriesArgs A, 
                         }
                     } else {
                         float ai = x;
-                        float aold = __fmul_rn(__fadd_rn((float)myrow[(i - wv) & (MVS_RING - 1)], coff), cscale);
+                        float aold = myrow[(i - wv) & (MVS_RING - 1)];
                         const float delta = __fsub_rn(ai, aold);
                         aold = __fsub_rn(aold, amean);
                         amean = __fadd_rn(amean, __fmul_rn(delta, cinv_v));
@@ -676,7 +740,7 @@ __global__ void __launch_bounds__(MVS_LANES) mvs_series_kernel(MvsSeriesArgs A, 
                         asum = __fadd_rn(asum, x);
                         if (i == wm - 1) myom[i - base_i] = __fdiv_rn(asum, (float)wm);
                     } else {
-                        const float aold = __fmul_rn(__fadd_rn((float)myrow[(i - wm) & (MVS_RING - 1)], coff), cscale);
+                        const float aold = myrow[(i - wm) & (MVS_RING - 1)];
                         asum = __fadd_rn(asum, __fsub_rn(x, aold));
                         myom[i - base_i] = __fmul_rn(asum, cinv_m);
                     }
@@ -687,14 +751,21 @@ __global__ void __launch_bounds__(MVS_LANES) mvs_series_kernel(MvsSeriesArgs A, 
         // ---- coalesced row stores of the valid entries ----
         {
             const int i = base_i + lane;
+            if (base_i >= wmax && base_i + MVS_C <= Lmin) {
+#pragma unroll 8
+                for (int row = 0; row < 32; row++) {
+                    const MvsRow t = tab[row];
+                    t.gvp[i] = ov[row * MVS_OUT_STRIDE + lane];
+                    t.gmp[i] = om[row * MVS_OUT_STRIDE + lane];
+                }
+            } else {
 #pragma unroll 4
-            for (int row = 0; row < 32; row++) {
-                const int Lr = __shfl_sync(ADB_FULL, L, row);
-                const long long ro = __shfl_sync(ADB_FULL, myoff, row);
-                const int fl = __shfl_sync(ADB_FULL, flag, row);
-                if (i < Lr) {
-                    if ((fl & 1) && i >= wv - 1) gv[ro + i - (wv - 1)] = ov[row * MVS_OUT_STRIDE + lane];
-                    if ((fl & 2) && i >= wm - 1) gm[ro + i - (wm - 1)] = om[row * MVS_OUT_STRIDE + lane];
+                for (int row = 0; row < 32; row++) {
+                    const MvsRow t = tab[row];
+                    if (i < t.L) {
+                        if (i >= t.iminv) t.gvp[i] = ov[row * MVS_OUT_STRIDE + lane];
+                        if (i >= t.iminm) t.gmp[i] = om[row * MVS_OUT_STRIDE + lane];
+                    }
                 }
             }
         }

@@ -153,6 +153,61 @@ def detect_reads(adc: np.ndarray, offsets: np.ndarray, full_lens: np.ndarray, ca
     return res, status
 
 
+# ---- streaming poly(A) detector (adapted/detect/mvs.py:341-426) --------------------------------------------------------
+
+def mean_var_shift_polyA_detect_batch(batch_of_signals: np.ndarray, signal_lens: np.ndarray, params: Any = None,
+                                      device: int = 0) -> np.ndarray:
+    """mean_var_shift_polyA_detect for every row of a dense float32 [N, m] matrix (row i = its first signal_lens[i]
+    samples): poly(A) start per read, 0 where the reference returns 0."""
+    from .config import StreamingConfig, flatten_streaming_config
+
+    params = StreamingConfig() if params is None else params
+    b, keep = _dense_batch(batch_of_signals, signal_lens)
+    out = np.zeros(b.n_reads, dtype=np.int32)
+    if b.n_reads == 0:
+        return out
+    cfg = _lib.fill_stream_config(flatten_streaming_config(params))
+    ctx = _lib.default_context(device)
+    _lib.check(_lib.load().adb_mvs_stream_detect_host(ctx.handle, C.byref(b), C.byref(cfg), out.ctypes.data))
+    del keep
+    return out
+
+
+def mean_var_shift_polyA_detect(calibrated_signal: np.ndarray, params: Any = None, device: int = 0) -> int:
+    """Same signature as the reference's function: one calibrated signal -> poly(A) start or 0."""
+    x = np.ascontiguousarray(calibrated_signal, dtype=np.float32).reshape(1, -1)
+    if x.shape[1] == 0:
+        return 0
+    return int(mean_var_shift_polyA_detect_batch(x, np.array([x.shape[1]], np.int32), params, device)[0])
+
+
+def mean_var_shift_polyA_detect_i16(adc: np.ndarray, offsets: np.ndarray, calib_offset: np.ndarray,
+                                    calib_scale: np.ndarray, params: Any = None, window: Optional[int] = None,
+                                    device: int = 0) -> np.ndarray:
+    """Ragged int16 form (what a read-until cache holds): read i = adc[offsets[i]:offsets[i+1]], calibrated on the
+    device; `window` bounds the samples looked at per read (default: the longest read)."""
+    from .config import StreamingConfig, flatten_streaming_config
+
+    params = StreamingConfig() if params is None else params
+    adc = np.ascontiguousarray(adc, dtype=np.int16)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    lens = np.ascontiguousarray(np.diff(offsets), dtype=np.int32)
+    coff = np.ascontiguousarray(calib_offset, dtype=np.float32)
+    cscale = np.ascontiguousarray(calib_scale, dtype=np.float32)
+    n = lens.size
+    out = np.zeros(n, dtype=np.int32)
+    if n == 0:
+        return out
+    m = int(window) if window else int(lens.max())
+    b = _lib.AdbBatch(signal=adc.ctypes.data, sig_type=_lib.SIG_I16, n_reads=n, m=m, batch_size=n,
+                      offsets=offsets.ctypes.data, full_lens=lens.ctypes.data, calib_offset=coff.ctypes.data,
+                      calib_scale=cscale.ctypes.data)
+    cfg = _lib.fill_stream_config(flatten_streaming_config(params))
+    ctx = _lib.default_context(device)
+    _lib.check(_lib.load().adb_mvs_stream_detect_host(ctx.handle, C.byref(b), C.byref(cfg), out.ctypes.data))
+    return out
+
+
 # ---- kernel-level mirrors of the Cython module (adapted/detect/_c_llr.pyx) ---------------------------------------
 
 def c_llr_trace(raw_signal, start, end, min_obs, border_trim, stride=1, adapter_early_stopping=0,

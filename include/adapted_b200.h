@@ -236,6 +236,21 @@ int adb_downscale_host(adb_ctx *ctx, const adb_batch *batch, int32_t col0, int32
 /* CNN scores of BoundariesCNN (adapted/detect/cnn.py:16-52,85-98) on prepared inputs x[n, L] -> scores[n, 2, L_out] */
 int adb_cnn_scores_host(adb_ctx *ctx, const float *x, int32_t n, int32_t L, const float *cnn_weights, float *scores);
 
+/* ---- streaming poly(A) detector --------------------------------------------------------- */
+/* StreamingConfig (adapted/config/sig_proc.py:140-158); open range ends are +-inf */
+typedef struct adb_stream_config {
+    int32_t min_obs_adapter, min_obs_post_loc, search_increment_step;
+    int32_t pA_mean_window, pA_var_window, median_shift_window, polyA_window, _pad;
+    double pA_mean_range[2], pA_var_range[2], median_shift_range[2], polyA_med_range[2], polyA_local_range[2];
+} adb_stream_config;
+/*
+ * Drop-in for mean_var_shift_polyA_detect(calibrated_signal, params)            adapted/detect/mvs.py:341-426
+ * (read-until / streaming poly(A) detection on an accumulating signal cache; no caller inside the reference) for
+ * every read of `batch` at once (HOST buffers; read i is its first min(full_lens[i], m) samples, I16 or F32 form).
+ * polya_start[i] = the detected poly(A) start or 0.
+ */
+int adb_mvs_stream_detect_host(adb_ctx *ctx, const adb_batch *batch, const adb_stream_config *cfg, int32_t *polya_start);
+
 /* ---- result tables ---------------------------------------------------------------------- */
 /*
  * Drop-in for save_detected_boundaries(processing_results, filename, save_fail_reasons)   adapted/output.py:26-51

@@ -48,6 +48,21 @@ CASES = [
 ]
 
 
+STREAM_WINDOW = 20000  # samples of the read-until cache looked at per read
+STREAM_CASES = [
+    # name, chemistry of the synthetic reads, n, seed, generator kwargs, StreamingConfig overrides
+    ("defaults_rna002", "rna002", 48, 51, {}, {}),
+    ("defaults_rna004", "rna004", 48, 52, {}, {}),
+    ("stress_short", "rna002", 48, 53, {"stress": True, "short_frac": 0.3}, {}),
+    # a tight median window and local range reject the first matches: the offset loop advances by the step
+    ("retry_loop", "rna004", 48, 54, {}, {"min_obs_adapter": 500, "pA_mean_range": [60.0, 130.0], "pA_var_range": [None, 70.0],
+                                          "polyA_med_range": [100.3, 115.7], "polyA_local_range": [0.0, 8.3],
+                                          "search_increment_step": 37, "median_shift_range": [12.5, None]}),
+    ("odd_windows", "rna002", 32, 55, {}, {"pA_mean_window": 33, "pA_var_window": 64, "median_shift_window": 700,
+                                           "polyA_window": 150, "min_obs_post_loc": 1200, "polyA_local_range": [None, None]}),
+]
+
+
 def read_ids_for(name: str, n: int):
     """deterministic uuid-shaped read ids (what pod5 gives the reference, file_proc.py:175)"""
     import uuid
@@ -169,6 +184,26 @@ def main():
         with gzip.GzipFile(path, "wb", mtime=0) as f:
             f.write(json.dumps(rec).encode())
         print(f"{name}: n={n} pass={n_pass} -> {os.path.relpath(path, ROOT)} ({os.path.getsize(path)} B)")
+
+    # streaming poly(A) detector (mean_var_shift_polyA_detect, mvs.py:341-426): expected start per read
+    from adapted.config.sig_proc import StreamingConfig
+    from adapted.detect.mvs import mean_var_shift_polyA_detect
+
+    stream = []
+    for name, chem, n, seed, kw, overrides in STREAM_CASES:
+        p = StreamingConfig()
+        for k, v in overrides.items():
+            setattr(p, k, tuple(v) if isinstance(v, list) else v)
+        batch = make_reads(n, chem, STREAM_WINDOW, seed=seed, **kw)
+        x = batch.to_dense_pa()
+        lens = np.minimum(batch.full_lens, STREAM_WINDOW)
+        want = [int(mean_var_shift_polyA_detect(x[i, : lens[i]], p)) for i in range(n)]
+        stream.append(dict(name=name, chemistry=chem, n=n, seed=seed, gen_kwargs=kw, overrides=overrides,
+                           m=STREAM_WINDOW, adc_sha256=hashlib.sha256(batch.adc.tobytes()).hexdigest(),
+                           polya_start=want))
+        print(f"mvs_stream {name}: found {sum(w > 0 for w in want)}/{n}")
+    with gzip.GzipFile(os.path.join(GOLDEN, "mvs_stream.json.gz"), "wb", mtime=0) as f:
+        f.write(json.dumps(dict(versions=versions, cases=stream)).encode())
 
     # kernel-level golden vectors for c_llr_trace incl. the early-stop dispatch branches
     from adapted.detect._c_llr import c_llr_trace

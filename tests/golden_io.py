@@ -50,3 +50,20 @@ def load_case(name: str) -> Dict[str, Any]:
 def load_cnn_weights() -> Dict[str, np.ndarray]:
     with np.load(os.path.join(GOLDEN, "cnn_weights_rna004_130bps_v0.2.4.npz")) as z:
         return {k: z[k] for k in z.files}
+
+
+def load_stream_cases():
+    """tests/golden/mvs_stream.json.gz: expected poly(A) starts of mean_var_shift_polyA_detect (executed reference)."""
+    from adapted_b200.config import StreamingConfig
+
+    with gzip.open(os.path.join(GOLDEN, "mvs_stream.json.gz"), "rb") as f:
+        doc = json.loads(f.read().decode())
+    out = []
+    for c in doc["cases"]:
+        p = StreamingConfig()
+        for k, v in c["overrides"].items():
+            setattr(p, k, tuple(v) if isinstance(v, list) else v)
+        batch = make_reads(c["n"], c["chemistry"], c["m"], seed=c["seed"], **c["gen_kwargs"])
+        assert hashlib.sha256(batch.adc.tobytes()).hexdigest() == c["adc_sha256"], "synthetic generator drifted"
+        out.append(dict(name=c["name"], params=p, batch=batch, m=c["m"], want=np.asarray(c["polya_start"], dtype=np.int64)))
+    return out

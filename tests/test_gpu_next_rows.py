@@ -111,3 +111,40 @@ def test_gpu_records_to_reference_csv(name, method):
                     continue
                 assert col in FLOAT_FIELDS, (col, g, w)
                 assert abs(float(g) - float(w)) <= 0.0011 + 1e-5 * abs(float(w)), (col, g, w)
+
+
+# ---- row f4: streaming poly(A) detector -----------------------------------------------------------------------------
+from tests.golden_io import load_stream_cases  # noqa: E402
+
+STREAM_CASES = load_stream_cases()
+
+
+@pytest.mark.parametrize("case", STREAM_CASES, ids=[c["name"] for c in STREAM_CASES])
+def test_stream_detector_golden(case):
+    """GPU mean_var_shift_polyA_detect == executed reference (dense float32 and ragged int16 ingest), exact"""
+    from adapted_b200.detect import mean_var_shift_polyA_detect_batch, mean_var_shift_polyA_detect_i16
+
+    b = case["batch"]
+    lens = np.minimum(b.full_lens, case["m"]).astype(np.int32)
+    got = mean_var_shift_polyA_detect_batch(b.to_dense_pa(), lens, case["params"])
+    assert np.array_equal(got, case["want"])
+    got16 = mean_var_shift_polyA_detect_i16(b.adc, b.offsets, b.calib_offset, b.calib_scale, case["params"], window=case["m"])
+    assert np.array_equal(got16, case["want"])
+
+
+def test_stream_detector_matches_oracle_and_single_call():
+    from adapted_b200.config import StreamingConfig
+    from adapted_b200.detect import mean_var_shift_polyA_detect, mean_var_shift_polyA_detect_batch
+
+    p = StreamingConfig(min_obs_adapter=1000, search_increment_step=250, polyA_local_range=(0.0, 9.1),
+                        polyA_med_range=(101.7, 113.9), median_shift_range=(19.3, None))
+    b = make_reads(96, "rna004", 17500, seed=801, short_frac=0.2)
+    x = b.to_dense_pa()
+    lens = np.minimum(b.full_lens, 17500).astype(np.int32)
+    want = np.array([detect_ref.mvs_stream_detect(x[i, : lens[i]], p) for i in range(b.n)])
+    got = mean_var_shift_polyA_detect_batch(x, lens, p)
+    assert np.array_equal(got, want)
+    assert (want > 0).any() and (want == 0).any()
+    i = int(np.flatnonzero(want > 0)[0])
+    assert mean_var_shift_polyA_detect(x[i, : lens[i]], p) == want[i]
+    assert mean_var_shift_polyA_detect(x[i, :200], p) == 0  # shorter than min_obs_adapter + windows
