@@ -18,11 +18,14 @@
 // (|x| >= 65504: pathological reads only) set a per-read flag; flagged reads are recomputed by the FP32-pipe kernel
 // (cnn_conv64_kernel with a read filter), so the result never depends on the range.
 //
-// Pipeline (one persistent CTA per SM, 256 threads, tiles double-buffered in shared memory and in TMEM):
-//   iteration i:  (a) global loads of tile i+1 into registers           -- latency covered by (b)-(c)
-//                 (b) one thread issues the 84 MMAs of tile i            -- the tensor pipe works on them during (c)-(d)
-//                 (c) epilogue of tile i-1: TMEM -> registers -> bias + ReLU -> global
-//                 (d) split the prefetched registers into the hi / lo planes of the other tile buffer
+// Pipeline (one persistent CTA per SM, warp-specialised, tiles double-buffered in shared memory and in TMEM):
+//   issuer warp (one thread): waits for "tile buffer b built" and "accumulator b drained", issues the 84 MMAs of the
+//                 tile and commits them to the accumulator barrier -- it runs ahead of the workers by up to one tile
+//   8 worker warps, iteration i:
+//                 (a) global loads of tile i+1 into registers            -- latency covered by (c)
+//                 (c) epilogue of tile i-1: TMEM -> registers -> bias + ReLU -> global, accumulator handed back
+//                 (d) split the prefetched registers into the hi / lo planes of the other tile buffer, hand it over
+//   (mbarriers only; no CTA-wide barrier inside the loop)
 // Layer 1 (1 -> 64, 0.8 % of the flops) is fused into (d) of layer 2 on the FP32 pipe, the transposed convolution
 // (64 -> 2) stays in cnn_convT_kernel.
 #pragma once
@@ -30,7 +33,8 @@
 
 #include "adb_cnn.cuh"
 
-#define TC_THREADS 256
+#define TC_WORKERS 256                   // 8 worker warps
+#define TC_THREADS (TC_WORKERS + 32)      // + the MMA issuer warp
 #define TC_ROWS 128                      // output positions per job (one M = 128 tile)
 #define TC_RA (TC_ROWS + 8)              // rows of the activation tile (6 halo rows, rounded to a multiple of 8)
 #define TC_NQ (TC_ROWS + 6)              // rows actually filled
@@ -39,7 +43,7 @@
 #define TC_WBYTES (CNN_K * 2 * TC_WPART) // resident weights of one layer: 114 688 B
 #define TC_NX (3 * TC_NQ + 6)            // x samples under one tile of layer 1 (FUSE_L1)
 #define TC_ITEMS (8 * TC_NQ)             // (octet, row) items of a tile: 8 channels each
-#define TC_ROUNDS ((TC_ITEMS + TC_THREADS - 1) / TC_THREADS)
+#define TC_ROUNDS ((TC_ITEMS + TC_WORKERS - 1) / TC_WORKERS)
 // instruction descriptor (cute/arch/mma_sm100_desc.hpp): D = f32 [4,6) = 1, A = B = f16 (0), both K-major,
 // N >> 3 at [17,23), M >> 4 at [24,29)
 #define TC_IDESC ((1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24))
@@ -135,11 +139,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const floa
     float *Xs = (float *)(Abuf + 4 * TC_PLANE);                 // FUSE_L1: x window of the tile being built
     float *W1s = Xs + TC_NX + 10;                               // [64][7] + [64]
     float *Bs = W1s + 64 * 8;                                   // bias [64]
-    uint64_t *accb = (uint64_t *)(((uintptr_t)(Bs + 64) + 15) & ~(uintptr_t)15);  // accumulator barriers [2]
-    uint32_t *tmem_slot = (uint32_t *)(accb + 2);
+    // barriers: accb[2] accumulator complete (tcgen05.commit), afull[2] tile buffer built (all workers), accfree[2]
+    // accumulator drained by the epilogue (all workers)
+    uint64_t *accb = (uint64_t *)(((uintptr_t)(Bs + 64) + 15) & ~(uintptr_t)15);
+    uint64_t *afull = accb + 2, *accfree = accb + 4;
+    uint32_t *tmem_slot = (uint32_t *)(accb + 6);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    if (tid == 0) { mbar_init(&accb[0], 1); mbar_init(&accb[1], 1); }
+    if (tid == 0) {
+        for (int b = 0; b < 2; b++) { mbar_init(&accb[b], 1); mbar_init(&afull[b], TC_WORKERS); mbar_init(&accfree[b], TC_WORKERS); }
+    }
     for (int i = tid; i < TC_WBYTES / 16; i += blockDim.x)
         reinterpret_cast<uint4 *>(Wsm)[i] = reinterpret_cast<const uint4 *>(wp)[i];
     if (FUSE_L1) {
@@ -169,14 +178,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const floa
             const int x0 = 3 * (t0 - 3) - 3;
 #pragma unroll
             for (int u = 0; u < 2; u++) {
-                const int i = tid + u * TC_THREADS, j = x0 + i;
+                const int i = tid + u * TC_WORKERS, j = x0 + i;
                 px[u] = (i < TC_NX && j >= 0 && j < Lx) ? xr[j] : 0.0f;
             }
         } else {
             const float *ar = in + (size_t)r * CNN_C * LP;
 #pragma unroll
             for (int u = 0; u < TC_ROUNDS; u++) {
-                const int i = tid + u * TC_THREADS;
+                const int i = tid + u * TC_WORKERS;
                 const int kc = i / TC_NQ, q = i % TC_NQ;
                 const int p = t0 - 3 + q;
                 const bool ok = (i < TC_ITEMS) && p >= 0 && p < L1;
@@ -191,13 +200,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const floa
         unsigned char *hi_plane = Abuf + (size_t)b * 2 * TC_PLANE, *lo_plane = hi_plane + TC_PLANE;
         bool bad = false;
         if (FUSE_L1) {
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_WORKERS) : "memory");  // every worker is done with the previous x window
 #pragma unroll
             for (int u = 0; u < 2; u++) {
-                const int i = tid + u * TC_THREADS;
+                const int i = tid + u * TC_WORKERS;
                 if (i < TC_NX) Xs[i] = px[u];
             }
-            __syncthreads();
-            for (int i = tid; i < TC_ITEMS; i += TC_THREADS) {
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_WORKERS) : "memory");
+            for (int i = tid; i < TC_ITEMS; i += TC_WORKERS) {
                 const int kc = i / TC_NQ, q = i % TC_NQ;
                 const int p = t0 - 3 + q;
                 float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // zero padding of layer 2's input outside [0, L1)
@@ -216,12 +226,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const floa
         } else {
 #pragma unroll
             for (int u = 0; u < TC_ROUNDS; u++) {
-                const int i = tid + u * TC_THREADS;
+                const int i = tid + u * TC_WORKERS;
                 if (i < TC_ITEMS) bad |= tc_split_store(hi_plane, lo_plane, i / TC_NQ, i % TC_NQ, pf[u]);
             }
         }
         if (bad) redo[r] = 1;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to the tensor core
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&afull[b])) : "memory");
     };
     // ---- (b) the 84 MMAs of one tile: 7 taps x 4 K-steps of 16 channels x (hi*hi, lo*hi, hi*lo) ----
     const uint32_t w_lo0 = tc_desc_lo(smem_u32(Wsm), 64 * 16), w_hi = tc_desc_hi(128);
@@ -260,31 +271,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const floa
         }
     };
 
-    int job = blockIdx.x;
-    if (job < n_jobs) {
-        prefetch(job);
-        build(job, 0);
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    int prev_job = -1;
-    uint32_t it = 0;
-    for (; job < n_jobs; job += gridDim.x, it++) {
-        const int b = (int)(it & 1u);
-        const int next = job + (int)gridDim.x;
-        const bool has_next = next < n_jobs;
-        if (has_next) prefetch(next);                                   // (a)
-        if (tid == 0) {                                                 // (b)
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            issue(b);
+    if (warp == TC_WORKERS / 32) {
+        // ---- MMA issuer ----
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int job = blockIdx.x; job < n_jobs; job += gridDim.x, it++) {
+                const int b = (int)(it & 1u);
+                mbar_wait(&afull[b], (it >> 1) & 1u);                          // tile buffer b built
+                if (it >= 2) mbar_wait(&accfree[b], ((it - 2) >> 1) & 1u);     // accumulator b drained (tile it - 2)
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                issue(b);
+            }
         }
-        if (prev_job >= 0) epilogue(prev_job, b ^ 1, ((it - 1) >> 1) & 1u);  // (c): also proves buffer b^1 is free
-        if (has_next) build(next, b ^ 1);                               // (d)
-        prev_job = job;
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
+        __syncwarp();
+    } else {
+        // ---- workers ----
+        int job = blockIdx.x;
+        if (job < n_jobs) {
+            prefetch(job);
+            build(job, 0);
+        }
+        int prev_job = -1;
+        uint32_t it = 0;
+        for (; job < n_jobs; job += gridDim.x, it++) {
+            const int b = (int)(it & 1u);
+            const int next = job + (int)gridDim.x;
+            const bool has_next = next < n_jobs;
+            if (has_next) prefetch(next);                                   // (a)
+            if (prev_job >= 0) {                                            // (c): also proves tile buffer b^1 is free
+                epilogue(prev_job, b ^ 1, ((it - 1) >> 1) & 1u);
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accfree[b ^ 1])) : "memory");
+            }
+            if (has_next) build(next, b ^ 1);                               // (d)
+            prev_job = job;
+        }
+        if (prev_job >= 0) epilogue(prev_job, (int)((it - 1) & 1u), ((it - 1) >> 1) & 1u);
     }
-    if (prev_job >= 0) epilogue(prev_job, (int)((it - 1) & 1u), ((it - 1) >> 1) & 1u);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
