@@ -127,7 +127,8 @@ template <bool FUSE_L1>
 __global__ void __launch_bounds__(CNN_THREADS, 1) cnn_conv64_kernel(const float *in, float *out, const float *packed_w,
                                                                    const float *bias, const float *w1, const float *b1,
                                                                    int n_reads, int Lx, int L1, int LP, const int *only) {
-    if (only) {  // nothing flagged for this CTA: leave before the 114.7 KB of weights are loaded
+    if (only) {  // nothing flagged (only[-1] == 0) or nothing flagged for this CTA: leave before the weights are loaded
+        if (only[-1] == 0) return;
         const int tiles_per_read = (L1 + CNN_TILE - 1) / CNN_TILE, n_tiles = n_reads * tiles_per_read;
         bool mine = false;
         for (int tile = blockIdx.x; tile < n_tiles && !mine; tile += gridDim.x) mine = only[tile / tiles_per_read] != 0;
@@ -547,9 +548,9 @@ static int cnn_forward_dev(adb_ctx *ctx, const float *x, int n, const CnnDims &D
     if (use_tc) {
         // split fp16 weights of both layers, then the per-read "outside the fp16 range" flags of one chunk
         const size_t wbytes = sizeof(__half) * 2 * CNN_K * 2 * 4096;
-        if (ctx->cnn_wtc.ensure(wbytes + sizeof(int) * (size_t)chunk)) { set_err("cudaMalloc cnn tc weights"); return ADB_ERR_CUDA; }
+        if (ctx->cnn_wtc.ensure(wbytes + sizeof(int) * ((size_t)chunk + 4))) { set_err("cudaMalloc cnn tc weights"); return ADB_ERR_CUDA; }
         wtc = (__half *)ctx->cnn_wtc.p;
-        redo = (int *)((unsigned char *)ctx->cnn_wtc.p + wbytes);
+        redo = (int *)((unsigned char *)ctx->cnn_wtc.p + wbytes) + 4;  // redo[-1] = "any read of the chunk flagged"
         {
             KernelTimer t(ctx, 5, st);
             cnn_tc_pack_weights_kernel<<<(2 * CNN_K * 4096 + 255) / 256, 256, 0, st>>>(w_dev, wtc);
@@ -562,7 +563,7 @@ static int cnn_forward_dev(adb_ctx *ctx, const float *x, int n, const CnnDims &D
         const int tiles = nc * ((D.L1 + CNN_TILE - 1) / CNN_TILE);
         const int grid = std::max(1, std::min(tiles, ctx->sm_count));
         if (use_tc) {
-            CUDA_TRY(cudaMemsetAsync(redo, 0, sizeof(int) * (size_t)nc, st));
+            CUDA_TRY(cudaMemsetAsync(redo - 4, 0, sizeof(int) * ((size_t)nc + 4), st));
             {
                 KernelTimer t(ctx, 5, st);
                 cnn_tc_launch(true, x + (size_t)r0 * D.Lx, a0, wtc, w_dev + CNN_B2, w_dev + CNN_W1, w_dev + CNN_B1, nc, D.Lx, D.L1,

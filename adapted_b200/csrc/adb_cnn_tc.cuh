@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const floa
                 if (i < TC_ITEMS) bad |= tc_split_store(hi_plane, lo_plane, i / TC_NQ, i % TC_NQ, pf[u]);
             }
         }
-        if (bad) redo[r] = 1;
+        if (bad) { redo[r] = 1; redo[-1] = 1; }  // redo[-1]: "any read flagged" (lets the FP32 pass leave at once)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to the tensor core
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&afull[b])) : "memory");
     };

@@ -48,6 +48,7 @@ CASES = [
 ]
 
 
+JOB = dict(n=150, seed=61, minibatch=50, batch_size_output=64)  # file-level job (ingest.detect_file)
 STREAM_WINDOW = 20000  # samples of the read-until cache looked at per read
 STREAM_CASES = [
     # name, chemistry of the synthetic reads, n, seed, generator kwargs, StreamingConfig overrides
@@ -184,6 +185,35 @@ def main():
         with gzip.GzipFile(path, "wb", mtime=0) as f:
             f.write(json.dumps(rec).encode())
         print(f"{name}: n={n} pass={n_pass} -> {os.path.relpath(path, ROOT)} ({os.path.getsize(path)} B)")
+
+    # a whole job: three minibatches through the seam + the saver threads' batching (file_proc.py:246-266,312-351)
+    from adapted.container_types import ReadResult
+    from adapted.output import save_detected_boundaries
+
+    spc = cfgs[("plain", "rna002")]
+    jb = make_reads(JOB["n"], "rna002", spc.sig_preload_size, seed=JOB["seed"], stress=True)
+    jx = jb.to_dense_pa()
+    jids = read_ids_for("job", JOB["n"])
+    queues = {"pass": [], "fail": []}
+    for s in range(0, JOB["n"], JOB["minibatch"]):
+        res = combined_detect_llr2(jx[s: s + JOB["minibatch"]], jb.full_lens[s: s + JOB["minibatch"]], spc)
+        rr = [ReadResult(read_id=i, success=r.success, fail_reason=r.fail_reason, detect_results=r)
+              for r, i in zip(res, jids[s: s + JOB["minibatch"]])]
+        queues["fail"] += [r for r in rr if not r.success]
+        queues["pass"] += [r for r in rr if r.success]
+    files = {}
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        for key, stem in (("pass", "boundaries/detected_boundaries"), ("fail", "failed_reads/failed_reads")):
+            for bi, s in enumerate(range(0, len(queues[key]), JOB["batch_size_output"])):
+                fn = os.path.join(d, "t.csv")
+                save_detected_boundaries(queues[key][s: s + JOB["batch_size_output"]], fn, save_fail_reasons=key == "fail")
+                with open(fn, newline="") as f:
+                    files[f"{stem}_{bi}.csv"] = f.read()
+    with gzip.GzipFile(os.path.join(GOLDEN, "job_llr_rna002.json.gz"), "wb", mtime=0) as f:
+        f.write(json.dumps(dict(versions=versions, job=JOB, m=int(spc.sig_preload_size), config=config_as_dict(spc),
+                                adc_sha256=hashlib.sha256(jb.adc.tobytes()).hexdigest(), read_ids=jids, files=files)).encode())
+    print("job_llr_rna002:", {k: len(v) for k, v in queues.items()}, sorted(files))
 
     # streaming poly(A) detector (mean_var_shift_polyA_detect, mvs.py:341-426): expected start per read
     from adapted.config.sig_proc import StreamingConfig

@@ -130,3 +130,28 @@ def test_native_csv_equals_pandas_on_random_records(seed):
         got = format_detected_boundaries(recs, ids, METHOD[seam], with_reason, sel, "" if seam == "llr2" else None)
         want = _pandas_csv([res[i] for i in sel], [ids[i] for i in sel], with_reason)
         assert got.decode() == want
+
+
+def test_container_roundtrip_and_processed_ids(tmp_path):
+    """the native signal container and the `continue` scan of finished tables (file_proc.py:103-130), no GPU"""
+    import gzip
+    import json
+
+    from adapted_b200.ingest import processed_read_ids, read_container, write_container
+    from adapted_b200.synth import make_reads
+    from tests.golden_io import GOLDEN
+
+    b = make_reads(6, "rna004", 17500, seed=3)
+    ids = [f"id-{i}" for i in range(6)]
+    p = write_container(str(tmp_path / "c"), b.adc, b.offsets, b.full_lens, b.calib_offset, b.calib_scale, ids)
+    c = read_container(p)
+    assert np.array_equal(c["adc"], b.adc) and np.array_equal(c["offsets"], b.offsets)
+    assert np.array_equal(c["calib_scale"], b.calib_scale) and list(c["read_ids"]) == ids
+    with gzip.open(os.path.join(GOLDEN, "job_llr_rna002.json.gz"), "rb") as f:
+        doc = json.loads(f.read().decode())
+    for rel, text in doc["files"].items():
+        os.makedirs(os.path.dirname(tmp_path / rel), exist_ok=True)
+        with open(tmp_path / rel, "w", newline="") as f:
+            f.write(text)
+    assert processed_read_ids(str(tmp_path)) == set(doc["read_ids"])
+    assert len(processed_read_ids(str(tmp_path), failed_only=True)) == 23

@@ -148,3 +148,67 @@ def test_stream_detector_matches_oracle_and_single_call():
     i = int(np.flatnonzero(want > 0)[0])
     assert mean_var_shift_polyA_detect(x[i, : lens[i]], p) == want[i]
     assert mean_var_shift_polyA_detect(x[i, :200], p) == 0  # shorter than min_obs_adapter + windows
+
+
+# ---- file-level job: container -> GPU -> boundary tables (configs[0]: CSV-for-CSV) ---------------------------------
+def _load_job():
+    import gzip
+    import hashlib
+    import json
+    import os
+
+    from tests.golden_io import GOLDEN
+
+    with gzip.open(os.path.join(GOLDEN, "job_llr_rna002.json.gz"), "rb") as f:
+        doc = json.loads(f.read().decode())
+    cfg = doc["config"]
+    for sec in cfg.values():
+        for k, v in sec.items():
+            if isinstance(v, list):
+                sec[k] = tuple(v)
+    spc = config_from_dict(cfg)
+    b = make_reads(doc["job"]["n"], "rna002", doc["m"], seed=doc["job"]["seed"], stress=True)
+    assert hashlib.sha256(b.adc.tobytes()).hexdigest() == doc["adc_sha256"]
+    return doc, spc, b
+
+
+def _assert_csv_close(got, want):
+    if got == want:
+        return
+    gh, grows = _cells(got)
+    wh, wrows = _cells(want)
+    assert gh == wh and len(grows) == len(wrows)
+    for gr, wr in zip(grows, wrows):
+        for col, g, w in zip(gh, gr, wr):
+            if g != w:
+                assert col in FLOAT_FIELDS, (col, g, w)
+                assert abs(float(g) - float(w)) <= 0.0011 + 1e-5 * abs(float(w)), (col, g, w)
+
+
+def test_detect_file_writes_the_reference_tables(tmp_path):
+    """three minibatches, 64 reads per table: same files, same rows, same text as the executed reference (floats
+    within the 1e-5 contract before rounding); then `continue` on a half-finished output directory"""
+    import os
+
+    from adapted_b200.ingest import detect_file, processed_read_ids, write_container
+
+    doc, spc, b = _load_job()
+    job = doc["job"]
+    path = write_container(str(tmp_path / "reads"), b.adc, b.offsets, b.full_lens, b.calib_offset, b.calib_scale, doc["read_ids"])
+    out = str(tmp_path / "out")
+    stats = detect_file(path, out, spc, minibatch_size=job["minibatch"], batch_size_output=job["batch_size_output"])
+    assert stats["reads"] == job["n"] and stats["lost"] == 0
+    written = sorted(os.path.join(sub, f) for sub in ("boundaries", "failed_reads") for f in os.listdir(os.path.join(out, sub)))
+    assert written == sorted(doc["files"])
+    for rel, want in doc["files"].items():
+        with open(os.path.join(out, rel), newline="") as f:
+            _assert_csv_close(f.read(), want)
+    assert processed_read_ids(out) == set(doc["read_ids"])
+    # continue: keep the first pass table only, rerun -> the missing reads are processed again, numbering continues
+    os.remove(os.path.join(out, "boundaries", "detected_boundaries_1.csv"))
+    os.remove(os.path.join(out, "failed_reads", "failed_reads_0.csv"))
+    stats2 = detect_file(path, out, spc, minibatch_size=job["minibatch"], batch_size_output=job["batch_size_output"],
+                         continue_run=True)
+    assert stats2["reads"] == job["n"] - job["batch_size_output"]
+    assert os.path.exists(os.path.join(out, "boundaries", "detected_boundaries_1.csv"))
+    assert processed_read_ids(out) == set(doc["read_ids"])
