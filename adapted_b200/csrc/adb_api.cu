@@ -619,12 +619,28 @@ extern "C" int adb_detect_pipelined_host(adb_ctx *ctx, const adb_batch *batch, c
         w_dev = (const float *)ctx->h_misc2.p;
     }
     const int n_batches = (batch->n_reads + batch->batch_size - 1) / batch->batch_size;
-    const int reads_per_chunk = chunk_batches * batch->batch_size;
-    const int n_chunks = (batch->n_reads + reads_per_chunk - 1) / reads_per_chunk;
+    // Chunk schedule (in minibatches).  The first copy and the last chunk's kernels cannot overlap anything, so the
+    // job starts and ends with small chunks (chunk_batches / 4, / 2) and runs full-size chunks in between, where the
+    // per-chunk launch overheads and kernel tails matter.
+    std::vector<int> sched;
+    {
+        const int q = std::max(1, chunk_batches / 4), h = std::max(1, chunk_batches / 2);
+        int left = n_batches;
+        std::vector<int> tail;
+        if (n_batches >= 2 * (q + h) + chunk_batches) {
+            sched.push_back(q); sched.push_back(h);
+            tail.push_back(h); tail.push_back(q);
+            left -= 2 * (q + h);
+        }
+        while (left > 0) { const int c = std::min(left, chunk_batches); sched.push_back(c); left -= c; }
+        sched.insert(sched.end(), tail.begin(), tail.end());
+    }
     cudaStream_t cs = ctx->copy_stream, ks = ctx->stream;
-    for (int ch = 0; ch < n_chunks; ch++) {
+    int b0 = 0;  // first minibatch of the chunk
+    for (int ch = 0; ch < (int)sched.size(); ch++) {
         const int slot = ch & 1;
-        const int r0 = ch * reads_per_chunk, r1 = std::min(batch->n_reads, r0 + reads_per_chunk), nr = r1 - r0;
+        const int r0 = b0 * batch->batch_size;
+        const int r1 = (int)std::min<long long>((long long)batch->n_reads, (long long)(b0 + sched[ch]) * batch->batch_size), nr = r1 - r0;
         const int nb = (nr + batch->batch_size - 1) / batch->batch_size;
         const int64_t e0 = batch->offsets[r0], e1 = batch->offsets[r1];
         // the slot is free once the D2H of the chunk that used it two iterations ago has finished
@@ -652,12 +668,12 @@ extern "C" int adb_detect_pipelined_host(adb_ctx *ctx, const adb_batch *batch, c
         if (rc) return rc;
         CUDA_TRY(cudaMemcpyAsync(out_records + r0, ctx->p_records[slot].p, sizeof(adb_record) * (size_t)nr, cudaMemcpyDeviceToHost, ks));
         if (batch_status)
-            CUDA_TRY(cudaMemcpyAsync(batch_status + (size_t)ch * chunk_batches, ctx->p_status[slot].p, sizeof(int) * (size_t)nb, cudaMemcpyDeviceToHost, ks));
+            CUDA_TRY(cudaMemcpyAsync(batch_status + b0, ctx->p_status[slot].p, sizeof(int) * (size_t)nb, cudaMemcpyDeviceToHost, ks));
         CUDA_TRY(cudaEventRecord(ctx->p_done[slot], ks));
+        b0 += sched[ch];
     }
     CUDA_TRY(cudaStreamSynchronize(ks));
     CUDA_TRY(cudaStreamSynchronize(cs));
-    (void)n_batches;
     return ADB_OK;
 }
 

@@ -139,7 +139,8 @@ def main():
     ap.add_argument("--reads", type=int, default=100000, help="reads per GPU")
     ap.add_argument("--chemistry", default="rna002")
     ap.add_argument("--minibatch", type=int, default=1000)
-    ap.add_argument("--chunk-batches", type=int, default=16, help="minibatches per H2D chunk of the pipelined ingest")
+    ap.add_argument("--chunk-batches", type=int, default=0,
+                    help="minibatches per full-size H2D chunk of the pipelined ingest (default: 16, CNN path 32)")
     ap.add_argument("--cpu-reads-per-worker", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -261,6 +262,10 @@ def main():
                            batch_size=args.minibatch, offsets=host["offsets"].data_ptr(),
                            full_lens=host["full_lens"].data_ptr(), calib_offset=host["calib_offset"].data_ptr(),
                            calib_scale=host["calib_scale"].data_ptr())
+
+    if args.chunk_batches <= 0:  # copy-bound LLR path: short tail; kernel-bound CNN path: fewer per-chunk overheads
+        args.chunk_batches = 32 if flat["primary_method"] == 1 else 16
+    config["e2e_chunk_minibatches"] = args.chunk_batches
 
     def e2e_step():
         _lib.check(L.adb_detect_pipelined_host(ctx.handle, C.byref(hbatch), C.byref(cfg),
