@@ -319,8 +319,32 @@ __device__ void seg_mean_std(ValCtx &C, int a, int b, double &mean_out, double &
     if (n <= 0) { mean_out = CUDART_NAN; std_out = CUDART_NAN; return; }
     const ReadSrc src = C.src;  // registers, not the context in local memory
     const int T = blockDim.x;
-    // the ADC sum is exact in integers: mean = (sum(adc)/n + offset) * scale would not be numpy's float32 sum, but the
-    // 1e-5 tolerance applies here; stay with float64 accumulation of the float32 pA values for clarity
+    if (src.i16) {
+        // int16 sources: exact integer sums of the ADC codes (order-independent, hence the same bits whichever kernel
+        // or launch geometry handles the read; identical to validate_fast_kernel).  numpy's float32 pairwise sums are
+        // not reproduced -- the contract for mean / std is 1e-5 relative.
+        const int16_t *p = src.i16 + a;
+        long long s1 = 0, s2 = 0;
+        for (int j = threadIdx.x; j < n; j += T) { const int c = p[j]; s1 += c; s2 += (long long)(c * c); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(ADB_FULL, s1, o); s2 += __shfl_xor_sync(ADB_FULL, s2, o); }
+        long long *lt = reinterpret_cast<long long *>(C.dtmp);
+        __syncthreads();
+        if (threadIdx.x == 0) { lt[0] = 0; lt[1] = 0; }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd((unsigned long long *)&lt[0], (unsigned long long)s1);
+            atomicAdd((unsigned long long *)&lt[1], (unsigned long long)s2);
+        }
+        __syncthreads();
+        const double mk = (double)lt[0] / n;
+        double vk = (double)lt[1] / n - mk * mk;
+        if (vk < 0) vk = 0;
+        __syncthreads();
+        mean_out = (double)(float)((mk + (double)src.coff) * (double)src.cscale);
+        std_out = (double)(float)(sqrt(vk) * fabs((double)src.cscale));
+        return;
+    }
     double s = 0.0;
     if (src.i16) {
         const int16_t *p = src.i16 + a;

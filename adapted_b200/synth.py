@@ -105,9 +105,11 @@ def make_reads(n: int, chemistry: str, m: int, seed: int, stress: bool = False,
         calib_offset=c_off, calib_scale=c_scale, truth=np.asarray(truth, dtype=np.int32).reshape(-1, 3), m=m)
 
 
-def make_reads_torch(n: int, chemistry: str, m: int, seed: int, device="cuda", chunk: int = 4000):
+def make_reads_torch(n: int, chemistry: str, m: int, seed: int, device="cuda", chunk: int = 4000, stress: bool = False,
+                     short_frac: float = 0.0, short_min: int = 50):
     """Same squiggle distribution as :func:`make_reads`, generated with torch on `device` (bench.py builds
-    10^5..10^7 reads directly in HBM).  Returns a dict of tensors: adc int16 [sum k_i], offsets int64 [n+1],
+    10^5..10^7 reads directly in HBM).  `stress`: poly(A) lengths up to the preload limit (BASELINE config 4: long
+    poly(A) / truncated preload); `short_frac`: that fraction of reads ends inside the adapter / poly(A).  Returns a dict of tensors: adc int16 [sum k_i], offsets int64 [n+1],
     full_lens int32 [n], calib_offset / calib_scale float32 [n], truth int32 [n, 3]."""
     import torch
 
@@ -124,9 +126,14 @@ def make_reads_torch(n: int, chemistry: str, m: int, seed: int, device="cuda", c
     for s in range(0, n, chunk):
         c = min(chunk, n - s)
         n_op, n_ad = randint(*spec.open_pore, c), randint(*spec.adapter, c)
-        n_pa, n_rna = randint(*spec.polya, c), randint(*spec.rna, c)
+        n_pa = randint(spec.polya[0], m, c) if stress else randint(*spec.polya, c)
+        n_rna = randint(*spec.rna, c)
         e0, e1, e2 = n_op, n_op + n_ad, n_op + n_ad + n_pa
         full = e2 + n_rna
+        if short_frac > 0:
+            short = torch.rand((c,), generator=g, device=dev) < short_frac
+            cut = short_min + (torch.rand((c,), generator=g, device=dev) * (e2 + 450).to(torch.float32)).to(torch.int64)
+            full = torch.where(short, cut, full)
         k = torch.clamp(full, max=m)
         z = torch.randn((c, m), generator=g, device=dev)
         nlev = m // spec.hold + 2

@@ -198,3 +198,69 @@ def test_cnn_full_size_general_kernel_agrees_and_shards(rna004):
     ok = base["success"] == 1
     ds = rna004["flat"]["downscale_factor"]
     assert np.median(np.abs(base["adapter_end"][ok] - truth[ok, 1])) <= 2 * ds
+
+
+# ---- BASELINE config 4: long poly(A) / truncated-preload stress set ---------------------------------------------------
+N_STRESS = min(N_READS, int(os.environ.get("ADB_FULL_SIZE_STRESS_READS", "40000")))
+
+
+def _dense_rows(data, m, r0, r1):
+    from adapted_b200.synth import calibrate
+
+    offs = data["offsets"].cpu().numpy()
+    adc = data["adc"][int(offs[r0]):int(offs[r1])].cpu().numpy()
+    coff = data["calib_offset"][r0:r1].cpu().numpy()
+    cs = data["calib_scale"][r0:r1].cpu().numpy()
+    x = np.full((r1 - r0, m), np.nan, np.float32)
+    for i in range(r1 - r0):
+        a = adc[offs[r0 + i] - offs[r0]: offs[r0 + i + 1] - offs[r0]]
+        x[i, :a.size] = calibrate(a, coff[i], cs[i])
+    return x, data["full_lens"][r0:r1].cpu().numpy()
+
+
+@pytest.mark.parametrize("chem", ["rna002", "rna004"])
+def test_stress_set_full_size(chem):
+    """poly(A) lengths up to the preload limit and 10 % reads ending early: poly(A) running past the window, "not
+    enough signal" after the adapter, failed first candidates (CNN hand-over incl. the second moving-statistics pass
+    and the hail-mary fallback).  Fast paths == general kernels on every read, records independent of the cut, one
+    minibatch against the oracle."""
+    import torch
+
+    from adapted_b200.detect import flatten_cnn_weights
+    from adapted_b200.records import records_to_results
+    from adapted_b200.synth import make_reads_torch
+    from oracle import detect_ref
+    from tests.golden_io import load_cnn_weights
+    from tests.test_gpu_cnn_path import _cnn_compare
+
+    spc = get_chemistry_specific_config(chem)
+    flat = flatten_config(spc)
+    n = N_STRESS
+    # LLR path: a read without a single downscaled sample loses its whole minibatch in the reference (SURVEY A.11,
+    # covered by the golden "lost minibatch" case); here the short reads keep at least a few trace samples
+    data = make_reads_torch(n, chem, flat["sig_preload_size"], seed=91, device="cuda", stress=True, short_frac=0.1,
+                            short_min=50 if flat["primary_method"] == 1 else flat["min_obs_adapter"] + 200)
+    torch.cuda.synchronize()
+    cnn = flat["primary_method"] == 1
+    w = flatten_cnn_weights(load_cnn_weights()) if cnn else None
+    base, st, _ = _run(data, flat, weights=w)
+    assert not st.any()
+    fails = base[base["success"] == 0]
+    assert 0.02 < len(fails) / n < 0.9
+    assert len(set(fails["fail_code"].tolist())) >= 3  # several different reasons are exercised
+    gen, st2, _ = _run(data, flat, weights=w, no_fast_validate=1, **({} if cnn else {"exact_global_select": 1}))
+    assert not st2.any()
+    _assert_records_equivalent(base, gen)
+    cut = (n // MBS) * 3 // 10 * MBS
+    a, _, _ = _run(data, flat, weights=w, lo=0, hi=cut)
+    b, _, _ = _run(data, flat, weights=w, lo=cut, hi=n)
+    assert np.concatenate([a, b]).tobytes() == base.tobytes()
+    r0 = (n // MBS // 2) * MBS
+    x, lens = _dense_rows(data, flat["sig_preload_size"], r0, r0 + MBS)
+    got = records_to_results(base[r0:r0 + MBS], flat["primary_method"], None if cnn else "")
+    if cnn:
+        want = detect_ref.detect_cnn(x, lens, load_cnn_weights(), spc)
+        _cnn_compare(got, want, flat["downscale_factor"])
+    else:
+        want = detect_ref.detect_llr2(x, lens, spc)
+        assert diff_results(got, want) == []
