@@ -396,6 +396,8 @@ static int launch_validate(adb_ctx *ctx, const BatchDev &B, const adb_config &cf
         A.pre_meta = M.meta;
     }
     A.done = nullptr;
+    A.pending = A.n_pending = nullptr;
+    A.work_counter = nullptr;
     ctx->vf_last_reads = 0;
     if (B.sig_type == ADB_SIG_I16 && !ctx->opt_no_fast_validate && !overwrite) {
         // int16 sources: counting-based validation (adb_vfast.cuh); what it leaves is picked up by validate_kernel
@@ -433,7 +435,8 @@ static int launch_validate(adb_ctx *ctx, const BatchDev &B, const adb_config &cf
                 M.meta = (int *)(lbase + 2 + B.n_reads);
                 int *cnt = (int *)ctx->mvs_perm.p, *list = cnt + MVS_NBUCKET;  // counting-sort scratch of the first pass
                 CUDA_TRY(cudaMemsetAsync(M.cursor, 0, 16, st));
-                CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(int), st));
+                CUDA_TRY(cudaMemsetAsync(cnt, 0, 2 * sizeof(int), st));  // [0] list length, [1] work counter of validate_kernel
+                A.pending = list; A.n_pending = cnt; A.work_counter = cnt + 1;
                 M.perm = list; M.n_active = cnt; M.all_cands = 1; M.n_cand = given_ntopk; M.ntopk_per_read = ntopk_per_read;
                 KernelTimer t(ctx, 7, st);
                 mvs_pending_kernel<<<(B.n_reads + 255) / 256, 256, 0, st>>>(F.done, B.n_reads, list, cnt);

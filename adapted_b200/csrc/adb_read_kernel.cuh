@@ -219,6 +219,11 @@ struct ValidateArgs {
     const long long *pre_off;         // [n_reads] row offset into the pools, -1: none
     const int *pre_meta;              // [n_reads][2] = (adapter_end, polya_end) of the row
     const unsigned char *done;        // optional [n_reads]: 1 = already written by validate_fast_kernel
+    // optional compact list of the reads still to do (mvs_pending_kernel) + a work counter: CTAs then take the next
+    // read of the list dynamically -- the handed-over reads are few and of very uneven cost (several poly(A)
+    // candidates, hail-mary trace), a static stride would leave most CTAs idle behind the unlucky ones
+    const int *pending, *n_pending;
+    int *work_counter;
 };
 
 __host__ __device__ inline size_t validate_smem_bytes(int win_bytes, int nds_max, int peak_cap) {
@@ -261,7 +266,20 @@ __global__ void __launch_bounds__(ADB_VAL_THREADS, 3) validate_kernel(ValidateAr
     C.series_a = A.series + (size_t)blockIdx.x * 2 * A.B.m;
     C.series_b = C.series_a + A.B.m;
 
-    for (int r = blockIdx.x; r < A.B.n_reads; r += gridDim.x) {
+    int *next_sh = (int *)(small + 200);
+    for (int step = blockIdx.x;; step += gridDim.x) {
+        int r;
+        if (A.pending) {
+            __syncthreads();
+            if (threadIdx.x == 0) *next_sh = atomicAdd(A.work_counter, 1);
+            __syncthreads();
+            const int idx = *next_sh;
+            if (idx >= *A.n_pending) break;
+            r = A.pending[idx];
+        } else {
+            r = step;
+            if (r >= A.B.n_reads) break;
+        }
         const int mb = r / A.B.batch_size;
         adb_record *rec = A.out + r;
         __syncthreads();
