@@ -520,8 +520,10 @@ static CnnDims cnn_dims(int m, int A0, int f) {
 // tensor-core version of the two 64 -> 64 convolutions (adb_cnn_tc.cuh)
 __global__ void cnn_tc_pack_weights_kernel(const float *w, __half *packed);
 static int cnn_tc_launch_setup();
-static void cnn_tc_launch(bool fuse_l1, const float *in, float *out, const __half *wp, const float *bias, const float *w1,
+static void cnn_tc_launch(int layer, const void *in, void *out, const __half *wp, const float *bias, const float *w1,
                           const float *b1, int n_reads, int Lx, int L1, int LP, int *redo, int sm_count, cudaStream_t st);
+static size_t cnn_tc_a0t_bytes_per_read();
+static int cnn_tc_max_l1();
 
 static int cnn_forward_dev(adb_ctx *ctx, const float *x, int n, const CnnDims &D, const float *w_dev, float *scores,
                            cudaStream_t st) {
@@ -542,8 +544,10 @@ static int cnn_forward_dev(adb_ctx *ctx, const float *x, int n, const CnnDims &D
     CUDA_TRY(cudaFuncSetAttribute(cnn_conv64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(cudaFuncSetAttribute(cnn_conv64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     float *a0 = (float *)ctx->cnn_act0.p, *a1 = (float *)ctx->cnn_act1.p;
-    const bool use_tc = !ctx->opt_cnn_fp32;
+    // tensor-core path: needs L1 within the tile layout of the intermediate activations, FP32 pipe otherwise
+    const bool use_tc = !ctx->opt_cnn_fp32 && D.L1 <= cnn_tc_max_l1();
     __half *wtc = nullptr;
+    unsigned char *a0t = nullptr;
     int *redo = nullptr;
     if (use_tc) {
         // split fp16 weights of both layers, then the per-read "outside the fp16 range" flags of one chunk
@@ -557,6 +561,14 @@ static int cnn_forward_dev(adb_ctx *ctx, const float *x, int n, const CnnDims &D
         }
         ctx->launches += 1;
         if (cnn_tc_launch_setup()) { set_err("cudaFuncSetAttribute cnn tc"); return ADB_ERR_CUDA; }
+        // layer 2 -> layer 3 activations in layer 3's tile layout; the padding rows are never written: zero them whenever
+        // the buffer is (re)allocated
+        const size_t a0t_bytes = cnn_tc_a0t_bytes_per_read() * (size_t)chunk;
+        const void *before = ctx->cnn_a0t.p;
+        const size_t cap_before = ctx->cnn_a0t.cap;
+        if (ctx->cnn_a0t.ensure(a0t_bytes)) { set_err("cudaMalloc cnn a0t"); return ADB_ERR_CUDA; }
+        if (ctx->cnn_a0t.p != before || ctx->cnn_a0t.cap != cap_before) CUDA_TRY(cudaMemsetAsync(ctx->cnn_a0t.p, 0, ctx->cnn_a0t.cap, st));
+        a0t = (unsigned char *)ctx->cnn_a0t.p;
     }
     for (int r0 = 0; r0 < n; r0 += chunk) {
         const int nc = std::min(chunk, n - r0);
@@ -566,12 +578,12 @@ static int cnn_forward_dev(adb_ctx *ctx, const float *x, int n, const CnnDims &D
             CUDA_TRY(cudaMemsetAsync(redo - 4, 0, sizeof(int) * ((size_t)nc + 4), st));
             {
                 KernelTimer t(ctx, 5, st);
-                cnn_tc_launch(true, x + (size_t)r0 * D.Lx, a0, wtc, w_dev + CNN_B2, w_dev + CNN_W1, w_dev + CNN_B1, nc, D.Lx, D.L1,
+                cnn_tc_launch(2, x + (size_t)r0 * D.Lx, a0t, wtc, w_dev + CNN_B2, w_dev + CNN_W1, w_dev + CNN_B1, nc, D.Lx, D.L1,
                               D.LP, redo, ctx->sm_count, st);
             }
             {
                 KernelTimer t(ctx, 5, st);
-                cnn_tc_launch(false, a0, a1, wtc + (size_t)CNN_K * 2 * 4096, w_dev + CNN_B3, nullptr, nullptr, nc, D.Lx, D.L1, D.LP,
+                cnn_tc_launch(3, a0t, a1, wtc + (size_t)CNN_K * 2 * 4096, w_dev + CNN_B3, nullptr, nullptr, nc, D.Lx, D.L1, D.LP,
                               redo, ctx->sm_count, st);
             }
             {

@@ -34,7 +34,7 @@
 #include "adb_cnn.cuh"
 
 #define TC_WORKERS 256                   // 8 worker warps
-#define TC_THREADS (TC_WORKERS + 32)      // + the MMA issuer warp
+#define TC_THREADS (TC_WORKERS + 64)      // + the MMA issuer warp + the tile loader warp (layer 3)
 #define TC_ROWS 128                      // output positions per job (one M = 128 tile)
 #define TC_RA (TC_ROWS + 8)              // rows of the activation tile (6 halo rows, rounded to a multiple of 8)
 #define TC_NQ (TC_ROWS + 6)              // rows actually filled
@@ -47,10 +47,6 @@
 // instruction descriptor (cute/arch/mma_sm100_desc.hpp): D = f32 [4,6) = 1, A = B = f16 (0), both K-major,
 // N >> 3 at [17,23), M >> 4 at [24,29)
 #define TC_IDESC ((1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24))
-
-__host__ __device__ inline size_t cnn_tc_smem_bytes() {
-    return (size_t)TC_WBYTES + 4 * (size_t)TC_PLANE + (size_t)(TC_NX + 10) * 4 + 64 * 8 * 4 + 64 * 4 + 64 + 1024;
-}
 
 // weights: torch layout w[co][ci][k] -> [layer][tap][hi, lo][ci / 8][co][ci % 8] fp16
 __global__ void cnn_tc_pack_weights_kernel(const float *w, __half *packed) {
@@ -90,6 +86,20 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint32_t a_lo, uint3
         : "memory");
 }
 
+// one lane of a converged warp (elect.sync): ptxas then knows that a single thread issues the tcgen05 instructions and
+// does not wrap each of them into a per-value serialisation loop
+__device__ __forceinline__ bool tc_elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -126,32 +136,51 @@ __device__ __forceinline__ bool tc_split_store(unsigned char *hi_plane, unsigned
     return bad;
 }
 
-// in  : FUSE_L1 ? x [N][Lx] : act [N][64][LP]        out : act [N][64][LP]
+// Intermediate activations between the two layers ("A0T"): layer 2's epilogue writes its output already split into the
+// fp16 hi / lo planes and in the row order of layer 3's shared-memory tile,
+//     A0T[read][plane][ci / 8][rho = position + 3][ci % 8]      (16 B per row, TC_A0T_ROWS rows per octet),
+// so that the operand tile of a layer-3 job is 16 contiguous runs of 134 rows: sixteen cp.async.bulk copies per tile,
+// no thread touches the data.  Rows outside [0, L1) are layer 3's zero padding: rows >= L1 are written as zeros, the
+// three rows in front of position 0 and the tail rows are never written and stay zero from the buffer's memset.
+#define TC_A0T_ROWS (5 * TC_ROWS + 6)                       // enough for L1 <= 640 (RNA004: 550)
+#define TC_A0T_READ_BYTES (2 * 8 * TC_A0T_ROWS * 16)        // bytes per read
+#define TC_TILE_RUN (TC_NQ * 16)                            // bytes of one (plane, octet) run of a tile
+
+__host__ __device__ inline size_t cnn_tc_smem_bytes_layer(int layer) {
+    const int nbuf = layer == 3 ? 3 : 2;
+    return (size_t)TC_WBYTES + (size_t)nbuf * 2 * TC_PLANE + (size_t)(TC_NX + 10) * 4 + 64 * 8 * 4 + 64 * 4 + 160 + 1024;
+}
+
+// LAYER 2: in = x [N][Lx] (layer 1 fused into the operand build), out = A0T.
+// LAYER 3: in = A0T,                                                 out = act [N][64][LP] (float32, for convT).
 // wp  : packed weights of this layer, [7][2][4096] fp16 (cnn_tc_pack_weights_kernel)
 // redo: [N] set to 1 for reads with a value outside the fp16 range (recomputed on the FP32 pipe afterwards)
-template <bool FUSE_L1>
-__global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const float *in, float *out, const __half *wp,
+template <int LAYER>
+__global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const void *in, void *out, const __half *wp,
                                                                      const float *bias, const float *w1, const float *b1,
                                                                      int n_reads, int Lx, int L1, int LP, int *redo) {
+    constexpr int NBUF = LAYER == 3 ? 3 : 2;
     extern __shared__ __align__(1024) unsigned char tsm[];
     unsigned char *Wsm = tsm;                                   // resident weights [7][hi, lo][8][64][8] fp16
-    unsigned char *Abuf = tsm + TC_WBYTES;                      // 2 buffers x (hi plane, lo plane)
-    float *Xs = (float *)(Abuf + 4 * TC_PLANE);                 // FUSE_L1: x window of the tile being built
+    unsigned char *Abuf = tsm + TC_WBYTES;                      // NBUF tile buffers x (hi plane, lo plane)
+    float *Xs = (float *)(Abuf + NBUF * 2 * TC_PLANE);          // LAYER 2: x window of the tile being built
     float *W1s = Xs + TC_NX + 10;                               // [64][7] + [64]
     float *Bs = W1s + 64 * 8;                                   // bias [64]
-    // barriers: accb[2] accumulator complete (tcgen05.commit), afull[2] tile buffer built (all workers), accfree[2]
-    // accumulator drained by the epilogue (all workers)
+    // barriers: accb[2] accumulator complete (tcgen05.commit), afull[NBUF] tile buffer ready (layer 2: all workers,
+    // layer 3: the bulk copies), accfree[2] accumulator drained by the epilogue (all workers)
     uint64_t *accb = (uint64_t *)(((uintptr_t)(Bs + 64) + 15) & ~(uintptr_t)15);
-    uint64_t *afull = accb + 2, *accfree = accb + 4;
-    uint32_t *tmem_slot = (uint32_t *)(accb + 6);
+    uint64_t *afull = accb + 2, *accfree = accb + 2 + NBUF;
+    uint64_t *sfree = accfree + 2;  // [NBUF] layer 3: the MMAs reading tile buffer b are complete (second commit)
+    uint32_t *tmem_slot = (uint32_t *)(sfree + NBUF);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int b = 0; b < 2; b++) { mbar_init(&accb[b], 1); mbar_init(&afull[b], TC_WORKERS); mbar_init(&accfree[b], TC_WORKERS); }
+        for (int b = 0; b < 2; b++) { mbar_init(&accb[b], 1); mbar_init(&accfree[b], TC_WORKERS); }
+        for (int b = 0; b < NBUF; b++) { mbar_init(&afull[b], LAYER == 3 ? 1 : TC_WORKERS); mbar_init(&sfree[b], 1); }
     }
     for (int i = tid; i < TC_WBYTES / 16; i += blockDim.x)
         reinterpret_cast<uint4 *>(Wsm)[i] = reinterpret_cast<const uint4 *>(wp)[i];
-    if (FUSE_L1) {
+    if (LAYER == 2) {
         for (int i = tid; i < CNN_C * CNN_K; i += blockDim.x) W1s[i] = w1[i];
         for (int i = tid; i < CNN_C; i += blockDim.x) W1s[CNN_C * CNN_K + i] = b1[i];
     }
@@ -160,6 +189,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const floa
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the weights were written with generic stores
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -168,79 +198,66 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const floa
     const int jobs_per_read = (L1 + TC_ROWS - 1) / TC_ROWS;
     const int n_jobs = n_reads * jobs_per_read;
 
-    // ---- tile building: (a) loads into registers, (d) split into the planes of buffer `b` ----
-    float pf[TC_ROUNDS][8];   // !FUSE_L1: 8 channels of TC_ROUNDS (octet, row) items
-    float px[2];              // FUSE_L1: two samples of the x window
+    // ---- LAYER 2 tile building by the workers: x window -> layer 1 on the FP32 pipe -> hi / lo planes of buffer b ----
+    float px[2];
     auto prefetch = [&](int job) {
         const int r = job / jobs_per_read, t0 = (job % jobs_per_read) * TC_ROWS;
-        if (FUSE_L1) {
-            const float *xr = in + (size_t)r * Lx;
-            const int x0 = 3 * (t0 - 3) - 3;
+        const float *xr = (const float *)in + (size_t)r * Lx;
+        const int x0 = 3 * (t0 - 3) - 3;
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
-                const int i = tid + u * TC_WORKERS, j = x0 + i;
-                px[u] = (i < TC_NX && j >= 0 && j < Lx) ? xr[j] : 0.0f;
-            }
-        } else {
-            const float *ar = in + (size_t)r * CNN_C * LP;
-#pragma unroll
-            for (int u = 0; u < TC_ROUNDS; u++) {
-                const int i = tid + u * TC_WORKERS;
-                const int kc = i / TC_NQ, q = i % TC_NQ;
-                const int p = t0 - 3 + q;
-                const bool ok = (i < TC_ITEMS) && p >= 0 && p < L1;
-                const float *src = ar + (size_t)(kc * 8) * LP + p;
-#pragma unroll
-                for (int j = 0; j < 8; j++) pf[u][j] = ok ? src[(size_t)j * LP] : 0.0f;
-            }
+        for (int u = 0; u < 2; u++) {
+            const int i = tid + u * TC_WORKERS, j = x0 + i;
+            px[u] = (i < TC_NX && j >= 0 && j < Lx) ? xr[j] : 0.0f;
         }
     };
     auto build = [&](int job, int b) {
         const int r = job / jobs_per_read, t0 = (job % jobs_per_read) * TC_ROWS;
         unsigned char *hi_plane = Abuf + (size_t)b * 2 * TC_PLANE, *lo_plane = hi_plane + TC_PLANE;
         bool bad = false;
-        if (FUSE_L1) {
-            asm volatile("bar.sync 1, %0;" ::"n"(TC_WORKERS) : "memory");  // every worker is done with the previous x window
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_WORKERS) : "memory");  // every worker is done with the previous x window
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
-                const int i = tid + u * TC_WORKERS;
-                if (i < TC_NX) Xs[i] = px[u];
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(TC_WORKERS) : "memory");
-            for (int i = tid; i < TC_ITEMS; i += TC_WORKERS) {
-                const int kc = i / TC_NQ, q = i % TC_NQ;
-                const int p = t0 - 3 + q;
-                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // zero padding of layer 2's input outside [0, L1)
-                if (p >= 0 && p < L1) {
+        for (int u = 0; u < 2; u++) {
+            const int i = tid + u * TC_WORKERS;
+            if (i < TC_NX) Xs[i] = px[u];
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_WORKERS) : "memory");
+        for (int i = tid; i < TC_ITEMS; i += TC_WORKERS) {
+            const int kc = i / TC_NQ, q = i % TC_NQ;
+            const int p = t0 - 3 + q;
+            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // zero padding of layer 2's input outside [0, L1)
+            if (p >= 0 && p < L1) {
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const int ci = kc * 8 + j;
-                        float a = W1s[CNN_C * CNN_K + ci];
+                for (int j = 0; j < 8; j++) {
+                    const int ci = kc * 8 + j;
+                    float a = W1s[CNN_C * CNN_K + ci];
 #pragma unroll
-                        for (int k = 0; k < CNN_K; k++) a = fmaf(W1s[ci * CNN_K + k], Xs[3 * q + k], a);
-                        v[j] = fmaxf(a, 0.0f);
-                    }
+                    for (int k = 0; k < CNN_K; k++) a = fmaf(W1s[ci * CNN_K + k], Xs[3 * q + k], a);
+                    v[j] = fmaxf(a, 0.0f);
                 }
-                bad |= tc_split_store(hi_plane, lo_plane, kc, q, v);
             }
-        } else {
-#pragma unroll
-            for (int u = 0; u < TC_ROUNDS; u++) {
-                const int i = tid + u * TC_WORKERS;
-                if (i < TC_ITEMS) bad |= tc_split_store(hi_plane, lo_plane, i / TC_NQ, i % TC_NQ, pf[u]);
-            }
+            bad |= tc_split_store(hi_plane, lo_plane, kc, q, v);
         }
         if (bad) { redo[r] = 1; redo[-1] = 1; }  // redo[-1]: "any read flagged" (lets the FP32 pass leave at once)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to the tensor core
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&afull[b])) : "memory");
     };
-    // ---- (b) the 84 MMAs of one tile: 7 taps x 4 K-steps of 16 channels x (hi*hi, lo*hi, hi*lo) ----
+    // ---- LAYER 3 tile loading: sixteen bulk copies (plane x octet runs of 134 rows) completing on afull[b] ----
+    auto load_tile = [&](int job, int b) {
+        const int r = job / jobs_per_read, t0 = (job % jobs_per_read) * TC_ROWS;
+        const unsigned char *src = (const unsigned char *)in + (size_t)r * TC_A0T_READ_BYTES + (size_t)t0 * 16;
+        unsigned char *dst = Abuf + (size_t)b * 2 * TC_PLANE;
+        mbar_expect_tx(&afull[b], 16 * TC_TILE_RUN);
+#pragma unroll 1
+        for (int pk = 0; pk < 16; pk++)  // pk = plane * 8 + octet
+            tma_bulk_g2s(dst + (size_t)pk * (TC_RA * 16), src + (size_t)pk * (TC_A0T_ROWS * 16), TC_TILE_RUN, &afull[b]);
+    };
+    // ---- the 84 MMAs of one tile: 7 taps x 4 K-steps of 16 channels x (hi*hi, lo*hi, hi*lo) ----
     const uint32_t w_lo0 = tc_desc_lo(smem_u32(Wsm), 64 * 16), w_hi = tc_desc_hi(128);
     const uint32_t a_hi_word = tc_desc_hi(128);
-    auto issue = [&](int b) {
-        const uint32_t ah0 = tc_desc_lo(smem_u32(Abuf + (size_t)b * 2 * TC_PLANE), TC_RA * 16);
+    auto issue = [&](int sb, int tb) {
+        const uint32_t ah0 = tc_desc_lo(smem_u32(Abuf + (size_t)sb * 2 * TC_PLANE), TC_RA * 16);
         const uint32_t al0 = ah0 + (TC_PLANE >> 4);
-        const uint32_t d = tmem + (uint32_t)(b * 64);
+        const uint32_t d = tmem + (uint32_t)(tb * 64);
 #pragma unroll
         for (int k = 0; k < CNN_K; k++) {
 #pragma unroll
@@ -252,42 +269,80 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const floa
                 tc_mma_f16(d, ah0 + a_off, a_hi_word, w_lo0 + w_off + (TC_WPART >> 4), w_hi, 1u);
             }
         }
-        tc_commit(&accb[b]);
+        tc_commit(&accb[tb]);
     };
-    // ---- (c) epilogue of one tile: warp w reads TMEM lanes (w % 4) * 32.., columns (w / 4) * 32.. of buffer b ----
-    auto epilogue = [&](int job, int b, uint32_t phase) {
+    // ---- epilogue of one tile: warp w reads TMEM lanes (w % 4) * 32.., columns (w / 4) * 32.. of accumulator tb ----
+    auto epilogue = [&](int job, int tb, uint32_t phase) {
         const int r = job / jobs_per_read, t0 = (job % jobs_per_read) * TC_ROWS;
-        mbar_wait(&accb[b], phase);
+        mbar_wait(&accb[tb], phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = (warp & 3) * 32 + lane, ch0 = (warp >> 2) * 32;
         const int p = t0 + q;
-        const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(b * 64 + ch0);
+        const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(tb * 64 + ch0);
         uint32_t v[32];
         tc_ld32(taddr, v);
-        if (p < L1) {
-            float *orow = out + (size_t)r * CNN_C * LP + (size_t)ch0 * LP + p;
+        if (LAYER == 3) {
+            if (p < L1) {
+                float *orow = (float *)out + (size_t)r * CNN_C * LP + (size_t)ch0 * LP + p;
 #pragma unroll
-            for (int c = 0; c < 32; c++) orow[(size_t)c * LP] = fmaxf(__fadd_rn(__uint_as_float(v[c]), Bs[ch0 + c]), 0.0f);
+                for (int c = 0; c < 32; c++) orow[(size_t)c * LP] = fmaxf(__fadd_rn(__uint_as_float(v[c]), Bs[ch0 + c]), 0.0f);
+            }
+        } else {
+            // bias + ReLU, split, and straight into layer 3's tile layout (rows >= L1: zeros = its padding)
+            unsigned char *base = (unsigned char *)out + (size_t)r * TC_A0T_READ_BYTES + (size_t)(p + 3) * 16;
+            bool bad = false;
+#pragma unroll
+            for (int o = 0; o < 4; o++) {
+                __half2 h[4], l[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    float f0 = fmaxf(__fadd_rn(__uint_as_float(v[8 * o + 2 * j]), Bs[ch0 + 8 * o + 2 * j]), 0.0f);
+                    float f1 = fmaxf(__fadd_rn(__uint_as_float(v[8 * o + 2 * j + 1]), Bs[ch0 + 8 * o + 2 * j + 1]), 0.0f);
+                    if (p >= L1) { f0 = 0.0f; f1 = 0.0f; }
+                    const __half h0 = __float2half_rn(f0), h1 = __float2half_rn(f1);
+                    const float g0 = __half2float(h0), g1 = __half2float(h1);
+                    bad |= !(fabsf(g0) <= 65504.0f) || !(fabsf(g1) <= 65504.0f);
+                    h[j] = __halves2half2(h0, h1);
+                    l[j] = __halves2half2(__float2half_rn(__fsub_rn(f0, g0)), __float2half_rn(__fsub_rn(f1, g1)));
+                }
+                const size_t off = (size_t)((ch0 >> 3) + o) * (TC_A0T_ROWS * 16);
+                *reinterpret_cast<uint4 *>(base + off) = *reinterpret_cast<const uint4 *>(h);
+                *reinterpret_cast<uint4 *>(base + (size_t)8 * (TC_A0T_ROWS * 16) + off) = *reinterpret_cast<const uint4 *>(l);
+            }
+            if (bad) { redo[r] = 1; redo[-1] = 1; }
         }
     };
 
     if (warp == TC_WORKERS / 32) {
         // ---- MMA issuer ----
-        if (lane == 0) {
+        if (tc_elect_one()) {
             uint32_t it = 0;
             for (int job = blockIdx.x; job < n_jobs; job += gridDim.x, it++) {
-                const int b = (int)(it & 1u);
-                mbar_wait(&afull[b], (it >> 1) & 1u);                          // tile buffer b built
-                if (it >= 2) mbar_wait(&accfree[b], ((it - 2) >> 1) & 1u);     // accumulator b drained (tile it - 2)
+                const int tb = (int)(it & 1u), sb = (int)(it % NBUF);
+                mbar_wait(&afull[sb], (it / NBUF) & 1u);                       // tile buffer ready
+                if (it >= 2) mbar_wait(&accfree[tb], ((it - 2) >> 1) & 1u);    // accumulator drained (tile it - 2)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                issue(b);
+                issue(sb, tb);
+                if (LAYER == 3) tc_commit(&sfree[sb]);                         // tile buffer free once these MMAs are done
+            }
+        }
+        __syncwarp();
+    } else if (warp == TC_WORKERS / 32 + 1) {
+        // ---- tile loader (layer 3): runs up to NBUF tiles ahead; tile it reuses the buffer of tile it - NBUF, whose
+        // next release needs the tile loaded here, so the parity wait cannot be overtaken ----
+        if (LAYER == 3 && lane == 0) {
+            uint32_t it = 0;
+            for (int job = blockIdx.x; job < n_jobs; job += gridDim.x, it++) {
+                const int sb = (int)(it % NBUF);
+                if (it >= NBUF) mbar_wait(&sfree[sb], ((it / NBUF) - 1) & 1u);
+                load_tile(job, sb);
             }
         }
         __syncwarp();
     } else {
         // ---- workers ----
         int job = blockIdx.x;
-        if (job < n_jobs) {
+        if (LAYER == 2 && job < n_jobs) {
             prefetch(job);
             build(job, 0);
         }
@@ -297,13 +352,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const floa
             const int b = (int)(it & 1u);
             const int next = job + (int)gridDim.x;
             const bool has_next = next < n_jobs;
-            if (has_next) prefetch(next);                                   // (a)
-            if (prev_job >= 0) {                                            // (c): also proves tile buffer b^1 is free
+            if (LAYER == 2 && has_next) prefetch(next);
+            if (prev_job >= 0) {  // layer 2: also proves tile buffer b^1 is free
                 epilogue(prev_job, b ^ 1, ((it - 1) >> 1) & 1u);
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accfree[b ^ 1])) : "memory");
             }
-            if (has_next) build(next, b ^ 1);                               // (d)
+            if (LAYER == 2 && has_next) build(next, b ^ 1);
             prev_job = job;
         }
         if (prev_job >= 0) epilogue(prev_job, (int)((it - 1) & 1u), ((it - 1) >> 1) & 1u);
@@ -314,17 +369,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const floa
 }
 
 static int cnn_tc_launch_setup() {
-    const int smem = (int)cnn_tc_smem_bytes();
-    if (cudaFuncSetAttribute(cnn_conv64_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
-    if (cudaFuncSetAttribute(cnn_conv64_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(cnn_conv64_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cnn_tc_smem_bytes_layer(2)) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(cnn_conv64_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cnn_tc_smem_bytes_layer(3)) != cudaSuccess) return -1;
     return 0;
 }
 
-static void cnn_tc_launch(bool fuse_l1, const float *in, float *out, const __half *wp, const float *bias, const float *w1,
+// layer 2: in = x, out = A0T;  layer 3: in = A0T, out = act [N][64][LP]
+static void cnn_tc_launch(int layer, const void *in, void *out, const __half *wp, const float *bias, const float *w1,
                           const float *b1, int n_reads, int Lx, int L1, int LP, int *redo, int sm_count, cudaStream_t st) {
     const int jobs = n_reads * ((L1 + TC_ROWS - 1) / TC_ROWS);
     const int grid = std::max(1, std::min(jobs, sm_count));
-    const size_t smem = cnn_tc_smem_bytes();
-    if (fuse_l1) cnn_conv64_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(in, out, wp, bias, w1, b1, n_reads, Lx, L1, LP, redo);
-    else cnn_conv64_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(in, out, wp, bias, w1, b1, n_reads, Lx, L1, LP, redo);
+    const size_t smem = cnn_tc_smem_bytes_layer(layer);
+    if (layer == 2) cnn_conv64_tc_kernel<2><<<grid, TC_THREADS, smem, st>>>(in, out, wp, bias, w1, b1, n_reads, Lx, L1, LP, redo);
+    else cnn_conv64_tc_kernel<3><<<grid, TC_THREADS, smem, st>>>(in, out, wp, bias, w1, b1, n_reads, Lx, L1, LP, redo);
 }
+
+static size_t cnn_tc_a0t_bytes_per_read() { return (size_t)TC_A0T_READ_BYTES; }
+static int cnn_tc_max_l1() { return 5 * TC_ROWS; }
