@@ -237,7 +237,8 @@ __host__ __device__ inline size_t cnn_conv_smem_bytes() {
 // in[ci][u], in[ci][u+1]:  out[3u] = x[u+1] w0 + x[u] w3 + x[u-1] w6,  out[3u+1] = x[u+1] w1 + x[u] w4,
 // out[3u+2] = x[u+1] w2 + x[u] w5  (three coalesced loads and 14 FMAs per input channel; the per-output summation
 // order -- channels ascending, taps ascending -- is unchanged).
-__global__ void __launch_bounds__(256) cnn_convT_kernel(const float *act, const float *w4, const float *b4, int L1, int LP,
+#define CNN_CONVT_THREADS 192  // 3 CTAs cover the 550 positions of an RNA004 read with 4 % idle threads
+__global__ void __launch_bounds__(CNN_CONVT_THREADS) cnn_convT_kernel(const float *act, const float *w4, const float *b4, int L1, int LP,
                                                         int Lout, float *scores) {
     __shared__ __align__(16) float ws[CNN_C * 16];  // per ci: co0 k0..6, pad, co1 k0..6, pad
     for (int i = threadIdx.x; i < CNN_C * 16; i += blockDim.x) {
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(256) cnn_convT_kernel(const float *act, const 
     const float bias0 = b4[0], bias1 = b4[1];
     float o[2][3] = {{bias0, bias0, bias0}, {bias1, bias1, bias1}};
     const bool has_m = (u - 1 >= 0) && (u - 1 < L1), has_c = u < L1, has_p = u + 1 < L1;
-#pragma unroll 4
+#pragma unroll 8
     for (int ci = 0; ci < CNN_C; ci++) {
         const float *ap = ar + (size_t)ci * LP;
         const float xm = has_m ? ap[u - 1] : 0.0f, xc = has_c ? ap[u] : 0.0f, xp = has_p ? ap[u + 1] : 0.0f;
@@ -609,8 +610,8 @@ static int cnn_forward_dev(adb_ctx *ctx, const float *x, int n, const CnnDims &D
         }
         {
             KernelTimer t(ctx, 5, st);
-            dim3 g(((D.Lout + 2) / 3 + 255) / 256, nc);
-            cnn_convT_kernel<<<g, 256, 0, st>>>(a1, w_dev + CNN_W4, w_dev + CNN_B4, D.L1, D.LP, D.Lout,
+            dim3 g(((D.Lout + 2) / 3 + CNN_CONVT_THREADS - 1) / CNN_CONVT_THREADS, nc);
+            cnn_convT_kernel<<<g, CNN_CONVT_THREADS, 0, st>>>(a1, w_dev + CNN_W4, w_dev + CNN_B4, D.L1, D.LP, D.Lout,
                                                 scores + (size_t)r0 * 2 * D.Lout);
         }
         ctx->launches += 3;

@@ -200,6 +200,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const void
 
     // ---- LAYER 2 tile building by the workers: x window -> layer 1 on the FP32 pipe -> hi / lo planes of buffer b ----
     float px[2];
+    float w1r[8][CNN_K], b1r[8];  // layer-1 weights of this warp's channel octet
+    if (LAYER == 2 && warp < TC_WORKERS / 32) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            b1r[j] = W1s[CNN_C * CNN_K + warp * 8 + j];
+#pragma unroll
+            for (int k = 0; k < CNN_K; k++) w1r[j][k] = W1s[(warp * 8 + j) * CNN_K + k];
+        }
+    }
     auto prefetch = [&](int job) {
         const int r = job / jobs_per_read, t0 = (job % jobs_per_read) * TC_ROWS;
         const float *xr = (const float *)in + (size_t)r * Lx;
@@ -221,21 +230,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const void
             if (i < TC_NX) Xs[i] = px[u];
         }
         asm volatile("bar.sync 1, %0;" ::"n"(TC_WORKERS) : "memory");
-        for (int i = tid; i < TC_ITEMS; i += TC_WORKERS) {
-            const int kc = i / TC_NQ, q = i % TC_NQ;
+        // warp w builds channel octet w (its 8 x 7 layer-1 weights live in registers), lanes walk the rows
+        for (int q = lane; q < TC_NQ; q += 32) {
             const int p = t0 - 3 + q;
             float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // zero padding of layer 2's input outside [0, L1)
             if (p >= 0 && p < L1) {
+                float xs[CNN_K];
+#pragma unroll
+                for (int k = 0; k < CNN_K; k++) xs[k] = Xs[3 * q + k];
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    const int ci = kc * 8 + j;
-                    float a = W1s[CNN_C * CNN_K + ci];
+                    float a = b1r[j];
 #pragma unroll
-                    for (int k = 0; k < CNN_K; k++) a = fmaf(W1s[ci * CNN_K + k], Xs[3 * q + k], a);
+                    for (int k = 0; k < CNN_K; k++) a = fmaf(w1r[j][k], xs[k], a);
                     v[j] = fmaxf(a, 0.0f);
                 }
             }
-            bad |= tc_split_store(hi_plane, lo_plane, kc, q, v);
+            bad |= tc_split_store(hi_plane, lo_plane, warp, q, v);
         }
         if (bad) { redo[r] = 1; redo[-1] = 1; }  // redo[-1]: "any read flagged" (lets the FP32 pass leave at once)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to the tensor core
