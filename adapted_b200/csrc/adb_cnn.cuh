@@ -238,8 +238,10 @@ __host__ __device__ inline size_t cnn_conv_smem_bytes() {
 // out[3u+2] = x[u+1] w2 + x[u] w5  (three coalesced loads and 14 FMAs per input channel; the per-output summation
 // order -- channels ascending, taps ascending -- is unchanged).
 #define CNN_CONVT_THREADS 192  // 3 CTAs cover the 550 positions of an RNA004 read with 4 % idle threads
+// `only` (optional): just the reads flagged there (tensor-core path: reads recomputed on the FP32 pipe).
 __global__ void __launch_bounds__(CNN_CONVT_THREADS) cnn_convT_kernel(const float *act, const float *w4, const float *b4, int L1, int LP,
-                                                        int Lout, float *scores) {
+                                                        int Lout, float *scores, const int *only) {
+    if (only && (only[-1] == 0 || only[blockIdx.y] == 0)) return;
     __shared__ __align__(16) float ws[CNN_C * 16];  // per ci: co0 k0..6, pad, co1 k0..6, pad
     for (int i = threadIdx.x; i < CNN_C * 16; i += blockDim.x) {
         const int ci = i >> 4, e = i & 15, co = e >> 3, k = e & 7;
@@ -568,7 +570,10 @@ static int cnn_forward_dev(adb_ctx *ctx, const float *x, int n, const CnnDims &D
         const void *before = ctx->cnn_a0t.p;
         const size_t cap_before = ctx->cnn_a0t.cap;
         if (ctx->cnn_a0t.ensure(a0t_bytes)) { set_err("cudaMalloc cnn a0t"); return ADB_ERR_CUDA; }
-        if (ctx->cnn_a0t.p != before || ctx->cnn_a0t.cap != cap_before) CUDA_TRY(cudaMemsetAsync(ctx->cnn_a0t.p, 0, ctx->cnn_a0t.cap, st));
+        // (also when L1 changes: rows between the old and the new end would keep activations of the old geometry)
+        if (ctx->cnn_a0t.p != before || ctx->cnn_a0t.cap != cap_before || ctx->cnn_a0t_l1 != D.L1)
+            CUDA_TRY(cudaMemsetAsync(ctx->cnn_a0t.p, 0, ctx->cnn_a0t.cap, st));
+        ctx->cnn_a0t_l1 = D.L1;
         a0t = (unsigned char *)ctx->cnn_a0t.p;
     }
     for (int r0 = 0; r0 < n; r0 += chunk) {
@@ -584,8 +589,9 @@ static int cnn_forward_dev(adb_ctx *ctx, const float *x, int n, const CnnDims &D
             }
             {
                 KernelTimer t(ctx, 5, st);
-                cnn_tc_launch(3, a0t, a1, wtc + (size_t)CNN_K * 2 * 4096, w_dev + CNN_B3, nullptr, nullptr, nc, D.Lx, D.L1, D.LP,
-                              redo, ctx->sm_count, st);
+                // layer 3 + the transposed convolution: scores straight from the epilogue
+                cnn_tc_launch(3, a0t, scores + (size_t)r0 * 2 * D.Lout, wtc + (size_t)CNN_K * 2 * 4096, w_dev + CNN_B3,
+                              w_dev + CNN_W4, w_dev + CNN_B4, nc, D.Lout, D.L1, D.LP, redo, ctx->sm_count, st);
             }
             {
                 // reads with a value outside the fp16 range (flagged by either layer): both layers again on the FP32 pipe
@@ -609,10 +615,12 @@ static int cnn_forward_dev(adb_ctx *ctx, const float *x, int n, const CnnDims &D
         }
         }
         {
+            // FP32 path: every read; tensor-core path: only the reads redone on the FP32 pipe (the others got their
+            // scores from layer 3's epilogue)
             KernelTimer t(ctx, 5, st);
             dim3 g(((D.Lout + 2) / 3 + CNN_CONVT_THREADS - 1) / CNN_CONVT_THREADS, nc);
             cnn_convT_kernel<<<g, CNN_CONVT_THREADS, 0, st>>>(a1, w_dev + CNN_W4, w_dev + CNN_B4, D.L1, D.LP, D.Lout,
-                                                scores + (size_t)r0 * 2 * D.Lout);
+                                                scores + (size_t)r0 * 2 * D.Lout, use_tc ? redo : nullptr);
         }
         ctx->launches += 3;
     }

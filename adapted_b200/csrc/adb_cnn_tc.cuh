@@ -138,21 +138,31 @@ __device__ __forceinline__ bool tc_split_store(unsigned char *hi_plane, unsigned
 
 // Intermediate activations between the two layers ("A0T"): layer 2's epilogue writes its output already split into the
 // fp16 hi / lo planes and in the row order of layer 3's shared-memory tile,
-//     A0T[read][plane][ci / 8][rho = position + 3][ci % 8]      (16 B per row, TC_A0T_ROWS rows per octet),
+//     A0T[read][plane][ci / 8][rho = position + TC_A0T_PAD][ci % 8]      (16 B per row, TC_A0T_ROWS rows per octet),
 // so that the operand tile of a layer-3 job is 16 contiguous runs of 134 rows: sixteen cp.async.bulk copies per tile,
 // no thread touches the data.  Rows outside [0, L1) are layer 3's zero padding: rows >= L1 are written as zeros, the
 // three rows in front of position 0 and the tail rows are never written and stay zero from the buffer's memset.
-#define TC_A0T_ROWS (5 * TC_ROWS + 6)                       // enough for L1 <= 640 (RNA004: 550)
+#define TC_A0T_PAD 4                                        // zero rows in front of position 0
+#define TC_A0T_ROWS (5 * TC_ROWS + 6)                       // positions -4 .. 641
+#define TC_L3_STRIDE (TC_ROWS - 2)                          // layer 3 tiles overlap by two rows (fused convT, see below)
 #define TC_A0T_READ_BYTES (2 * 8 * TC_A0T_ROWS * 16)        // bytes per read
 #define TC_TILE_RUN (TC_NQ * 16)                            // bytes of one (plane, octet) run of a tile
 
 __host__ __device__ inline size_t cnn_tc_smem_bytes_layer(int layer) {
-    const int nbuf = layer == 3 ? 3 : 2;
-    return (size_t)TC_WBYTES + (size_t)nbuf * 2 * TC_PLANE + (size_t)(TC_NX + 10) * 4 + 64 * 8 * 4 + 64 * 4 + 160 + 1024;
+    if (layer == 3)  // weights + 3 tile buffers + W4s [2][64][8] + edge sums + bias + barriers
+        return (size_t)TC_WBYTES + 3 * 2 * (size_t)TC_PLANE + 1024 * 4 + 64 * 4 + 64 * 4 + 160 + 256;
+    return (size_t)TC_WBYTES + 2 * 2 * (size_t)TC_PLANE + (size_t)(TC_NX + 10) * 4 + 64 * 8 * 4 + 64 * 4 + 160 + 1024;
 }
 
 // LAYER 2: in = x [N][Lx] (layer 1 fused into the operand build), out = A0T.
-// LAYER 3: in = A0T,                                                 out = act [N][64][LP] (float32, for convT).
+// LAYER 3: in = A0T, out = scores [N][2][Lout]: the transposed convolution (64 -> 2, k = 7, stride 3, pad 3) is fused
+//   into the epilogue, layer 3's activations never leave the SM.  out[co][3u + c] needs the activations of positions
+//   u - 1, u, u + 1; tiles of 128 rows therefore advance by 126 positions (rows t0 .. t0 + 127 with t0 = 126 j - 1
+//   produce the outputs of u = t0 + 1 .. t0 + 126) and nothing is exchanged between tiles.  Warp w (rows (w % 4) * 32 ..)
+//   reads all 64 channels of its rows from TMEM and accumulates, for output channel co = w / 4, the seven per-tap
+//   partial sums P_k = sum_ci act[ci][row] * W4[ci][co][k]; then out[3u] = P0(u+1) + P3(u) + P6(u-1),
+//   out[3u+1] = P1(u+1) + P4(u), out[3u+2] = P2(u+1) + P5(u) with the neighbours' sums by shuffle (warp edges through
+//   a 256-byte shared buffer, one named barrier per tile).  `w1` / `b1` carry W4 / b4, `Lx` carries Lout.
 // wp  : packed weights of this layer, [7][2][4096] fp16 (cnn_tc_pack_weights_kernel)
 // redo: [N] set to 1 for reads with a value outside the fp16 range (recomputed on the FP32 pipe afterwards)
 template <int LAYER>
@@ -164,8 +174,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const void
     unsigned char *Wsm = tsm;                                   // resident weights [7][hi, lo][8][64][8] fp16
     unsigned char *Abuf = tsm + TC_WBYTES;                      // NBUF tile buffers x (hi plane, lo plane)
     float *Xs = (float *)(Abuf + NBUF * 2 * TC_PLANE);          // LAYER 2: x window of the tile being built
-    float *W1s = Xs + TC_NX + 10;                               // [64][7] + [64]
-    float *Bs = W1s + 64 * 8;                                   // bias [64]
+    float *W1s = Xs + TC_NX + 10;                               // LAYER 2: [64][7] + [64]
+    float *W4s = Xs;                                            // LAYER 3: [co][ci][8] (7 taps + pad) = 1024 floats
+    float *Eg = W4s + 1024;                                     // LAYER 3: [2 tiles][2 co][4 warps][4] edge partial sums
+    float *Bs = (LAYER == 3 ? Eg + 64 : W1s + 64 * 8);          // bias [64]
     // barriers: accb[2] accumulator complete (tcgen05.commit), afull[NBUF] tile buffer ready (layer 2: all workers,
     // layer 3: the bulk copies), accfree[2] accumulator drained by the epilogue (all workers)
     uint64_t *accb = (uint64_t *)(((uintptr_t)(Bs + 64) + 15) & ~(uintptr_t)15);
@@ -183,6 +195,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const void
     if (LAYER == 2) {
         for (int i = tid; i < CNN_C * CNN_K; i += blockDim.x) W1s[i] = w1[i];
         for (int i = tid; i < CNN_C; i += blockDim.x) W1s[CNN_C * CNN_K + i] = b1[i];
+    } else {
+        for (int i = tid; i < 1024; i += blockDim.x) {  // torch layout W4[ci][co][k]
+            const int co = i >> 9, ci = (i >> 3) & 63, k = i & 7;
+            W4s[i] = (k < CNN_K) ? w1[(ci * 2 + co) * CNN_K + k] : 0.0f;
+        }
     }
     if (tid < CNN_C) Bs[tid] = bias[tid];
     if (warp == 0) {
@@ -195,7 +212,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const void
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
 
-    const int jobs_per_read = (L1 + TC_ROWS - 1) / TC_ROWS;
+    // layer 2 tiles: t0 = 128 j; layer 3 tiles: t0 = 126 j - 1
+    const int jobs_per_read = LAYER == 3 ? (L1 + TC_L3_STRIDE - 1) / TC_L3_STRIDE : (L1 + TC_ROWS - 1) / TC_ROWS;
     const int n_jobs = n_reads * jobs_per_read;
 
     // ---- LAYER 2 tile building by the workers: x window -> layer 1 on the FP32 pipe -> hi / lo planes of buffer b ----
@@ -254,8 +272,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const void
     };
     // ---- LAYER 3 tile loading: sixteen bulk copies (plane x octet runs of 134 rows) completing on afull[b] ----
     auto load_tile = [&](int job, int b) {
-        const int r = job / jobs_per_read, t0 = (job % jobs_per_read) * TC_ROWS;
-        const unsigned char *src = (const unsigned char *)in + (size_t)r * TC_A0T_READ_BYTES + (size_t)t0 * 16;
+        // rows of positions t0 - 3 .. t0 + 130 with t0 = 126 j - 1: rho = position + 4 starts at 126 j
+        const int r = job / jobs_per_read, rho0 = (job % jobs_per_read) * TC_L3_STRIDE;
+        const unsigned char *src = (const unsigned char *)in + (size_t)r * TC_A0T_READ_BYTES + (size_t)rho0 * 16;
         unsigned char *dst = Abuf + (size_t)b * 2 * TC_PLANE;
         mbar_expect_tx(&afull[b], 16 * TC_TILE_RUN);
 #pragma unroll 1
@@ -283,24 +302,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const void
         tc_commit(&accb[tb]);
     };
     // ---- epilogue of one tile: warp w reads TMEM lanes (w % 4) * 32.., columns (w / 4) * 32.. of accumulator tb ----
-    auto epilogue = [&](int job, int tb, uint32_t phase) {
-        const int r = job / jobs_per_read, t0 = (job % jobs_per_read) * TC_ROWS;
+    auto epilogue = [&](int job, int tb, uint32_t phase, int eb) {
+        const int r = job / jobs_per_read;
+        const int t0 = LAYER == 3 ? (job % jobs_per_read) * TC_L3_STRIDE - 1 : (job % jobs_per_read) * TC_ROWS;
         mbar_wait(&accb[tb], phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = (warp & 3) * 32 + lane, ch0 = (warp >> 2) * 32;
         const int p = t0 + q;
-        const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(tb * 64 + ch0);
         uint32_t v[32];
-        tc_ld32(taddr, v);
         if (LAYER == 3) {
-            if (p < L1) {
-                float *orow = (float *)out + (size_t)r * CNN_C * LP + (size_t)ch0 * LP + p;
+            const int co = warp >> 2, wq = warp & 3;
+            const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(tb * 64);
+            const bool live = p >= 0 && p < L1;   // rows outside the read are zero padding for the transposed convolution
+            float P[CNN_K] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const float4 *wv = reinterpret_cast<const float4 *>(W4s + co * 512);
 #pragma unroll
-                for (int c = 0; c < 32; c++) orow[(size_t)c * LP] = fmaxf(__fadd_rn(__uint_as_float(v[c]), Bs[ch0 + c]), 0.0f);
+            for (int hh = 0; hh < 2; hh++) {
+                tc_ld32(taddr + (uint32_t)(hh * 32), v);
+                if (hh == 1) {  // both halves are in registers: hand the accumulator back
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accfree[tb])) : "memory");
+                }
+#pragma unroll
+                for (int c = 0; c < 32; c++) {
+                    const int ci = hh * 32 + c;
+                    const float a = live ? fmaxf(__fadd_rn(__uint_as_float(v[c]), Bs[ci]), 0.0f) : 0.0f;
+                    const float4 w0 = wv[ci * 2], w1v = wv[ci * 2 + 1];
+                    P[0] = fmaf(a, w0.x, P[0]); P[1] = fmaf(a, w0.y, P[1]); P[2] = fmaf(a, w0.z, P[2]); P[3] = fmaf(a, w0.w, P[3]);
+                    P[4] = fmaf(a, w1v.x, P[4]); P[5] = fmaf(a, w1v.y, P[5]); P[6] = fmaf(a, w1v.z, P[6]);
+                }
+            }
+            // neighbours: P0..P2 of row q + 1, P6 of row q - 1
+            float up0 = __shfl_down_sync(ADB_FULL, P[0], 1), up1 = __shfl_down_sync(ADB_FULL, P[1], 1);
+            float up2 = __shfl_down_sync(ADB_FULL, P[2], 1), dn6 = __shfl_up_sync(ADB_FULL, P[6], 1);
+            float *eg = Eg + ((eb * 2 + co) * 4) * 4;
+            if (lane == 0) { eg[wq * 4 + 0] = P[0]; eg[wq * 4 + 1] = P[1]; eg[wq * 4 + 2] = P[2]; }
+            if (lane == 31) eg[wq * 4 + 3] = P[6];
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_WORKERS) : "memory");
+            if (lane == 31 && wq < 3) { up0 = eg[(wq + 1) * 4 + 0]; up1 = eg[(wq + 1) * 4 + 1]; up2 = eg[(wq + 1) * 4 + 2]; }
+            if (lane == 0 && wq > 0) dn6 = eg[(wq - 1) * 4 + 3];
+            const int Lout = Lx;
+            if (q >= 1 && q <= TC_L3_STRIDE && p < L1 && 3 * p < Lout) {
+                const float bco = b1[co];
+                float *orow = (float *)out + ((size_t)r * 2 + co) * Lout + 3 * p;
+                orow[0] = __fadd_rn(bco, __fadd_rn(__fadd_rn(up0, P[3]), dn6));
+                if (3 * p + 1 < Lout) orow[1] = __fadd_rn(bco, __fadd_rn(up1, P[4]));
+                if (3 * p + 2 < Lout) orow[2] = __fadd_rn(bco, __fadd_rn(up2, P[5]));
             }
         } else {
             // bias + ReLU, split, and straight into layer 3's tile layout (rows >= L1: zeros = its padding)
-            unsigned char *base = (unsigned char *)out + (size_t)r * TC_A0T_READ_BYTES + (size_t)(p + 3) * 16;
+            const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(tb * 64 + ch0);
+            tc_ld32(taddr, v);
+            unsigned char *base = (unsigned char *)out + (size_t)r * TC_A0T_READ_BYTES + (size_t)(p + TC_A0T_PAD) * 16;
             bool bad = false;
 #pragma unroll
             for (int o = 0; o < 4; o++) {
@@ -365,14 +418,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const void
             const bool has_next = next < n_jobs;
             if (LAYER == 2 && has_next) prefetch(next);
             if (prev_job >= 0) {  // layer 2: also proves tile buffer b^1 is free
-                epilogue(prev_job, b ^ 1, ((it - 1) >> 1) & 1u);
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accfree[b ^ 1])) : "memory");
+                epilogue(prev_job, b ^ 1, ((it - 1) >> 1) & 1u, b ^ 1);
+                if (LAYER == 2) {  // (layer 3 hands the accumulator back inside its epilogue)
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accfree[b ^ 1])) : "memory");
+                }
             }
             if (LAYER == 2 && has_next) build(next, b ^ 1);
             prev_job = job;
         }
-        if (prev_job >= 0) epilogue(prev_job, (int)((it - 1) & 1u), ((it - 1) >> 1) & 1u);
+        if (prev_job >= 0) epilogue(prev_job, (int)((it - 1) & 1u), ((it - 1) >> 1) & 1u, (int)((it - 1) & 1u));
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -385,10 +440,10 @@ static int cnn_tc_launch_setup() {
     return 0;
 }
 
-// layer 2: in = x, out = A0T;  layer 3: in = A0T, out = act [N][64][LP]
+// layer 2: in = x, out = A0T;  layer 3: in = A0T, out = scores [N][2][Lout] (w1 / b1 = W4 / b4, Lx = Lout)
 static void cnn_tc_launch(int layer, const void *in, void *out, const __half *wp, const float *bias, const float *w1,
                           const float *b1, int n_reads, int Lx, int L1, int LP, int *redo, int sm_count, cudaStream_t st) {
-    const int jobs = n_reads * ((L1 + TC_ROWS - 1) / TC_ROWS);
+    const int jobs = n_reads * (layer == 3 ? (L1 + TC_L3_STRIDE - 1) / TC_L3_STRIDE : (L1 + TC_ROWS - 1) / TC_ROWS);
     const int grid = std::max(1, std::min(jobs, sm_count));
     const size_t smem = cnn_tc_smem_bytes_layer(layer);
     if (layer == 2) cnn_conv64_tc_kernel<2><<<grid, TC_THREADS, smem, st>>>(in, out, wp, bias, w1, b1, n_reads, Lx, L1, LP, redo);
@@ -396,4 +451,4 @@ static void cnn_tc_launch(int layer, const void *in, void *out, const __half *wp
 }
 
 static size_t cnn_tc_a0t_bytes_per_read() { return (size_t)TC_A0T_READ_BYTES; }
-static int cnn_tc_max_l1() { return 5 * TC_ROWS; }
+static int cnn_tc_max_l1() { return 5 * TC_L3_STRIDE; }  // layer 3's last tile must stay inside the rows of A0T

@@ -67,6 +67,7 @@ struct adb_ctx {
     DevBuf mvs_perm;           // length-sorted read order of mvs_series_kernel
     DevBuf vf_done;            // per-read flags of validate_fast_kernel
     int opt_no_fast_validate = 0;
+    int cnn_a0t_l1 = -1;       // L1 the tile-layout activation buffer was last zeroed for
     int opt_cnn_fp32 = 0;      // adb_ctx_set_option("cnn_fp32_pipe"): 64->64 convolutions on the FP32 pipe instead of tcgen05
     int vf_last_reads = 0;
     int gsb_last_batches = 0;
