@@ -395,13 +395,15 @@ __global__ void __launch_bounds__(128) cnn_peaks_kernel(const float *scores, int
 // _select_by_peak_distance, keeps the survivors whose midpoint lies in row r, sorts those by (-height, position)
 // and writes the first k positions (row-local).  cand[r][k] (0-padded), ncand[r].
 #define CNN_WS_CAP 2560
+#define CNN_WS_SORT 4096  // power of two >= CNN_WS_CAP
 __global__ void __launch_bounds__(128) cnn_topk_kernel(const float *scores, int Lout, int batch_size, int n_reads, int k,
                                                        int dist, const long long *pk_pos, const int *pk_cnt, int *cand,
                                                        int *ncand) {
     __shared__ long long pos[CNN_WS_CAP];   // flattened positions, ascending
     __shared__ float hgt[CNN_WS_CAP];
-    __shared__ unsigned short ord[CNN_WS_CAP];  // indices sorted by priority (ascending height, ties: lower index first)
-    __shared__ unsigned char keep[CNN_WS_CAP];
+    __shared__ unsigned short ord[CNN_WS_SORT];  // indices sorted by priority (ascending height, ties: lower index first)
+    __shared__ unsigned short prio[CNN_WS_CAP];  // rank of every peak in that order
+    __shared__ unsigned char keep[CNN_WS_CAP];   // 2 undecided, 1 kept, 0 removed
     __shared__ int n_sh;
     const int r = blockIdx.x;
     const int mb = r / batch_size;
@@ -416,51 +418,89 @@ __global__ void __launch_bounds__(128) cnn_topk_kernel(const float *scores, int 
                 const long long p = pk_pos[(size_t)(V.r0 + rr) * CNN_PK_CAP + i];
                 pos[n + i] = p;
                 hgt[n + i] = V.at(p);
-                keep[n + i] = 1;
+                keep[n + i] = 2;
             }
         }
         n = min(n + c, CNN_WS_CAP);
     }
+    // priority order (np.argsort of the heights; scipy walks it from the back): bitonic sort of the indices by
+    // (height, index) ascending; padding entries sort last
+    int np2 = 2;
+    while (np2 < n) np2 <<= 1;
+    for (int i = threadIdx.x; i < np2; i += blockDim.x) ord[i] = (i < n) ? (unsigned short)i : (unsigned short)0xffff;
     __syncthreads();
-    // priority order: rank by counting (n is a few hundred): ascending height, ties -> lower index first,
-    // processed from the back like scipy (np.argsort read backwards)
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const float h = hgt[i];
-        int rank = 0;
-        for (int j = 0; j < n; j++) {
-            const float hj = hgt[j];
-            rank += (hj < h) || (hj == h && j < i);
+    auto before = [&](unsigned a, unsigned b) {  // does entry a sort before entry b
+        if (a == 0xffffu) return false;
+        if (b == 0xffffu) return true;
+        const float ha = hgt[a], hb = hgt[b];
+        return (ha < hb) || (ha == hb && a < b);
+    };
+    for (int kk = 2; kk <= np2; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (np2 >> 1); t += blockDim.x) {
+                const int i = ((t / j) * 2 * j) + (t % j), p = i + j;
+                const bool up = (i & kk) == 0;
+                const unsigned a = ord[i], b = ord[p];
+                const bool swap = up ? before(b, a) : before(a, b);
+                if (swap) { ord[i] = (unsigned short)b; ord[p] = (unsigned short)a; }
+            }
+            __syncthreads();
         }
-        ord[rank] = (unsigned short)i;
+    }
+    for (int q = threadIdx.x; q < n; q += blockDim.x) prio[ord[q]] = (unsigned short)q;
+    __syncthreads();
+    // _select_by_peak_distance: in priority order a kept peak removes everything closer than `dist`; equivalently a peak
+    // is kept iff no KEPT peak of higher priority lies within the distance.  Resolved in parallel rounds: a peak
+    // decides once all its higher-priority neighbours have decided (the highest of every neighbourhood at once).
+    if (dist > 0) {
+        bool pending = true;
+        while (__syncthreads_or(pending)) {
+            pending = false;
+            unsigned char newst[(CNN_WS_CAP + 127) / 128];
+            int cnt = 0;
+            for (int i = threadIdx.x; i < n; i += blockDim.x, cnt++) {
+                unsigned char st = keep[i];
+                if (st == 2) {
+                    bool killed = false, wait = false;
+                    const unsigned pi = prio[i];
+                    for (int t = i - 1; t >= 0 && pos[i] - pos[t] < dist; t--)
+                        if (prio[t] > pi) { const unsigned char s2 = keep[t]; killed |= (s2 == 1); wait |= (s2 == 2); }
+                    for (int t = i + 1; t < n && pos[t] - pos[i] < dist; t++)
+                        if (prio[t] > pi) { const unsigned char s2 = keep[t]; killed |= (s2 == 1); wait |= (s2 == 2); }
+                    if (killed) st = 0;
+                    else if (!wait) st = 1;
+                    else pending = true;
+                }
+                newst[cnt] = st;
+            }
+            __syncthreads();
+            cnt = 0;
+            for (int i = threadIdx.x; i < n; i += blockDim.x, cnt++) keep[i] = newst[cnt];
+        }
+    } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) keep[i] = 1;
     }
     __syncthreads();
-    if (threadIdx.x == 0 && dist > 0) {
-        for (int q = n - 1; q >= 0; q--) {
-            const int j = ord[q];
-            if (!keep[j]) continue;
-            for (int t = j - 1; t >= 0 && pos[j] - pos[t] < dist; t--) keep[t] = 0;
-            for (int t = j + 1; t < n && pos[t] - pos[j] < dist; t++) keep[t] = 0;
-        }
-    }
-    __syncthreads();
-    // survivors in row r, best first: (-height, position); selection by counting
+    // survivors in row r, best first: (-height, position); compacted, then ranked by counting among themselves
     const long long lo = (long long)rl * Lout, hi = lo + Lout;
     if (threadIdx.x == 0) n_sh = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        if (!keep[i] || pos[i] < lo || pos[i] >= hi) continue;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        if (keep[i] == 1 && pos[i] >= lo && pos[i] < hi) ord[atomicAdd(&n_sh, 1)] = (unsigned short)i;
+    __syncthreads();
+    const int ns = n_sh;
+    for (int a = threadIdx.x; a < ns; a += blockDim.x) {
+        const int i = ord[a];
         const float h = hgt[i];
         int rank = 0;
-        for (int j = 0; j < n; j++) {
-            if (!keep[j] || pos[j] < lo || pos[j] >= hi) continue;
+        for (int b = 0; b < ns; b++) {
+            const int j = ord[b];
             const float hj = hgt[j];
             rank += (hj > h) || (hj == h && j < i);
         }
         if (rank < k) cand[(size_t)r * k + rank] = (int)(pos[i] - lo);
-        atomicAdd(&n_sh, 1);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) ncand[r] = n_sh;
+    if (threadIdx.x == 0) ncand[r] = ns;
 }
 
 // groups of candidates are assigned to rows in order of appearance (cnn.py:149-158): read r's candidates land in row
@@ -533,7 +573,7 @@ static int cnn_forward_dev(adb_ctx *ctx, const float *x, int n, const CnnDims &D
     if (ctx->cnn_w.ensure(sizeof(float) * 2 * CNN_C * CNN_K * CNN_C)) { set_err("cudaMalloc cnn weights"); return ADB_ERR_CUDA; }
     float *packed = (float *)ctx->cnn_w.p;
     {
-        KernelTimer t(ctx, 5, st);
+        KernelTimer t(ctx, 6, st);
         cnn_pack_weights_kernel<<<(2 * CNN_C * CNN_K * CNN_C + 255) / 256, 256, 0, st>>>(w_dev, packed);
     }
     ctx->launches += 1;
@@ -559,7 +599,7 @@ static int cnn_forward_dev(adb_ctx *ctx, const float *x, int n, const CnnDims &D
         wtc = (__half *)ctx->cnn_wtc.p;
         redo = (int *)((unsigned char *)ctx->cnn_wtc.p + wbytes) + 4;  // redo[-1] = "any read of the chunk flagged"
         {
-            KernelTimer t(ctx, 5, st);
+            KernelTimer t(ctx, 6, st);
             cnn_tc_pack_weights_kernel<<<(2 * CNN_K * 4096 + 255) / 256, 256, 0, st>>>(w_dev, wtc);
         }
         ctx->launches += 1;
@@ -595,7 +635,7 @@ static int cnn_forward_dev(adb_ctx *ctx, const float *x, int n, const CnnDims &D
             }
             {
                 // reads with a value outside the fp16 range (flagged by either layer): both layers again on the FP32 pipe
-                KernelTimer t(ctx, 5, st);
+                KernelTimer t(ctx, 7, st);
                 cnn_conv64_kernel<true><<<grid, CNN_THREADS, smem, st>>>(x + (size_t)r0 * D.Lx, a0, packed, w_dev + CNN_B2,
                                                                           w_dev + CNN_W1, w_dev + CNN_B1, nc, D.Lx, D.L1, D.LP, redo);
                 cnn_conv64_kernel<false><<<grid, CNN_THREADS, smem, st>>>(a0, a1, packed + CNN_C * CNN_K * CNN_C, w_dev + CNN_B3,
@@ -617,7 +657,7 @@ static int cnn_forward_dev(adb_ctx *ctx, const float *x, int n, const CnnDims &D
         {
             // FP32 path: every read; tensor-core path: only the reads redone on the FP32 pipe (the others got their
             // scores from layer 3's epilogue)
-            KernelTimer t(ctx, 5, st);
+            KernelTimer t(ctx, use_tc ? 7 : 5, st);
             dim3 g(((D.Lout + 2) / 3 + CNN_CONVT_THREADS - 1) / CNN_CONVT_THREADS, nc);
             cnn_convT_kernel<<<g, CNN_CONVT_THREADS, 0, st>>>(a1, w_dev + CNN_W4, w_dev + CNN_B4, D.L1, D.LP, D.Lout,
                                                 scores + (size_t)r0 * 2 * D.Lout, use_tc ? redo : nullptr);
@@ -645,7 +685,7 @@ static int cnn_primary_boundaries(adb_ctx *ctx, const BatchDev &B, const adb_con
     {
         const size_t smem = (((size_t)D.Lx * 4 + 15) & ~(size_t)15) + ((ADB_SEL_SMEM_BYTES + 15) & ~15) + 64;
         CUDA_TRY(cudaFuncSetAttribute(cnn_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        KernelTimer t(ctx, 5, st);
+        KernelTimer t(ctx, 6, st);
         cnn_prep_kernel<<<n, 256, smem, st>>>(B, cfg.min_obs_adapter, cfg.downscale_factor, D.Lx, x);
         ctx->launches += 1;
     }
@@ -663,24 +703,24 @@ static int cnn_primary_boundaries(adb_ctx *ctx, const BatchDev &B, const adb_con
     const int nadp = (cfg.max_obs_adapter - cfg.min_obs_adapter) / cfg.downscale_factor;
     const int n_batches = (n + B.batch_size - 1) / B.batch_size;
     {
-        KernelTimer t(ctx, 5, st);
+        KernelTimer t(ctx, 6, st);
         cnn_mask_kernel<<<n, 256, 0, st>>>(scores, D.Lout, nadp, k, apos, ppos);
     }
     ctx->launches += 1;
     if (k > 1) {
         CUDA_TRY(cudaMemsetAsync(cand, 0, sizeof(int) * (size_t)n * k, st));
         {
-            KernelTimer t(ctx, 5, st);
+            KernelTimer t(ctx, 6, st);
             cnn_peaks_kernel<<<n, 128, 0, st>>>(scores, D.Lout, B.batch_size, n, pk_pos, pk_cnt);
         }
         {
-            KernelTimer t(ctx, 5, st);
+            KernelTimer t(ctx, 6, st);
             cnn_topk_kernel<<<n, 128, 0, st>>>(scores, D.Lout, B.batch_size, n, k, 5, pk_pos, pk_cnt, cand, ncand);
         }
         ctx->launches += 2;
     }
     {
-        KernelTimer t(ctx, 5, st);
+        KernelTimer t(ctx, 6, st);
         cnn_shift_kernel<<<n_batches, 256, 0, st>>>(apos, ppos, cand, ncand, B.batch_size, n, k, cfg.downscale_factor,
                                                     cfg.min_obs_adapter, given);
     }

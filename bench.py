@@ -310,7 +310,8 @@ def main():
     # 1 its small sample / plan / finish kernels, 2 validate_fast_kernel, 3 llr_primary_kernel, 4 the length sort +
     # mvs_series_kernel, 5 CNN, 6 start-peak, 7 hand-over kernels (exact multi-pass select, histogram validate kernel)
     cls_names = ["global_select_pass", "global_select_small", "validate_fast_kernel", "llr_primary_kernel",
-                 "mvs_series_kernel", "cnn", "start_peak", "handover_kernels"]
+                 "mvs_series_kernel", "cnn_conv_kernels", "cnn_pre_post" if flat["primary_method"] == 1 else "start_peak",
+                 "handover_kernels"]
     per_cls = {cls_names[i]: {"ms": tim[2 * i], "launches": int(tim[2 * i + 1])} for i in range(8) if tim[2 * i + 1] > 0}
     dom = max(range(8), key=lambda i: tim[2 * i])
     alg_bytes_per_step = 2.0 * samples + (8 + 4 + 512) * n
@@ -324,13 +325,26 @@ def main():
     achieved = alg_launch / (avg_ms / 1e3) / 1e9 if avg_ms > 0 else 0.0
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(cls_names[dom])
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get("cnn") if dom == 5 else tj.get(cls_names[dom])
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": cls_names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                 "algorithmic_bytes_per_launch": alg_launch, "avg_launch_ms": avg_ms, "kernel_classes": per_cls,
                 "whole_step_frac": (alg_bytes_per_step / ((ms / args.steps) / 1e3) / 1e9) / peak}
+    if dom == 5:
+        # the tensor-core convolutions (cnn_conv64_tc_kernel<2>, <3>; two launches per chunk of reads) are a dense
+        # contraction: 64 556 800 algorithmic flop per read; every product is executed as three fp16 split
+        # products, so the tensor pipe does 3x this work.  Peak: measured dense bf16/fp16 tensor throughput.
+        tpeak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 2250.0)))
+        flops_step = 64556800.0 * n
+        tf = flops_step * args.steps / (tim[2 * dom] / 1e3) / 1e12 if tim[2 * dom] > 0 else 0.0
+        roofline.update({"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
+                         "algorithmic_flops_per_launch": flops_step * args.steps / launches_dom,
+                         "executed_tensor_flops_factor": 3.0,
+                         "hbm_view": {"achieved_GBps": achieved, "peak_GBps": peak, "frac": achieved / peak}})
+        roofline.pop("algorithmic_bytes_per_launch", None)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,

@@ -197,7 +197,9 @@ int adb_detect_pipelined_host(adb_ctx *ctx, const adb_batch *batch, const adb_co
  * class 0 streaming pass of the minibatch-global median / MAD (multi-pass histogram kernels when forced),
  * 1 its sample / plan / finish kernels (scan kernels of the multi-pass select when forced), 2 validate kernel
  * (counting-based for int16 reads, histogram-based otherwise), 3 LLR-primary kernel, 4 moving-statistics kernels,
- * 5 CNN kernels, 6 start-peak kernels, 7 hand-over kernels (what the fast paths pass on to the general kernels).
+ * 5 the CNN's convolution kernels (tcgen05 layers 2 / 3; FP32-pipe kernels + convT when selected), 6 start-peak kernels
+ * and the CNN's pre- / post-processing (prep, peak search, top-k), 7 hand-over kernels (what the fast paths pass on
+ * to the general kernels, incl. the FP32-pipe redo of reads outside the tensor-core kernels' fp16 range).
  * adb_ctx_get_timing fills out[16] = {ms, launches} x 8; call it after synchronising the stream. */
 int adb_ctx_set_timing(adb_ctx *ctx, int on);
 int adb_ctx_get_timing(adb_ctx *ctx, double *out);
