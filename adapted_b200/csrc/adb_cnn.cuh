@@ -409,13 +409,50 @@ __global__ void __launch_bounds__(128) cnn_topk_kernel(const float *scores, int 
     const int mb = r / batch_size;
     FlatView V{scores, Lout, mb * batch_size, min(batch_size, n_reads - mb * batch_size)};
     const int rl = r - V.r0;
-    // gather (lists are already ascending and rows are consecutive -> concatenation is ascending)
+    // gather: the peaks of this row plus those of the neighbouring rows that can interact with them.  The distance
+    // suppression only propagates through consecutive peaks closer than `dist`, so from either end of the row the
+    // neighbour's list is followed only while its gaps stay below `dist` (usually not a single peak: the head of every
+    // row is the masked stretch in front of the adapter end).  Lists are ascending and rows consecutive, so the
+    // concatenation is ascending.
+    __shared__ int take_sh[2];
+    const int c_mid = pk_cnt[r];
+    const long long lo = (long long)rl * Lout, hi = lo + Lout;
+    if (threadIdx.x == 0) {
+        int tl = 0, tr = 0;
+        const long long *pm = pk_pos + (size_t)r * CNN_PK_CAP;
+        long long first_pos = (c_mid > 0) ? pm[0] : 0x7fffffffffffffffLL, last_pos = (c_mid > 0) ? pm[c_mid - 1] : -1;
+        if (rl > 0) {
+            // trailing peaks of the previous row's list: a plateau that starts there can have its midpoint in this row
+            // (always taken); further back only while the gaps stay below dist
+            const long long *pl = pk_pos + (size_t)(r - 1) * CNN_PK_CAP;
+            const int cl = pk_cnt[r - 1];
+            long long nxt = first_pos;
+            while (tl < cl) {
+                const long long p = pl[cl - 1 - tl];
+                if (!(p >= lo || (dist > 0 && nxt != 0x7fffffffffffffffLL && nxt - p < dist))) break;
+                nxt = p; tl++;
+                if (last_pos < 0) last_pos = p;
+            }
+        }
+        if (rl + 1 < V.nr && dist > 0 && last_pos >= 0) {
+            const long long *pr = pk_pos + (size_t)(r + 1) * CNN_PK_CAP;
+            const int cr = pk_cnt[r + 1];
+            long long prv = last_pos;
+            while (tr < cr && pr[tr] - prv < dist) { prv = pr[tr]; tr++; }
+        }
+        take_sh[0] = tl; take_sh[1] = tr;
+    }
+    __syncthreads();
     int n = 0;
-    for (int rr = max(rl - 1, 0); rr <= min(rl + 1, V.nr - 1); rr++) {
-        const int c = pk_cnt[V.r0 + rr];
+    for (int part = 0; part < 3; part++) {
+        const int rr = r - 1 + part;
+        int c, first;
+        if (part == 0) { c = take_sh[0]; first = (c > 0) ? pk_cnt[r - 1] - c : 0; }
+        else if (part == 1) { c = c_mid; first = 0; }
+        else { c = take_sh[1]; first = 0; }
         for (int i = threadIdx.x; i < c; i += blockDim.x) {
             if (n + i < CNN_WS_CAP) {
-                const long long p = pk_pos[(size_t)(V.r0 + rr) * CNN_PK_CAP + i];
+                const long long p = pk_pos[(size_t)rr * CNN_PK_CAP + first + i];
                 pos[n + i] = p;
                 hgt[n + i] = V.at(p);
                 keep[n + i] = 2;
@@ -482,7 +519,6 @@ __global__ void __launch_bounds__(128) cnn_topk_kernel(const float *scores, int 
     }
     __syncthreads();
     // survivors in row r, best first: (-height, position); compacted, then ranked by counting among themselves
-    const long long lo = (long long)rl * Lout, hi = lo + Lout;
     if (threadIdx.x == 0) n_sh = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x)
