@@ -914,7 +914,11 @@ __device__ float series_nanmedian(ValCtx &C, const float *p, int n) {
     if (threadIdx.x == 0) C.itmp[7] = 0;
     __syncthreads();
     int cnt = 0;
-    {
+    // int16 sources with a finite calibration have no NaN samples, so neither have their moving statistics
+    const bool nan_free = C.src.i16 != nullptr && isfinite(C.src.coff) && isfinite(C.src.cscale);
+    if (nan_free) {
+        if (threadIdx.x == 0) C.itmp[7] = n;
+    } else {
         const int T = blockDim.x;
         int j = threadIdx.x;
         for (; j + 3 * T < n; j += 4 * T) {
