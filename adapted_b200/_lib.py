@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("ADB_LIB_PATH") or os.path.join(HERE, "csrc", "libadapted_b200.so")
 
 ADB_MAX_CAND = 16
-ADB_MAX_OPEN_PORES = 20
+ADB_MAX_OPEN_PORES = 48
 SIG_F32, SIG_I16 = 0, 1
 CNN_NPARAMS = 58882
 
@@ -80,7 +80,7 @@ RECORD_DTYPE = np.dtype([
     ("sp_idx", "<i4"), ("sp_next_idx", "<i4"), ("sp_open_pore_idx", "<i4"), ("sp_flag", "<i4"),
     ("sp_pa", "<f4"), ("sp_next_pa", "<f4"),
     ("stats", "<f8", (3, 4)), ("mvs", "<f8", (5,)), ("real", "<f8", (3,)), ("med_shift", "<f8"),
-    ("_reserved", "u1", (120,)),
+    ("_reserved", "u1", (8,)),
 ])
 assert RECORD_DTYPE.itemsize == 512
 

@@ -24,7 +24,7 @@ extern "C" {
 
 #define ADB_ABI_VERSION 1
 #define ADB_MAX_CAND 16        /* >= cnn_boundaries.polya_cand_k (10 / 15 in the shipped configs)            */
-#define ADB_MAX_OPEN_PORES 20  /* open-pore run starts kept per read in the record; n_open_pores is the true count */
+#define ADB_MAX_OPEN_PORES 48  /* open-pore run starts kept per read in the record; n_open_pores is the true count */
 
 typedef enum adb_status {
     ADB_OK = 0,
@@ -126,7 +126,7 @@ typedef struct adb_record {
     double mvs[5];       /* mvs_detect_{mean_at_loc,var_at_loc,polya_med,polya_local_range,med_shift}          */
     double real[3];      /* real_adapter_{mean_start,mean_end,local_range}                                      */
     double med_shift;    /* adapter_rna_median_shift                                                            */
-    uint8_t _reserved[120];
+    uint8_t _reserved[8];
 } adb_record;
 
 /* ---- library ---------------------------------------------------------------------------------------- */
