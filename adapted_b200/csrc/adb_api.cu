@@ -67,6 +67,7 @@ extern "C" int adb_ctx_create(int device, adb_ctx **out) {
 extern "C" int adb_ctx_set_timing(adb_ctx *c, int on);
 extern "C" void adb_ctx_destroy(adb_ctx *c) {
     if (!c) return;
+    if (c->twin) { adb_ctx_destroy(c->twin); c->twin = nullptr; }
     cudaSetDevice(c->device);
     DevBuf *all[] = {&c->states, &c->hist, &c->series, &c->given, &c->status, &c->cnn_x, &c->cnn_act0,
                      &c->cnn_act1, &c->cnn_scores, &c->cnn_w, &c->cnn_aux, &c->cnn_post, &c->sp_rows, &c->h_signal, &c->h_offsets,
@@ -638,43 +639,65 @@ extern "C" int adb_detect_pipelined_host(adb_ctx *ctx, const adb_batch *batch, c
         while (left > 0) { const int c = std::min(left, chunk_batches); sched.push_back(c); left -= c; }
         sched.insert(sched.end(), tail.begin(), tail.end());
     }
-    cudaStream_t cs = ctx->copy_stream, ks = ctx->stream;
+    // consecutive chunks alternate between this context and its twin: each has its own compute stream and scratch arena,
+    // the copies of all chunks go through one copy stream in order
+    if (!ctx->twin && sched.size() >= 3) {
+        rc = adb_ctx_create(ctx->device, &ctx->twin);
+        if (rc) return rc;
+    }
+    if (ctx->twin) {
+        ctx->twin->opt_no_fast_validate = ctx->opt_no_fast_validate;
+        ctx->twin->opt_cnn_fp32 = ctx->opt_cnn_fp32;
+        ctx->twin->opt_exact_gsel = ctx->opt_exact_gsel;
+    }
+    adb_ctx *cc[2] = {ctx, ctx->twin ? ctx->twin : ctx};
+    const float *w_devs[2] = {w_dev, w_dev};
+    if (w_dev && ctx->twin) {
+        if (ctx->twin->h_misc2.ensure(sizeof(float) * ADB_CNN_NPARAMS)) { set_err("cudaMalloc weights"); return ADB_ERR_CUDA; }
+        CUDA_TRY(cudaMemcpyAsync(ctx->twin->h_misc2.p, cnn_weights, sizeof(float) * ADB_CNN_NPARAMS, cudaMemcpyHostToDevice, ctx->twin->stream));
+        w_devs[1] = (const float *)ctx->twin->h_misc2.p;
+    }
+    cudaStream_t cs = ctx->copy_stream;
     int b0 = 0;  // first minibatch of the chunk
     for (int ch = 0; ch < (int)sched.size(); ch++) {
-        const int slot = ch & 1;
+        adb_ctx *c = cc[ch & 1];
+        const int slot = ctx->twin ? 0 : (ch & 1);
+        cudaStream_t ks = c->stream;
         const int r0 = b0 * batch->batch_size;
         const int r1 = (int)std::min<long long>((long long)batch->n_reads, (long long)(b0 + sched[ch]) * batch->batch_size), nr = r1 - r0;
         const int nb = (nr + batch->batch_size - 1) / batch->batch_size;
         const int64_t e0 = batch->offsets[r0], e1 = batch->offsets[r1];
         // the slot is free once the D2H of the chunk that used it two iterations ago has finished
-        if (ch >= 2) CUDA_TRY(cudaEventSynchronize(ctx->p_done[slot]));
-        if (ctx->p_signal[slot].ensure((size_t)(e1 - e0) * 2 + 64) || ctx->p_offsets[slot].ensure(sizeof(int64_t) * ((size_t)nr + 1)) ||
-            ctx->p_lens[slot].ensure(sizeof(int32_t) * (size_t)nr + 16) || ctx->p_coff[slot].ensure(sizeof(float) * (size_t)nr + 16) ||
-            ctx->p_cscale[slot].ensure(sizeof(float) * (size_t)nr + 16) || ctx->p_records[slot].ensure(sizeof(adb_record) * (size_t)nr) ||
-            ctx->p_status[slot].ensure(sizeof(int) * (size_t)nb + 16)) { set_err("cudaMalloc pipeline staging"); return ADB_ERR_CUDA; }
-        CUDA_TRY(cudaMemcpyAsync(ctx->p_signal[slot].p, (const int16_t *)batch->signal + e0, (size_t)(e1 - e0) * 2, cudaMemcpyHostToDevice, cs));
-        CUDA_TRY(cudaMemcpyAsync(ctx->p_offsets[slot].p, batch->offsets + r0, sizeof(int64_t) * ((size_t)nr + 1), cudaMemcpyHostToDevice, cs));
-        CUDA_TRY(cudaMemcpyAsync(ctx->p_lens[slot].p, batch->full_lens + r0, sizeof(int32_t) * (size_t)nr, cudaMemcpyHostToDevice, cs));
-        CUDA_TRY(cudaMemcpyAsync(ctx->p_coff[slot].p, batch->calib_offset + r0, sizeof(float) * (size_t)nr, cudaMemcpyHostToDevice, cs));
-        CUDA_TRY(cudaMemcpyAsync(ctx->p_cscale[slot].p, batch->calib_scale + r0, sizeof(float) * (size_t)nr, cudaMemcpyHostToDevice, cs));
-        CUDA_TRY(cudaEventRecord(ctx->p_copied[slot], cs));
-        CUDA_TRY(cudaStreamWaitEvent(ks, ctx->p_copied[slot], 0));
+        if (ch >= 2) CUDA_TRY(cudaEventSynchronize(c->p_done[slot]));
+        if (c->p_signal[slot].ensure((size_t)(e1 - e0) * 2 + 64) || c->p_offsets[slot].ensure(sizeof(int64_t) * ((size_t)nr + 1)) ||
+            c->p_lens[slot].ensure(sizeof(int32_t) * (size_t)nr + 16) || c->p_coff[slot].ensure(sizeof(float) * (size_t)nr + 16) ||
+            c->p_cscale[slot].ensure(sizeof(float) * (size_t)nr + 16) || c->p_records[slot].ensure(sizeof(adb_record) * (size_t)nr) ||
+            c->p_status[slot].ensure(sizeof(int) * (size_t)nb + 16)) { set_err("cudaMalloc pipeline staging"); return ADB_ERR_CUDA; }
+        CUDA_TRY(cudaMemcpyAsync(c->p_signal[slot].p, (const int16_t *)batch->signal + e0, (size_t)(e1 - e0) * 2, cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(cudaMemcpyAsync(c->p_offsets[slot].p, batch->offsets + r0, sizeof(int64_t) * ((size_t)nr + 1), cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(cudaMemcpyAsync(c->p_lens[slot].p, batch->full_lens + r0, sizeof(int32_t) * (size_t)nr, cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(cudaMemcpyAsync(c->p_coff[slot].p, batch->calib_offset + r0, sizeof(float) * (size_t)nr, cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(cudaMemcpyAsync(c->p_cscale[slot].p, batch->calib_scale + r0, sizeof(float) * (size_t)nr, cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(cudaEventRecord(c->p_copied[slot], cs));
+        CUDA_TRY(cudaStreamWaitEvent(ks, c->p_copied[slot], 0));
         adb_batch d = *batch;
         // offsets stay absolute: rebase the blob pointer so that blob[offsets[i]] is the staged copy
-        d.signal = (const int16_t *)ctx->p_signal[slot].p - e0;
-        d.offsets = (const int64_t *)ctx->p_offsets[slot].p;
-        d.full_lens = (const int32_t *)ctx->p_lens[slot].p;
-        d.calib_offset = (const float *)ctx->p_coff[slot].p;
-        d.calib_scale = (const float *)ctx->p_cscale[slot].p;
+        d.signal = (const int16_t *)c->p_signal[slot].p - e0;
+        d.offsets = (const int64_t *)c->p_offsets[slot].p;
+        d.full_lens = (const int32_t *)c->p_lens[slot].p;
+        d.calib_offset = (const float *)c->p_coff[slot].p;
+        d.calib_scale = (const float *)c->p_cscale[slot].p;
         d.n_reads = nr;
-        rc = adb_detect_dev(ctx, &d, cfg, w_dev, (adb_record *)ctx->p_records[slot].p, (int *)ctx->p_status[slot].p, ks);
+        rc = adb_detect_dev(c, &d, cfg, w_devs[ch & 1], (adb_record *)c->p_records[slot].p, (int *)c->p_status[slot].p, ks);
         if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(out_records + r0, ctx->p_records[slot].p, sizeof(adb_record) * (size_t)nr, cudaMemcpyDeviceToHost, ks));
+        CUDA_TRY(cudaMemcpyAsync(out_records + r0, c->p_records[slot].p, sizeof(adb_record) * (size_t)nr, cudaMemcpyDeviceToHost, ks));
         if (batch_status)
-            CUDA_TRY(cudaMemcpyAsync(batch_status + b0, ctx->p_status[slot].p, sizeof(int) * (size_t)nb, cudaMemcpyDeviceToHost, ks));
-        CUDA_TRY(cudaEventRecord(ctx->p_done[slot], ks));
+            CUDA_TRY(cudaMemcpyAsync(batch_status + b0, c->p_status[slot].p, sizeof(int) * (size_t)nb, cudaMemcpyDeviceToHost, ks));
+        CUDA_TRY(cudaEventRecord(c->p_done[slot], ks));
         b0 += sched[ch];
     }
+    if (ctx->twin) CUDA_TRY(cudaStreamSynchronize(ctx->twin->stream));
+    cudaStream_t ks = ctx->stream;
     CUDA_TRY(cudaStreamSynchronize(ks));
     CUDA_TRY(cudaStreamSynchronize(cs));
     return ADB_OK;

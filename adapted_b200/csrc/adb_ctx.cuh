@@ -53,6 +53,10 @@ struct adb_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     int64_t launches = 0;
+    // second context of the pipelined ingest: consecutive chunks alternate between the two (own stream, own scratch), so
+    // the thin tail of one chunk (moving statistics of its longest reads, handed-over reads) runs under the wide head
+    // of the next
+    adb_ctx *twin = nullptr;
     // optional per-kernel-class timing (bench.py roofline): events bracket every launch of a class
     int timing = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[8];  // see ADB_TC_* in adb_api.cu
