@@ -2,19 +2,21 @@
 //
 //   cnn_prep_kernel     prepare_data (cnn.py:70-82): mean-pool downscale of batch[:, min_obs_adapter:], per-read
 //                       nanmedian / MAD normalisation (no clipping), nan_to_num(-5).
-//   cnn_conv64_kernel   layers 2 and 3 (Conv1d 64->64, k=7, pad 3, ReLU) as a register-tiled implicit GEMM on the FP32
-//                       pipes; layer 1 (Conv1d 1->64, k=7, stride 3, pad 3, ReLU) is fused into layer 2's input stage.
-//   cnn_convT_kernel    layer 4 (ConvTranspose1d 64->2, k=7, stride 3, pad 3) -> scores [N, 2, L_out].
+//   cnn_conv64_tc_kernel (adb_cnn_tc.cuh)  layers 2 and 3 (Conv1d 64->64, k=7, pad 3, ReLU) on the tcgen05 tensor
+//                       cores; layer 1 fused into layer 2's operand build, layer 4 into layer 3's epilogue.
+//   cnn_conv64_kernel   the same two layers as a register-tiled implicit GEMM on the FP32 pipe: recomputes the reads the
+//                       tensor-core kernels flag (values outside their fp16 split), or every read with the
+//                       "cnn_fp32_pipe" option; layer 1 (Conv1d 1->64, k=7, stride 3, pad 3, ReLU) fused into layer 2.
+//   cnn_convT_kernel    layer 4 (ConvTranspose1d 64->2, k=7, stride 3, pad 3) -> scores [N, 2, L_out] for that path.
 //   cnn_mask_kernel / cnn_peaks_* / cnn_topk_kernel / cnn_shift_kernel
 //                       cnn_predict's post-processing (cnn.py:117-160): adapter argmax, masking, poly(A) argmax,
 //                       find_peaks(flattened scores, distance=5) with its cross-read plateau / distance coupling,
 //                       per-read top-k by height, and the "groups shift up when a read has no peak" behaviour
 //                       (SURVEY.md A.6), then cnn_detect's coordinate mapping (cnn.py:173-179).
 //
-// Precision: weights and activations are float32 and every product is accumulated with fmaf in float32, like the
-// reference's torch CPU forward (whose summation order is oneDNN's and not reproducible bit for bit); the contract is
-// "boundaries within +-1 downscaled step" (north_star).  The convolutions are ~64.6 MFLOP per read and compute bound
-// (SURVEY.md section 8d); a tcgen05 (3xTF32) version of cnn_conv64_kernel is the planned next step, see DESIGN.md.
+// Precision: the reference is float32 (torch CPU, oneDNN's summation order, not reproducible bit for bit); the contract
+// is "boundaries within +-1 downscaled step" (north_star).  The FP32-pipe kernels accumulate every product with fmaf in
+// float32; the tensor-core kernels keep ~22 bits per operand (fp16 hi / lo split) and accumulate in float32.
 #pragma once
 #include <cuda_fp16.h>
 #include <float.h>
