@@ -337,7 +337,13 @@ def main():
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tj.get("cnn") if dom == 5 else tj.get(cls_names[dom])
+        # the committed captures are per workload: RNA002 keys are bare class names, others carry the chemistry
+        if dom == 5:
+            traffic = tj.get("cnn")
+        elif args.chemistry.lower() == "rna002":
+            traffic = tj.get(cls_names[dom])
+        else:
+            traffic = tj.get(f"{cls_names[dom]} ({args.chemistry.lower()})")
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": cls_names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
