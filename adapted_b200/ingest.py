@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import logging
 import os
-from typing import Any, Dict, Optional, Sequence, Set
+from typing import Any, Dict, Iterable, Iterator, List, Optional, Sequence, Set, Tuple
 
 import numpy as np
 
@@ -36,6 +36,143 @@ def write_container(path: str, adc: np.ndarray, offsets: np.ndarray, full_lens: 
 def read_container(path: str) -> Dict[str, np.ndarray]:
     with np.load(path) as z:
         return {k: z[k] for k in CONTAINER_KEYS}
+
+
+class ContainerSource:
+    """Reads of one native container, in file order: (read_id, int16 samples, calibration offset, scale, num_samples)."""
+
+    def __init__(self, path: str):
+        self.path = path
+
+    def reads(self, selection: Optional[Set[str]] = None):
+        c = read_container(self.path)
+        off = c["offsets"]
+        for i in range(c["full_lens"].size):
+            rid = str(c["read_ids"][i])
+            if selection is not None and rid not in selection:
+                continue
+            yield rid, c["adc"][off[i]: off[i + 1]], float(c["calib_offset"][i]), float(c["calib_scale"][i]), int(c["full_lens"][i])
+
+
+class Pod5Source:
+    """The same interface over a pod5 file through the ``pod5`` package (``Reader.reads(selection=..., missing_ok=True)``,
+    ``ReadRecord.signal`` / ``.calibration`` / ``.num_samples`` / ``.read_id`` -- the calls of file_proc.py:164-175 with
+    the raw ADC signal instead of ``signal_pa``).  ``pod5`` is not installable in the build image: this adapter is
+    written against the package's documented API and is UNTESTED here (parity unpinned)."""
+
+    def __init__(self, path: str):
+        self.path = path
+
+    def reads(self, selection: Optional[Set[str]] = None):
+        import pod5  # noqa: F401 -- raises ImportError where the package is missing
+
+        with pod5.Reader(self.path) as reader:
+            it = reader.reads(selection=list(selection), missing_ok=True) if selection else reader.reads()
+            for rr in it:
+                cal = rr.calibration
+                yield str(rr.read_id), np.asarray(rr.signal, dtype=np.int16), float(cal.offset), float(cal.scale), int(rr.num_samples)
+
+
+def open_source(path: str):
+    return Pod5Source(path) if path.endswith(".pod5") else ContainerSource(path)
+
+
+def yield_minibatches(files: Iterable[str], read_ids_incl: Optional[Set[str]], read_ids_excl: Optional[Set[str]],
+                      batch_size: int, preload_size: int) -> Iterator[Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray,
+                                                                             np.ndarray, List[str]]]:
+    """yield_signals_from_pod5 (file_proc.py:143-190) for the int16 ingest: minibatches of ``batch_size`` reads in file
+    order, running across file boundaries, every read truncated to ``preload_size`` samples; yields
+    (adc blob, offsets [n+1], full_lens, calib_offset, calib_scale, read_ids).  Selection semantics as there: with both
+    sets given the exclusions are taken out of the inclusions; an inclusion set selects, an exclusion set skips."""
+    incl = set(read_ids_incl) if read_ids_incl else set()
+    excl = set(read_ids_excl) if read_ids_excl else set()
+    if incl and excl:
+        incl = incl.difference(excl)
+        excl = set()
+    selection = incl if incl else None
+    m = int(preload_size)
+
+    def fresh():
+        return [], [0], [], [], [], []
+
+    chunks, offs, lens, coff, cscale, ids = fresh()
+    for fn in files:
+        for rid, sig, c_off, c_scale, n_samples in open_source(fn).reads(selection):
+            if rid in excl:
+                continue
+            k = min(m, int(n_samples), int(sig.size))
+            chunks.append(np.asarray(sig[:k], dtype=np.int16))
+            offs.append(offs[-1] + k)
+            lens.append(int(n_samples))
+            coff.append(c_off)
+            cscale.append(c_scale)
+            ids.append(rid)
+            if len(ids) == batch_size:
+                yield (np.concatenate(chunks) if chunks else np.zeros(0, np.int16), np.asarray(offs, np.int64),
+                       np.asarray(lens, np.int32), np.asarray(coff, np.float32), np.asarray(cscale, np.float32), ids)
+                chunks, offs, lens, coff, cscale, ids = fresh()
+    if ids:
+        yield (np.concatenate(chunks), np.asarray(offs, np.int64), np.asarray(lens, np.int32), np.asarray(coff, np.float32),
+               np.asarray(cscale, np.float32), ids)
+
+
+def detect_files(files: Sequence[str], out_dir: str, spc: Any, model: Any = None, read_ids_incl: Optional[Set[str]] = None,
+                 minibatch_size: int = 1000, batch_size_output: int = 4000, continue_run: bool = False, device: int = 0,
+                 minibatches_per_call: int = 64) -> Dict[str, int]:
+    """``adapted detect`` / ``continue`` between the reader and the tables for any number of input files (containers or,
+    where the package exists, pod5): minibatches run across file boundaries like the reference's producer; groups of
+    ``minibatches_per_call`` go through the CUDA library in one call (pipelined H2D inside)."""
+    from .detect import detect_reads
+
+    flat = flatten_config(spc)
+    method = flat["primary_method"]
+    log = "" if method == 0 else None
+    excl = processed_read_ids(out_dir) if continue_run else None
+    if continue_run:
+        writer = BoundaryTableWriter.continue_from(out_dir, method, batch_size_output=batch_size_output, llr_detect_log=log)
+    else:
+        writer = BoundaryTableWriter(os.path.join(out_dir, "boundaries"), os.path.join(out_dir, "failed_reads"), method,
+                                     batch_size_output=batch_size_output, llr_detect_log=log)
+    stats = {"reads": 0, "pass": 0, "fail": 0, "lost": 0}
+
+    def run(group):
+        adc = np.concatenate([g[0] for g in group])
+        lens_per = [g[1][-1] for g in group]
+        off = np.zeros(sum(len(g[5]) for g in group) + 1, dtype=np.int64)
+        pos, base = 1, 0
+        for g, tot in zip(group, lens_per):
+            off[pos: pos + len(g[5])] = g[1][1:] + base
+            pos += len(g[5])
+            base += int(tot)
+        ids = [i for g in group for i in g[5]]
+        recs, status = detect_reads(adc, off, np.concatenate([g[2] for g in group]), np.concatenate([g[3] for g in group]),
+                                    np.concatenate([g[4] for g in group]), spc, model=model, minibatch_size=minibatch_size,
+                                    device=device, return_records=True)
+        n = len(ids)
+        stats["reads"] += n
+        for bi, st in enumerate(status):
+            a, b = bi * minibatch_size, min((bi + 1) * minibatch_size, n)
+            if st != 0:
+                logging.error("minibatch of %d reads lost (status %d), like the reference's handle_completed_future", b - a, int(st))
+                stats["lost"] += b - a
+                continue
+            writer.add(recs[a:b], ids[a:b])
+            ok = int((recs[a:b]["success"] != 0).sum())
+            stats["pass"] += ok
+            stats["fail"] += (b - a) - ok
+
+    with writer:
+        group = []
+        for mbatch in yield_minibatches(files, read_ids_incl, excl, minibatch_size, flat["sig_preload_size"]):
+            group.append(mbatch)
+            # only complete minibatches may be followed by another one inside a call
+            if len(group) == minibatches_per_call or len(mbatch[5]) < minibatch_size:
+                run(group)
+                group = []
+        if group:
+            run(group)
+    stats["files"] = len(writer.files)
+    return stats
 
 
 def processed_read_ids(continue_from: str, failed_only: bool = False) -> Set[str]:

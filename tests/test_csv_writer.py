@@ -155,3 +155,29 @@ def test_container_roundtrip_and_processed_ids(tmp_path):
             f.write(text)
     assert processed_read_ids(str(tmp_path)) == set(doc["read_ids"])
     assert len(processed_read_ids(str(tmp_path), failed_only=True)) == 23
+
+
+def test_yield_minibatches_selection_and_file_boundaries(tmp_path):
+    """yield_signals_from_pod5 semantics (file_proc.py:143-190) on the int16 ingest: file order, minibatches running
+    across files, truncation to the preload window, inclusion / exclusion sets"""
+    from adapted_b200.ingest import write_container, yield_minibatches
+    from adapted_b200.synth import make_reads
+
+    files, all_ids, lens = [], [], []
+    for f, n in enumerate((7, 5, 9)):
+        b = make_reads(n, "rna004", 30000, seed=100 + f)
+        ids = [f"f{f}-r{i}" for i in range(n)]
+        files.append(write_container(str(tmp_path / f"c{f}"), b.adc, b.offsets, b.full_lens, b.calib_offset, b.calib_scale, ids))
+        all_ids += ids
+        lens += b.full_lens.tolist()
+    m = 17500
+    got = list(yield_minibatches(files, None, None, 4, m))
+    assert [len(g[5]) for g in got] == [4, 4, 4, 4, 4, 1]
+    assert [i for g in got for i in g[5]] == all_ids
+    for g in got:
+        assert np.array_equal(np.diff(g[1]), np.minimum(g[2], m)) and g[0].size == g[1][-1]
+    assert np.concatenate([g[2] for g in got]).tolist() == lens
+    incl, excl = {all_ids[1], all_ids[8], all_ids[20], "missing"}, {all_ids[8]}
+    assert [i for g in yield_minibatches(files, incl, None, 4, m) for i in g[5]] == [all_ids[1], all_ids[8], all_ids[20]]
+    assert [i for g in yield_minibatches(files, incl, excl, 4, m) for i in g[5]] == [all_ids[1], all_ids[20]]
+    assert [i for g in yield_minibatches(files, None, excl, 50, m) for i in g[5]] == [i for i in all_ids if i != all_ids[8]]

@@ -212,3 +212,26 @@ def test_detect_file_writes_the_reference_tables(tmp_path):
     assert stats2["reads"] == job["n"] - job["batch_size_output"]
     assert os.path.exists(os.path.join(out, "boundaries", "detected_boundaries_1.csv"))
     assert processed_read_ids(out) == set(doc["read_ids"])
+
+
+def test_detect_files_minibatches_run_across_files(tmp_path):
+    """the job's reads split over two containers (70 + 80): minibatches of 50 cross the file boundary like the
+    reference's producer fills them (file_proc.py:159-187) -> the very same tables"""
+    import os
+
+    from adapted_b200.ingest import detect_files, write_container
+
+    doc, spc, b = _load_job()
+    job, ids = doc["job"], doc["read_ids"]
+    paths = []
+    for k, (a, e) in enumerate(((0, 70), (70, job["n"]))):
+        o = b.offsets
+        paths.append(write_container(str(tmp_path / f"part{k}"), b.adc[o[a]: o[e]], o[a: e + 1] - o[a], b.full_lens[a:e],
+                                     b.calib_offset[a:e], b.calib_scale[a:e], ids[a:e]))
+    out = str(tmp_path / "out")
+    stats = detect_files(paths, out, spc, minibatch_size=job["minibatch"], batch_size_output=job["batch_size_output"],
+                         minibatches_per_call=2)
+    assert stats["reads"] == job["n"] and stats["lost"] == 0
+    for rel, want in doc["files"].items():
+        with open(os.path.join(out, rel), newline="") as f:
+            _assert_csv_close(f.read(), want)

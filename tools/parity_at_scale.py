@@ -53,7 +53,29 @@ def main():
     ap.add_argument("--minibatch", type=int, default=1000)
     ap.add_argument("--stress", action="store_true")
     ap.add_argument("--seed", type=int, default=4242)
+    ap.add_argument("--chunks", type=int, default=1, help="repeat with seeds seed, seed+1, ... (bounds host memory)")
     args = ap.parse_args()
+    if args.chunks > 1:
+        import subprocess
+
+        tot = None
+        for c in range(args.chunks):
+            cmd = [sys.executable, os.path.abspath(__file__), "--chemistry", args.chemistry, "--reads", str(args.reads),
+                   "--minibatch", str(args.minibatch), "--seed", str(args.seed + c)] + (["--stress"] if args.stress else [])
+            out = subprocess.run(cmd, capture_output=True, text=True).stdout.strip().splitlines()
+            d = json.loads(out[-1])
+            if tot is None:
+                tot = d
+                tot["seeds"] = [args.seed]
+            else:
+                for k in ("reads", "lost_minibatches", "identical", "primary_moved_by_one_step", "other_differences",
+                          "gpu_s_incl_host_conversion", "oracle_s"):
+                    tot[k] += d[k]
+                tot["examples"] = (tot["examples"] + d["examples"])[:5]
+                tot["seeds"].append(args.seed + c)
+        tot.pop("pass_fraction_oracle", None)
+        print(json.dumps(tot))
+        return 0 if tot["other_differences"] == 0 else 1
 
     import multiprocessing as mp
     from concurrent.futures import ProcessPoolExecutor
