@@ -603,8 +603,8 @@ __global__ void cnn_tc_pack_weights_kernel(const float *w, __half *packed);
 static int cnn_tc_launch_setup();
 static void cnn_tc_launch(int layer, const void *in, void *out, const __half *wp, const float *bias, const float *w1,
                           const float *b1, int n_reads, int Lx, int L1, int LP, int *redo, int sm_count, cudaStream_t st);
-static size_t cnn_tc_a0t_bytes_per_read();
-static int cnn_tc_max_l1();
+static size_t cnn_tc_a0t_bytes_per_read(int L1);
+static int cnn_tc_a0t_rows_host(int L1);
 
 static int cnn_forward_dev(adb_ctx *ctx, const float *x, int n, const CnnDims &D, const float *w_dev, float *scores,
                            cudaStream_t st) {
@@ -625,8 +625,7 @@ static int cnn_forward_dev(adb_ctx *ctx, const float *x, int n, const CnnDims &D
     CUDA_TRY(cudaFuncSetAttribute(cnn_conv64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(cudaFuncSetAttribute(cnn_conv64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     float *a0 = (float *)ctx->cnn_act0.p, *a1 = (float *)ctx->cnn_act1.p;
-    // tensor-core path: needs L1 within the tile layout of the intermediate activations, FP32 pipe otherwise
-    const bool use_tc = !ctx->opt_cnn_fp32 && D.L1 <= cnn_tc_max_l1();
+    const bool use_tc = !ctx->opt_cnn_fp32;
     __half *wtc = nullptr;
     unsigned char *a0t = nullptr;
     int *redo = nullptr;
@@ -644,7 +643,7 @@ static int cnn_forward_dev(adb_ctx *ctx, const float *x, int n, const CnnDims &D
         if (cnn_tc_launch_setup()) { set_err("cudaFuncSetAttribute cnn tc"); return ADB_ERR_CUDA; }
         // layer 2 -> layer 3 activations in layer 3's tile layout; the padding rows are never written: zero them whenever
         // the buffer is (re)allocated
-        const size_t a0t_bytes = cnn_tc_a0t_bytes_per_read() * (size_t)chunk;
+        const size_t a0t_bytes = cnn_tc_a0t_bytes_per_read(D.L1) * (size_t)chunk;
         const void *before = ctx->cnn_a0t.p;
         const size_t cap_before = ctx->cnn_a0t.cap;
         if (ctx->cnn_a0t.ensure(a0t_bytes)) { set_err("cudaMalloc cnn a0t"); return ADB_ERR_CUDA; }
@@ -663,13 +662,14 @@ static int cnn_forward_dev(adb_ctx *ctx, const float *x, int n, const CnnDims &D
             {
                 KernelTimer t(ctx, 5, st);
                 cnn_tc_launch(2, x + (size_t)r0 * D.Lx, a0t, wtc, w_dev + CNN_B2, w_dev + CNN_W1, w_dev + CNN_B1, nc, D.Lx, D.L1,
-                              D.LP, redo, ctx->sm_count, st);
+                              cnn_tc_a0t_rows_host(D.L1), redo, ctx->sm_count, st);
             }
             {
                 KernelTimer t(ctx, 5, st);
                 // layer 3 + the transposed convolution: scores straight from the epilogue
                 cnn_tc_launch(3, a0t, scores + (size_t)r0 * 2 * D.Lout, wtc + (size_t)CNN_K * 2 * 4096, w_dev + CNN_B3,
-                              w_dev + CNN_W4, w_dev + CNN_B4, nc, D.Lout, D.L1, D.LP, redo, ctx->sm_count, st);
+                              w_dev + CNN_W4, w_dev + CNN_B4, nc, D.Lout, D.L1, cnn_tc_a0t_rows_host(D.L1), redo,
+                              ctx->sm_count, st);
             }
             {
                 // reads with a value outside the fp16 range (flagged by either layer): both layers again on the FP32 pipe

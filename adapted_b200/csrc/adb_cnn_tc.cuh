@@ -138,14 +138,19 @@ __device__ __forceinline__ bool tc_split_store(unsigned char *hi_plane, unsigned
 
 // Intermediate activations between the two layers ("A0T"): layer 2's epilogue writes its output already split into the
 // fp16 hi / lo planes and in the row order of layer 3's shared-memory tile,
-//     A0T[read][plane][ci / 8][rho = position + TC_A0T_PAD][ci % 8]      (16 B per row, TC_A0T_ROWS rows per octet),
+//     A0T[read][plane][ci / 8][rho = position + TC_A0T_PAD][ci % 8]      (16 B per row, `a0t_rows` rows per octet),
 // so that the operand tile of a layer-3 job is 16 contiguous runs of 134 rows: sixteen cp.async.bulk copies per tile,
 // no thread touches the data.  Rows outside [0, L1) are layer 3's zero padding: rows >= L1 are written as zeros, the
 // three rows in front of position 0 and the tail rows are never written and stay zero from the buffer's memset.
 #define TC_A0T_PAD 4                                        // zero rows in front of position 0
-#define TC_A0T_ROWS (5 * TC_ROWS + 6)                       // positions -4 .. 641
 #define TC_L3_STRIDE (TC_ROWS - 2)                          // layer 3 tiles overlap by two rows (fused convT, see below)
-#define TC_A0T_READ_BYTES (2 * 8 * TC_A0T_ROWS * 16)        // bytes per read
+// rows per octet for a layer-1 length L1: what layer 2's tiles write (positions 0 .. 128 J2 - 1) and what layer 3's last
+// tile reads (rho up to 126 (J3 - 1) + 133), whichever is larger; the kernels get it in their `LP` argument
+__host__ __device__ inline int cnn_tc_a0t_rows(int L1) {
+    const int j2 = (L1 + TC_ROWS - 1) / TC_ROWS, j3 = (L1 + TC_L3_STRIDE - 1) / TC_L3_STRIDE;
+    const int w = TC_ROWS * j2 + TC_A0T_PAD, rd = TC_L3_STRIDE * (j3 - 1) + TC_NQ;
+    return ((w > rd ? w : rd) + 7) & ~7;
+}
 #define TC_TILE_RUN (TC_NQ * 16)                            // bytes of one (plane, octet) run of a tile
 
 __host__ __device__ inline size_t cnn_tc_smem_bytes_layer(int layer) {
@@ -170,6 +175,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const void
                                                                      const float *bias, const float *w1, const float *b1,
                                                                      int n_reads, int Lx, int L1, int LP, int *redo) {
     constexpr int NBUF = LAYER == 3 ? 3 : 2;
+    const int a0t_rows = LP;                                    // rows per octet of A0T (cnn_tc_a0t_rows)
+    const size_t a0t_read_bytes = (size_t)2 * 8 * a0t_rows * 16;
     extern __shared__ __align__(1024) unsigned char tsm[];
     unsigned char *Wsm = tsm;                                   // resident weights [7][hi, lo][8][64][8] fp16
     unsigned char *Abuf = tsm + TC_WBYTES;                      // NBUF tile buffers x (hi plane, lo plane)
@@ -274,12 +281,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const void
     auto load_tile = [&](int job, int b) {
         // rows of positions t0 - 3 .. t0 + 130 with t0 = 126 j - 1: rho = position + 4 starts at 126 j
         const int r = job / jobs_per_read, rho0 = (job % jobs_per_read) * TC_L3_STRIDE;
-        const unsigned char *src = (const unsigned char *)in + (size_t)r * TC_A0T_READ_BYTES + (size_t)rho0 * 16;
+        const unsigned char *src = (const unsigned char *)in + (size_t)r * a0t_read_bytes + (size_t)rho0 * 16;
         unsigned char *dst = Abuf + (size_t)b * 2 * TC_PLANE;
         mbar_expect_tx(&afull[b], 16 * TC_TILE_RUN);
 #pragma unroll 1
         for (int pk = 0; pk < 16; pk++)  // pk = plane * 8 + octet
-            tma_bulk_g2s(dst + (size_t)pk * (TC_RA * 16), src + (size_t)pk * (TC_A0T_ROWS * 16), TC_TILE_RUN, &afull[b]);
+            tma_bulk_g2s(dst + (size_t)pk * (TC_RA * 16), src + (size_t)pk * ((size_t)a0t_rows * 16), TC_TILE_RUN, &afull[b]);
     };
     // ---- the 84 MMAs of one tile: 7 taps x 4 K-steps of 16 channels x (hi*hi, lo*hi, hi*lo) ----
     const uint32_t w_lo0 = tc_desc_lo(smem_u32(Wsm), 64 * 16), w_hi = tc_desc_hi(128);
@@ -353,7 +360,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const void
             // bias + ReLU, split, and straight into layer 3's tile layout (rows >= L1: zeros = its padding)
             const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(tb * 64 + ch0);
             tc_ld32(taddr, v);
-            unsigned char *base = (unsigned char *)out + (size_t)r * TC_A0T_READ_BYTES + (size_t)(p + TC_A0T_PAD) * 16;
+            unsigned char *base = (unsigned char *)out + (size_t)r * a0t_read_bytes + (size_t)(p + TC_A0T_PAD) * 16;
             bool bad = false;
 #pragma unroll
             for (int o = 0; o < 4; o++) {
@@ -369,9 +376,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const void
                     h[j] = __halves2half2(h0, h1);
                     l[j] = __halves2half2(__float2half_rn(__fsub_rn(f0, g0)), __float2half_rn(__fsub_rn(f1, g1)));
                 }
-                const size_t off = (size_t)((ch0 >> 3) + o) * (TC_A0T_ROWS * 16);
+                const size_t off = (size_t)((ch0 >> 3) + o) * ((size_t)a0t_rows * 16);
                 *reinterpret_cast<uint4 *>(base + off) = *reinterpret_cast<const uint4 *>(h);
-                *reinterpret_cast<uint4 *>(base + (size_t)8 * (TC_A0T_ROWS * 16) + off) = *reinterpret_cast<const uint4 *>(l);
+                *reinterpret_cast<uint4 *>(base + (size_t)8 * ((size_t)a0t_rows * 16) + off) = *reinterpret_cast<const uint4 *>(l);
             }
             if (bad) { redo[r] = 1; redo[-1] = 1; }
         }
@@ -450,5 +457,5 @@ static void cnn_tc_launch(int layer, const void *in, void *out, const __half *wp
     else cnn_conv64_tc_kernel<3><<<grid, TC_THREADS, smem, st>>>(in, out, wp, bias, w1, b1, n_reads, Lx, L1, LP, redo);
 }
 
-static size_t cnn_tc_a0t_bytes_per_read() { return (size_t)TC_A0T_READ_BYTES; }
-static int cnn_tc_max_l1() { return 5 * TC_L3_STRIDE; }  // layer 3's last tile must stay inside the rows of A0T
+static size_t cnn_tc_a0t_bytes_per_read(int L1) { return (size_t)2 * 8 * cnn_tc_a0t_rows(L1) * 16; }
+static int cnn_tc_a0t_rows_host(int L1) { return cnn_tc_a0t_rows(L1); }

@@ -145,3 +145,19 @@ def test_cnn_scores_outside_fp16_range_take_the_fp32_pipe():
     for r in range(x.shape[0]):
         scale = np.abs(want[r]).max()
         assert np.abs(got[r] - want[r]).max() <= 2e-5 * scale + 1e-4, r
+
+
+@pytest.mark.parametrize("L", [40, 300, 1149, 2400, 4000])
+def test_cnn_scores_other_lengths(L):
+    """the tensor-core path tiles any layer-1 length (one tile, ragged last tiles, more than five tiles)"""
+    from adapted_b200.detect import cnn_scores
+
+    rng = np.random.default_rng(L)
+    w = load_cnn_weights()
+    x = rng.normal(0, 1.5, size=(5, L)).astype(np.float32)
+    x[1, L // 2:] = -5.0
+    got = cnn_scores(x, w)
+    want = detect_ref.cnn_forward(x, w)
+    assert got.shape == want.shape
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() <= 2e-5 * scale + 1e-4
