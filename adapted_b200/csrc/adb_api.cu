@@ -342,7 +342,17 @@ static int launch_validate(adb_ctx *ctx, const BatchDev &B, const adb_config &cf
     // an average poly(A) share of 1/4 of the window; reads that do not fit fall back to the in-CTA path (same result)
     const bool overwrite = cfg.mvs_detect_check && cfg.mvs_detect_overwrite;  // general kernel only (row f3)
     const bool pre = cfg.mvs_detect_check != 0 && !overwrite;
-    const long long pool_cap = std::max<long long>(1 << 20, (long long)B.n_reads * B.m / 4);
+    // Pool sized for the worst case -- every read's poly(A) candidate at the end of the window (the long-poly(A) stress
+    // set gets close, and rows are handed out longest first, so a pool that is too small starves the many short rows)
+    // -- as far as a third of the free device memory allows; an ordinary job touches about a tenth of it.
+    long long pool_cap = std::max<long long>(1 << 20, (long long)B.n_reads * B.m);
+    if ((size_t)pool_cap * sizeof(float) * 2 > ctx->cnn_aux.cap) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            const long long budget = (long long)((free_b + ctx->cnn_aux.cap) / 3 / (2 * sizeof(float)));
+            pool_cap = std::max<long long>(std::min<long long>(pool_cap, budget), std::max<long long>(1 << 20, (long long)B.n_reads * B.m / 4));
+        }
+    }
     if (pre && (ctx->cnn_aux.ensure((size_t)pool_cap * sizeof(float) * 2) ||
                 ctx->h_misc3.ensure(sizeof(int) * 2 * (size_t)B.n_reads + sizeof(long long) * ((size_t)B.n_reads + 2)))) {
         set_err("cudaMalloc moving-statistics scratch");
@@ -405,20 +415,29 @@ static int launch_validate(adb_ctx *ctx, const BatchDev &B, const adb_config &cf
         const size_t fsm = vfast_smem_bytes(A.win_bytes);
         if ((int)fsm <= ctx->max_smem_optin) {
             if (ctx->vf_done.ensure((size_t)B.n_reads + 16)) { set_err("cudaMalloc done flags"); return ADB_ERR_CUDA; }
-            CUDA_TRY(cudaMemsetAsync(ctx->vf_done.p, 0, (size_t)B.n_reads, st));
+            CUDA_TRY(cudaMemsetAsync(ctx->vf_done.p, 0, (size_t)B.n_reads + 16, st));
             VfastArgs F;
             F.B = B; F.given = given; F.given_stride = given_stride; F.given_ntopk = given_ntopk; F.ntopk_per_read = ntopk_per_read;
             F.mode = mode; F.win_bytes = A.win_bytes; F.out = out; F.batch_status = batch_status;
             F.pre_var = A.pre_var; F.pre_mean = A.pre_mean; F.pre_off = A.pre_off; F.pre_meta = A.pre_meta;
             F.done = (unsigned char *)ctx->vf_done.p;
-            CUDA_TRY(cudaFuncSetAttribute(validate_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+            F.n_long = (int *)((unsigned char *)ctx->vf_done.p + (((size_t)B.n_reads + 3) & ~(size_t)3));
+            F.long_min = (mode == ADB_METHOD_CNN && given_ntopk > 1) ? std::max(1, B.n_reads / 5) : 1;
+            CUDA_TRY(cudaFuncSetAttribute(validate_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+            CUDA_TRY(cudaFuncSetAttribute(validate_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
             int focc = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&focc, validate_fast_kernel, VF_THREADS, fsm));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&focc, validate_fast_kernel<false>, VF_THREADS, fsm));
             if (focc < 1) focc = 1;
             const int fgrid = std::max(1, std::min(B.n_reads, ctx->sm_count * focc));
             {
                 KernelTimer t(ctx, 2, st);
-                validate_fast_kernel<<<fgrid, VF_THREADS, fsm, st>>>(F, cfg);
+                validate_fast_kernel<false><<<fgrid, VF_THREADS, fsm, st>>>(F, cfg);
+            }
+            if (pre) {
+                // reads whose poly(A) series exceed the window memory (long-poly(A) stress sets); leaves at once otherwise
+                KernelTimer t(ctx, 2, st);
+                validate_fast_kernel<true><<<fgrid, VF_THREADS, fsm, st>>>(F, cfg);
+                ctx->launches += 1;
             }
             ctx->launches += 1;
             A.done = F.done;

@@ -547,13 +547,17 @@ __device__ void vf_mean_std3(const VfRead &R, VfScratch &S, const int sa[3], con
 // the bracket; those are gathered and ranked directly (float keys are nearly all distinct, so isolating a single key
 // by bisection would take ~22 passes; isolating 64 of ~3000 takes ~6).  CTA-wide.
 #define VF_NCAND 64
+// STAGED = false (series longer than `buf`: poly(A) segments beyond half the window, the long-poly(A) stress set): every
+// pass reads the 16-byte aligned rows from the pools (L2 resident) and forms the keys on the fly -- same passes, same
+// result.
+template <bool STAGED>
 __device__ void vf_series_medians(VfScratch &S, const float *g0, int n0, const float *g1, int n1, uint32_t *buf, float out[2]) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t *k0 = buf, *k1 = buf + ((n0 + 3) & ~3);
     __syncthreads();
     uint32_t mn[2] = {0xffffffffu, 0xffffffffu}, mx[2] = {0u, 0u};
-    for (int j = tid; j < n0; j += VF_THREADS) { const uint32_t k = f32_key(g0[j]); k0[j] = k; mn[0] = min(mn[0], k); mx[0] = max(mx[0], k); }
-    for (int j = tid; j < n1; j += VF_THREADS) { const uint32_t k = f32_key(g1[j]); k1[j] = k; mn[1] = min(mn[1], k); mx[1] = max(mx[1], k); }
+    for (int j = tid; j < n0; j += VF_THREADS) { const uint32_t k = f32_key(g0[j]); if (STAGED) k0[j] = k; mn[0] = min(mn[0], k); mx[0] = max(mx[0], k); }
+    for (int j = tid; j < n1; j += VF_THREADS) { const uint32_t k = f32_key(g1[j]); if (STAGED) k1[j] = k; mn[1] = min(mn[1], k); mx[1] = max(mx[1], k); }
     for (int q = 0; q < 2; q++) { mn[q] = warp_min_u(mn[q]); mx[q] = warp_max_u(mx[q]); }
     if (tid < 4) S.utmp[tid] = (tid < 2) ? 0xffffffffu : 0u;
     if (tid < 6) S.cnt[tid] = 0;
@@ -568,6 +572,8 @@ __device__ void vf_series_medians(VfScratch &S, const float *g0, int n0, const f
     uint32_t lo[2] = {S.utmp[0], S.utmp[1]}, hi[2] = {S.utmp[2], S.utmp[3]};
     const int nn[2] = {n0, n1};
     const uint32_t *kk[2] = {k0, k1};
+    const float *gg[2] = {g0, g1};
+    auto key_at = [&](int q, int j) -> uint32_t { return STAGED ? kk[q][j] : f32_key(gg[q][j]); };
     const unsigned rank[2] = {n0 > 0 ? (unsigned)(n0 - 1) / 2 : 0u, n1 > 0 ? (unsigned)(n1 - 1) / 2 : 0u};
     unsigned cnt_hi[2] = {(unsigned)n0, (unsigned)n1}, cnt_lo[2] = {0u, 0u};
     auto open = [&](int q) { return nn[q] > 0 && lo[q] < hi[q] && cnt_hi[q] - cnt_lo[q] > VF_NCAND; };
@@ -578,14 +584,22 @@ __device__ void vf_series_medians(VfScratch &S, const float *g0, int n0, const f
             mid[q] = lo[q] + ((hi[q] - lo[q]) >> 1);
             if (!open(q)) continue;
             int c = 0;
-            const uint4 *V = reinterpret_cast<const uint4 *>(kk[q]);
             const int nv = nn[q] >> 2;
-            for (int v = tid; v < nv; v += VF_THREADS) {
-                const uint4 x = V[v];
-                c += (x.x <= mid[q]) + (x.y <= mid[q]) + (x.z <= mid[q]) + (x.w <= mid[q]);
+            if (STAGED) {
+                const uint4 *V = reinterpret_cast<const uint4 *>(kk[q]);
+                for (int v = tid; v < nv; v += VF_THREADS) {
+                    const uint4 x = V[v];
+                    c += (x.x <= mid[q]) + (x.y <= mid[q]) + (x.z <= mid[q]) + (x.w <= mid[q]);
+                }
+            } else {
+                const float4 *V = reinterpret_cast<const float4 *>(gg[q]);
+                for (int v = tid; v < nv; v += VF_THREADS) {
+                    const float4 x = V[v];
+                    c += (f32_key(x.x) <= mid[q]) + (f32_key(x.y) <= mid[q]) + (f32_key(x.z) <= mid[q]) + (f32_key(x.w) <= mid[q]);
+                }
             }
             const int j = (nv << 2) + tid;
-            if (j < nn[q]) c += (kk[q][j] <= mid[q]);
+            if (j < nn[q]) c += (key_at(q, j) <= mid[q]);
             c = __reduce_add_sync(ADB_FULL, c);
             if (lane == 0 && c) atomicAdd(&S.cnt[q + 2 * (pass % 3)], (unsigned)c);
         }
@@ -604,7 +618,7 @@ __device__ void vf_series_medians(VfScratch &S, const float *g0, int n0, const f
     for (int q = 0; q < 2; q++) {
         if (nn[q] <= 0 || lo[q] == hi[q]) continue;
         for (int j = tid; j < nn[q]; j += VF_THREADS) {
-            const uint32_t k = kk[q][j];
+            const uint32_t k = key_at(q, j);
             if (k >= lo[q] && k <= hi[q]) { const int p = atomicAdd(&S.ncand[q], 1); if (p < VF_NCAND) S.cand[q][p] = k; }
         }
     }
@@ -648,7 +662,7 @@ __device__ void vf_series_medians(VfScratch &S, const float *g0, int n0, const f
             if (tid == 0) S.utmp[3] = 0xffffffffu;
             __syncthreads();
             uint32_t best = 0xffffffffu;
-            for (int j = tid; j < nn[q]; j += VF_THREADS) { const uint32_t k = kk[q][j]; if (k > hi[q]) best = min(best, k); }
+            for (int j = tid; j < nn[q]; j += VF_THREADS) { const uint32_t k = key_at(q, j); if (k > hi[q]) best = min(best, k); }
             best = warp_min_u(best);
             if (lane == 0) atomicMin(&S.utmp[3], best);
             __syncthreads();
@@ -669,6 +683,8 @@ struct VfastArgs {
     int given_stride;
     int given_ntopk;            // entries per read when ntopk_per_read == nullptr (-1: None)
     const int *ntopk_per_read;
+    int *n_long;                // device counter: reads left to the LONG instantiation
+    int long_min;               // the LONG instantiation runs only if at least that many reads wait for it
     int mode;                   // ADB_METHOD_*
     int win_bytes;              // capacity of the staged window (bytes)
     adb_record *out;
@@ -774,6 +790,10 @@ __device__ float vf_mad_of(const VfRead &R, VfScratch &S, int q) {
     return __fdiv_rn(__fadd_rn(d0, d1), 2.0f);
 }
 
+// LONG = false: every read whose two moving-statistics series fit into the window memory (all but pathological reads).
+// LONG = true: a second launch for the others (poly(A) longer than about half the window) with the series bisected
+// from global memory; the two launches split the reads by the same predicate on the primary boundaries.
+template <bool LONG>
 __global__ void __launch_bounds__(VF_THREADS, 4) validate_fast_kernel(VfastArgs A, adb_config cfg) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *winbuf = smem;
@@ -786,6 +806,9 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_fast_kernel(VfastArgs 
     __syncthreads();
     uint32_t phase = 0;
 
+    // nothing (or, with several poly(A) candidates per read, too little) to gain from the second launch: with top-k
+    // candidates a long first candidate is mostly a wrong one, the read fails it and goes to validate_kernel anyway
+    if (LONG && *A.n_long < A.long_min) return;
     for (int r = blockIdx.x; r < A.B.n_reads; r += gridDim.x) {
         const int mb = r / A.B.batch_size;
         adb_record *rec = A.out + r;
@@ -812,6 +835,20 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_fast_kernel(VfastArgs 
                               !(size < a_end + msw);
         const bool win_var = !(pe0 - a_end <= cfg.pA_var_window + 2), win_mean = !(pe0 - a_end <= cfg.pA_mean_window + 2);
         const float *pv_series = nullptr, *pm_series = nullptr;
+        {
+            bool long_series = false;
+            if (mvs_geom && (win_var || win_mean)) {
+                int ga = a_end, gb = pe0;
+                clip_seg(ga, gb, size);
+                const int Lg = gb - ga;
+                const int gnv = win_var ? Lg - (cfg.pA_var_window - 1) : 0, gnm = win_mean ? Lg - (cfg.pA_mean_window - 1) : 0;
+                long_series = (size_t)(((gnv + 3) & ~3) + gnm) * 4 > win_cap;
+            }
+            if (long_series != LONG) {
+                if (!LONG && tid == 0) atomicAdd(A.n_long, 1);  // tells the second launch that it has work
+                continue;
+            }
+        }
         if (mvs_geom && (win_var || win_mean)) {
             const long long po = A.pre_off ? A.pre_off[r] : -1;
             if (!(po >= 0 && A.pre_meta[2 * r] == a_end && A.pre_meta[2 * r + 1] == pe0)) continue;  // not precomputed
@@ -992,8 +1029,9 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_fast_kernel(VfastArgs 
                 // the staged window is not needed any more: its memory now holds the ordered keys of the two series
                 float smed[2] = {0.f, 0.f};
                 const int nv = win_var ? L - (cfg.pA_var_window - 1) : 0, nm = win_mean ? L - (cfg.pA_mean_window - 1) : 0;
-                if ((size_t)(((nv + 3) & ~3) + nm) * 4 > win_cap) defer = true;  // does not fit: left to validate_kernel
-                else if (nv > 0 || nm > 0) vf_series_medians(S, pv_series, nv, pm_series, nm, (uint32_t *)winbuf, smed);
+                if (LONG) vf_series_medians<false>(S, pv_series, nv, pm_series, nm, (uint32_t *)winbuf, smed);
+                else if ((size_t)(((nv + 3) & ~3) + nm) * 4 > win_cap) defer = true;  // (cannot happen: split by the same predicate)
+                else if (nv > 0 || nm > 0) vf_series_medians<true>(S, pv_series, nv, pm_series, nm, (uint32_t *)winbuf, smed);
                 const float var32 = win_var ? smed[0] : small_var;
                 const float mean32 = win_mean ? smed[1] : small_mean;
                 const float shift32 = __fsub_rn(medAF, medBF);

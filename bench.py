@@ -143,6 +143,8 @@ def main():
                     help="minibatches per full-size H2D chunk of the pipelined ingest (default: 16, CNN path 32)")
     ap.add_argument("--cpu-reads-per-worker", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stress", action="store_true",
+                    help="BASELINE config 4: poly(A) lengths up to the preload limit, 10 %% of the reads ending early")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -210,7 +212,11 @@ def main():
     m = flat["sig_preload_size"]
     config["preload_window"] = m
     n = args.reads
-    data = make_reads_torch(n, args.chemistry, m, seed=1234 + rank, device=dev)
+    gen_kw = {}
+    if args.stress:
+        gen_kw = dict(stress=True, short_frac=0.1, short_min=50 if flat["primary_method"] == 1 else flat["min_obs_adapter"] + 200)
+        config["workload"] += " -- stress set (config 4: long poly(A) / truncated preload, short reads)"
+    data = make_reads_torch(n, args.chemistry, m, seed=1234 + rank, device=dev, **gen_kw)
     torch.cuda.synchronize()
     samples = int(data["offsets"][-1].item())
     L = _lib.load()
