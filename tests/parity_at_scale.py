@@ -2,7 +2,7 @@
 """Parity at scale: N synthetic reads through the CUDA path (int16 ingest) and through the CPU oracle, every
 DetectResults field of every read compared.  Test infrastructure (imports oracle/); run by hand on a GPU box:
 
-    python tools/parity_at_scale.py --chemistry rna004 --reads 100000 [--stress]
+    python tests/parity_at_scale.py --chemistry rna004 --reads 100000 [--stress]
 
 LLR path: every field must be identical (floats within 1e-5).  CNN path: the float32 convolutions are summed in a
 different order than torch's CPU kernels, so a primary coordinate may move by one downscaled step (north_star: +-1
