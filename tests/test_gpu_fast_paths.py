@@ -142,3 +142,40 @@ def test_start_peak_int16_ingest_matches_oracle():
     got, st = detect_reads(b.adc, b.offsets, b.full_lens, b.calib_offset, b.calib_scale, spc, minibatch_size=b.n)
     assert not st.any()
     assert diff_results(got, want) == []
+
+
+@pytest.mark.parametrize("chem", ["rna002", "rna004"])
+def test_pipelined_ingest_equals_one_shot(chem):
+    """adb_detect_pipelined_host (ramped chunk schedule, chunks alternating between two contexts, one copy stream) gives
+    byte-identical records to adb_detect_host on the same reads"""
+    import ctypes as C
+
+    from adapted_b200 import _lib
+    from adapted_b200.config import flatten_config, get_chemistry_specific_config
+    from adapted_b200.detect import flatten_cnn_weights
+    from adapted_b200.synth import make_reads
+    from tests.golden_io import load_cnn_weights
+
+    spc = get_chemistry_specific_config(chem)
+    flat = flatten_config(spc)
+    mbs, n = 24, 24 * 9 + 7
+    b = make_reads(n, chem, flat["sig_preload_size"], seed=55, short_frac=0.05 if chem == "rna004" else 0.0)
+    cfg = _lib.fill_config(flat)
+    w = flatten_cnn_weights(load_cnn_weights()) if flat["primary_method"] == 1 else None
+    wptr = w.ctypes.data if w is not None else None
+    batch = _lib.AdbBatch(signal=b.adc.ctypes.data, sig_type=_lib.SIG_I16, n_reads=n, m=flat["sig_preload_size"], batch_size=mbs,
+                          offsets=b.offsets.ctypes.data, full_lens=b.full_lens.ctypes.data,
+                          calib_offset=b.calib_offset.ctypes.data, calib_scale=b.calib_scale.ctypes.data)
+    L = _lib.load()
+    ctx = _lib.default_context(0)
+    nb = (n + mbs - 1) // mbs
+    one = np.zeros(n, dtype=_lib.RECORD_DTYPE)
+    st1 = np.zeros(nb, np.int32)
+    _lib.check(L.adb_detect_host(ctx.handle, C.byref(batch), C.byref(cfg), wptr, one.ctypes.data, st1.ctypes.data))
+    for chunk in (1, 2, 3, 64):
+        got = np.zeros(n, dtype=_lib.RECORD_DTYPE)
+        st2 = np.full(nb, -99, np.int32)
+        _lib.check(L.adb_detect_pipelined_host(ctx.handle, C.byref(batch), C.byref(cfg), wptr, got.ctypes.data,
+                                               st2.ctypes.data, chunk))
+        assert got.tobytes() == one.tobytes(), chunk
+        assert np.array_equal(st1, st2), chunk
