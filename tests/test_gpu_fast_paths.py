@@ -179,3 +179,19 @@ def test_pipelined_ingest_equals_one_shot(chem):
                                                st2.ctypes.data, chunk))
         assert got.tobytes() == one.tobytes(), chunk
         assert np.array_equal(st1, st2), chunk
+
+
+def test_cnn_tensor_core_and_fp32_pipe_agree():
+    """A/B of the two convolution back ends through the whole CNN seam: the tcgen05 kernels (fp16 hi / lo split, fused
+    layer 1 and transposed convolution) against the FP32-pipe kernels; records identical except where a primary
+    coordinate moves by at most one downscaled step"""
+    from tests.golden_io import load_cnn_weights
+    from tests.test_gpu_cnn_path import _cnn_compare
+
+    spc = get_chemistry_specific_config("rna004")
+    w = load_cnn_weights()
+    b = make_reads(300, "rna004", spc.sig_preload_size, seed=611, short_frac=0.1)
+    tc, st = _detect(b, spc, 100, model=w)
+    fp, st2 = _detect(b, spc, 100, model=w, cnn_fp32_pipe=1)
+    assert not st.any() and not st2.any()
+    _cnn_compare(tc, fp, spc.core.downscale_factor)
