@@ -12,8 +12,11 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/adapted_b200.h"
@@ -183,9 +186,35 @@ struct Out {
     void put(char c) { put(&c, 1); }
 };
 
+// A value that is a multiple of 1/1000 with at most 15 significant digits (what round(3) leaves): its shortest
+// round-trip text is k / 1000 written out, so the digits come from integer arithmetic (libstdc++'s floating-point
+// to_chars serialises threads).  Returns false when the value is not of that form.
+static bool fmt_thousandths(double x, double max_k, std::string &s) {
+    const double kd = std::nearbyint(x * 1000.0);
+    if (!(std::fabs(kd) < max_k) || kd / 1000.0 != x) return false;
+    long long k = (long long)kd;
+    char buf[40];
+    char *p = buf;
+    if (std::signbit(x)) { *p++ = '-'; k = -k; }
+    auto r = std::to_chars(p, buf + sizeof buf, k / 1000);
+    p = r.ptr;
+    *p++ = '.';
+    const int frac = (int)(k % 1000);
+    if (frac == 0) *p++ = '0';
+    else {
+        char d[3] = {(char)('0' + frac / 100), (char)('0' + (frac / 10) % 10), (char)('0' + frac % 10)};
+        int n = 3;
+        while (n > 1 && d[n - 1] == '0') n--;
+        for (int i = 0; i < n; i++) *p++ = d[i];
+    }
+    s.assign(buf, p);
+    return true;
+}
+
 // Python's repr(float) for the magnitudes that occur here (|x| < 1e16 after round(3)): shortest round-trip digits in
 // fixed notation, always with a fractional part.
 void fmt_float(double x, std::string &s) {
+    if (std::isfinite(x) && fmt_thousandths(x, 1e15, s)) return;
     s.clear();
     if (std::isinf(x)) { s = x < 0 ? "-inf" : "inf"; return; }
     char buf[400];
@@ -213,6 +242,11 @@ void fmt_float(double x, std::string &s) {
 // the same for a float32 column (all cells np.float32, no None): pandas keeps float32, numpy rounds in float32 and
 // the text is the shortest float32 round-trip
 void fmt_float32(float x, std::string &s) {
+    // (float32: six significant digits are unambiguous)
+    if (std::isfinite(x) && std::fabs(x) < 999.0f) {
+        const float kf = std::nearbyintf(x * 1000.0f);
+        if (kf / 1000.0f == x && fmt_thousandths((double)kf / 1000.0, 1e6, s)) return;
+    }
     s.clear();
     if (std::isinf(x)) { s = x < 0 ? "-inf" : "inf"; return; }
     char buf[128];
@@ -258,13 +292,13 @@ void fmt_int_array(const int32_t *a, int n, std::string &s) {
     size_t width = 0;
     char buf[16];
     for (int i = 0; i < n; i++) {
-        const size_t l = (size_t)snprintf(buf, sizeof buf, "%d", a[i]);
+        const size_t l = (size_t)(std::to_chars(buf, buf + sizeof buf, a[i]).ptr - buf);
         if (l > width) width = l;
     }
     const size_t elem_width = 75 - 1;
     std::string line = " ", word;
     for (int i = 0; i < n; i++) {
-        const int l = snprintf(buf, sizeof buf, "%d", a[i]);
+        const int l = (int)(std::to_chars(buf, buf + sizeof buf, a[i]).ptr - buf);
         word.assign(width - (size_t)l, ' ');
         word.append(buf, (size_t)l);
         if (line.size() + word.size() > elem_width && line.size() > 1) {
@@ -295,50 +329,29 @@ void put_field(Out &o, const char *s, size_t n) {  // csv.QUOTE_MINIMAL with the
 
 }  // namespace
 
-extern "C" int64_t adb_format_csv(const adb_record *recs, const int32_t *sel, int32_t n_sel,
-                                  const char *const *read_ids, int32_t primary_method, const char *llr_detect_log,
-                                  int32_t save_fail_reasons, char *out, int64_t cap) {
-    if ((n_sel > 0 && !recs) || n_sel < 0 || (cap > 0 && !out)) return ADB_ERR_ARG;
-    Out o{out, cap};
-    if (n_sel == 0) {  // pd.DataFrame([]).round(3).to_csv(index=False) writes one empty line
-        o.put('\n');
-        return o.len;
-    }
-    const int n_cols = save_fail_reasons ? N_COLS : N_COLS - 1;
-    auto rec_of = [&](int k) -> const adb_record & { return recs[sel ? sel[k] : k]; };
-    auto id_of = [&](int k) -> const char * { return read_ids ? read_ids[sel ? sel[k] : k] : nullptr; };
-    // pass 1: per column, is there a None and is there a value (pandas' maybe_convert_objects on the column)
-    std::vector<uint8_t> has_none(n_cols, 0), has_val(n_cols, 0), not_f32(n_cols, 0);
-    std::string scratch;
-    for (int k = 0; k < n_sel; k++) {
-        const adb_record &r = rec_of(k);
-        const char *reason = save_fail_reasons ? fail_reason(r, scratch) : nullptr;
-        for (int c = 0; c < n_cols; c++) {
-            const Cell cell = get_cell(r, c, primary_method, id_of(k), llr_detect_log, reason);
-            if (cell.kind == K_NONE) has_none[c] = 1;
-            else has_val[c] = 1;
-            if (!(cell.kind == K_FLT && cell.f32)) not_f32[c] = 1;
-        }
-    }
-    for (int c = 0; c < n_cols; c++) {
-        if (c) o.put(',');
-        o.put(COL_NAMES[c], strlen(COL_NAMES[c]));
-    }
-    o.put('\n');
-    std::string text;
+// rows [k0, k1) of the table body into `o` (column types already inferred)
+static void format_rows(Out &o, int k0, int k1, int n_cols, const adb_record *recs, const int32_t *sel, const char *const *read_ids,
+                        int primary_method, const char *llr_detect_log, bool save_fail_reasons, const uint8_t *has_none,
+                        const uint8_t *not_f32) {
+    std::string text, scratch;
     char buf[32];
-    for (int k = 0; k < n_sel; k++) {
-        const adb_record &r = rec_of(k);
+    for (int k = k0; k < k1; k++) {
+        const int idx = sel ? sel[k] : k;
+        const adb_record &r = recs[idx];
+        const char *id = read_ids ? read_ids[idx] : nullptr;
         const char *reason = save_fail_reasons ? fail_reason(r, scratch) : nullptr;
         for (int c = 0; c < n_cols; c++) {
             if (c) o.put(',');
-            const Cell cell = get_cell(r, c, primary_method, id_of(k), llr_detect_log, reason);
+            const Cell cell = get_cell(r, c, primary_method, id, llr_detect_log, reason);
             switch (cell.kind) {
             case K_NONE: break;
             case K_INT:
                 // ints + None in one column -> float64 column (NaN for None): "123.0"
                 if (has_none[c]) { fmt_float((double)cell.i, text); o.put(text); }
-                else o.put(buf, (size_t)snprintf(buf, sizeof buf, "%lld", (long long)cell.i));
+                else {
+                    auto res = std::to_chars(buf, buf + sizeof buf, (long long)cell.i);
+                    o.put(buf, (size_t)(res.ptr - buf));
+                }
                 break;
             case K_FLT:
                 if (std::isnan(cell.f)) break;  // na_rep = ""
@@ -353,5 +366,74 @@ extern "C" int64_t adb_format_csv(const adb_record *recs, const int32_t *sel, in
         }
         o.put('\n');
     }
+}
+
+extern "C" int64_t adb_format_csv(const adb_record *recs, const int32_t *sel, int32_t n_sel,
+                                  const char *const *read_ids, int32_t primary_method, const char *llr_detect_log,
+                                  int32_t save_fail_reasons, char *out, int64_t cap) {
+    if ((n_sel > 0 && !recs) || n_sel < 0 || (cap > 0 && !out)) return ADB_ERR_ARG;
+    Out o{out, cap};
+    if (n_sel == 0) {  // pd.DataFrame([]).round(3).to_csv(index=False) writes one empty line
+        o.put('\n');
+        return o.len;
+    }
+    const int n_cols = save_fail_reasons ? N_COLS : N_COLS - 1;
+    // pass 1: per column, is there a None (pandas' maybe_convert_objects turns an int column with a None into float64)
+    // and are all cells np.float32 scalars (the column then stays float32).  Only the validity bits and the method
+    // decide that, not the values: one cheap probe per row.
+    std::vector<uint8_t> has_none(n_cols, 0), not_f32(n_cols, 0);
+    {
+        std::string scratch;
+        uint32_t seen_valid_masks[64];
+        int n_seen = 0;
+        for (int k = 0; k < n_sel; k++) {
+            const adb_record &r = recs[sel ? sel[k] : k];
+            // the None / float32 pattern of a row is a function of (valid bits, sp_flag in {1, 2}, fail_code != 0)
+            const uint32_t key = r.valid ^ ((uint32_t)(r.sp_flag == 1 || r.sp_flag == 2) << 30) ^ ((uint32_t)(r.fail_code != 0) << 31);
+            bool known = false;
+            for (int t = 0; t < n_seen; t++) known |= (seen_valid_masks[t] == key);
+            if (known) continue;
+            if (n_seen < 64) seen_valid_masks[n_seen++] = key;
+            const char *reason = save_fail_reasons ? fail_reason(r, scratch) : nullptr;
+            for (int c = 0; c < n_cols; c++) {
+                const Cell cell = get_cell(r, c, primary_method, "", llr_detect_log, reason);
+                if (cell.kind == K_NONE) has_none[c] = 1;
+                if (!(cell.kind == K_FLT && cell.f32)) not_f32[c] = 1;
+            }
+        }
+    }
+    for (int c = 0; c < n_cols; c++) {
+        if (c) o.put(',');
+        o.put(COL_NAMES[c], strlen(COL_NAMES[c]));
+    }
+    o.put('\n');
+    // pass 2: the rows; large tables are formatted by several threads into private buffers and stitched in order
+    unsigned hw = std::thread::hardware_concurrency();
+    int n_thr = (n_sel >= 8192) ? (int)std::min<unsigned>(hw ? hw : 1u, 16u) : 1;
+    if (n_thr <= 1) {
+        format_rows(o, 0, n_sel, n_cols, recs, sel, read_ids, primary_method, llr_detect_log, save_fail_reasons != 0,
+                    has_none.data(), not_f32.data());
+        return o.len;
+    }
+    std::vector<std::vector<char>> parts(n_thr);
+    std::vector<int64_t> lens(n_thr, 0);
+    std::vector<std::thread> pool;
+    const int per = (n_sel + n_thr - 1) / n_thr;
+    for (int t = 0; t < n_thr; t++) {
+        pool.emplace_back([&, t]() {
+            const int k0 = std::min(n_sel, t * per), k1 = std::min(n_sel, k0 + per);
+            parts[t].resize((size_t)(k1 - k0) * 512 + 64);
+            for (;;) {
+                Out po{parts[t].data(), (int64_t)parts[t].size()};
+                format_rows(po, k0, k1, n_cols, recs, sel, read_ids, primary_method, llr_detect_log, save_fail_reasons != 0,
+                            has_none.data(), not_f32.data());
+                lens[t] = po.len;
+                if (po.len <= (int64_t)parts[t].size()) break;
+                parts[t].resize((size_t)po.len);
+            }
+        });
+    }
+    for (auto &th : pool) th.join();
+    for (int t = 0; t < n_thr; t++) o.put(parts[t].data(), (size_t)lens[t]);
     return o.len;
 }

@@ -17,10 +17,13 @@ import numpy as np
 from . import _lib
 
 
-def _id_array(read_ids: Sequence) -> Tuple[C.Array, list]:
-    enc = [str(i).encode() for i in read_ids]
-    arr = (C.c_char_p * len(enc))(*enc)
-    return arr, enc
+def _id_array(read_ids: Sequence):
+    """NUL-terminated ids in one fixed-width numpy buffer + the array of pointers into it (char **)."""
+    ids = np.asarray(read_ids, dtype=object)
+    enc = np.array([str(i).encode() for i in ids], dtype="S") if ids.size else np.zeros(0, "S1")
+    enc = enc.astype(f"S{enc.dtype.itemsize + 1}")  # one more byte: numpy pads with NULs
+    ptrs = enc.ctypes.data + np.arange(enc.size, dtype=np.uint64) * np.uint64(enc.dtype.itemsize)
+    return np.ascontiguousarray(ptrs, dtype=np.uint64), enc
 
 
 def format_detected_boundaries(recs: np.ndarray, read_ids: Sequence, primary_method: int,
@@ -40,16 +43,16 @@ def format_detected_boundaries(recs: np.ndarray, read_ids: Sequence, primary_met
             raise IndexError("selection outside the record array")
         n_sel, sel_ptr = int(sel_arr.size), sel_arr.ctypes.data
     log = None if llr_detect_log is None else llr_detect_log.encode()
-    cap = 1024 + 640 * n_sel
+    cap = 1024 + 400 * n_sel
     while True:
-        buf = C.create_string_buffer(cap)
-        n = L.adb_format_csv(recs.ctypes.data, sel_ptr, n_sel, ids, int(primary_method), log,
-                             int(bool(save_fail_reasons)), buf, cap)
+        buf = np.empty(cap, dtype=np.uint8)
+        n = L.adb_format_csv(recs.ctypes.data, sel_ptr, n_sel, ids.ctypes.data, int(primary_method), log,
+                             int(bool(save_fail_reasons)), buf.ctypes.data, cap)
         if n < 0:
             raise _lib.AdbError(int(n), "adb_format_csv: invalid argument")
         if n <= cap:
             del keep
-            return buf.raw[:n]
+            return buf[:n].tobytes()
         cap = int(n)
 
 
