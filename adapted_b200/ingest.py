@@ -20,22 +20,62 @@ from .config import flatten_config
 from .output import BoundaryTableWriter
 
 CONTAINER_KEYS = ("adc", "offsets", "full_lens", "calib_offset", "calib_scale", "read_ids")
+_MAGIC = b"ADBSIG01"
 
 
 def write_container(path: str, adc: np.ndarray, offsets: np.ndarray, full_lens: np.ndarray, calib_offset: np.ndarray,
                     calib_scale: np.ndarray, read_ids: Sequence[str]) -> str:
-    """One file: int16 blob + int64 offsets + int32 lengths + float32 calibration pairs + read ids."""
-    if not path.endswith(".npz"):
-        path += ".npz"
-    np.savez(path, adc=np.ascontiguousarray(adc, np.int16), offsets=np.ascontiguousarray(offsets, np.int64),
-             full_lens=np.ascontiguousarray(full_lens, np.int32), calib_offset=np.ascontiguousarray(calib_offset, np.float32),
-             calib_scale=np.ascontiguousarray(calib_scale, np.float32), read_ids=np.asarray(list(read_ids), dtype="U36"))
+    """One file: magic, a JSON header, then 64-byte aligned raw sections (int64 offsets, int32 lengths, float32
+    calibration pairs, fixed-width read ids, the int16 blob) -- read back as memory maps, nothing is parsed or copied."""
+    import json
+
+    if not path.endswith(".adbsig"):
+        path += ".adbsig"
+    ids = np.asarray([str(i).encode() for i in read_ids], dtype="S") if len(read_ids) else np.zeros(0, "S1")
+    arrays = [("offsets", np.ascontiguousarray(offsets, np.int64)), ("full_lens", np.ascontiguousarray(full_lens, np.int32)),
+              ("calib_offset", np.ascontiguousarray(calib_offset, np.float32)),
+              ("calib_scale", np.ascontiguousarray(calib_scale, np.float32)), ("read_ids", ids),
+              ("adc", np.ascontiguousarray(adc, np.int16))]
+    pos, sections = 0, []
+    for name, a in arrays:
+        sections.append({"name": name, "dtype": a.dtype.str, "shape": list(a.shape), "offset": pos})
+        pos += (a.nbytes + 63) & ~63
+    header = json.dumps({"version": 1, "sections": sections}).encode()
+    base = (len(_MAGIC) + 8 + len(header) + 63) & ~63
+    with open(path, "wb") as f:
+        f.write(_MAGIC)
+        f.write(np.uint64(len(header)).tobytes())
+        f.write(header)
+        f.write(b"\0" * (base - f.tell()))
+        for (name, a), sec in zip(arrays, sections):
+            f.seek(base + sec["offset"])
+            a.tofile(f)
+        f.truncate(base + pos)
     return path
 
 
 def read_container(path: str) -> Dict[str, np.ndarray]:
-    with np.load(path) as z:
-        return {k: z[k] for k in CONTAINER_KEYS}
+    """Memory maps of the sections (read-only); ``read_ids`` comes back as a fixed-width bytes array."""
+    import json
+
+    with open(path, "rb") as f:
+        if f.read(len(_MAGIC)) != _MAGIC:
+            raise ValueError(f"{path}: not an adapted_b200 signal container")
+        hlen = int(np.frombuffer(f.read(8), np.uint64)[0])
+        header = json.loads(f.read(hlen).decode())
+    base = (len(_MAGIC) + 8 + hlen + 63) & ~63
+    out = {}
+    for sec in header["sections"]:
+        shape = tuple(sec["shape"])
+        if int(np.prod(shape)) == 0:
+            out[sec["name"]] = np.zeros(shape, dtype=np.dtype(sec["dtype"]))
+        else:
+            out[sec["name"]] = np.memmap(path, dtype=np.dtype(sec["dtype"]), mode="r", offset=base + sec["offset"], shape=shape)
+    return out
+
+
+def _id_str(x) -> str:
+    return x.decode() if isinstance(x, (bytes, np.bytes_)) else str(x)
 
 
 class ContainerSource:
@@ -48,7 +88,7 @@ class ContainerSource:
         c = read_container(self.path)
         off = c["offsets"]
         for i in range(c["full_lens"].size):
-            rid = str(c["read_ids"][i])
+            rid = _id_str(c["read_ids"][i])
             if selection is not None and rid not in selection:
                 continue
             yield rid, c["adc"][off[i]: off[i + 1]], float(c["calib_offset"][i]), float(c["calib_scale"][i]), int(c["full_lens"][i])
@@ -125,6 +165,13 @@ def detect_files(files: Sequence[str], out_dir: str, spc: Any, model: Any = None
     from .detect import detect_reads
 
     flat = flatten_config(spc)
+    if len(files) == 1 and not str(files[0]).endswith(".pod5"):
+        # one container: whole groups of minibatches are sliced out of the blob, no per-read python work
+        c = read_container(files[0])
+        if int(np.diff(c["offsets"]).max(initial=0)) <= flat["sig_preload_size"]:
+            return detect_file(files[0], out_dir, spc, model=model, minibatch_size=minibatch_size,
+                               batch_size_output=batch_size_output, continue_run=continue_run, device=device,
+                               reads_per_call=minibatches_per_call * minibatch_size, read_ids_incl=read_ids_incl, container=c)
     method = flat["primary_method"]
     log = "" if method == 0 else None
     excl = processed_read_ids(out_dir) if continue_run else None
@@ -192,18 +239,26 @@ def processed_read_ids(continue_from: str, failed_only: bool = False) -> Set[str
 
 def detect_file(path: str, out_dir: str, spc: Any, model: Any = None, minibatch_size: int = 1000,
                 batch_size_output: int = 4000, continue_run: bool = False, device: int = 0,
-                reads_per_call: int = 64000) -> Dict[str, int]:
+                reads_per_call: int = 64000, read_ids_incl: Optional[Set[str]] = None,
+                container: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, int]:
     """Run the detection over every read of a container and write ``<out_dir>/boundaries/detected_boundaries_<i>.csv``
     and ``<out_dir>/failed_reads/failed_reads_<i>.csv``.  ``continue_run`` skips reads already in the tables of
     ``out_dir`` and continues the file numbering (``adapted continue``)."""
     from .detect import detect_reads
 
-    c = read_container(path)
-    ids = c["read_ids"]
+    c = container if container is not None else read_container(path)
+    ids = np.asarray(c["read_ids"])
     keep = np.arange(ids.size)
+
+    def as_ids(strings):
+        return np.asarray(sorted(x.encode() for x in strings), dtype=ids.dtype if ids.dtype.kind == "S" else None)
+
+    if read_ids_incl:
+        keep = keep[np.isin(ids, as_ids(read_ids_incl))]
     if continue_run:
         done = processed_read_ids(out_dir)
-        keep = np.array([i for i in keep if str(ids[i]) not in done], dtype=np.int64)
+        if done:
+            keep = keep[~np.isin(ids[keep], as_ids(done))]
     flat = flatten_config(spc)
     method = flat["primary_method"]
     log = "" if method == 0 else None
@@ -236,7 +291,7 @@ def detect_file(path: str, out_dir: str, spc: Any, model: Any = None, minibatch_
                     stats["lost"] += b - a
                     continue
                 r = recs[a:b]
-                writer.add(r, [str(x) for x in ids[sel[a:b]]])
+                writer.add(r, [_id_str(x) for x in ids[sel[a:b]]])
                 n_ok = int((r["success"] != 0).sum())
                 stats["pass"] += n_ok
                 stats["fail"] += (b - a) - n_ok

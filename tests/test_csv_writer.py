@@ -146,7 +146,7 @@ def test_container_roundtrip_and_processed_ids(tmp_path):
     p = write_container(str(tmp_path / "c"), b.adc, b.offsets, b.full_lens, b.calib_offset, b.calib_scale, ids)
     c = read_container(p)
     assert np.array_equal(c["adc"], b.adc) and np.array_equal(c["offsets"], b.offsets)
-    assert np.array_equal(c["calib_scale"], b.calib_scale) and list(c["read_ids"]) == ids
+    assert np.array_equal(c["calib_scale"], b.calib_scale) and [x.decode() for x in c["read_ids"]] == ids
     with gzip.open(os.path.join(GOLDEN, "job_llr_rna002.json.gz"), "rb") as f:
         doc = json.loads(f.read().decode())
     for rel, text in doc["files"].items():
