@@ -434,8 +434,9 @@ static int launch_validate(adb_ctx *ctx, const BatchDev &B, const adb_config &cf
                 validate_fast_kernel<false><<<fgrid, VF_THREADS, fsm, st>>>(F, cfg);
             }
             if (pre) {
-                // reads whose poly(A) series exceed the window memory (long-poly(A) stress sets); leaves at once otherwise
-                KernelTimer t(ctx, 2, st);
+                // reads whose poly(A) series exceed the window memory (long-poly(A) stress sets); leaves at once otherwise.
+                // Timed with the hand-over kernels: it works on what the first launch left.
+                KernelTimer t(ctx, 7, st);
                 validate_fast_kernel<true><<<fgrid, VF_THREADS, fsm, st>>>(F, cfg);
                 ctx->launches += 1;
             }

@@ -341,6 +341,10 @@ def main():
         alg_launch = 2.0 * float(torch.clamp(data["offsets"][1:] - data["offsets"][:-1], max=flat["max_obs_trace"]).sum().item())
     else:
         launches_dom = max(per_cls[cls_names[dom]]["launches"], 1)
+        if dom in (1, 6, 7):
+            # classes of several different kernels per step (small select kernels, CNN pre / post-processing, hand-over
+            # kernels): the unit is the class's time per step, not an average over unlike launches
+            launches_dom = args.steps
         alg_launch = alg_bytes_per_step
     avg_ms = tim[2 * dom] / launches_dom
     achieved = alg_launch / (avg_ms / 1e3) / 1e9 if avg_ms > 0 else 0.0
