@@ -250,8 +250,11 @@ def main():
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
+    # clocks are sampled by rank 0 only (its own GPU): one nvidia-smi process every 100 ms per rank would load the host
+    # and the driver lock of an 8-GPU box enough to show in the end-to-end number
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     L.adb_ctx_set_timing(ctx.handle, 1)
     launches0 = ctx.launches
     barrier()
@@ -304,7 +307,8 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
     sampler.stop_flag = True
-    sampler.join(timeout=2)
+    if rank == 0:
+        sampler.join(timeout=2)
     h2d = sum(host[k].numel() * host[k].element_size() for k in host)
     d2h = rec_host.numel() + st_host.numel() * 4
     same = bool(torch.equal(rec_host, records.cpu()))
