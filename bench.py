@@ -130,6 +130,33 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(max(self.smax)), "reasons": sorted(self.reasons)}
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Run this rank on the CPUs of its GPU's NUMA node before any pinned host buffer is allocated (first touch puts the
+    pages there): on a two-socket 8-GPU box half of the host -> device copies would otherwise cross the socket link.
+    Best effort: returns the node or None."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(local_rank)
+        dev = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{dev}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:  # noqa: BLE001 -- topology files missing (containers): keep the inherited affinity
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -187,6 +214,8 @@ def main():
         sys.exit("bench.py needs a CUDA device (adapted_b200 has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
+    config["host_numa_node_rank0"] = numa_node
     dist = None
     if world > 1:
         import torch.distributed as dist
