@@ -91,71 +91,106 @@ def fail_reason_text(code: int, mask: int) -> Optional[str]:
     return _FAIL_TEXT[code]
 
 
+_TEMPLATE = {k: None for k in FIELD_ORDER}
+
+
+def _new_result(success: bool):
+    """DetectResults(success=...) without running the 56-argument dataclass __init__ (all other fields None)"""
+    d = object.__new__(DetectResults)
+    d.__dict__.update(_TEMPLATE)
+    d.__dict__["success"] = success
+    return d
+
+
 def records_to_results(recs: np.ndarray, primary_method: int, llr_log: Optional[str]) -> List[Any]:
-    """adb_record[N] -> list[DetectResults]."""
+    """adb_record[N] -> list[DetectResults].  Columns are pulled out of the structured array once (python lists / typed
+    numpy columns); the per-read loop only builds the objects."""
     out = []
     method = _METHOD[primary_method]
-    for r in recs:
-        valid = int(r["valid"])
-        reason = fail_reason_text(int(r["fail_code"]), int(r["mvs_fail_mask"]))
+    n = len(recs)
+    if n == 0:
+        return out
+    col = {k: recs[k].tolist() for k in ("valid", "fail_code", "mvs_fail_mask", "success", "adapter_start", "adapter_end",
+                                         "polya_end", "preloaded", "n_cand", "n_open_pores", "mvs_adapter_end", "sp_flag")}
+    signal_len = recs["signal_len"].astype(np.int32)
+    a_end64, p_end64 = recs["adapter_end"].astype(np.int64), recs["polya_end"].astype(np.int64)
+    prim_ae, prim_pe = recs["primary_adapter_end"].astype(np.int64), recs["primary_polya_end"].astype(np.int64)
+    stats = recs["stats"].tolist()
+    mvs = recs["mvs"].tolist()
+    real32 = recs["real"][:, :2].astype(np.float32)
+    real_lr = recs["real"][:, 2].astype(np.float64)
+    med_shift = recs["med_shift"].astype(np.float32)
+    cand = recs["cand"].astype(np.int64)
+    open_pores = recs["open_pores"].astype(np.int64)
+    sp_idx, sp_next = recs["sp_idx"].astype(np.int64), recs["sp_next_idx"].astype(np.int64)
+    sp_op = recs["sp_open_pore_idx"].astype(np.int64)
+    sp_pa, sp_next_pa = recs["sp_pa"].astype(np.float32), recs["sp_next_pa"].astype(np.float32)
+    cap_op = open_pores.shape[1]
+    ae_key, pe_key = f"{method}_adapter_end", f"{method}_polya_end"
+    parts = (("adapter", V_ADAPTER), ("polya", V_POLYA), ("rna_preloaded", V_RNA))
+    for i in range(n):
+        valid = col["valid"][i]
+        reason = fail_reason_text(col["fail_code"][i], col["mvs_fail_mask"][i])
         if not valid & V_FIELDS:  # died on an exception: DetectResults(success=False, fail_reason=str(e))
             out.append(DetectResults(success=False, fail_reason=reason))
             continue
-        a_start, a_end, p_end = int(r["adapter_start"]), int(r["adapter_end"]), int(r["polya_end"])
-        size = int(r["preloaded"])
-        d = DetectResults(success=bool(r["success"]))
-        d.signal_len = np.int32(r["signal_len"])
-        d.preloaded = size
-        d.adapter_end = np.int64(a_end)
+        a_start, a_end, p_end, size = col["adapter_start"][i], col["adapter_end"][i], col["polya_end"][i], col["preloaded"][i]
+        d = _new_result(bool(col["success"][i]))
+        dd = d.__dict__
+        dd["signal_len"] = signal_len[i]
+        dd["preloaded"] = size
+        dd["adapter_end"] = a_end64[i]
         # mvs_detect_overwrite can leave polya_end = trace_early_stop_pos = None (combined.py:560-562)
         polya_none = bool(valid & V_POLYA_NONE)
-        d.polya_end = None if polya_none else np.int64(p_end)
-        d.fail_reason = reason
-        d.llr_detect_log = llr_log
-        d.mvs_llr_polya_end_adjust_ignored = False
-        d.mvs_llr_polya_end_to_early_stop = bool(valid & V_TO_EARLY_STOP)
+        dd["polya_end"] = None if polya_none else p_end64[i]
+        dd["fail_reason"] = reason
+        dd["llr_detect_log"] = llr_log
+        dd["mvs_llr_polya_end_adjust_ignored"] = False
+        dd["mvs_llr_polya_end_to_early_stop"] = bool(valid & V_TO_EARLY_STOP)
         if valid & V_MVS_ADAPTER_END:
-            d.mvs_adapter_end = int(r["mvs_adapter_end"])
+            dd["mvs_adapter_end"] = col["mvs_adapter_end"][i]
         # partitions (signal_partitions.py:65-96)
-        for idx, (name, s0, s1, bit) in enumerate((("adapter", a_start, a_end, V_ADAPTER),
-                                                    ("polya", a_end, p_end, V_POLYA),
-                                                    ("rna_preloaded", p_end, size, V_RNA))):
-            setattr(d, f"{name}_start", None if (polya_none and name == "rna_preloaded") else s0)
+        bounds = ((a_start, a_end), (a_end, p_end), (p_end, size))
+        st = stats[i]
+        for idx, (name, bit) in enumerate(parts):
+            s0, s1 = bounds[idx]
+            dd[name + "_start"] = None if (polya_none and idx == 2) else s0
             if valid & bit:
-                setattr(d, f"{name}_len", s1 - s0)
-                for q, key in enumerate(("mean", "std", "med", "mad")):
-                    setattr(d, f"{name}_{key}", float(r["stats"][idx][q]))
+                dd[name + "_len"] = s1 - s0
+                q = st[idx]
+                dd[name + "_mean"], dd[name + "_std"], dd[name + "_med"], dd[name + "_mad"] = q[0], q[1], q[2], q[3]
         if valid & V_CAND:
-            d.polya_candidates = np.asarray(r["cand"][: int(r["n_cand"])], dtype=np.int64)
-        setattr(d, f"{method}_adapter_end", np.int64(r["primary_adapter_end"]))
-        setattr(d, f"{method}_polya_end", np.int64(r["primary_polya_end"]))
+            dd["polya_candidates"] = cand[i, : col["n_cand"][i]].copy()
+        dd[ae_key] = prim_ae[i]
+        dd[pe_key] = prim_pe[i]
         if valid & V_MVS:
-            (d.mvs_detect_mean_at_loc, d.mvs_detect_var_at_loc, d.mvs_detect_polya_med,
-             d.mvs_detect_polya_local_range, d.mvs_detect_med_shift) = (float(v) for v in r["mvs"])
+            m = mvs[i]
+            (dd["mvs_detect_mean_at_loc"], dd["mvs_detect_var_at_loc"], dd["mvs_detect_polya_med"],
+             dd["mvs_detect_polya_local_range"], dd["mvs_detect_med_shift"]) = m[0], m[1], m[2], m[3], m[4]
         if valid & V_REAL_MEANS:
-            d.real_adapter_mean_start = np.float32(r["real"][0])
-            d.real_adapter_mean_end = np.float32(r["real"][1])
+            dd["real_adapter_mean_start"] = real32[i, 0]
+            dd["real_adapter_mean_end"] = real32[i, 1]
         if valid & V_REAL_RANGE:
-            d.real_adapter_local_range = np.float64(r["real"][2])
+            dd["real_adapter_local_range"] = real_lr[i]
         if valid & V_OPEN:
-            n_op = int(r["n_open_pores"])
-            if n_op > r["open_pores"].size:
+            n_op = col["n_open_pores"][i]
+            if n_op > cap_op:
                 raise OverflowError(
-                    f"read has {n_op} open-pore runs; the record keeps {r['open_pores'].size} "
+                    f"read has {n_op} open-pore runs; the record keeps {cap_op} "
                     "(ADB_MAX_OPEN_PORES) -- rebuild with a larger cap")
-            d.open_pores = np.asarray(r["open_pores"][:n_op], dtype=np.int64)
+            dd["open_pores"] = open_pores[i, :n_op].copy()
         if valid & V_MEDSHIFT:
-            d.adapter_rna_median_shift = np.float32(r["med_shift"])
+            dd["adapter_rna_median_shift"] = med_shift[i]
         if valid & V_SP:
-            d.start_peak_idx = np.int64(r["sp_idx"])
-            d.start_peak_pa = np.float32(r["sp_pa"])
-            d.start_peak_next_max_idx = np.int64(r["sp_next_idx"])
-            d.start_peak_next_max_pa = np.float32(r["sp_next_pa"])
+            dd["start_peak_idx"] = sp_idx[i]
+            dd["start_peak_pa"] = sp_pa[i]
+            dd["start_peak_next_max_idx"] = sp_next[i]
+            dd["start_peak_next_max_pa"] = sp_next_pa[i]
             if valid & V_SP_OPEN:
-                d.start_peak_open_pore_idx = np.int64(r["sp_open_pore_idx"])
-                d.start_peak_open_pore_type = _SP_FLAGS.get(int(r["sp_flag"]))
+                dd["start_peak_open_pore_idx"] = sp_op[i]
+                dd["start_peak_open_pore_type"] = _SP_FLAGS.get(col["sp_flag"][i])
                 # combined.py:340-347: a flagged read fails; the type is appended only if it had failed already
-                if int(r["fail_code"]) != 0:
-                    d.fail_reason = reason + "+" + d.start_peak_open_pore_type
+                if col["fail_code"][i] != 0 and dd["start_peak_open_pore_type"] is not None:
+                    dd["fail_reason"] = reason + "+" + dd["start_peak_open_pore_type"]
         out.append(d)
     return out

@@ -181,3 +181,22 @@ def test_yield_minibatches_selection_and_file_boundaries(tmp_path):
     assert [i for g in yield_minibatches(files, incl, None, 4, m) for i in g[5]] == [all_ids[1], all_ids[8], all_ids[20]]
     assert [i for g in yield_minibatches(files, incl, excl, 4, m) for i in g[5]] == [all_ids[1], all_ids[20]]
     assert [i for g in yield_minibatches(files, None, excl, 50, m) for i in g[5]] == [i for i in all_ids if i != all_ids[8]]
+
+
+@pytest.mark.parametrize("seam,name", CASES)
+def test_records_round_trip_to_results(seam, name):
+    """adb_record -> DetectResults (adapted_b200.records.records_to_results, the host side of the seam) restores every
+    field of what the executed reference returned, values and None pattern alike (CPU, no GPU needed)"""
+    from adapted_b200.records import records_to_results
+    from tests.helpers import diff_results
+
+    rec = load_case(name)
+    if "raises" in rec:
+        pytest.skip("minibatch lost by the reference")
+    recs = results_to_records(rec["results"], METHOD[seam])
+    back = records_to_results(recs, METHOD[seam], rec["results"][0].get("llr_detect_log"))
+    assert diff_results(back, rec["results"], exact_floats=True) == []
+    for b, w in zip(back, rec["results"]):
+        for k, v in w.items():
+            if v is None:
+                assert getattr(b, k) is None, k
