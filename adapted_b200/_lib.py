@@ -23,6 +23,7 @@ CNN_NPARAMS = 58882
 STATUS_TEXT = {
     0: "ok", -1: "CUDA error", -2: "invalid argument", -3: "MAD normalization failed: scale is 0",
     -4: "attempt to get argmin of an empty sequence", -5: "unsupported configuration",
+    -6: "open-pore list longer than the record keeps and no overflow row supplied",
 }
 
 D2 = C.c_double * 2
@@ -133,6 +134,10 @@ def load() -> C.CDLL:
     L.adb_mvs_stream_detect_host.restype = ip
     L.adb_format_csv.argtypes = [vp, vp, C.c_int32, vp, C.c_int32, C.c_char_p, C.c_int32, vp, C.c_int64]
     L.adb_format_csv.restype = C.c_int64
+    L.adb_format_csv_ex.argtypes = [vp, vp, C.c_int32, vp, C.c_int32, C.c_char_p, C.c_int32, vp, vp, vp, vp, C.c_int64]
+    L.adb_format_csv_ex.restype = C.c_int64
+    L.adb_open_pores_host.argtypes = [vp, C.POINTER(AdbBatch), vp, C.c_int32, vp, vp, vp, vp, C.c_int64]
+    L.adb_open_pores_host.restype = ip
     for f in ("adb_detect_pipelined_host", "adb_ctx_set_timing", "adb_ctx_get_timing", "adb_ctx_create", "adb_detect_host", "adb_detect_dev", "adb_llr_trace_host",
               "adb_global_med_mad_host", "adb_downscale_host", "adb_cnn_scores_host"):
         getattr(L, f).restype = ip

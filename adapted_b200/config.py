@@ -120,6 +120,7 @@ _SECTIONS = {
     "cnn_boundaries": CNNBoundariesConfig,
     "med_shift": MedShiftConfig,
     "rna_start_peak": RNAStartPeakConfig,
+    "streaming": StreamingConfig,  # Optional in the reference (sig_proc.py: `streaming: Optional[StreamingConfig]`)
 }
 
 
@@ -132,6 +133,7 @@ class SigProcConfig:
     cnn_boundaries: CNNBoundariesConfig = field(default_factory=CNNBoundariesConfig)
     med_shift: MedShiftConfig = field(default_factory=MedShiftConfig)
     rna_start_peak: RNAStartPeakConfig = field(default_factory=RNAStartPeakConfig)
+    streaming: Optional[StreamingConfig] = None
     primary_method: Optional[str] = None
     sig_preload_size: int = 0
 
@@ -324,7 +326,9 @@ def config_as_dict(spc: Any) -> Dict[str, Any]:
     """Nested plain dict (for fixtures / command.json style dumps)."""
     out = {}
     for name in _SECTIONS:
-        sec = getattr(spc, name)
+        sec = getattr(spc, name, None)
+        if sec is None:  # the optional [streaming] section
+            continue
         if is_dataclass(sec):
             out[name] = {f.name: getattr(sec, f.name) for f in fields(sec)}
         else:

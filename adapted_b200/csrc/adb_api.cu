@@ -555,6 +555,20 @@ static int detect_dev_pass(adb_ctx *ctx, const adb_batch *batch, const adb_confi
 }
 
 // ---- host-buffer convenience wrappers ------------------------------------------------------------------------------
+// Error paths of the *_host entry points: asynchronous copies into / out of the CALLER's buffers may still be in
+// flight when a later step fails; the streams are drained before the status is returned, so the caller may free its
+// buffers as soon as the call is back.
+struct StreamDrain {
+    cudaStream_t s[4] = {nullptr, nullptr, nullptr, nullptr};
+    int n = 0;
+    bool armed = true;
+    void add(cudaStream_t st) { if (st && n < 4) s[n++] = st; }
+    ~StreamDrain() {
+        if (!armed) return;
+        for (int i = 0; i < n; i++) cudaStreamSynchronize(s[i]);
+    }
+};
+
 struct StagedBatch {
     adb_batch dev;
     size_t signal_bytes;
@@ -599,6 +613,8 @@ extern "C" int adb_detect_host(adb_ctx *ctx, const adb_batch *batch, const adb_c
     CUDA_TRY(cudaSetDevice(ctx->device));
     if (batch->n_reads == 0) return ADB_OK;
     cudaStream_t st = ctx->stream;
+    StreamDrain drain;
+    drain.add(st);
     StagedBatch sb;
     rc = stage_batch(ctx, batch, &sb, st);
     if (rc) return rc;
@@ -678,6 +694,10 @@ extern "C" int adb_detect_pipelined_host(adb_ctx *ctx, const adb_batch *batch, c
         w_devs[1] = (const float *)ctx->twin->h_misc2.p;
     }
     cudaStream_t cs = ctx->copy_stream;
+    StreamDrain drain;
+    drain.add(cs);
+    drain.add(ctx->stream);
+    if (ctx->twin) drain.add(ctx->twin->stream);
     int b0 = 0;  // first minibatch of the chunk
     for (int ch = 0; ch < (int)sched.size(); ch++) {
         adb_ctx *c = cc[ch & 1];
@@ -930,6 +950,91 @@ extern "C" int adb_downscale_host(adb_ctx *ctx, const adb_batch *batch, int32_t 
     ctx->launches += 1;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out, ctx->h_records.p, sizeof(float) * (size_t)ncols * batch->n_reads, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return ADB_OK;
+}
+
+// ---- full open-pore lists (reads whose list overflows the record) ---------------------------------------------------
+#include "adb_openpore.cuh"
+
+extern "C" int adb_open_pores_host(adb_ctx *ctx, const adb_batch *batch, const int32_t *sel, int32_t n_sel,
+                                   const int32_t *seg_begin, const int32_t *seg_end, int64_t *out_offsets,
+                                   int32_t *out_pos, int64_t cap) {
+    if (!ctx || !sel || !seg_begin || !seg_end || !out_offsets || n_sel < 0 || cap < 0 || (cap > 0 && !out_pos)) {
+        set_err("invalid argument");
+        return ADB_ERR_ARG;
+    }
+    int rc = check_batch(batch);
+    if (rc) return rc;
+    out_offsets[0] = 0;
+    if (n_sel == 0) return ADB_OK;
+    // compact sub-batch of the selected reads (host side gather: the call is rare and touches a few reads)
+    std::vector<int64_t> offs((size_t)n_sel + 1, 0);
+    std::vector<int32_t> lens(n_sel), seg((size_t)n_sel * 2);
+    std::vector<float> coff(n_sel), cscale(n_sel);
+    std::vector<unsigned char> blob;
+    const size_t esz = batch->sig_type == ADB_SIG_F32 ? 4 : 2;
+    for (int k = 0; k < n_sel; k++) {
+        const int r = sel[k];
+        if (r < 0 || r >= batch->n_reads) { set_err("selection outside the batch"); return ADB_ERR_ARG; }
+        int64_t o0, n;
+        if (batch->sig_type == ADB_SIG_F32) { o0 = (int64_t)r * batch->m; n = batch->m; }
+        else {
+            o0 = batch->offsets[r];
+            n = std::min<int64_t>(batch->offsets[r + 1] - o0, batch->m);
+            coff[k] = batch->calib_offset[r];
+            cscale[k] = batch->calib_scale[r];
+        }
+        lens[k] = batch->full_lens[r];
+        seg[2 * k] = seg_begin[k];
+        seg[2 * k + 1] = seg_end[k];
+        const unsigned char *src = (const unsigned char *)batch->signal + (size_t)o0 * esz;
+        blob.insert(blob.end(), src, src + (size_t)n * esz);
+        offs[k + 1] = offs[k] + n;
+    }
+    adb_batch sub = *batch;
+    sub.signal = blob.data();
+    sub.n_reads = n_sel;
+    sub.batch_size = n_sel;
+    sub.full_lens = lens.data();
+    if (batch->sig_type == ADB_SIG_I16) { sub.offsets = offs.data(); sub.calib_offset = coff.data(); sub.calib_scale = cscale.data(); }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    StagedBatch sb;
+    rc = stage_batch(ctx, &sub, &sb, st);
+    if (rc) return rc;
+    const size_t nb_seg = sizeof(int) * 2 * (size_t)n_sel, nb_cnt = sizeof(long long) * ((size_t)n_sel + 1);
+    if (ctx->h_misc.ensure(nb_seg + 2 * nb_cnt + 64)) { set_err("cudaMalloc open-pore scratch"); return ADB_ERR_CUDA; }
+    int *d_seg = (int *)ctx->h_misc.p;
+    long long *d_cnt = (long long *)((unsigned char *)ctx->h_misc.p + ((nb_seg + 15) & ~(size_t)15));
+    long long *d_off = d_cnt + n_sel + 1;
+    CUDA_TRY(cudaMemcpyAsync(d_seg, seg.data(), nb_seg, cudaMemcpyHostToDevice, st));
+    OpenPoreArgs A;
+    A.B = to_dev_view(sb.dev);
+    A.seg = d_seg;
+    A.counts = d_cnt;
+    A.offs = nullptr;
+    A.out = nullptr;
+    A.cap = 0;
+    open_pores_full_kernel<<<n_sel, ADB_OP_THREADS, 0, st>>>(A);
+    std::vector<long long> cnt(n_sel);
+    CUDA_TRY(cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(long long) * (size_t)n_sel, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    std::vector<long long> off((size_t)n_sel + 1, 0);
+    for (int k = 0; k < n_sel; k++) { off[k + 1] = off[k] + cnt[k]; out_offsets[k + 1] = off[k + 1]; }
+    ctx->launches += 1;
+    const long long total = off[n_sel];
+    if (total == 0 || cap < total) return ADB_OK;  // cap too small: the caller sizes the buffer from out_offsets[n_sel]
+    if (ctx->h_records.ensure(sizeof(int) * (size_t)total)) { set_err("cudaMalloc open-pore output"); return ADB_ERR_CUDA; }
+    CUDA_TRY(cudaMemcpyAsync(d_off, off.data(), sizeof(long long) * ((size_t)n_sel + 1), cudaMemcpyHostToDevice, st));
+    A.counts = nullptr;
+    A.offs = d_off;
+    A.out = (int *)ctx->h_records.p;
+    A.cap = total;
+    open_pores_full_kernel<<<n_sel, ADB_OP_THREADS, 0, st>>>(A);
+    ctx->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out_pos, A.out, sizeof(int) * (size_t)total, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return ADB_OK;
 }

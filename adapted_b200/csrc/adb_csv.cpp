@@ -112,8 +112,17 @@ Cell cell_bool(bool v) { Cell c; c.kind = K_BOOL; c.i = v; return c; }
 Cell cell_str(const char *s) { Cell c; if (s) { c.kind = K_STR; c.s = s; } return c; }
 Cell cell_arr(const int32_t *a, int n) { Cell c; c.kind = K_ARR; c.arr = a; c.n = n; return c; }
 
+// full open-pore lists of the records whose list does not fit the record (adb_open_pores_host): index[i] = -1 or the
+// row k of record i, whose positions are pos[offs[k] .. offs[k + 1])
+struct OpOver {
+    const int32_t *index = nullptr;
+    const int64_t *offs = nullptr;
+    const int32_t *pos = nullptr;
+};
+
 // One cell of the table; mirrors adapted_b200/records.py:records_to_results field by field.
-Cell get_cell(const adb_record &r, int col, int method, const char *read_id, const char *llr_log, const char *reason) {
+Cell get_cell(const adb_record &r, int col, int method, const char *read_id, const char *llr_log, const char *reason,
+              const OpOver &ov = OpOver(), int rec_idx = -1) {
     if (col == C_READ_ID) return cell_str(read_id ? read_id : "");
     if (col == C_FAIL_REASON) return cell_str(reason);
     const uint32_t v = r.valid;
@@ -167,9 +176,13 @@ Cell get_cell(const adb_record &r, int col, int method, const char *read_id, con
     case C_REAL_END: return (v & ADB_V_REAL_MEANS) ? cell_f32(r.real[1]) : Cell();
     case C_REAL_RANGE: return (v & ADB_V_REAL_RANGE) ? cell_flt(r.real[2]) : Cell();
     case C_OPEN_PORES:
-        return (v & ADB_V_OPEN_PORES)
-                   ? cell_arr(r.open_pores, r.n_open_pores < ADB_MAX_OPEN_PORES ? r.n_open_pores : ADB_MAX_OPEN_PORES)
-                   : Cell();
+        if (!(v & ADB_V_OPEN_PORES)) return Cell();
+        if (r.n_open_pores > ADB_MAX_OPEN_PORES && ov.index && rec_idx >= 0 && ov.index[rec_idx] >= 0) {
+            const int k = ov.index[rec_idx];
+            return cell_arr(ov.pos + ov.offs[k], (int)(ov.offs[k + 1] - ov.offs[k]));
+        }
+        // (a list beyond the record's capacity without its overflow row is refused by adb_format_csv_ex)
+        return cell_arr(r.open_pores, r.n_open_pores < ADB_MAX_OPEN_PORES ? r.n_open_pores : ADB_MAX_OPEN_PORES);
     case C_LLR_LOG: return cell_str(llr_log);
     default: return Cell();  // polya_truncated, llr_*_adjust, llr_trace_early_stop_pos: None in v0.2.4
     }
@@ -332,7 +345,7 @@ void put_field(Out &o, const char *s, size_t n) {  // csv.QUOTE_MINIMAL with the
 // rows [k0, k1) of the table body into `o` (column types already inferred)
 static void format_rows(Out &o, int k0, int k1, int n_cols, const adb_record *recs, const int32_t *sel, const char *const *read_ids,
                         int primary_method, const char *llr_detect_log, bool save_fail_reasons, const uint8_t *has_none,
-                        const uint8_t *not_f32) {
+                        const uint8_t *not_f32, const OpOver &ov) {
     std::string text, scratch;
     char buf[32];
     for (int k = k0; k < k1; k++) {
@@ -342,7 +355,7 @@ static void format_rows(Out &o, int k0, int k1, int n_cols, const adb_record *re
         const char *reason = save_fail_reasons ? fail_reason(r, scratch) : nullptr;
         for (int c = 0; c < n_cols; c++) {
             if (c) o.put(',');
-            const Cell cell = get_cell(r, c, primary_method, id, llr_detect_log, reason);
+            const Cell cell = get_cell(r, c, primary_method, id, llr_detect_log, reason, ov, idx);
             switch (cell.kind) {
             case K_NONE: break;
             case K_INT:
@@ -368,10 +381,23 @@ static void format_rows(Out &o, int k0, int k1, int n_cols, const adb_record *re
     }
 }
 
-extern "C" int64_t adb_format_csv(const adb_record *recs, const int32_t *sel, int32_t n_sel,
-                                  const char *const *read_ids, int32_t primary_method, const char *llr_detect_log,
-                                  int32_t save_fail_reasons, char *out, int64_t cap) {
+extern "C" int64_t adb_format_csv_ex(const adb_record *recs, const int32_t *sel, int32_t n_sel,
+                                     const char *const *read_ids, int32_t primary_method, const char *llr_detect_log,
+                                     int32_t save_fail_reasons, const int32_t *op_index, const int64_t *op_offsets,
+                                     const int32_t *op_pos, char *out, int64_t cap) {
     if ((n_sel > 0 && !recs) || n_sel < 0 || (cap > 0 && !out)) return ADB_ERR_ARG;
+    OpOver ov;
+    if (op_index && op_offsets && op_pos) { ov.index = op_index; ov.offs = op_offsets; ov.pos = op_pos; }
+    // never truncate silently: a list longer than the record keeps needs its overflow row
+    for (int k = 0; k < n_sel; k++) {
+        const int idx = sel ? sel[k] : k;
+        const adb_record &r = recs[idx];
+        if ((r.valid & ADB_V_FIELDS) && (r.valid & ADB_V_OPEN_PORES) && r.n_open_pores > ADB_MAX_OPEN_PORES) {
+            if (!ov.index || ov.index[idx] < 0) return ADB_ERR_OVERFLOW;
+            const int row = ov.index[idx];
+            if (ov.offs[row + 1] - ov.offs[row] != r.n_open_pores) return ADB_ERR_OVERFLOW;
+        }
+    }
     Out o{out, cap};
     if (n_sel == 0) {  // pd.DataFrame([]).round(3).to_csv(index=False) writes one empty line
         o.put('\n');
@@ -412,7 +438,7 @@ extern "C" int64_t adb_format_csv(const adb_record *recs, const int32_t *sel, in
     int n_thr = (n_sel >= 8192) ? (int)std::min<unsigned>(hw ? hw : 1u, 16u) : 1;
     if (n_thr <= 1) {
         format_rows(o, 0, n_sel, n_cols, recs, sel, read_ids, primary_method, llr_detect_log, save_fail_reasons != 0,
-                    has_none.data(), not_f32.data());
+                    has_none.data(), not_f32.data(), ov);
         return o.len;
     }
     std::vector<std::vector<char>> parts(n_thr);
@@ -426,7 +452,7 @@ extern "C" int64_t adb_format_csv(const adb_record *recs, const int32_t *sel, in
             for (;;) {
                 Out po{parts[t].data(), (int64_t)parts[t].size()};
                 format_rows(po, k0, k1, n_cols, recs, sel, read_ids, primary_method, llr_detect_log, save_fail_reasons != 0,
-                            has_none.data(), not_f32.data());
+                            has_none.data(), not_f32.data(), ov);
                 lens[t] = po.len;
                 if (po.len <= (int64_t)parts[t].size()) break;
                 parts[t].resize((size_t)po.len);
@@ -436,4 +462,11 @@ extern "C" int64_t adb_format_csv(const adb_record *recs, const int32_t *sel, in
     for (auto &th : pool) th.join();
     for (int t = 0; t < n_thr; t++) o.put(parts[t].data(), (size_t)lens[t]);
     return o.len;
+}
+
+extern "C" int64_t adb_format_csv(const adb_record *recs, const int32_t *sel, int32_t n_sel,
+                                  const char *const *read_ids, int32_t primary_method, const char *llr_detect_log,
+                                  int32_t save_fail_reasons, char *out, int64_t cap) {
+    return adb_format_csv_ex(recs, sel, n_sel, read_ids, primary_method, llr_detect_log, save_fail_reasons, nullptr,
+                             nullptr, nullptr, out, cap);
 }

@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(ADB_TRACE_THREADS, 7) llr_primary_kernel(Prima
     extern __shared__ __align__(16) unsigned char smem[];
     const TraceScratch T = trace_scratch_from(smem, A.nds_max, A.peak_cap);
     float *ds = (float *)T.trace;
-    const int Tm = cfg.max_obs_trace, A0 = cfg.min_obs_adapter, f = cfg.downscale_factor;
+    // the reference slices batch[:, :max_obs_trace] (combined.py:128-136): a matrix narrower than that keeps its own width
+    const int Tm = min(cfg.max_obs_trace, A.B.m), A0 = cfg.min_obs_adapter, f = cfg.downscale_factor;
     for (int r = blockIdx.x; r < A.B.n_reads; r += gridDim.x) {
         const int mb = r / A.B.batch_size;
         __syncthreads();

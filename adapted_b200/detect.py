@@ -51,9 +51,24 @@ def _dense_batch(batch_of_signals: np.ndarray, full_signal_lens: np.ndarray):
         raise ValueError("batch_of_signals must be a 2-D float32 array")
     lens = np.ascontiguousarray(full_signal_lens, dtype=np.int32)
     n, m = x.shape
+    if lens.ndim != 1 or lens.size != n:
+        raise ValueError(f"full_signal_lens must hold one length per row ({n}), got {lens.size}")
     b = _lib.AdbBatch(signal=x.ctypes.data, sig_type=_lib.SIG_F32, n_reads=n, m=m, batch_size=max(n, 1),
                       offsets=None, full_lens=lens.ctypes.data, calib_offset=None, calib_scale=None)
     return b, (x, lens)
+
+
+def _check_ragged(adc: np.ndarray, offsets: np.ndarray, n: int, coff: np.ndarray, cscale: np.ndarray) -> None:
+    """The device trusts the ragged description (a read's sample count is offsets[r + 1] - offsets[r]): refuse
+    inconsistent ones here instead of faulting on the GPU."""
+    if n == 0 and offsets.size <= 1:
+        return
+    if offsets.ndim != 1 or offsets.size != n + 1:
+        raise ValueError(f"offsets must hold n_reads + 1 = {n + 1} entries, got {offsets.size}")
+    if coff.size != n or cscale.size != n:
+        raise ValueError("one calibration offset and scale per read")
+    if n and (offsets[0] < 0 or np.any(offsets[1:] < offsets[:-1]) or offsets[-1] > adc.size):
+        raise ValueError("offsets must be non-negative, non-decreasing and end inside the ADC blob")
 
 
 def _raise_minibatch_error(status: int) -> None:
@@ -76,7 +91,7 @@ def combined_detect_llr2(batch_of_signals: np.ndarray, full_signal_lens: np.ndar
     flat["primary_method"] = 0
     recs, status, cfg = _run_flat(b, flat, None, device, keep)
     _raise_minibatch_error(int(status[0]))
-    return records_to_results(recs, 0, "")
+    return records_to_results(recs, 0, "", open_pore_overflow(b, recs, device))
 
 
 def combined_detect_cnn(batch_of_signals: np.ndarray, full_signal_lens: np.ndarray, model: Any, spc: Any,
@@ -88,7 +103,7 @@ def combined_detect_cnn(batch_of_signals: np.ndarray, full_signal_lens: np.ndarr
     flat["primary_method"] = 1
     recs, status, cfg = _run_flat(b, flat, w, device, keep)
     _raise_minibatch_error(int(status[0]))
-    res = records_to_results(recs, 1, None)
+    res = records_to_results(recs, 1, None, open_pore_overflow(b, recs, device))
     return res if len(res) > 1 else res[0]
 
 
@@ -104,7 +119,42 @@ def combined_detect_start_peak(batch_of_signals: np.ndarray, full_signal_lens: n
     if int(status[0]) == -4:
         raise ValueError("attempt to get argmax of an empty sequence")  # start_peak.py:25-29, outside the try
     _raise_minibatch_error(int(status[0]))
-    return records_to_results(recs, 2, None)
+    return records_to_results(recs, 2, None, open_pore_overflow(b, recs, device))
+
+
+def open_pore_overflow(batch: _lib.AdbBatch, recs: np.ndarray, device: int = 0) -> Optional[dict]:
+    """Full open-pore lists (find_open_pores, adapted/detect/anomalies.py:15-35) of the reads of ``batch`` whose list
+    does not fit the fixed-size record, computed on the GPU (adb_open_pores_host): {record index: int32 positions}, or
+    None when no read overflows (the ordinary case).  ``batch`` must still describe the HOST buffers of the call that
+    produced ``recs``."""
+    over = np.flatnonzero((recs["n_open_pores"] > _lib.ADB_MAX_OPEN_PORES) & ((recs["valid"] & (1 << 6)) != 0)
+                          & ((recs["valid"] & (1 << 11)) != 0)).astype(np.int32)
+    if over.size == 0:
+        return None
+    seg0 = np.zeros(over.size, dtype=np.int32)                            # validate_boundaries scans from adapter_start = 0
+    seg1 = np.ascontiguousarray(recs["primary_adapter_end"][over], dtype=np.int32)   # ... to the primary adapter end
+    offs = np.zeros(over.size + 1, dtype=np.int64)
+    L, ctx = _lib.load(), _lib.default_context(device)
+    _lib.check(L.adb_open_pores_host(ctx.handle, C.byref(batch), over.ctypes.data, int(over.size), seg0.ctypes.data,
+                                     seg1.ctypes.data, offs.ctypes.data, None, 0))
+    pos = np.zeros(max(int(offs[-1]), 1), dtype=np.int32)
+    _lib.check(L.adb_open_pores_host(ctx.handle, C.byref(batch), over.ctypes.data, int(over.size), seg0.ctypes.data,
+                                     seg1.ctypes.data, offs.ctypes.data, pos.ctypes.data, int(pos.size)))
+    return {int(i): pos[offs[k]:offs[k + 1]] for k, i in enumerate(over)}
+
+
+def overflow_tables(overflow: Optional[dict], n_records: int):
+    """{record index: positions} -> the (op_index, op_offsets, op_pos) arrays of adb_format_csv_ex."""
+    if not overflow:
+        return None
+    index = np.full(n_records, -1, dtype=np.int32)
+    offs = np.zeros(len(overflow) + 1, dtype=np.int64)
+    parts = []
+    for k, (i, p) in enumerate(sorted(overflow.items())):
+        index[i] = k
+        parts.append(np.asarray(p, dtype=np.int32))
+        offs[k + 1] = offs[k] + parts[-1].size
+    return index, offs, np.ascontiguousarray(np.concatenate(parts) if parts else np.zeros(1, np.int32))
 
 
 def _run_flat(batch: _lib.AdbBatch, flat: dict, weights: Optional[np.ndarray], device: int, keep):
@@ -122,7 +172,7 @@ def _run_flat(batch: _lib.AdbBatch, flat: dict, weights: Optional[np.ndarray], d
 
 def detect_reads(adc: np.ndarray, offsets: np.ndarray, full_lens: np.ndarray, calib_offset: np.ndarray,
                  calib_scale: np.ndarray, spc: Any, model: Any = None, minibatch_size: int = 1000,
-                 device: int = 0, return_records: bool = False):
+                 device: int = 0, return_records: bool = False, return_overflow: bool = False):
     """Native ingest: ragged int16 ADC reads (pod5-equivalent information) -> per-read results.
 
     Reads are processed in consecutive minibatches of ``minibatch_size`` (parser.py:95-99), which is the unit
@@ -135,17 +185,23 @@ def detect_reads(adc: np.ndarray, offsets: np.ndarray, full_lens: np.ndarray, ca
     coff = np.ascontiguousarray(calib_offset, dtype=np.float32)
     cscale = np.ascontiguousarray(calib_scale, dtype=np.float32)
     n = lens.size
+    _check_ragged(adc, offsets, n, coff, cscale)
     flat = flatten_config(spc)
     w = flatten_cnn_weights(model) if flat["primary_method"] == 1 else None
     b = _lib.AdbBatch(signal=adc.ctypes.data, sig_type=_lib.SIG_I16, n_reads=n, m=int(flat["sig_preload_size"]),
                       batch_size=int(minibatch_size), offsets=offsets.ctypes.data, full_lens=lens.ctypes.data,
                       calib_offset=coff.ctypes.data, calib_scale=cscale.ctypes.data)
     if n == 0:
+        if return_records:
+            empty = (np.zeros(0, _lib.RECORD_DTYPE), np.zeros(0, np.int32))
+            return empty + (None,) if return_overflow else empty
         return ([], np.zeros(0, np.int32))
     recs, status, cfg = _run_flat(b, flat, w, device, (adc, offsets, lens, coff, cscale))
+    over = open_pore_overflow(b, recs, device)
     if return_records:
-        return recs, status
-    res = records_to_results(recs, flat["primary_method"], "" if flat["primary_method"] == 0 else None)
+        # return_overflow: also the full open-pore lists of the records beyond ADB_MAX_OPEN_PORES ({index: positions})
+        return (recs, status, over) if return_overflow else (recs, status)
+    res = records_to_results(recs, flat["primary_method"], "" if flat["primary_method"] == 0 else None, over)
     for bi, s in enumerate(status):
         if s != 0:
             for i in range(bi * minibatch_size, min((bi + 1) * minibatch_size, n)):
@@ -161,6 +217,8 @@ def mean_var_shift_polyA_detect_batch(batch_of_signals: np.ndarray, signal_lens:
     samples): poly(A) start per read, 0 where the reference returns 0."""
     from .config import StreamingConfig, flatten_streaming_config
 
+    if hasattr(params, "streaming"):  # a whole SigProcConfig: its optional [streaming] section
+        params = params.streaming
     params = StreamingConfig() if params is None else params
     b, keep = _dense_batch(batch_of_signals, signal_lens)
     out = np.zeros(b.n_reads, dtype=np.int32)
@@ -188,6 +246,8 @@ def mean_var_shift_polyA_detect_i16(adc: np.ndarray, offsets: np.ndarray, calib_
     device; `window` bounds the samples looked at per read (default: the longest read)."""
     from .config import StreamingConfig, flatten_streaming_config
 
+    if hasattr(params, "streaming"):  # a whole SigProcConfig: its optional [streaming] section
+        params = params.streaming
     params = StreamingConfig() if params is None else params
     adc = np.ascontiguousarray(adc, dtype=np.int16)
     offsets = np.ascontiguousarray(offsets, dtype=np.int64)
@@ -195,6 +255,7 @@ def mean_var_shift_polyA_detect_i16(adc: np.ndarray, offsets: np.ndarray, calib_
     coff = np.ascontiguousarray(calib_offset, dtype=np.float32)
     cscale = np.ascontiguousarray(calib_scale, dtype=np.float32)
     n = lens.size
+    _check_ragged(adc, offsets, n, coff, cscale)
     out = np.zeros(n, dtype=np.int32)
     if n == 0:
         return out

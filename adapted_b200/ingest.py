@@ -192,9 +192,9 @@ def detect_files(files: Sequence[str], out_dir: str, spc: Any, model: Any = None
             pos += len(g[5])
             base += int(tot)
         ids = [i for g in group for i in g[5]]
-        recs, status = detect_reads(adc, off, np.concatenate([g[2] for g in group]), np.concatenate([g[3] for g in group]),
-                                    np.concatenate([g[4] for g in group]), spc, model=model, minibatch_size=minibatch_size,
-                                    device=device, return_records=True)
+        recs, status, over = detect_reads(adc, off, np.concatenate([g[2] for g in group]), np.concatenate([g[3] for g in group]),
+                                          np.concatenate([g[4] for g in group]), spc, model=model, minibatch_size=minibatch_size,
+                                          device=device, return_records=True, return_overflow=True)
         n = len(ids)
         stats["reads"] += n
         for bi, st in enumerate(status):
@@ -203,7 +203,7 @@ def detect_files(files: Sequence[str], out_dir: str, spc: Any, model: Any = None
                 logging.error("minibatch of %d reads lost (status %d), like the reference's handle_completed_future", b - a, int(st))
                 stats["lost"] += b - a
                 continue
-            writer.add(recs[a:b], ids[a:b])
+            writer.add(recs[a:b], ids[a:b], {i - a: v for i, v in over.items() if a <= i < b} if over else None)
             ok = int((recs[a:b]["success"] != 0).sum())
             stats["pass"] += ok
             stats["fail"] += (b - a) - ok
@@ -281,8 +281,9 @@ def detect_file(path: str, out_dir: str, spc: Any, model: Any = None, minibatch_
                 adc = c["adc"][offsets[sel[0]]: offsets[sel[-1] + 1]]
             else:
                 adc = np.concatenate([c["adc"][offsets[i]: offsets[i + 1]] for i in sel]) if sel.size else np.zeros(0, np.int16)
-            recs, status = detect_reads(adc, off, c["full_lens"][sel], c["calib_offset"][sel], c["calib_scale"][sel], spc,
-                                        model=model, minibatch_size=minibatch_size, device=device, return_records=True)
+            recs, status, over = detect_reads(adc, off, c["full_lens"][sel], c["calib_offset"][sel], c["calib_scale"][sel], spc,
+                                              model=model, minibatch_size=minibatch_size, device=device, return_records=True,
+                                              return_overflow=True)
             for bi, st in enumerate(status):
                 a, b = bi * minibatch_size, min((bi + 1) * minibatch_size, sel.size)
                 if st != 0:
@@ -291,7 +292,8 @@ def detect_file(path: str, out_dir: str, spc: Any, model: Any = None, minibatch_
                     stats["lost"] += b - a
                     continue
                 r = recs[a:b]
-                writer.add(r, [_id_str(x) for x in ids[sel[a:b]]])
+                writer.add(r, [_id_str(x) for x in ids[sel[a:b]]],
+                           {i - a: v for i, v in over.items() if a <= i < b} if over else None)
                 n_ok = int((r["success"] != 0).sum())
                 stats["pass"] += n_ok
                 stats["fail"] += (b - a) - n_ok

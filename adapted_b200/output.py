@@ -28,8 +28,10 @@ def _id_array(read_ids: Sequence):
 
 def format_detected_boundaries(recs: np.ndarray, read_ids: Sequence, primary_method: int,
                                save_fail_reasons: bool = False, sel: Optional[Iterable[int]] = None,
-                               llr_detect_log: Optional[str] = None) -> bytes:
-    """CSV text of the reads ``sel`` (default: all) of ``recs``, as the reference's pandas path writes it."""
+                               llr_detect_log: Optional[str] = None, open_pore_overflow: Optional[dict] = None) -> bytes:
+    """CSV text of the reads ``sel`` (default: all) of ``recs``, as the reference's pandas path writes it.
+    ``open_pore_overflow``: {record index: full open-pore list} for records beyond ADB_MAX_OPEN_PORES
+    (``detect.open_pore_overflow``); such a record without its list raises OverflowError -- never truncated."""
     recs = np.ascontiguousarray(recs, dtype=_lib.RECORD_DTYPE)
     if len(read_ids) != recs.size:
         raise ValueError("one read id per record")
@@ -43,11 +45,18 @@ def format_detected_boundaries(recs: np.ndarray, read_ids: Sequence, primary_met
             raise IndexError("selection outside the record array")
         n_sel, sel_ptr = int(sel_arr.size), sel_arr.ctypes.data
     log = None if llr_detect_log is None else llr_detect_log.encode()
+    from .detect import overflow_tables
+
+    tabs = overflow_tables(open_pore_overflow, recs.size)
+    op = (None, None, None) if tabs is None else tuple(t.ctypes.data for t in tabs)
     cap = 1024 + 400 * n_sel
     while True:
         buf = np.empty(cap, dtype=np.uint8)
-        n = L.adb_format_csv(recs.ctypes.data, sel_ptr, n_sel, ids.ctypes.data, int(primary_method), log,
-                             int(bool(save_fail_reasons)), buf.ctypes.data, cap)
+        n = L.adb_format_csv_ex(recs.ctypes.data, sel_ptr, n_sel, ids.ctypes.data, int(primary_method), log,
+                                int(bool(save_fail_reasons)), op[0], op[1], op[2], buf.ctypes.data, cap)
+        if n == -6:
+            raise OverflowError("a record's open-pore list is longer than ADB_MAX_OPEN_PORES and its overflow list was "
+                                "not supplied (adapted_b200.detect.open_pore_overflow)")
         if n < 0:
             raise _lib.AdbError(int(n), "adb_format_csv: invalid argument")
         if n <= cap:
@@ -58,10 +67,11 @@ def format_detected_boundaries(recs: np.ndarray, read_ids: Sequence, primary_met
 
 def save_detected_boundaries(recs: np.ndarray, read_ids: Sequence, filename: str, primary_method: int,
                              save_fail_reasons: bool = False, sel: Optional[Iterable[int]] = None,
-                             llr_detect_log: Optional[str] = None) -> None:
+                             llr_detect_log: Optional[str] = None, open_pore_overflow: Optional[dict] = None) -> None:
     """adapted/output.py:26-51 for record arrays."""
     with open(filename, "wb") as f:
-        f.write(format_detected_boundaries(recs, read_ids, primary_method, save_fail_reasons, sel, llr_detect_log))
+        f.write(format_detected_boundaries(recs, read_ids, primary_method, save_fail_reasons, sel, llr_detect_log,
+                                           open_pore_overflow))
 
 
 class BoundaryTableWriter:
@@ -80,6 +90,7 @@ class BoundaryTableWriter:
         self._recs = {"pass": [], "fail": []}
         self._ids = {"pass": [], "fail": []}
         self._count = {"pass": 0, "fail": 0}
+        self._over = {}  # read id -> full open-pore list of a record beyond ADB_MAX_OPEN_PORES
         self.files: List[str] = []
         for d in self.dirs.values():
             os.makedirs(d, exist_ok=True)
@@ -97,11 +108,14 @@ class BoundaryTableWriter:
                    bidx_pass=next_idx("boundaries", "detected_boundaries_"),
                    bidx_fail=next_idx("failed_reads", "failed_reads_"), **kw)
 
-    def add(self, recs: np.ndarray, read_ids: Sequence) -> None:
-        """One minibatch: split by ``success`` (file_proc.py:246-266) and flush complete files."""
+    def add(self, recs: np.ndarray, read_ids: Sequence, open_pore_overflow: Optional[dict] = None) -> None:
+        """One minibatch: split by ``success`` (file_proc.py:246-266) and flush complete files.
+        ``open_pore_overflow``: {index into recs: full open-pore list} (``detect.open_pore_overflow``)."""
         recs = np.asarray(recs, dtype=_lib.RECORD_DTYPE)
         ok = recs["success"] != 0
         ids = np.asarray(read_ids, dtype=object)
+        for i, lst in (open_pore_overflow or {}).items():
+            self._over[ids[i]] = np.asarray(lst, dtype=np.int32)
         for key, mask in (("fail", ~ok), ("pass", ok)):
             if mask.any():
                 self._recs[key].append(recs[mask])
@@ -113,8 +127,9 @@ class BoundaryTableWriter:
     def _flush(self, key: str, n: int) -> None:
         allr = np.concatenate(self._recs[key]) if len(self._recs[key]) != 1 else self._recs[key][0]
         fn = os.path.join(self.dirs[key], f"{self.names[key]}_{self.bidx[key]}.csv")
+        over = {i: self._over.pop(rid) for i, rid in enumerate(self._ids[key][:n]) if rid in self._over} if self._over else None
         save_detected_boundaries(allr[:n], self._ids[key][:n], fn, self.method, save_fail_reasons=(key == "fail"),
-                                 llr_detect_log=self.log)
+                                 llr_detect_log=self.log, open_pore_overflow=over)
         self.files.append(fn)
         self._recs[key] = [allr[n:]] if allr.size > n else []
         self._ids[key] = self._ids[key][n:]

@@ -102,9 +102,12 @@ def _new_result(success: bool):
     return d
 
 
-def records_to_results(recs: np.ndarray, primary_method: int, llr_log: Optional[str]) -> List[Any]:
+def records_to_results(recs: np.ndarray, primary_method: int, llr_log: Optional[str],
+                       open_pore_overflow: Optional[dict] = None) -> List[Any]:
     """adb_record[N] -> list[DetectResults].  Columns are pulled out of the structured array once (python lists / typed
-    numpy columns); the per-read loop only builds the objects."""
+    numpy columns); the per-read loop only builds the objects.  ``open_pore_overflow`` maps a record index to the full
+    open-pore list of a read whose list does not fit the record (``detect.open_pore_overflow``); without it such a
+    read raises instead of being truncated."""
     out = []
     method = _METHOD[primary_method]
     n = len(recs)
@@ -175,10 +178,14 @@ def records_to_results(recs: np.ndarray, primary_method: int, llr_log: Optional[
         if valid & V_OPEN:
             n_op = col["n_open_pores"][i]
             if n_op > cap_op:
-                raise OverflowError(
-                    f"read has {n_op} open-pore runs; the record keeps {cap_op} "
-                    "(ADB_MAX_OPEN_PORES) -- rebuild with a larger cap")
-            dd["open_pores"] = open_pores[i, :n_op].copy()
+                full = None if open_pore_overflow is None else open_pore_overflow.get(i)
+                if full is None or len(full) != n_op:
+                    raise OverflowError(
+                        f"read has {n_op} open-pore runs; the record keeps {cap_op} (ADB_MAX_OPEN_PORES) and no "
+                        "overflow list was supplied (adapted_b200.detect.open_pore_overflow)")
+                dd["open_pores"] = np.asarray(full, dtype=np.int64).copy()
+            else:
+                dd["open_pores"] = open_pores[i, :n_op].copy()
         if valid & V_MEDSHIFT:
             dd["adapter_rna_median_shift"] = med_shift[i]
         if valid & V_SP:

@@ -33,7 +33,9 @@ typedef enum adb_status {
     ADB_ERR_MAD_ZERO = -3,      /* global MAD == 0: the reference raises ValueError (normalize.py:56-59)        */
     ADB_ERR_EMPTY_TRACE = -4,   /* a read has no downscaled sample: the reference raises ValueError (llr.py:136)
                                    outside any try and loses the minibatch (combined.py:145-211)              */
-    ADB_ERR_UNSUPPORTED = -5    /* configuration outside the built scope (e.g. windows larger than the build caps)  */
+    ADB_ERR_UNSUPPORTED = -5,   /* configuration outside the built scope (e.g. windows larger than the build caps)  */
+    ADB_ERR_OVERFLOW = -6       /* a record's open-pore list is longer than ADB_MAX_OPEN_PORES and its overflow row
+                                   (adb_open_pores_host) was not supplied: nothing is ever truncated silently     */
 } adb_status;
 
 /* signal element types */
@@ -266,6 +268,27 @@ int adb_mvs_stream_detect_host(adb_ctx *ctx, const adb_batch *batch, const adb_s
 int64_t adb_format_csv(const adb_record *recs, const int32_t *sel, int32_t n_sel, const char *const *read_ids,
                        int32_t primary_method, const char *llr_detect_log, int32_t save_fail_reasons, char *out,
                        int64_t cap);
+
+/* Same with the overflow rows of the open-pore lists: records with n_open_pores > ADB_MAX_OPEN_PORES print the full
+ * list op_pos[op_offsets[k] .. op_offsets[k + 1]) with k = op_index[i] (op_index: one entry per record of `recs`, -1 =
+ * no row).  A record beyond the cap without a row of exactly n_open_pores entries makes both functions return
+ * ADB_ERR_OVERFLOW (the reference prints the whole array, combined.py:412-419; nothing is truncated silently). */
+int64_t adb_format_csv_ex(const adb_record *recs, const int32_t *sel, int32_t n_sel, const char *const *read_ids,
+                          int32_t primary_method, const char *llr_detect_log, int32_t save_fail_reasons,
+                          const int32_t *op_index, const int64_t *op_offsets, const int32_t *op_pos, char *out,
+                          int64_t cap);
+
+/*
+ * find_open_pores(signal[adapter_start:adapter_end])                 adapted/detect/anomalies.py:15-35
+ * in full for the reads sel[0..n_sel) of `batch` (HOST buffers) over the sample range [seg_begin[k], seg_end[k]) --
+ * the overflow path of the fixed-size record: validate_boundaries scans [0, primary adapter_end)
+ * (combined.py:411-419), the record keeps the first ADB_MAX_OPEN_PORES positions and the true count.
+ * out_offsets[n_sel + 1] always receives the prefix sums of the list lengths; the positions (window coordinates) are
+ * written only if cap >= out_offsets[n_sel] (call with cap = 0 to size the buffer).
+ */
+int adb_open_pores_host(adb_ctx *ctx, const adb_batch *batch, const int32_t *sel, int32_t n_sel,
+                        const int32_t *seg_begin, const int32_t *seg_end, int64_t *out_offsets, int32_t *out_pos,
+                        int64_t cap);
 
 #ifdef __cplusplus
 }

@@ -4,6 +4,8 @@ DetectResults field of every read compared.  Test infrastructure (imports oracle
 
     python tests/parity_at_scale.py --chemistry rna004 --reads 100000 [--stress]
 
+The same comparison runs as a -m gpu test (tests/test_gpu_parity_at_scale.py, sizes from ADB_PARITY_READS).
+
 LLR path: every field must be identical (floats within 1e-5).  CNN path: the float32 convolutions are summed in a
 different order than torch's CPU kernels, so a primary coordinate may move by one downscaled step (north_star: +-1
 step); the script counts the reads that are field-for-field identical, those whose primaries moved by <= 1 step, and
@@ -77,6 +79,17 @@ def main():
         print(json.dumps(tot))
         return 0 if tot["other_differences"] == 0 else 1
 
+    d = run(args.chemistry, args.reads, args.minibatch, args.stress, args.seed)
+    print(json.dumps(d))
+    return 0 if d["other_differences"] == 0 else 1
+
+
+def run(chemistry: str, reads: int, minibatch: int = 1000, stress: bool = False, seed: int = 4242) -> dict:
+    """One comparison: `reads` synthetic reads through the CUDA path (int16 ingest) and through the CPU oracle on all
+    host cores; returns the counts (see the module docstring)."""
+    import argparse as _ap
+
+    args = _ap.Namespace(chemistry=chemistry, reads=reads, minibatch=minibatch, stress=stress, seed=seed)
     import multiprocessing as mp
     from concurrent.futures import ProcessPoolExecutor
 
@@ -130,12 +143,13 @@ def main():
             bad += 1
             if len(examples) < 5:
                 examples.append({"read": i, "diff": d[:3]})
-    print(json.dumps({"chemistry": args.chemistry, "stress": args.stress, "reads": n, "lost_minibatches": int((status != 0).sum()),
-                      "pass_fraction_oracle": float(np.mean([bool(as_dict(w)["success"]) for w in want])),
-                      "identical": identical, "primary_moved_by_one_step": moved, "other_differences": bad,
-                      "examples": examples, "gpu_s_incl_host_conversion": round(t_gpu, 2), "oracle_s": round(t_cpu, 2),
-                      "cores": os.cpu_count()}))
-    return 0 if bad == 0 else 1
+    return {"chemistry": args.chemistry, "stress": args.stress, "reads": n, "lost_minibatches": int((status != 0).sum()),
+            "pass_fraction_oracle": float(np.mean([bool(as_dict(w)["success"]) for w in want])),
+            "identical": identical, "primary_moved_by_one_step": moved, "other_differences": bad,
+            "examples": examples, "gpu_s_incl_host_conversion": round(t_gpu, 2), "oracle_s": round(t_cpu, 2),
+            "cores": os.cpu_count(), "seed": args.seed}
+
+
 
 
 if __name__ == "__main__":

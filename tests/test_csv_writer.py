@@ -200,3 +200,54 @@ def test_records_round_trip_to_results(seam, name):
         for k, v in w.items():
             if v is None:
                 assert getattr(b, k) is None, k
+
+
+def test_open_pore_lists_beyond_the_record_are_never_truncated():
+    """A record keeps ADB_MAX_OPEN_PORES run starts and the true count.  Both host paths refuse a longer list without
+    its overflow row (no silent truncation) and print the full array -- numpy's wrapped str(), like the reference
+    (combined.py:412-419, output.py:26-51) -- when the row is supplied."""
+    from adapted_b200.records import records_to_results
+
+    rng = np.random.default_rng(5)
+    base = results_to_records(load_case("llr_rna002_basic")["results"], 0)
+    recs = base[base["success"] != 0][:6].copy()
+    ids = [f"read-{i}" for i in range(recs.size)]
+    full = {}
+    for i, n in ((1, 49), (4, 137)):
+        lst = np.sort(rng.choice(12000, size=n, replace=False)).astype(np.int32)
+        recs["n_open_pores"][i] = n
+        recs["open_pores"][i] = lst[: _lib.ADB_MAX_OPEN_PORES]
+        full[i] = lst
+    with pytest.raises(OverflowError):
+        format_detected_boundaries(recs, ids, 0)
+    with pytest.raises(OverflowError):
+        records_to_results(recs, 0, "")
+    with pytest.raises(OverflowError):  # a row of the wrong length is refused as well
+        format_detected_boundaries(recs, ids, 0, open_pore_overflow={1: full[1], 4: full[4][:-1]})
+    res = records_to_results(recs, 0, "", full)
+    assert np.array_equal(res[4].open_pores, full[4]) and res[4].open_pores.dtype == np.int64
+    got = format_detected_boundaries(recs, ids, 0, open_pore_overflow=full)
+    assert got.decode() == _pandas_csv(res, ids, False)
+    # a selection that leaves the long records out needs no rows
+    sel = [0, 2, 3, 5]
+    assert format_detected_boundaries(recs, ids, 0, sel=sel).decode() == _pandas_csv([res[i] for i in sel], [ids[i] for i in sel], False)
+
+
+def test_table_writer_carries_overflow_rows(tmp_path):
+    from adapted_b200.records import records_to_results
+
+    base = results_to_records(load_case("llr_rna002_basic")["results"], 0)
+    recs = base[base["success"] != 0][:10].copy()
+    ids = [f"read-{i}" for i in range(recs.size)]
+    lst = np.arange(100, 100 + 60 * 15, 15, dtype=np.int32)
+    recs["n_open_pores"][7] = lst.size
+    recs["open_pores"][7] = lst[: _lib.ADB_MAX_OPEN_PORES]
+    out = str(tmp_path)
+    with BoundaryTableWriter(os.path.join(out, "boundaries"), os.path.join(out, "failed_reads"), 0, batch_size_output=4,
+                             llr_detect_log="") as w:
+        w.add(recs[:5], ids[:5])
+        w.add(recs[5:], ids[5:], {2: lst})  # index 2 of this minibatch = read 7
+    res = records_to_results(recs, 0, "", {7: lst})
+    text = "".join(open(os.path.join(out, "boundaries", f"detected_boundaries_{i}.csv"), newline="").read().split("\n", 1)[1]
+                   for i in range(3))
+    assert text == _pandas_csv(res, ids, False).split("\n", 1)[1]

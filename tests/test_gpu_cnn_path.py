@@ -2,8 +2,9 @@
 
 CNN tolerance (north_star): primary coordinates within +-1 downscaled step.  The float32 convolutions are summed in a
 different order than torch's CPU kernels, so coordinates that come from an argmax / peak ranking may move by one
-step; everything derived from identical primaries must then agree exactly.  In practice the tests demand that at
-least 99 % of reads are field-for-field identical and that no primary coordinate is off by more than one step."""
+step; everything derived from identical primaries must then agree exactly.  The tests demand that at least 99.9 % of
+the reads are field-for-field identical (at most one read in a minibatch of fewer than 1000) and that no primary
+coordinate is off by more than one step."""
 import numpy as np
 import pytest
 
@@ -36,7 +37,9 @@ def _cnn_compare(got, want, ds):
         cand_same = (g.get("polya_candidates") is None and w.get("polya_candidates") is None) or np.array_equal(
             g.get("polya_candidates"), w.get("polya_candidates"))
         assert not (same_primary and cand_same), f"identical primaries but different results: {d}"
-    assert exact >= 0.99 * n, f"only {exact}/{n} reads identical"
+    # >= 99.9 % of the reads identical (observed at scale: 99.98 %, tests/test_gpu_parity_at_scale.py); a minibatch of
+    # fewer than 1000 reads cannot express that rate: at most one moved read is accepted there
+    assert n - exact <= max(1, int(0.001 * n)), f"only {exact}/{n} reads identical"
     return exact
 
 
