@@ -70,6 +70,14 @@ class AdbBatch(C.Structure):
     ]
 
 
+class AdbSvbBatch(C.Structure):
+    _fields_ = [
+        ("comp", C.c_void_p), ("comp_offsets", C.c_void_p), ("n_samples", C.c_void_p),
+        ("n_reads", C.c_int32), ("m", C.c_int32), ("batch_size", C.c_int32), ("_pad", C.c_int32),
+        ("full_lens", C.c_void_p), ("calib_offset", C.c_void_p), ("calib_scale", C.c_void_p),
+    ]
+
+
 # numpy mirror of adb_record (512 bytes)
 RECORD_DTYPE = np.dtype([
     ("success", "<i4"), ("fail_code", "<i4"), ("mvs_fail_mask", "<i4"), ("valid", "<u4"),
@@ -138,6 +146,10 @@ def load() -> C.CDLL:
     L.adb_format_csv_ex.restype = C.c_int64
     L.adb_open_pores_host.argtypes = [vp, C.POINTER(AdbBatch), vp, C.c_int32, vp, vp, vp, vp, C.c_int64]
     L.adb_open_pores_host.restype = ip
+    L.adb_svb16_decode_host.argtypes = [vp, C.POINTER(AdbSvbBatch), vp]
+    L.adb_svb16_decode_host.restype = ip
+    L.adb_detect_pipelined_svb_host.argtypes = [vp, C.POINTER(AdbSvbBatch), C.POINTER(AdbConfig), vp, vp, vp, C.c_int32]
+    L.adb_detect_pipelined_svb_host.restype = ip
     for f in ("adb_detect_pipelined_host", "adb_ctx_set_timing", "adb_ctx_get_timing", "adb_ctx_create", "adb_detect_host", "adb_detect_dev", "adb_llr_trace_host",
               "adb_global_med_mad_host", "adb_downscale_host", "adb_cnn_scores_host"):
         getattr(L, f).restype = ip

@@ -75,7 +75,8 @@ extern "C" void adb_ctx_destroy(adb_ctx *c) {
                      &c->gsb_plan, &c->gsb_hist, &c->gsb_tab, &c->gsb_bases, &c->gsb_active, &c->vf_done, &c->mvs_perm, &c->cnn_wtc, &c->cnn_a0t};
     for (DevBuf *b : all) b->release();
     for (int k = 0; k < 2; k++) {
-        DevBuf *pb[] = {&c->p_signal[k], &c->p_offsets[k], &c->p_lens[k], &c->p_coff[k], &c->p_cscale[k], &c->p_records[k], &c->p_status[k]};
+        DevBuf *pb[] = {&c->p_signal[k], &c->p_offsets[k], &c->p_lens[k], &c->p_coff[k], &c->p_cscale[k], &c->p_records[k], &c->p_status[k],
+                        &c->p_comp[k], &c->p_coffs[k], &c->p_nsamp[k]};
         for (DevBuf *b : pb) b->release();
         if (c->p_done[k]) cudaEventDestroy(c->p_done[k]);
         if (c->p_copied[k]) cudaEventDestroy(c->p_copied[k]);
@@ -93,6 +94,7 @@ extern "C" int adb_ctx_set_option(adb_ctx *c, const char *name, int value) {
     if (!strcmp(name, "exact_global_select")) { c->opt_exact_gsel = value; return ADB_OK; }
     if (!strcmp(name, "no_fast_validate")) { c->opt_no_fast_validate = value; return ADB_OK; }
     if (!strcmp(name, "cnn_fp32_pipe")) { c->opt_cnn_fp32 = value; return ADB_OK; }
+    if (!strcmp(name, "pipeline_copy_only")) { c->opt_copy_only = value; return ADB_OK; }
     set_err(std::string("unknown option: ") + name);
     return ADB_ERR_ARG;
 }
@@ -728,8 +730,10 @@ extern "C" int adb_detect_pipelined_host(adb_ctx *ctx, const adb_batch *batch, c
         d.calib_offset = (const float *)c->p_coff[slot].p;
         d.calib_scale = (const float *)c->p_cscale[slot].p;
         d.n_reads = nr;
-        rc = adb_detect_dev(c, &d, cfg, w_devs[ch & 1], (adb_record *)c->p_records[slot].p, (int *)c->p_status[slot].p, ks);
-        if (rc) return rc;
+        if (!ctx->opt_copy_only) {
+            rc = adb_detect_dev(c, &d, cfg, w_devs[ch & 1], (adb_record *)c->p_records[slot].p, (int *)c->p_status[slot].p, ks);
+            if (rc) return rc;
+        }
         CUDA_TRY(cudaMemcpyAsync(out_records + r0, c->p_records[slot].p, sizeof(adb_record) * (size_t)nr, cudaMemcpyDeviceToHost, ks));
         if (batch_status)
             CUDA_TRY(cudaMemcpyAsync(batch_status + b0, c->p_status[slot].p, sizeof(int) * (size_t)nb, cudaMemcpyDeviceToHost, ks));
@@ -1038,3 +1042,5 @@ extern "C" int adb_open_pores_host(adb_ctx *ctx, const adb_batch *batch, const i
     CUDA_TRY(cudaStreamSynchronize(st));
     return ADB_OK;
 }
+
+#include "adb_ingest.cuh"

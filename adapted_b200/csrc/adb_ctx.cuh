@@ -64,6 +64,8 @@ struct adb_ctx {
     int64_t timing_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // double-buffered staging for the pipelined host entry point
     DevBuf p_signal[2], p_offsets[2], p_lens[2], p_coff[2], p_cscale[2], p_records[2], p_status[2];
+    DevBuf p_comp[2], p_coffs[2], p_nsamp[2];  // compressed ingest: svb16 streams, their offsets, samples per read
+    int opt_copy_only = 0;     // adb_ctx_set_option("pipeline_copy_only"): pipelined entry points skip the kernels
     cudaEvent_t p_done[2] = {nullptr, nullptr}, p_copied[2] = {nullptr, nullptr};
     // scratch (device)
     DevBuf states, hist, series, given, status;

@@ -209,6 +209,65 @@ def detect_reads(adc: np.ndarray, offsets: np.ndarray, full_lens: np.ndarray, ca
     return res, status
 
 
+def svb16_decode(comp: np.ndarray, comp_offsets: np.ndarray, n_samples: np.ndarray, m: Optional[int] = None,
+                 device: int = 0):
+    """svb16 + zig-zag + delta decode on the GPU (adb_svb16_decode_host) -> (adc int16, offsets int64 [n + 1])."""
+    comp = np.ascontiguousarray(comp, dtype=np.uint8)
+    coff = np.ascontiguousarray(comp_offsets, dtype=np.int64)
+    ns = np.ascontiguousarray(n_samples, dtype=np.int32)
+    n = ns.size
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(ns, out=off[1:])
+    out = np.zeros(int(off[-1]), dtype=np.int16)
+    if n == 0:
+        return out, off
+    if coff.size != n + 1 or np.any(coff[1:] < coff[:-1]) or coff[0] < 0 or coff[-1] + 16 > comp.size or np.any(coff % 16):
+        raise ValueError("comp_offsets must hold n + 1 non-decreasing 16-byte aligned offsets inside the blob (16 bytes of slack)")
+    lens = ns.copy()
+    zeros = np.zeros(n, np.float32)
+    b = _lib.AdbSvbBatch(comp=comp.ctypes.data, comp_offsets=coff.ctypes.data, n_samples=ns.ctypes.data, n_reads=n,
+                         m=int(m if m else max(int(ns.max()), 1)), batch_size=max(n, 1), full_lens=lens.ctypes.data,
+                         calib_offset=zeros.ctypes.data, calib_scale=zeros.ctypes.data)
+    ctx = _lib.default_context(device)
+    _lib.check(_lib.load().adb_svb16_decode_host(ctx.handle, C.byref(b), out.ctypes.data))
+    return out, off
+
+
+def detect_reads_svb(comp: np.ndarray, comp_offsets: np.ndarray, n_samples: np.ndarray, full_lens: np.ndarray,
+                     calib_offset: np.ndarray, calib_scale: np.ndarray, spc: Any, model: Any = None,
+                     minibatch_size: int = 1000, chunk_minibatches: int = 16, device: int = 0):
+    """Compressed ingest: svb16 streams (adapted_b200.svb16) travel to the GPU compressed, are decoded there and
+    detected (adb_detect_pipelined_svb_host).  Returns (records, batch_status)."""
+    comp = np.ascontiguousarray(comp, dtype=np.uint8)
+    coff = np.ascontiguousarray(comp_offsets, dtype=np.int64)
+    ns = np.ascontiguousarray(n_samples, dtype=np.int32)
+    lens = np.ascontiguousarray(full_lens, dtype=np.int32)
+    co = np.ascontiguousarray(calib_offset, dtype=np.float32)
+    cs = np.ascontiguousarray(calib_scale, dtype=np.float32)
+    n = lens.size
+    flat = flatten_config(spc)
+    m = int(flat["sig_preload_size"])
+    if ns.size != n or co.size != n or cs.size != n or (n and (coff.size != n + 1 or np.any(coff[1:] < coff[:-1]) or coff[0] < 0
+                                                              or coff[-1] + 16 > comp.size or np.any(coff % 16))):
+        raise ValueError("inconsistent compressed batch description")
+    if n and (ns.min() < 0 or ns.max() > m):
+        raise ValueError("n_samples must lie in [0, sig_preload_size]")
+    w = flatten_cnn_weights(model) if flat["primary_method"] == 1 else None
+    n_batches = (n + minibatch_size - 1) // minibatch_size
+    recs = np.zeros(n, dtype=_lib.RECORD_DTYPE)
+    status = np.zeros(max(n_batches, 1), dtype=np.int32)
+    if n == 0:
+        return recs, status[:0]
+    b = _lib.AdbSvbBatch(comp=comp.ctypes.data, comp_offsets=coff.ctypes.data, n_samples=ns.ctypes.data, n_reads=n, m=m,
+                         batch_size=int(minibatch_size), full_lens=lens.ctypes.data, calib_offset=co.ctypes.data,
+                         calib_scale=cs.ctypes.data)
+    cfg = _lib.fill_config(flat)
+    ctx = _lib.default_context(device)
+    _lib.check(_lib.load().adb_detect_pipelined_svb_host(ctx.handle, C.byref(b), C.byref(cfg), w.ctypes.data if w is not None else None,
+                                                         recs.ctypes.data, status.ctypes.data, int(chunk_minibatches)))
+    return recs, status
+
+
 # ---- streaming poly(A) detector (adapted/detect/mvs.py:341-426) --------------------------------------------------------
 
 def mean_var_shift_polyA_detect_batch(batch_of_signals: np.ndarray, signal_lens: np.ndarray, params: Any = None,

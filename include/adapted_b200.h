@@ -290,6 +290,36 @@ int adb_open_pores_host(adb_ctx *ctx, const adb_batch *batch, const int32_t *sel
                         const int32_t *seg_begin, const int32_t *seg_end, int64_t *out_offsets, int32_t *out_pos,
                         int64_t cap);
 
+/* ---- compressed ingest -------------------------------------------------------------------- */
+/*
+ * VBZ-style compressed reads: what pod5 stores per signal chunk minus its zstd stage, i.e. svb16(zigzag(delta)) of
+ * the int16 samples (pod5 c++/pod5_format/svb16; replaces the decode inside pod5's ReadRecord.signal that
+ * yield_signals_from_pod5 calls, adapted/file_proc.py:165-175).  Read i's stream starts at comp[comp_offsets[i]]
+ * (16-byte aligned): ceil(n / 8) key bytes (bit j % 8 of byte j / 8: 0 = one data byte, 1 = two, little endian), zero
+ * padded to a multiple of 4, then the data bytes of the n = n_samples[i] <= m values; 16 bytes of slack follow the
+ * last stream.  About 1.15 bytes per sample on nanopore signal instead of 2.
+ */
+typedef struct adb_svb_batch {
+    const uint8_t *comp;
+    const int64_t *comp_offsets; /* [n_reads + 1] */
+    const int32_t *n_samples;    /* [n_reads] stored samples per read = min(full length, preload window)  */
+    int32_t n_reads, m, batch_size, _pad;
+    const int32_t *full_lens;
+    const float *calib_offset, *calib_scale;
+} adb_svb_batch;
+
+/* svb16 + zig-zag + delta decode on the GPU, HOST buffers in and out (kernel-level test entry): out_adc receives the
+ * reads back to back (read i at the exclusive prefix sum of n_samples). */
+int adb_svb16_decode_host(adb_ctx *ctx, const adb_svb_batch *batch, int16_t *out_adc);
+/*
+ * adb_detect_pipelined_host for compressed reads: every chunk travels host -> device COMPRESSED (pinned host buffers
+ * for asynchronous copies), is decoded by svb16_decode_kernel into the ragged int16 layout and detected; records
+ * return per chunk.  Replaces producer thread + pod5 decode + process pool (file_proc.py:143-214,738-784) for one GPU.
+ * ctx option "pipeline_copy_only" = 1 skips the kernels (bench.py: the box's host -> device ceiling for these chunks).
+ */
+int adb_detect_pipelined_svb_host(adb_ctx *ctx, const adb_svb_batch *batch, const adb_config *cfg, const float *cnn_weights,
+                                  adb_record *out_records, int32_t *batch_status, int32_t chunk_batches);
+
 #ifdef __cplusplus
 }
 #endif
