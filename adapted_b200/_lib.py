@@ -78,6 +78,20 @@ class AdbSvbBatch(C.Structure):
     ]
 
 
+class AdbFileJob(C.Structure):
+    _fields_ = [
+        ("paths", C.POINTER(C.c_char_p)), ("n_paths", C.c_int32), ("minibatch_size", C.c_int32),
+        ("keep", C.POINTER(C.c_void_p)), ("out_dir", C.c_char_p),
+        ("batch_size_output", C.c_int32), ("chunk_batches", C.c_int32), ("bidx_pass", C.c_int32), ("bidx_fail", C.c_int32),
+        ("n_copy_threads", C.c_int32), ("n_format_threads", C.c_int32), ("write_csv", C.c_int32), ("_pad", C.c_int32),
+    ]
+
+
+class AdbFileStats(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in ("reads", "n_pass", "n_fail", "lost", "files", "comp_bytes", "h2d_bytes")] + [
+        (k, C.c_double) for k in ("seconds", "read_s", "gpu_wait_s", "write_s")]
+
+
 # numpy mirror of adb_record (512 bytes)
 RECORD_DTYPE = np.dtype([
     ("success", "<i4"), ("fail_code", "<i4"), ("mvs_fail_mask", "<i4"), ("valid", "<u4"),
@@ -150,6 +164,8 @@ def load() -> C.CDLL:
     L.adb_svb16_decode_host.restype = ip
     L.adb_detect_pipelined_svb_host.argtypes = [vp, C.POINTER(AdbSvbBatch), C.POINTER(AdbConfig), vp, vp, vp, C.c_int32]
     L.adb_detect_pipelined_svb_host.restype = ip
+    L.adb_detect_files.argtypes = [vp, C.POINTER(AdbFileJob), C.POINTER(AdbConfig), vp, C.POINTER(AdbFileStats)]
+    L.adb_detect_files.restype = ip
     for f in ("adb_detect_pipelined_host", "adb_ctx_set_timing", "adb_ctx_get_timing", "adb_ctx_create", "adb_detect_host", "adb_detect_dev", "adb_llr_trace_host",
               "adb_global_med_mad_host", "adb_downscale_host", "adb_cnn_scores_host"):
         getattr(L, f).restype = ip

@@ -69,6 +69,7 @@ extern "C" void adb_ctx_destroy(adb_ctx *c) {
     if (!c) return;
     if (c->twin) { adb_ctx_destroy(c->twin); c->twin = nullptr; }
     cudaSetDevice(c->device);
+    if (c->file_ring && c->file_ring_free) { c->file_ring_free(c->file_ring); c->file_ring = nullptr; }
     DevBuf *all[] = {&c->states, &c->hist, &c->series, &c->given, &c->status, &c->cnn_x, &c->cnn_act0,
                      &c->cnn_act1, &c->cnn_scores, &c->cnn_w, &c->cnn_aux, &c->cnn_post, &c->sp_rows, &c->h_signal, &c->h_offsets,
                      &c->h_lens, &c->h_coff, &c->h_cscale, &c->h_records, &c->h_misc, &c->h_misc2, &c->h_misc3,
@@ -1044,3 +1045,4 @@ extern "C" int adb_open_pores_host(adb_ctx *ctx, const adb_batch *batch, const i
 }
 
 #include "adb_ingest.cuh"
+#include "adb_files.cuh"

@@ -66,6 +66,9 @@ struct adb_ctx {
     DevBuf p_signal[2], p_offsets[2], p_lens[2], p_coff[2], p_cscale[2], p_records[2], p_status[2];
     DevBuf p_comp[2], p_coffs[2], p_nsamp[2];  // compressed ingest: svb16 streams, their offsets, samples per read
     int opt_copy_only = 0;     // adb_ctx_set_option("pipeline_copy_only"): pipelined entry points skip the kernels
+    // pinned slot ring of adb_detect_files, kept between calls (pinning gigabytes costs seconds)
+    void *file_ring = nullptr;
+    void (*file_ring_free)(void *) = nullptr;
     cudaEvent_t p_done[2] = {nullptr, nullptr}, p_copied[2] = {nullptr, nullptr};
     // scratch (device)
     DevBuf states, hist, series, given, status;

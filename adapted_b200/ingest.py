@@ -54,6 +54,167 @@ def write_container(path: str, adc: np.ndarray, offsets: np.ndarray, full_lens: 
     return path
 
 
+# ---- container version 2: binary header, compressed signal (the native pipeline's input, adb_files.cuh) ----------------
+_MAGIC2 = b"ADBSIG02"
+_HDR2 = np.dtype([("magic", "S8"), ("version", "<u4"), ("flags", "<u4"), ("n_reads", "<u8"), ("id_width", "<u4"),
+                  ("reserved0", "<u4"), ("off_comp_offsets", "<u8"), ("off_n_samples", "<u8"), ("off_full_lens", "<u8"),
+                  ("off_calib_offset", "<u8"), ("off_calib_scale", "<u8"), ("off_read_ids", "<u8"), ("off_blob", "<u8"),
+                  ("blob_bytes", "<u8"), ("reserved", "u1", (32,))])
+assert _HDR2.itemsize == 128
+F_SVB16, F_ZSTD = 1, 2
+
+
+def _zstd():
+    import ctypes
+
+    z = ctypes.CDLL("libzstd.so.1")
+    z.ZSTD_compressBound.restype = ctypes.c_size_t
+    z.ZSTD_compressBound.argtypes = [ctypes.c_size_t]
+    z.ZSTD_compress.restype = ctypes.c_size_t
+    z.ZSTD_compress.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+    z.ZSTD_decompress.restype = ctypes.c_size_t
+    z.ZSTD_decompress.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t]
+    z.ZSTD_isError.restype = ctypes.c_uint
+    z.ZSTD_isError.argtypes = [ctypes.c_size_t]
+    return z
+
+
+def write_container_v2(path: str, adc: np.ndarray, offsets: np.ndarray, full_lens: np.ndarray, calib_offset: np.ndarray,
+                       calib_scale: np.ndarray, read_ids: Sequence[str], compress: bool = True, zstd: bool = False,
+                       preload_size: Optional[int] = None, encoded=None) -> str:
+    """"ADBSIG02": 128-byte binary header + 64-byte aligned sections.  Per read the first ``preload_size`` samples (all
+    by default) as an svb16 + zig-zag + delta stream (``compress``; adapted_b200.svb16), optionally wrapped in one zstd
+    frame per read (``zstd``: pod5's VBZ), or raw int16.  ``encoded`` = (comp, comp_offsets, n_samples) skips the
+    encoder (bench.py encodes on the GPU)."""
+    from . import svb16
+
+    if not path.endswith(".adbsig"):
+        path += ".adbsig"
+    offsets = np.ascontiguousarray(offsets, np.int64)
+    n = offsets.size - 1
+    if encoded is not None:
+        blob, coffs, ns = encoded
+        flags = F_SVB16
+    else:
+        adc = np.ascontiguousarray(adc, np.int16)
+        if preload_size is not None and n and int(np.diff(offsets).max(initial=0)) > preload_size:
+            keep = np.minimum(np.diff(offsets), preload_size)
+            adc = np.concatenate([adc[offsets[i]: offsets[i] + keep[i]] for i in range(n)])
+            offsets = np.concatenate([[0], np.cumsum(keep)]).astype(np.int64)
+        if compress:
+            blob, coffs, ns = svb16.encode_reads(adc, offsets)
+            flags = F_SVB16
+        else:
+            blob = adc[offsets[0]: offsets[-1]].view(np.uint8) if n else np.zeros(0, np.uint8)
+            coffs = (offsets - offsets[0]) * 2
+            ns = np.diff(offsets).astype(np.int32)
+            flags = 0
+    if zstd:
+        z = _zstd()
+        frames, zoff = [], [0]
+        for i in range(n):
+            src = np.ascontiguousarray(blob[coffs[i]: coffs[i + 1]])
+            dst = np.empty(int(z.ZSTD_compressBound(src.size)), np.uint8)
+            got = z.ZSTD_compress(dst.ctypes.data, dst.size, src.ctypes.data, src.size, 1)
+            if z.ZSTD_isError(got):
+                raise RuntimeError("ZSTD_compress failed")
+            frames.append(dst[:got])
+            zoff.append(zoff[-1] + int(got))
+        blob = np.concatenate(frames + [np.zeros(16, np.uint8)]) if frames else np.zeros(16, np.uint8)
+        coffs = np.asarray(zoff, np.int64)
+        flags |= F_ZSTD
+    ids = np.asarray([str(i).encode() for i in read_ids], dtype="S") if len(read_ids) else np.zeros(0, "S1")
+    ids = ids.astype(f"S{ids.dtype.itemsize + 1}")  # NUL terminated
+    arrays = [("off_comp_offsets", np.ascontiguousarray(coffs, np.int64)), ("off_n_samples", np.ascontiguousarray(ns, np.int32)),
+              ("off_full_lens", np.ascontiguousarray(full_lens, np.int32)), ("off_calib_offset", np.ascontiguousarray(calib_offset, np.float32)),
+              ("off_calib_scale", np.ascontiguousarray(calib_scale, np.float32)), ("off_read_ids", ids),
+              ("off_blob", np.ascontiguousarray(blob, np.uint8))]
+    hdr = np.zeros(1, _HDR2)
+    hdr["magic"], hdr["version"], hdr["flags"], hdr["n_reads"], hdr["id_width"] = _MAGIC2, 2, flags, n, ids.dtype.itemsize
+    pos = 128
+    for name, a in arrays:
+        hdr[name] = pos
+        pos += (a.nbytes + 63) & ~63
+    hdr["blob_bytes"] = arrays[-1][1].nbytes
+    with open(path, "wb") as f:
+        f.write(hdr.tobytes())
+        for name, a in arrays:
+            f.seek(int(hdr[name][0]))
+            a.tofile(f)
+        f.truncate(pos)
+    return path
+
+
+def read_container_v2(path: str) -> Dict[str, Any]:
+    """Memory maps of an ADBSIG02 container: comp, comp_offsets, n_samples, full_lens, calib_offset, calib_scale,
+    read_ids (fixed-width bytes) and flags."""
+    hdr = np.fromfile(path, dtype=_HDR2, count=1)
+    if hdr.size != 1 or bytes(hdr["magic"][0]) != _MAGIC2:
+        raise ValueError(f"{path}: not an ADBSIG02 signal container")
+    h = hdr[0]
+    n, w = int(h["n_reads"]), int(h["id_width"])
+
+    def mm(off, dtype, count):
+        return np.memmap(path, dtype=dtype, mode="r", offset=int(off), shape=(count,)) if count else np.zeros(0, dtype)
+
+    return {"flags": int(h["flags"]), "comp_offsets": mm(h["off_comp_offsets"], np.int64, n + 1), "n_samples": mm(h["off_n_samples"], np.int32, n),
+            "full_lens": mm(h["off_full_lens"], np.int32, n), "calib_offset": mm(h["off_calib_offset"], np.float32, n),
+            "calib_scale": mm(h["off_calib_scale"], np.float32, n), "read_ids": mm(h["off_read_ids"], f"S{w}", n),
+            "comp": mm(h["off_blob"], np.uint8, int(h["blob_bytes"]))}
+
+
+def detect_files_native(files: Sequence[str], out_dir: str, spc: Any, model: Any = None, read_ids_incl: Optional[Set[str]] = None,
+                        minibatch_size: int = 1000, batch_size_output: int = 4000, continue_run: bool = False, device: int = 0,
+                        chunk_minibatches: int = 16, write_csv: bool = True, copy_threads: int = 0, format_threads: int = 0) -> Dict[str, Any]:
+    """``adapted detect`` / ``continue`` between the reader and the tables through the native overlapped pipeline
+    (adb_detect_files): ADBSIG02 containers -> pinned ring -> H2D (compressed) -> device decode -> detection -> records
+    -> formatter threads.  Selection (file_proc.py:150-168) and the `continue` scan (file_proc.py:97-140) are resolved
+    here into per-file keep masks and first table indices; everything per read runs in the library."""
+    import ctypes as C
+
+    from . import _lib
+    from .detect import flatten_cnn_weights
+
+    flat = flatten_config(spc)
+    excl = processed_read_ids(out_dir) if continue_run else set()
+    incl = set(read_ids_incl) if read_ids_incl else set()
+    if incl and excl:
+        incl, excl = incl.difference(excl), set()
+    masks = []
+    if incl or excl:
+        for fn in files:
+            ids = read_container_v2(fn)["read_ids"]
+            w = ids.dtype.itemsize
+            if incl:
+                keep = np.isin(ids, np.asarray(sorted(x.encode() for x in incl), dtype=f"S{w}"))
+            else:
+                keep = ~np.isin(ids, np.asarray(sorted(x.encode() for x in excl), dtype=f"S{w}"))
+            masks.append(np.ascontiguousarray(keep, dtype=np.uint8))
+    bidx = {"pass": 0, "fail": 0}
+    if continue_run:
+        for key, sub, prefix in (("pass", "boundaries", "detected_boundaries_"), ("fail", "failed_reads", "failed_reads_")):
+            d = os.path.join(out_dir, sub)
+            idx = [int(f.split("_")[-1].split(".")[0]) for f in os.listdir(d) if f.startswith(prefix) and f.endswith(".csv")] \
+                if os.path.isdir(d) else []
+            bidx[key] = max(idx, default=-1) + 1
+    paths = (C.c_char_p * len(files))(*[os.fsencode(f) for f in files])
+    keep_arr = (C.c_void_p * len(files))(*[m.ctypes.data if m.size else None for m in masks]) if masks else None
+    job = _lib.AdbFileJob(paths=paths, n_paths=len(files), minibatch_size=int(minibatch_size),
+                          keep=keep_arr, out_dir=os.fsencode(out_dir), batch_size_output=int(batch_size_output),
+                          chunk_batches=int(chunk_minibatches), bidx_pass=bidx["pass"], bidx_fail=bidx["fail"],
+                          n_copy_threads=int(copy_threads), n_format_threads=int(format_threads), write_csv=int(bool(write_csv)))
+    w = flatten_cnn_weights(model) if flat["primary_method"] == 1 else None
+    cfg = _lib.fill_config(flat)
+    st = _lib.AdbFileStats()
+    ctx = _lib.default_context(device)
+    _lib.check(_lib.load().adb_detect_files(ctx.handle, C.byref(job), C.byref(cfg), w.ctypes.data if w is not None else None, C.byref(st)))
+    if st.lost:
+        logging.error("%d reads in minibatches lost like the reference's handle_completed_future (file_proc.py:726-731)", st.lost)
+    return {"reads": int(st.reads), "pass": int(st.n_pass), "fail": int(st.n_fail), "lost": int(st.lost), "files": int(st.files),
+            "comp_bytes": int(st.comp_bytes), "h2d_bytes": int(st.h2d_bytes), "seconds": float(st.seconds),
+            "reader_busy_s": float(st.read_s), "writer_wait_gpu_s": float(st.gpu_wait_s), "writer_busy_s": float(st.write_s)}
+
+
 def read_container(path: str) -> Dict[str, np.ndarray]:
     """Memory maps of the sections (read-only); ``read_ids`` comes back as a fixed-width bytes array."""
     import json

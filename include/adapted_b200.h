@@ -320,6 +320,39 @@ int adb_svb16_decode_host(adb_ctx *ctx, const adb_svb_batch *batch, int16_t *out
 int adb_detect_pipelined_svb_host(adb_ctx *ctx, const adb_svb_batch *batch, const adb_config *cfg, const float *cnn_weights,
                                   adb_record *out_records, int32_t *batch_status, int32_t chunk_batches);
 
+/* ---- file level: containers -> GPU -> boundary tables, all stages overlapped ------------- */
+/*
+ * Drop-in for the part of run_detect between the reader and the CSV files for ONE GPU
+ *   producer thread yield_signals_from_pod5        adapted/file_proc.py:143-214
+ *   process pool + worker seam                      adapted/file_proc.py:217-266, 738-784
+ *   saver threads / save_detected_boundaries        adapted/file_proc.py:312-457, adapted/output.py:26-51
+ * on "ADBSIG02" signal containers (adapted_b200/ingest.py:write_container_v2: per read the svb16 stream of its first
+ * min(length, preload window) samples, optionally one zstd frame per read = pod5's VBZ; or raw int16).  A reader
+ * thread fills a ring of pinned host slots (chunks of `chunk_batches` minibatches, cut in file order across file
+ * boundaries), this thread copies / decodes / detects on alternating contexts, a writer thread splits the records
+ * into the pass / fail lists in arrival order and formatter threads write <out_dir>/boundaries/
+ * detected_boundaries_<i>.csv and <out_dir>/failed_reads/failed_reads_<i>.csv (batch_size_output reads per table,
+ * numbering from bidx_pass / bidx_fail: `adapted continue`, file_proc.py:97-140).
+ */
+typedef struct adb_file_job {
+    const char *const *paths;
+    int32_t n_paths;
+    int32_t minibatch_size;        /* reads per minibatch (parser.py:95-99: 1000)                                  */
+    const uint8_t *const *keep;    /* optional [n_paths]: per file one byte per read, 0 = skip (selection / continue) */
+    const char *out_dir;
+    int32_t batch_size_output;     /* reads per table (parser.py:87-93: 4000)                                      */
+    int32_t chunk_batches;         /* minibatches per pipeline chunk (0: 16)                                       */
+    int32_t bidx_pass, bidx_fail;  /* first table indices                                                          */
+    int32_t n_copy_threads, n_format_threads; /* 0: defaults                                                       */
+    int32_t write_csv, _pad;       /* 0: detection only (records are dropped; statistics still filled)             */
+} adb_file_job;
+typedef struct adb_file_stats {
+    int64_t reads, pass, fail, lost, files, comp_bytes, h2d_bytes;
+    double seconds, read_s, gpu_wait_s, write_s; /* wall time of the call; busy time of the reader / writer stages */
+} adb_file_stats;
+int adb_detect_files(adb_ctx *ctx, const adb_file_job *job, const adb_config *cfg, const float *cnn_weights,
+                     adb_file_stats *stats);
+
 #ifdef __cplusplus
 }
 #endif

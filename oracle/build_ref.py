@@ -6,13 +6,16 @@ Two outputs:
   (``/root/reference/adapted/detect/_c_llr.pyx``) cythonized and compiled from the source
   where it lies.  The build product is git-ignored but travels to the GPU box, where it serves
   as the "reference" arm for the LLR-gains kernel.
-* a scratch tree under ``/tmp`` (never inside the repo) holding a copy of the pure-python
-  reference package with the two py>=3.11 dataclass fixes applied, plus a ``bottleneck``
-  stand-in that forwards to :mod:`oracle.bn_restate`.  ``oracle/make_golden.py`` and the
-  ``-m "not gpu"`` oracle-vs-reference tests import it from there; nothing under ``tests -m gpu``,
-  ``smoke()`` or ``bench.py`` touches it.
+* ``oracle/_ref/pkg`` (git-ignored like everything under ``oracle/_ref``, so it never enters the
+  history, but it travels to the GPU box with the snapshot): the runnable copy of the python
+  reference package with the two py>=3.11 dataclass fixes applied, the compiled ``_c_llr`` next to
+  its pyx, plus a ``bottleneck`` stand-in that forwards to :mod:`oracle.bn_restate`.
+  ``oracle/make_golden.py`` and the oracle-vs-reference tests import it from there, and
+  ``bench.py --impl reference`` times it as the CPU arm (``cpu_baseline.kind = "reference"``): the
+  reference's own ``combined_detect_cnn`` / ``combined_detect_llr2`` under a process pool.  Nothing
+  under ``tests -m gpu`` or ``smoke()`` touches it.
 
-No reference source is copied into the repository.
+No reference source is committed to the repository.
 """
 from __future__ import annotations
 
@@ -68,10 +71,18 @@ def build_c_llr(force: bool = False) -> str:
 _FIELD_RE = re.compile(r"^(\s+)(\w+): (\w+) = (\w+Config)\(\)$", re.M)
 
 
+PKG = os.path.join(REF_OUT, "pkg")
+
+
+def package_present() -> bool:
+    return os.path.exists(os.path.join(PKG, "built.stamp"))
+
+
 def build_scratch_package(force: bool = False) -> str:
-    """Patched python copy of the reference in SCRATCH; returns the directory to put on sys.path."""
-    root = os.path.join(SCRATCH, "pkg")
-    stamp = os.path.join(root, ".stamp")
+    """Patched python copy of the reference in oracle/_ref/pkg; returns the directory to put on sys.path."""
+    root = PKG
+    os.makedirs(REF_OUT, exist_ok=True)
+    stamp = os.path.join(root, "built.stamp")
     if os.path.exists(stamp) and not force:
         return root
     if os.path.exists(root):
@@ -90,8 +101,8 @@ def build_scratch_package(force: bool = False) -> str:
     os.makedirs(bn)
     with open(os.path.join(bn, "__init__.py"), "w") as f:
         f.write(
-            "import sys\n"
-            f"sys.path.insert(0, {os.path.dirname(HERE)!r})\n"
+            "import os, sys\n"
+            "sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), '..', '..', '..', '..')))\n"
             "from oracle.bn_restate import move_mean, move_var\n"
             "__version__ = '1.3.7'\n"
         )
@@ -100,8 +111,11 @@ def build_scratch_package(force: bool = False) -> str:
 
 
 def import_reference():
-    """Put the scratch copy on sys.path and return the reference's ``adapted`` package."""
-    root = build_scratch_package()
+    """Put the runnable copy on sys.path and return the reference's ``adapted`` package (built first where
+    /root/reference exists; on the GPU box the prebuilt oracle/_ref/pkg is used as it is)."""
+    root = build_scratch_package() if reference_present() else PKG
+    if not package_present():
+        raise ImportError("oracle/_ref/pkg has not been built (python -m oracle.build_ref where /root/reference exists)")
     if root not in sys.path:
         sys.path.insert(0, root)
     import warnings

@@ -81,3 +81,33 @@ def test_compressed_ingest_equals_plain_ingest(chem, kw):
                                    chunk_minibatches=3)
     assert np.array_equal(st_got, st_want)
     assert got.tobytes() == want.tobytes()
+
+
+@pytest.mark.parametrize("zstd", [False, True])
+def test_container_v2_round_trip(tmp_path, zstd):
+    """ADBSIG02 (the native pipeline's input): streams come back bit-exact through the numpy decoder, with and without
+    the zstd stage (pod5's VBZ = zstd over svb16); reads longer than the preload window are cut when written"""
+    from adapted_b200.ingest import F_SVB16, F_ZSTD, _zstd, read_container_v2, write_container_v2
+
+    b = make_reads(12, "rna004", 30000, seed=5, short_frac=0.3)
+    ids = [f"read-{i:04d}" for i in range(b.n)]
+    p = write_container_v2(str(tmp_path / "c"), b.adc, b.offsets, b.full_lens, b.calib_offset, b.calib_scale, ids, zstd=zstd,
+                           preload_size=17500)
+    c = read_container_v2(p)
+    assert c["flags"] == (F_SVB16 | (F_ZSTD if zstd else 0))
+    assert [x.decode() for x in c["read_ids"]] == ids and np.array_equal(c["full_lens"], b.full_lens)
+    comp, coff = np.asarray(c["comp"]), np.asarray(c["comp_offsets"])
+    if zstd:
+        z = _zstd()
+        streams, off = [], [0]
+        for i in range(b.n):
+            src = np.ascontiguousarray(comp[coff[i]: coff[i + 1]])
+            dst = np.zeros(80000, np.uint8)
+            got = z.ZSTD_decompress(dst.ctypes.data, dst.size, src.ctypes.data, src.size)
+            assert not z.ZSTD_isError(got)
+            streams.append(dst[: (got + 15) // 16 * 16])
+            off.append(off[-1] + streams[-1].size)
+        comp, coff = np.concatenate(streams + [np.zeros(16, np.uint8)]), np.asarray(off, np.int64)
+    dec, doff = svb16.decode_reads(comp, coff, np.asarray(c["n_samples"]))
+    want = np.concatenate([b.adc[b.offsets[i]: b.offsets[i] + min(17500, b.offsets[i + 1] - b.offsets[i])] for i in range(b.n)])
+    assert np.array_equal(dec, want)
