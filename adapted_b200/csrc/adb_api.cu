@@ -73,7 +73,7 @@ extern "C" void adb_ctx_destroy(adb_ctx *c) {
     DevBuf *all[] = {&c->states, &c->hist, &c->series, &c->given, &c->status, &c->cnn_x, &c->cnn_act0,
                      &c->cnn_act1, &c->cnn_scores, &c->cnn_w, &c->cnn_aux, &c->cnn_post, &c->sp_rows, &c->h_signal, &c->h_offsets,
                      &c->h_lens, &c->h_coff, &c->h_cscale, &c->h_records, &c->h_misc, &c->h_misc2, &c->h_misc3,
-                     &c->gsb_plan, &c->gsb_hist, &c->gsb_tab, &c->gsb_bases, &c->gsb_active, &c->vf_done, &c->mvs_perm, &c->cnn_wtc, &c->cnn_a0t};
+                     &c->gsb_plan, &c->gsb_hist, &c->gsb_tab, &c->gsb_bases, &c->gsb_active, &c->vf_done, &c->mvs_perm, &c->cnn_wtc, &c->cnn_a0t, &c->llr_cc};
     for (DevBuf *b : all) b->release();
     for (int k = 0; k < 2; k++) {
         DevBuf *pb[] = {&c->p_signal[k], &c->p_offsets[k], &c->p_lens[k], &c->p_coff[k], &c->p_cscale[k], &c->p_records[k], &c->p_status[k],
@@ -300,13 +300,16 @@ static int launch_llr_primary(adb_ctx *ctx, const BatchDev &B, const adb_config 
     A.given = given;
     A.ntopk = ntopk;
     A.batch_status = batch_status;
-    size_t smem = trace_smem_bytes(A.nds_max, A.peak_cap);
+    size_t smem = trace_smem_bytes(A.nds_max, A.peak_cap, true);
     if ((int)smem > ctx->max_smem_optin) { set_err("downscaled trace does not fit in shared memory"); return ADB_ERR_UNSUPPORTED; }
     CUDA_TRY(cudaFuncSetAttribute(llr_primary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, llr_primary_kernel, ADB_TRACE_THREADS, smem));
     if (occ < 1) occ = 1;
     int grid = std::max(1, std::min(B.n_reads, ctx->sm_count * occ));
+    // the prefix sums of the read a CTA works on: 2 x nds_max doubles per CTA in global memory
+    if (ctx->llr_cc.ensure(sizeof(double) * 2 * (size_t)A.nds_max * (size_t)grid)) { set_err("cudaMalloc llr prefix sums"); return ADB_ERR_CUDA; }
+    A.cc = (double *)ctx->llr_cc.p;
     {
         KernelTimer t(ctx, 3, st);
         llr_primary_kernel<<<grid, ADB_TRACE_THREADS, smem, st>>>(A, cfg);
@@ -1046,3 +1049,4 @@ extern "C" int adb_open_pores_host(adb_ctx *ctx, const adb_batch *batch, const i
 
 #include "adb_ingest.cuh"
 #include "adb_files.cuh"
+

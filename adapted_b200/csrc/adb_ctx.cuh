@@ -74,6 +74,7 @@ struct adb_ctx {
     DevBuf states, hist, series, given, status;
     DevBuf gsb_plan, gsb_hist, gsb_tab, gsb_bases, gsb_active;  // sampled one-pass global select
     DevBuf mvs_perm;           // length-sorted read order of mvs_series_kernel
+    DevBuf llr_cc;             // prefix sums of llr_primary_kernel (per resident CTA)
     DevBuf vf_done;            // per-read flags of validate_fast_kernel
     int opt_no_fast_validate = 0;
     int cnn_a0t_l1 = -1;       // L1 the tile-layout activation buffer was last zeroed for

@@ -22,7 +22,8 @@
 #include "adb_validate.cuh"
 #include "adb_vfast.cuh"
 
-#define ADB_TRACE_THREADS 128   // one warp per read: every phase of the LLR primary path is at most warp-wide
+#define ADB_TRACE_THREADS 64    // two warps per read and up to 16 reads in flight per SM: the serial pieces of one read
+                                // (prefix chains, peak walks on warp 0) run under the parallel pieces of the others
 #define ADB_VAL_THREADS 256
 
 // float32 mean of one downscale block in numpy's pairwise order.  f(k) = k-th sample of the block.
@@ -47,16 +48,18 @@ struct TraceScratch {
     double *dtmp;
 };
 
-__host__ __device__ inline size_t trace_smem_bytes(int nds_max, int peak_cap) {
-    return (size_t)nds_max * 24 + (((size_t)peak_cap * 6 + 15) & ~(size_t)15) + 128;
+// c_ext == true: the two prefix-sum arrays live in global memory (llr_primary_kernel: a third of the shared-memory
+// footprint per read, so that twice as many reads are in flight per SM)
+__host__ __device__ inline size_t trace_smem_bytes(int nds_max, int peak_cap, bool c_ext = false) {
+    return (size_t)nds_max * (c_ext ? 8 : 24) + (((size_t)peak_cap * 6 + 15) & ~(size_t)15) + 128;
 }
 
-__device__ __forceinline__ TraceScratch trace_scratch_from(unsigned char *base, int nds_max, int peak_cap) {
+__device__ __forceinline__ TraceScratch trace_scratch_from(unsigned char *base, int nds_max, int peak_cap, double *c_ext = nullptr) {
     TraceScratch T;
     T.trace = (double *)base;
-    T.c = T.trace + nds_max;
+    T.c = c_ext ? c_ext : T.trace + nds_max;
     T.c2 = T.c + nds_max;
-    unsigned char *after = (unsigned char *)(T.c2 + nds_max);
+    unsigned char *after = c_ext ? (unsigned char *)(T.trace + nds_max) : (unsigned char *)(T.c2 + nds_max);
     T.PS.cap = peak_cap;
     T.PS.pk = (unsigned short *)after;
     T.PS.stack = T.PS.pk + peak_cap;
@@ -133,12 +136,18 @@ struct PrimaryArgs {
     int *given;        // out: [n_reads][2]
     int *ntopk;        // out: [n_reads] (-1: None, 1: one candidate)
     int *batch_status;
+    double *cc;        // [gridDim.x][2][nds_max] prefix sums of the read a CTA works on (global memory, L1 / L2 resident)
 };
 
-__global__ void __launch_bounds__(ADB_TRACE_THREADS, 7) llr_primary_kernel(PrimaryArgs A, adb_config cfg) {
+__global__ void __launch_bounds__(ADB_TRACE_THREADS, 16) llr_primary_kernel(PrimaryArgs A, adb_config cfg) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const TraceScratch T = trace_scratch_from(smem, A.nds_max, A.peak_cap);
+    const TraceScratch T = trace_scratch_from(smem, A.nds_max, A.peak_cap, A.cc + (size_t)blockIdx.x * 2 * A.nds_max);
     float *ds = (float *)T.trace;
+    // While the downscaled row (float32) occupies the first half of the trace buffer, its second half holds a per-read
+    // table of the normalised values: for int16 reads the clipped, normalised sample is a function of the ADC code
+    // alone and the clip interval spans a few hundred codes, so the IEEE division runs once per code of that interval
+    // instead of once per raw sample (same operations on the same operands: bit-identical).
+    float *lut = ds + A.nds_max;
     // the reference slices batch[:, :max_obs_trace] (combined.py:128-136): a matrix narrower than that keeps its own width
     const int Tm = min(cfg.max_obs_trace, A.B.m), A0 = cfg.min_obs_adapter, f = cfg.downscale_factor;
     for (int r = blockIdx.x; r < A.B.n_reads; r += gridDim.x) {
@@ -176,19 +185,54 @@ __global__ void __launch_bounds__(ADB_TRACE_THREADS, 7) llr_primary_kernel(Prima
         const float hi = (float)((double)med + (double)mad * cfg.sig_norm_outlier_thresh);
         // all blocks but a zero-padded ragged last one are complete
         const int nfull = (Tm - A0) / f;
-        for (int b = threadIdx.x; b < nds; b += blockDim.x) {
-            const int j0 = A0 + b * f;
-            float v;
-            if (b < nfull && f == 20) v = block_mean_f32_fixed<20>([&](int k) { return norm_sample(src, j0 + k, lo, hi, med, mad); });
-            else if (b < nfull && f == 10) v = block_mean_f32_fixed<10>([&](int k) { return norm_sample(src, j0 + k, lo, hi, med, mad); });
-            else
-                v = block_mean_f32(
-                    [&](int k) {
-                        const int j = j0 + k;
-                        return (j >= Tm) ? 0.0f : norm_sample(src, j, lo, hi, med, mad);  // np.pad zero padding
-                    },
-                    f);
-            ds[b] = v;
+        // table of the normalised values over the codes of the clip interval (+ 2 codes on either side): everything
+        // below its first code clips to `lo`, everything above its last code to `hi` -- verified, else computed directly
+        int c_base = 0, c_top = -1;
+        if (src.i16 && src.cscale > 0.0f) {
+            const float fb = floorf(lo / src.cscale - src.coff) - 2.0f, ft = ceilf(hi / src.cscale - src.coff) + 2.0f;
+            if (fb >= -40000.0f && ft <= 40000.0f && ft >= fb) {
+                c_base = max((int)fb, -32768);
+                c_top = min((int)ft, 32767);
+                const bool ok = (c_top - c_base + 1 <= A.nds_max) && c_top >= c_base &&
+                                (c_base == -32768 || __fmul_rn(__fadd_rn((float)c_base, src.coff), src.cscale) <= lo) &&
+                                (c_top == 32767 || __fmul_rn(__fadd_rn((float)c_top, src.coff), src.cscale) >= hi);
+                if (!ok) c_top = c_base - 1;
+            }
+        }
+        const bool use_lut = c_top >= c_base;  // uniform: derived from per-read constants only
+        if (use_lut) {
+            for (int e = threadIdx.x; e <= c_top - c_base; e += blockDim.x) {
+                float v = __fmul_rn(__fadd_rn((float)(c_base + e), src.coff), src.cscale);
+                v = (v < lo) ? lo : ((v > hi) ? hi : v);
+                lut[e] = __fdiv_rn(__fsub_rn(v, med), mad);
+            }
+            __syncthreads();
+            const int top_e = c_top - c_base;
+            const int16_t *codes = src.i16;
+            auto look = [&](int j) { return lut[min(max((int)codes[j] - c_base, 0), top_e)]; };
+            for (int b = threadIdx.x; b < nds; b += blockDim.x) {
+                const int j0 = A0 + b * f;
+                float v;
+                if (b < nfull && f == 20) v = block_mean_f32_fixed<20>([&](int k) { return look(j0 + k); });
+                else if (b < nfull && f == 10) v = block_mean_f32_fixed<10>([&](int k) { return look(j0 + k); });
+                else v = block_mean_f32([&](int k) { const int j = j0 + k; return (j >= Tm) ? 0.0f : look(j); }, f);
+                ds[b] = v;
+            }
+        } else {
+            for (int b = threadIdx.x; b < nds; b += blockDim.x) {
+                const int j0 = A0 + b * f;
+                float v;
+                if (b < nfull && f == 20) v = block_mean_f32_fixed<20>([&](int k) { return norm_sample(src, j0 + k, lo, hi, med, mad); });
+                else if (b < nfull && f == 10) v = block_mean_f32_fixed<10>([&](int k) { return norm_sample(src, j0 + k, lo, hi, med, mad); });
+                else
+                    v = block_mean_f32(
+                        [&](int k) {
+                            const int j = j0 + k;
+                            return (j >= Tm) ? 0.0f : norm_sample(src, j, lo, hi, med, mad);  // np.pad zero padding
+                        },
+                        f);
+                ds[b] = v;
+            }
         }
         __syncthreads();
         int ae_ds, pe_ds;
