@@ -160,6 +160,8 @@ def load() -> C.CDLL:
     L.adb_format_csv_ex.restype = C.c_int64
     L.adb_open_pores_host.argtypes = [vp, C.POINTER(AdbBatch), vp, C.c_int32, vp, vp, vp, vp, C.c_int64]
     L.adb_open_pores_host.restype = ip
+    L.adb_find_peaks_host.argtypes = [vp, vp, vp, C.c_int32, vp, vp]
+    L.adb_find_peaks_host.restype = ip
     L.adb_svb16_decode_host.argtypes = [vp, C.POINTER(AdbSvbBatch), vp]
     L.adb_svb16_decode_host.restype = ip
     L.adb_detect_pipelined_svb_host.argtypes = [vp, C.POINTER(AdbSvbBatch), C.POINTER(AdbConfig), vp, vp, vp, C.c_int32]

@@ -896,6 +896,79 @@ extern "C" int adb_llr_trace_host(adb_ctx *ctx, const double *signals, const int
     return ADB_OK;
 }
 
+// ---- peak picking (kernel-level test entry) -----------------------------------------------------------------------------
+#define ADB_PEAKS_MAX_N 4096
+__global__ void __launch_bounds__(ADB_TRACE_THREADS) peaks_test_kernel(const double *traces, const int64_t *offs, const double *params,
+                                                                    int nds_max, int peak_cap, int *out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const TraceScratch T = trace_scratch_from(smem, nds_max, peak_cap);
+    const int t = blockIdx.x;
+    const int n = (int)(offs[t + 1] - offs[t]);
+    const double *p = params + (size_t)t * 8;
+    const int mode = (int)p[0], dist = (int)p[1], want = min(max((int)p[5], 0), 32), n2n = (int)p[6];
+    const double pmin = p[2], wmin = p[3], rel_height = p[4];
+    int *res = out + (size_t)t * 33;
+    double *g = T.trace;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) g[i] = traces[offs[t] + i];
+    __syncthreads();
+    if (mode == 0) {
+        TraceView W;
+        W.x = g; W.n = n; W.nan2num = n2n;
+        const int npk = cta_peaks_prepare(W, pmin, wmin, rel_height, T.PS, T.itmp);
+        if (threadIdx.x < 32) {
+            int pk[32];
+            const int k = warp_peaks_select(W, npk, dist, pmin, wmin, rel_height, want, pk, T.PS);
+            if (threadIdx.x == 0) {
+                res[0] = k;
+                for (int i = 0; i < k; i++) res[1 + i] = pk[i];
+            }
+        }
+    } else if (mode == 1) {
+        int s0, e0;
+        cta_trace_support(g, n, s0, e0, T.itmp);
+        if (threadIdx.x < 32) { const double sd = warp_nanstd(g, s0, e0); if (threadIdx.x == 0) T.dtmp[0] = sd; }
+        __syncthreads();
+        const int ae = cta_adapter_end(g, n, s0, e0, __dmul_rn(pmin, T.dtmp[0]), wmin, rel_height, T.PS, T.itmp + 4);
+        if (threadIdx.x == 0) { res[0] = 1; res[1] = ae; }
+    } else {
+        const int pe = cta_polya_end(g, n, T.PS, T.itmp + 4);
+        if (threadIdx.x == 0) { res[0] = 1; res[1] = pe; }
+    }
+}
+
+extern "C" int adb_find_peaks_host(adb_ctx *ctx, const double *traces, const int64_t *offsets, int32_t n_traces,
+                                   const double *params, int32_t *out) {
+    if (!ctx || !traces || !offsets || !params || !out || n_traces < 0) { set_err("null argument"); return ADB_ERR_ARG; }
+    if (n_traces == 0) return ADB_OK;
+    int n_max = 0;
+    for (int t = 0; t < n_traces; t++) {
+        const int64_t n = offsets[t + 1] - offsets[t];
+        if (n < 0 || n > ADB_PEAKS_MAX_N) { set_err("trace length outside [0, 4096]"); return ADB_ERR_ARG; }
+        n_max = std::max(n_max, (int)n);
+    }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t total = (size_t)offsets[n_traces];
+    DevBuf &dx = ctx->h_signal, &doff = ctx->h_offsets, &dp = ctx->h_misc, &dout = ctx->h_records;
+    if (dx.ensure(total * 8 + 8) || doff.ensure(sizeof(int64_t) * ((size_t)n_traces + 1)) || dp.ensure(sizeof(double) * 8 * (size_t)n_traces) ||
+        dout.ensure(sizeof(int) * 33 * (size_t)n_traces)) { set_err("cudaMalloc peak test buffers"); return ADB_ERR_CUDA; }
+    CUDA_TRY(cudaMemcpyAsync(dx.p, traces, total * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(doff.p, offsets, sizeof(int64_t) * ((size_t)n_traces + 1), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dp.p, params, sizeof(double) * 8 * (size_t)n_traces, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(dout.p, 0, sizeof(int) * 33 * (size_t)n_traces, st));
+    const int nds_max = std::max(64, n_max + 2), peak_cap = nds_max / 2 + 24;
+    const size_t smem = trace_smem_bytes(nds_max, peak_cap);
+    if ((int)smem > ctx->max_smem_optin) { set_err("trace does not fit in shared memory"); return ADB_ERR_UNSUPPORTED; }
+    CUDA_TRY(cudaFuncSetAttribute(peaks_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    peaks_test_kernel<<<n_traces, ADB_TRACE_THREADS, smem, st>>>((const double *)dx.p, (const int64_t *)doff.p, (const double *)dp.p,
+                                                                 nds_max, peak_cap, (int *)dout.p);
+    ctx->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, dout.p, sizeof(int) * 33 * (size_t)n_traces, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return ADB_OK;
+}
+
 // ---- legacy three-split detectors -----------------------------------------------------------------------------------
 extern "C" int adb_llr_detect_host(adb_ctx *ctx, const double *signals, const int64_t *sig_offsets, int32_t n_signals,
                                    const int64_t *params, int64_t *out) {

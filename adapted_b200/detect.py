@@ -425,6 +425,29 @@ def _legacy_traces(raw_signal, moa, bt, mop, device):
     return g_first, g_head, g_tail, g_polya
 
 
+def find_peaks_device(traces, mode: int = 0, distance: int = 0, prominence: float = 0.0, width: float = 0.0,
+                      rel_height: float = 0.5, want: int = 32, nan_to_num: bool = False, device: int = 0):
+    """Peak picking of the GPU kernels on given float64 traces (adb_find_peaks_host; kernel-level test entry).
+    mode 0: the first ``want`` peaks of scipy.signal.find_peaks(trace, distance, prominence, width, rel_height);
+    mode 1: adapter_end_from_trace (llr.py:204-259) -> index or -1; mode 2: detect_full_polya_trace_peak_with_spike
+    (llr.py:406-479) -> index or 0.  Returns one int64 array (mode 0) or int (modes 1, 2) per trace."""
+    tr = [np.ascontiguousarray(t, dtype=np.float64) for t in traces]
+    n = len(tr)
+    offs = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum([t.size for t in tr], out=offs[1:])
+    blob = np.concatenate(tr) if tr else np.zeros(0)
+    if blob.size == 0:
+        blob = np.zeros(1)
+    par = np.zeros((n, 8), dtype=np.float64)
+    par[:] = [mode, distance, prominence, width, rel_height, want, float(bool(nan_to_num)), 0]
+    out = np.zeros((n, 33), dtype=np.int32)
+    ctx = _lib.default_context(device)
+    _lib.check(_lib.load().adb_find_peaks_host(ctx.handle, blob.ctypes.data, offs.ctypes.data, n, par.ctypes.data, out.ctypes.data))
+    if mode == 0:
+        return [out[i, 1: 1 + out[i, 0]].astype(np.int64) for i in range(n)]
+    return [int(out[i, 1]) for i in range(n)]
+
+
 def cnn_scores(x: np.ndarray, model: Any, device: int = 0) -> np.ndarray:
     """BoundariesCNN forward (adapted/detect/cnn.py:16-52,85-98) on prepared inputs x[n, L] -> scores[n, 2, L_out]."""
     x = np.ascontiguousarray(x, dtype=np.float32)

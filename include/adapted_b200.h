@@ -230,6 +230,20 @@ int adb_llr_trace_host(adb_ctx *ctx, const double *signals, const int64_t *sig_o
 int adb_llr_detect_host(adb_ctx *ctx, const double *signals, const int64_t *sig_offsets, int32_t n_signals,
                         const int64_t *params, int64_t *out);
 
+/*
+ * Peak picking on given traces (kernel-level test entry for the scipy.signal.find_peaks subset and the corrections
+ * built on it; HOST buffers, trace i = traces[offsets[i] .. offsets[i+1]), float64, at most 4096 points each).
+ * params[i*8 .. i*8+8) (float64) = mode, distance, prominence, width, rel_height, want, nan_to_num, unused:
+ *   mode 0  find_peaks(trace, distance, prominence, width, rel_height): the first `want` (<= 32) peaks in ascending
+ *           order (scipy/signal/_peak_finding.py:729-1010 as used at llr.py:189,218,444; nan_to_num as llr.py:445)
+ *   mode 1  adapter_end_from_trace (llr.py:204-259): LLRTrace support, find_peaks(width, prominence * nanstd,
+ *           rel_height), correct_for_plateau, correct_for_split_peak -> cands[0] or -1 (no candidate)
+ *   mode 2  detect_full_polya_trace_peak_with_spike (llr.py:406-479) -> index or 0
+ * out[i*33] = number of values, out[i*33 + 1 ..] the values.
+ */
+int adb_find_peaks_host(adb_ctx *ctx, const double *traces, const int64_t *offsets, int32_t n_traces, const double *params,
+                        int32_t *out);
+
 /* Minibatch-global median / MAD of normalize_signal (adapted/detect/normalize.py:15-22,54), HOST buffers. */
 int adb_global_med_mad_host(adb_ctx *ctx, const adb_batch *batch, int32_t max_obs_trace, float *med_mad /*[n_batches*2]*/);
 
