@@ -96,6 +96,7 @@ extern "C" int adb_ctx_set_option(adb_ctx *c, const char *name, int value) {
     if (!strcmp(name, "no_fast_validate")) { c->opt_no_fast_validate = value; return ADB_OK; }
     if (!strcmp(name, "cnn_fp32_pipe")) { c->opt_cnn_fp32 = value; return ADB_OK; }
     if (!strcmp(name, "pipeline_copy_only")) { c->opt_copy_only = value; return ADB_OK; }
+    if (!strcmp(name, "no_cand_followup")) { c->opt_no_cand_followup = value; return ADB_OK; }
     set_err(std::string("unknown option: ") + name);
     return ADB_ERR_ARG;
 }
@@ -428,7 +429,10 @@ static int launch_validate(adb_ctx *ctx, const BatchDev &B, const adb_config &cf
             F.pre_var = A.pre_var; F.pre_mean = A.pre_mean; F.pre_off = A.pre_off; F.pre_meta = A.pre_meta;
             F.done = (unsigned char *)ctx->vf_done.p;
             F.n_long = (int *)((unsigned char *)ctx->vf_done.p + (((size_t)B.n_reads + 3) & ~(size_t)3));
-            F.long_min = (mode == ADB_METHOD_CNN && given_ntopk > 1) ? std::max(1, B.n_reads / 5) : 1;
+            F.cand_followup = (pre && mode == ADB_METHOD_CNN && (ntopk_per_read || given_ntopk > 1) && !ctx->opt_no_cand_followup) ? 1 : 0;
+            // without the candidate follow-up a long first candidate (mostly a wrong one) fails and goes to validate_kernel
+            // anyway: the LONG instance then only pays when many reads wait for it
+            F.long_min = (mode == ADB_METHOD_CNN && given_ntopk > 1 && !F.cand_followup) ? std::max(1, B.n_reads / 5) : 1;
             CUDA_TRY(cudaFuncSetAttribute(validate_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
             CUDA_TRY(cudaFuncSetAttribute(validate_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
             int focc = 0;
@@ -469,6 +473,14 @@ static int launch_validate(adb_ctx *ctx, const BatchDev &B, const adb_config &cf
                 mvs_pending_kernel<<<(B.n_reads + 255) / 256, 256, 0, st>>>(F.done, B.n_reads, list, cnt);
                 mvs_series_kernel<<<(B.n_reads + MVS_LANES - 1) / MVS_LANES, MVS_LANES, mvs_smem_bytes(), st>>>(M, cfg);
                 ctx->launches += 2;
+                if (F.cand_followup) {
+                    // the further candidates of the reads whose first one failed, from the rows of the pass above
+                    VfastArgs F2 = F;
+                    F2.pre_var = M.var_pool; F2.pre_mean = M.mean_pool; F2.pre_off = M.row_off; F2.pre_meta = M.meta;
+                    CUDA_TRY(cudaFuncSetAttribute(validate_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+                    validate_cand_kernel<<<fgrid, VF_THREADS, fsm, st>>>(F2, cfg, list, cnt);
+                    ctx->launches += 1;
+                }
             }
         }
     }
@@ -691,6 +703,7 @@ extern "C" int adb_detect_pipelined_host(adb_ctx *ctx, const adb_batch *batch, c
         ctx->twin->opt_no_fast_validate = ctx->opt_no_fast_validate;
         ctx->twin->opt_cnn_fp32 = ctx->opt_cnn_fp32;
         ctx->twin->opt_exact_gsel = ctx->opt_exact_gsel;
+        ctx->twin->opt_no_cand_followup = ctx->opt_no_cand_followup;
     }
     adb_ctx *cc[2] = {ctx, ctx->twin ? ctx->twin : ctx};
     const float *w_devs[2] = {w_dev, w_dev};

@@ -214,6 +214,7 @@ extern "C" int adb_detect_files(adb_ctx *ctx, const adb_file_job *job, const adb
     ctx->twin->opt_no_fast_validate = ctx->opt_no_fast_validate;
     ctx->twin->opt_cnn_fp32 = ctx->opt_cnn_fp32;
     ctx->twin->opt_exact_gsel = ctx->opt_exact_gsel;
+        ctx->twin->opt_no_cand_followup = ctx->opt_no_cand_followup;
     adb_ctx *cc[2] = {ctx, ctx->twin};
     const float *w_devs[2] = {nullptr, nullptr};
     if (cfg->primary_method == ADB_METHOD_CNN)

@@ -549,7 +549,7 @@ struct MvsSeriesArgs {
 // reads still to be validated after validate_fast_kernel -> compact list (order irrelevant: rows are independent)
 __global__ void mvs_pending_kernel(const unsigned char *done, int n_reads, int *list, int *count) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool p = r < n_reads && !done[r];
+    const bool p = r < n_reads && done[r] != 1;  // (2 = first candidate settled by the fast kernel, the others pending)
     const unsigned m = __ballot_sync(ADB_FULL, p);
     if (!m) return;
     const int lane = threadIdx.x & 31;

@@ -717,7 +717,9 @@ struct VfastArgs {
     const float *pre_var, *pre_mean;  // compact pools of precomputed moving statistics (mvs_series_kernel)
     const long long *pre_off;
     const int *pre_meta;
-    unsigned char *done;        // [n_reads], zeroed before the launch; 1 = record written by this kernel
+    unsigned char *done;        // [n_reads], zeroed before the launch; 1 = record written by this kernel,
+                                // 2 = record written with the FIRST poly(A) candidate's outcome, further candidates pending
+    int cand_followup;          // 1: validate_cand_kernel runs behind this kernel (CNN path with several candidates)
 };
 
 __host__ __device__ inline size_t vfast_smem_bytes(int win_bytes) {
@@ -1015,7 +1017,7 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_fast_kernel(VfastArgs 
                 }
             }
         }
-        bool exception = false, defer = false, need_mvs = false;
+        bool exception = false, defer = false, need_mvs = false, followup = false;
         double mlo = cfg.pA_mean_range[0], mhi = cfg.pA_mean_range[1];
         if (success && cfg.mvs_detect_check) {
             if (pe_best == 0) {
@@ -1077,7 +1079,12 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_fast_kernel(VfastArgs 
             } else {
                 success = false; fail = ADB_FAIL_MVS_NOT_ENOUGH; fail_mask = 0;
             }
-            if (!ok && topk1 != 0) defer = true;  // the reference goes on to the next candidate
+            if (!ok && topk1 != 0) {
+                // the reference goes on to the next candidates (combined.py:464-515): their moving statistics are
+                // prefixes of one more series pass, so validate_cand_kernel finishes the read from this record
+                const bool fits = A.cand_followup != 0;  // (series beyond the window memory are bisected from the pools there)
+                if (fits) followup = true; else defer = true;
+            }
         }
         if (!exception && success && cfg.detect_med_shift) {
             const float sh = __fsub_rn(medMA, medMB);
@@ -1138,7 +1145,156 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_fast_kernel(VfastArgs 
             for (int i = 0; i < 5; i++) rec->mvs[i] = mvs_v[i];
             for (int i = 0; i < 3; i++) rec->real[i] = real_v[i];
             rec->med_shift = med_shift;
-            A.done[r] = 1;
+            if (followup) *reinterpret_cast<float *>(rec->_reserved) = medA0;  // scales the mean range of the later candidates
+            __threadfence();
+            A.done[r] = followup ? 2 : 1;
+        }
+    }
+}
+
+// ---- further poly(A) candidates of the reads whose first one failed (CNN path, combined.py:464-515) ---------------------
+// `success` is never reset once a candidate has failed, so the loop of the reference runs to its last non-zero
+// candidate whatever happens: the mvs_detect_* values of the record are those of the LAST candidate, the fail reason
+// that of the last candidate that failed (scanning backwards from the end until one fails).  Everything else of the
+// record -- incl. polya_end = the first candidate and the partition statistics -- stands as validate_fast_kernel wrote
+// it.  One evaluation = mean_var_shift_polyA_check (mvs.py:45-158) of one candidate: poly(A) median, p85 - p15, the two
+// medians around adapter_end, and the medians of the moving statistics, which are prefixes of the rows the second
+// mvs_series_kernel pass computed up to the largest candidate.  A read this kernel cannot settle (series not
+// precomputed) goes back to validate_kernel (done = 0).
+__global__ void __launch_bounds__(VF_THREADS, 4) validate_cand_kernel(VfastArgs A, adb_config cfg, const int *pending,
+                                                                      const int *n_pending) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char *winbuf = smem;
+    const size_t win_cap = (((size_t)A.win_bytes + 48 + 15) & ~(size_t)15);
+    __shared__ VfScratch S;
+    __shared__ uint64_t bar_storage;
+    uint64_t *bar = &bar_storage;
+    const int tid = threadIdx.x;
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    uint32_t phase = 0;
+    const int n_list = *n_pending;
+    const int msw = cfg.median_shift_window;
+    for (int li = blockIdx.x; li < n_list; li += gridDim.x) {
+        const int r = pending[li];
+        if (A.done[r] != 2) continue;
+        adb_record *rec = A.out + r;
+        const ReadSrc gsrc = make_src(A.B, r);
+        const int size = gsrc.n;
+        const int *g = A.given + (size_t)r * A.given_stride;
+        const int a_end = g[0];
+        const int n_topk = A.ntopk_per_read ? A.ntopk_per_read[r] : A.given_ntopk;
+        int n_eval = 0;
+        while (n_eval < n_topk && g[1 + n_eval] != 0) n_eval++;
+        const long long po = A.pre_off ? A.pre_off[r] : -1;
+        const bool have_rows = po >= 0 && A.pre_meta[2 * r] == a_end;
+        const int row_pe = have_rows ? A.pre_meta[2 * r + 1] : 0;
+        const float medA0 = *reinterpret_cast<const float *>(rec->_reserved);
+        double mlo = cfg.pA_mean_range[0], mhi = cfg.pA_mean_range[1];
+        if (cfg.pA_mean_range_empty && !cfg.pA_mean_scale_range_empty) {
+            mlo = __dmul_rn(cfg.pA_mean_scale_range[0], (double)medA0);
+            mhi = __dmul_rn(cfg.pA_mean_scale_range[1], (double)medA0);
+        }
+        double last_v[5] = {0, 0, 0, 0, 0};
+        int fail = rec->fail_code, fail_mask = rec->mvs_fail_mask;  // the first candidate's, unless a later one failed
+        bool bail = false, fail_known = false;
+        for (int t = n_eval - 1; t >= 1 && !fail_known && !bail; t--) {
+            const int pe = g[1 + t];
+            double v[5] = {0, 0, 0, 0, 0};
+            bool ok = false;
+            const bool geom = !(pe == 0 || a_end == 0 || pe < a_end || pe - a_end <= 2) && !(size < a_end + msw);
+            if (geom) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncthreads();
+                VfRead R;
+                {
+                    unsigned char *w = cta_stage_window(winbuf, (const unsigned char *)gsrc.i16, size * 2, bar, phase);
+                    R.W16 = reinterpret_cast<const uint16_t *>(winbuf);
+                    R.s0 = (int)(w - winbuf) >> 1;
+                }
+                R.n = size; R.coff = gsrc.coff; R.cscale = gsrc.cscale;
+                vf_minmax(R, S, R.kmin, R.kmax);  // (the first pass has verified 0 <= code < VF_KEY_LIMIT)
+                int pa_ = a_end, pb_ = pe;
+                clip_seg(pa_, pb_, size);
+                const int nP = pb_ - pa_;
+                const bool win_var = !(pe - a_end <= cfg.pA_var_window + 2), win_mean = !(pe - a_end <= cfg.pA_mean_window + 2);
+                const int nv = win_var ? nP - (cfg.pA_var_window - 1) : 0, nm = win_mean ? nP - (cfg.pA_mean_window - 1) : 0;
+                if ((win_var || win_mean) && !(have_rows && row_pe >= pe)) { bail = true; break; }
+                const bool big = (size_t)(((max(nv, 0) + 3) & ~3) + max(nm, 0)) * 4 > win_cap;  // series beyond the window memory
+                const double vP85 = __dmul_rn((double)(nP - 1), 0.85), vP15 = __dmul_rn((double)(nP - 1), 0.15);
+                int nt = 0, rot = 0;
+                __syncthreads();
+                const int tP = vf_add_rank(S, R, nt, rot, a_end, pe, 0);
+                const int tP15 = (nP > 0) ? vf_add_rank(S, R, nt, rot, a_end, pe, (int)floor(vP15)) : -1;
+                const int tP85 = (nP > 0) ? vf_add_rank(S, R, nt, rot, a_end, pe, (int)floor(vP85)) : -1;
+                const int tAF = vf_add_rank(S, R, nt, rot, a_end, min(a_end + msw, size), 0);
+                const int tBF = vf_add_rank(S, R, nt, rot, max(a_end - msw, 0), a_end, 0);
+                __syncthreads();
+                if (tid < nt && tid != tP15 && tid != tP85) { VfTask &q = S.task[tid]; q.k = (q.b - q.a - 1) / 2; }
+                if (tid == 0) { S.ntask = nt; S.vtotal = rot; }
+                vf_task_bounds(R, S);
+                vf_run(R, S);
+                const float medP = vf_median_of(R, S, tP), medAF = vf_median_of(R, S, tAF), medBF = vf_median_of(R, S, tBF);
+                double lrP = CUDART_NAN;
+                if (tP15 >= 0 && tP85 >= 0) {
+                    const int l15 = (int)floor(vP15), l85 = (int)floor(vP85);
+                    int a15, b15, a85, b85;
+                    vf_rank_pair(R, S, tP15, min(l15 + 1, nP - 1) != l15, a15, b15);
+                    vf_rank_pair(R, S, tP85, min(l85 + 1, nP - 1) != l85, a85, b85);
+                    const double p85 = np_lerp_f32(vf_pa(R, a85), vf_pa(R, b85), __dsub_rn(vP85, (double)l85));
+                    const double p15 = np_lerp_f32(vf_pa(R, a15), vf_pa(R, b15), __dsub_rn(vP15, (double)l15));
+                    lrP = __dsub_rn(p85, p15);
+                }
+                __syncthreads();
+                if (!win_var || !win_mean) {  // exact numpy mean / variance of a short segment (one thread, pairwise order)
+                    if (tid == 0) {
+                        const uint16_t *p = R.W16 + R.s0 + pa_;
+                        const float co = R.coff, cs = R.cscale;
+                        const float mean = __fdiv_rn(np_sum_f32([&](int i) { return __fmul_rn(__fadd_rn((float)(int)p[i], co), cs); }, nP), (float)nP);
+                        S.ftmp[0] = mean;
+                        S.ftmp[1] = __fdiv_rn(np_sum_f32([&](int i) { const float d = __fsub_rn(__fmul_rn(__fadd_rn((float)(int)p[i], co), cs), mean); return __fmul_rn(d, d); }, nP), (float)nP);
+                    }
+                    __syncthreads();
+                }
+                const float small_mean = S.ftmp[0], small_var = S.ftmp[1];
+                __syncthreads();
+                float smed[2] = {0.f, 0.f};
+                if (big) vf_series_medians<false>(S, A.pre_var + po, max(nv, 0), A.pre_mean + po, max(nm, 0), (uint32_t *)winbuf, smed);
+                else if (nv > 0 || nm > 0) vf_series_medians<true>(S, A.pre_var + po, max(nv, 0), A.pre_mean + po, max(nm, 0), (uint32_t *)winbuf, smed);
+                v[0] = (double)(win_mean ? smed[1] : small_mean);
+                v[1] = (double)(win_var ? smed[0] : small_var);
+                v[2] = (double)medP; v[3] = lrP; v[4] = (double)__fsub_rn(medAF, medBF);
+                const double mr[2] = {mlo, mhi};
+                int mask = 0;
+                if (!in_range_d(v[0], mr)) mask |= 1;
+                if (!in_range_d(v[1], cfg.pA_var_range)) mask |= 2;
+                if (!in_range_d(v[2], cfg.polyA_med_range)) mask |= 4;
+                if (!in_range_d(v[3], cfg.polyA_local_range)) mask |= 8;
+                if (!in_range_d(v[4], cfg.median_shift_range)) mask |= 16;
+                ok = (mask == 0);
+                if (!ok) {
+                    if (v[0] == 0.0) { fail = ADB_FAIL_MVS_NOT_ENOUGH; fail_mask = 0; }
+                    else { fail = ADB_FAIL_MVS_CHECKS; fail_mask = mask; }
+                    fail_known = true;
+                }
+            } else {  // the early return of mean_var_shift_polyA_check: zeros, "not enough signal"
+                fail = ADB_FAIL_MVS_NOT_ENOUGH; fail_mask = 0;
+                fail_known = true;
+            }
+            if (t == n_eval - 1) for (int i = 0; i < 5; i++) last_v[i] = v[i];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (bail) {
+                A.done[r] = 0;  // validate_kernel redoes the read from scratch
+            } else {
+                for (int i = 0; i < 5; i++) rec->mvs[i] = last_v[i];
+                rec->fail_code = fail;
+                rec->mvs_fail_mask = fail_mask;
+                for (int i = 0; i < 8; i++) rec->_reserved[i] = 0;
+                __threadfence();
+                A.done[r] = 1;
+            }
         }
     }
 }

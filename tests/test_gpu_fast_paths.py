@@ -195,3 +195,29 @@ def test_cnn_tensor_core_and_fp32_pipe_agree():
     fp, st2 = _detect(b, spc, 100, model=w, cnn_fp32_pipe=1)
     assert not st.any() and not st2.any()
     _cnn_compare(tc, fp, spc.core.downscale_factor)
+
+
+@pytest.mark.parametrize("seed,kw", [(631, {}), (632, {"stress": True}), (633, {"short_frac": 0.2})])
+def test_cnn_candidate_follow_up_equals_general_kernel(seed, kw):
+    """reads whose first poly(A) candidate fails: validate_cand_kernel (further candidates from the fast path) writes
+    the same records, byte for byte, as the general validate kernel taking them over (option no_cand_followup), and
+    both take noticeably many such reads"""
+    from adapted_b200 import _lib
+    from adapted_b200.detect import detect_reads
+
+    spc = get_chemistry_specific_config("rna004")
+    w = load_cnn_weights()
+    b = make_reads(3000, "rna004", spc.sig_preload_size, seed=seed, **kw)
+    ctx = _lib.default_context(0)
+    out = {}
+    for opt in (0, 1):
+        ctx.set_option("no_cand_followup", opt)
+        try:
+            recs, st = detect_reads(b.adc, b.offsets, b.full_lens, b.calib_offset, b.calib_scale, spc, model=w, minibatch_size=1000,
+                                    return_records=True)
+            out[opt] = (recs.copy(), ctx.query("validate_handovers"))
+        finally:
+            ctx.set_option("no_cand_followup", 0)
+        assert not st.any()
+    assert out[0][0].tobytes() == out[1][0].tobytes()
+    assert out[0][1] < out[1][1], (out[0][1], out[1][1])  # reads left the general kernel
