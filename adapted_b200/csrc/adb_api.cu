@@ -360,6 +360,7 @@ static int launch_validate(adb_ctx *ctx, const BatchDev &B, const adb_config &cf
             pool_cap = std::max<long long>(std::min<long long>(pool_cap, budget), std::max<long long>(1 << 20, (long long)B.n_reads * B.m / 4));
         }
     }
+    pool_cap &= ~3LL;  // the second pool starts pool_cap floats behind the first: rows stay 16-byte aligned in both
     if (pre && (ctx->cnn_aux.ensure((size_t)pool_cap * sizeof(float) * 2) ||
                 ctx->h_misc3.ensure(sizeof(int) * 2 * (size_t)B.n_reads + sizeof(long long) * ((size_t)B.n_reads + 2)))) {
         set_err("cudaMalloc moving-statistics scratch");

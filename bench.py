@@ -248,6 +248,7 @@ class Runner:
         self.local_rank, self.rank, self.world = local_rank, rank, world
         self.dev = torch.device("cuda", local_rank)
         self.ctx = _lib.Context(local_rank)
+        _lib._default_ctx[local_rank] = self.ctx  # the file-level block runs on the same context (one scratch arena per GPU)
         self.barrier, self.all_reduce = barrier, all_reduce
         self.tstream = torch.cuda.Stream(device=self.dev)
         torch.cuda.set_stream(self.tstream)
@@ -272,6 +273,7 @@ class Runner:
             gen_kw = dict(stress=True, short_frac=0.1, short_min=50 if flat["primary_method"] == 1 else flat["min_obs_adapter"] + 200)
         data = make_reads_torch(n, chem, m, seed=1234 + self.rank, device=dev, **gen_kw)
         torch.cuda.synchronize()
+        torch.cuda.empty_cache()  # the generator's temporaries: the library allocates with cudaMalloc, not from torch's cache
         samples = int(data["offsets"][-1].item())
         trace_samples = int(torch.clamp(data["offsets"][1:] - data["offsets"][:-1], max=flat["max_obs_trace"]).sum().item())
         cfg = _lib.fill_config(flat)
@@ -329,6 +331,7 @@ class Runner:
         if e2e and not args.profile_steps_only:
             comp, coff, ns = svb16.encode_reads_torch(data["adc"], data["offsets"], m)
             torch.cuda.synchronize()
+            torch.cuda.empty_cache()
             host = {}
             for k, t in (("comp", comp), ("coff", coff), ("ns", ns), ("full_lens", data["full_lens"]),
                          ("calib_offset", data["calib_offset"]), ("calib_scale", data["calib_scale"])):
@@ -337,6 +340,7 @@ class Runner:
                 host[k] = h
             comp_bytes = int(coff[-1].item()) + 16
             del comp
+            torch.cuda.empty_cache()
             rec_host = torch.zeros(n * 512, dtype=torch.uint8).pin_memory()
             st_host = torch.zeros(n_batches, dtype=torch.int32).pin_memory()
             sb = _lib.AdbSvbBatch(comp=host["comp"].data_ptr(), comp_offsets=host["coff"].data_ptr(), n_samples=host["ns"].data_ptr(),
@@ -388,15 +392,15 @@ class Runner:
                                               encoded=(host["comp"][: cend + 16].numpy(), host["coff"][: nf + 1].numpy(), host["ns"][:nf].numpy()))
                     size = os.path.getsize(path)
                     detect_files_native([path], os.path.join(tmp, "warm"), spc, model=_cnn_weights() if w_host is not None else None,
-                                        minibatch_size=mbs, chunk_minibatches=chunk)  # warm-up: page cache, pinned ring, contexts
+                                        minibatch_size=mbs, chunk_minibatches=chunk, device=self.local_rank)  # warm-up: page cache, pinned ring, contexts
                     self.barrier()
                     t0 = time.perf_counter()
                     st = detect_files_native([path], os.path.join(tmp, "out"), spc, model=_cnn_weights() if w_host is not None else None,
-                                             minibatch_size=mbs, chunk_minibatches=chunk)
+                                             minibatch_size=mbs, chunk_minibatches=chunk, device=self.local_rank)
                     dt = time.perf_counter() - t0
                     self.barrier()
                     st2 = detect_files_native([path], os.path.join(tmp, "nocsv"), spc, model=_cnn_weights() if w_host is not None else None,
-                                              minibatch_size=mbs, chunk_minibatches=chunk, write_csv=False)
+                                              minibatch_size=mbs, chunk_minibatches=chunk, write_csv=False, device=self.local_rank)
                     out["file"] = {"reads": nf, "seconds": dt, "container_bytes": size, "tables": st["files"], "pass": st["pass"],
                                    "fail": st["fail"], "lost": st["lost"], "stage_busy_s": {k: st[k] for k in ("reader_busy_s", "writer_wait_gpu_s", "writer_busy_s")},
                                    "seconds_without_tables": st2["seconds"], "storage": os.path.dirname(path)}
