@@ -9,19 +9,20 @@
 #include "adb_common.cuh"
 #include "adb_peaks.cuh"
 
-// _c_llr.pyx:22-37
+// _c_llr.pyx:22-37.  The start == 0 branch of the reference drops the subtrahends; subtracting an exact 0.0 gives the
+// same doubles (x - 0.0 == x, also for -0.0 and non-finite x), so one straight-line body serves both cases.
 __device__ __forceinline__ double var_c(int start, int end, const double *c, const double *c2) {
     if (start == end) return 0.0;
-    if (start == 0) {
-        double m = __ddiv_rn(c[end - 1], (double)end);
-        return __dsub_rn(__ddiv_rn(c2[end - 1], (double)end), __dmul_rn(m, m));
-    }
-    double n = (double)(end - start);
-    double m = __ddiv_rn(__dsub_rn(c[end - 1], c[start - 1]), n);
-    return __dsub_rn(__ddiv_rn(__dsub_rn(c2[end - 1], c2[start - 1]), n), __dmul_rn(m, m));
+    const double s1 = start ? c[start - 1] : 0.0, s2 = start ? c2[start - 1] : 0.0;
+    const double n = (double)(end - start);
+    const double m = __ddiv_rn(__dsub_rn(c[end - 1], s1), n);
+    return __dsub_rn(__ddiv_rn(__dsub_rn(c2[end - 1], s2), n), __dmul_rn(m, m));
 }
 
 // _c_llr.pyx:82-86 for every i the reference loop visits; gains[] zero elsewhere (np.zeros_like, :80).  CTA-wide.
+// The two segment terms of a point run through ONE copy of the variance + log code (a rolled two-trip loop): with both
+// inlined side by side the body of the point loop did not fit the instruction cache next to the scheduler (ncu:
+// `no_instruction` was the largest stall of llr_primary_kernel, concentrated on these lines).
 __device__ void cta_llr_gains(const double *c, const double *c2, int n, int start, int end, int head, int tail,
                               int stride, double *gains) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) gains[i] = 0.0;
@@ -31,9 +32,14 @@ __device__ void cta_llr_gains(const double *c, const double *c2, int n, int star
         const double var_summed = __dmul_rn((double)(end - start), log(var_c(start, end, c, c2)));
         const int cnt = (i1 - i0 + stride - 1) / stride;
         for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
-            int i = i0 + k * stride;
-            double h = __dmul_rn((double)(i - start), log(var_c(start, i, c, c2)));
-            double t = __dmul_rn((double)(end - i), log(var_c(i, end, c, c2)));
+            const int i = i0 + k * stride;
+            double h = 0.0, t = 0.0;
+#pragma unroll 1
+            for (int side = 0; side < 2; side++) {
+                const int a = side ? i : start, b = side ? end : i;
+                const double term = __dmul_rn((double)(b - a), log(var_c(a, b, c, c2)));
+                if (side) t = term; else h = term;
+            }
             gains[i] = __dsub_rn(var_summed, __dadd_rn(h, t));
         }
     }
