@@ -2,6 +2,7 @@
 // .cuh files included below.  Build: adapted_b200/csrc/build.py (nvcc -gencode arch=compute_100a,code=sm_100a).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -19,6 +20,7 @@
 #include "adb_cnn.cuh"
 #include "adb_stream.cuh"
 #include "adb_cnn_tc.cuh"
+#include "adb_vhist.cuh"
 #include "adb_start_peak.cuh"
 #include "adb_legacy.cuh"
 
@@ -54,6 +56,7 @@ extern "C" int adb_ctx_create(int device, adb_ctx **out) {
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (const char *e = getenv("ADB_HIST_VALIDATE")) c->opt_hist_validate = atoi(e);  // A/B switch of the validation kernel
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int k = 0; k < 2; k++) {
@@ -94,6 +97,7 @@ extern "C" int adb_ctx_set_option(adb_ctx *c, const char *name, int value) {
     if (!c || !name) return ADB_ERR_ARG;
     if (!strcmp(name, "exact_global_select")) { c->opt_exact_gsel = value; return ADB_OK; }
     if (!strcmp(name, "no_fast_validate")) { c->opt_no_fast_validate = value; return ADB_OK; }
+    if (!strcmp(name, "hist_validate")) { c->opt_hist_validate = value; return ADB_OK; }
     if (!strcmp(name, "cnn_fp32_pipe")) { c->opt_cnn_fp32 = value; return ADB_OK; }
     if (!strcmp(name, "pipeline_copy_only")) { c->opt_copy_only = value; return ADB_OK; }
     if (!strcmp(name, "no_cand_followup")) { c->opt_no_cand_followup = value; return ADB_OK; }
@@ -362,7 +366,7 @@ static int launch_validate(adb_ctx *ctx, const BatchDev &B, const adb_config &cf
     }
     pool_cap &= ~3LL;  // the second pool starts pool_cap floats behind the first: rows stay 16-byte aligned in both
     if (pre && (ctx->cnn_aux.ensure((size_t)pool_cap * sizeof(float) * 2) ||
-                ctx->h_misc3.ensure(sizeof(int) * 2 * (size_t)B.n_reads + sizeof(long long) * ((size_t)B.n_reads + 2)))) {
+                ctx->h_misc3.ensure(sizeof(int) * 2 * (size_t)B.n_reads + sizeof(long long) * ((size_t)B.n_reads + 2) + sizeof(float) * 2 * (size_t)B.n_reads))) {
         set_err("cudaMalloc moving-statistics scratch");
         return ADB_ERR_CUDA;
     }
@@ -373,6 +377,7 @@ static int launch_validate(adb_ctx *ctx, const BatchDev &B, const adb_config &cf
     A.pre_var = A.pre_mean = nullptr;
     A.pre_off = nullptr;
     A.pre_meta = nullptr;
+    const float *series_med = nullptr;
     if (pre) {
         MvsSeriesArgs M;
         M.B = B;
@@ -404,6 +409,21 @@ static int launch_validate(adb_ctx *ctx, const BatchDev &B, const adb_config &cf
                 M.perm = perm;
                 CUDA_TRY(cudaFuncSetAttribute(mvs_series_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mvs_smem_bytes()));
                 mvs_series_kernel<<<(B.n_reads + MVS_LANES - 1) / MVS_LANES, MVS_LANES, mvs_smem_bytes(), st>>>(M, cfg);
+                if (!ctx->opt_no_fast_validate) {
+                    // medians of the two series of every row, one warp per series (consumed by validate_fast_kernel)
+                    SeriesMedianArgs SM;
+                    SM.B = B; SM.pre_var = M.var_pool; SM.pre_mean = M.mean_pool; SM.pre_off = M.row_off; SM.pre_meta = M.meta;
+                    SM.perm = perm; SM.n_reads = B.n_reads;
+                    SM.out = (float *)(M.meta + 2 * (size_t)B.n_reads);
+                    series_med = SM.out;
+                    const size_t ssm = series_median_smem_bytes();
+                    CUDA_TRY(cudaFuncSetAttribute(series_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
+                    int socc = 0;
+                    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&socc, series_median_kernel, SM_WARPS * 32, ssm));
+                    const int sgrid2 = std::max(1, std::min((2 * B.n_reads + SM_WARPS - 1) / SM_WARPS, ctx->sm_count * std::max(socc, 1)));
+                    series_median_kernel<<<sgrid2, SM_WARPS * 32, ssm, st>>>(SM, cfg);
+                    ctx->launches += 1;
+                }
             } else {
                 mvs_series_f32_kernel<<<(B.n_reads + 127) / 128, 128, 0, st>>>(M, cfg);
             }
@@ -428,28 +448,29 @@ static int launch_validate(adb_ctx *ctx, const BatchDev &B, const adb_config &cf
             F.B = B; F.given = given; F.given_stride = given_stride; F.given_ntopk = given_ntopk; F.ntopk_per_read = ntopk_per_read;
             F.mode = mode; F.win_bytes = A.win_bytes; F.out = out; F.batch_status = batch_status;
             F.pre_var = A.pre_var; F.pre_mean = A.pre_mean; F.pre_off = A.pre_off; F.pre_meta = A.pre_meta;
+            F.series_med = series_med;
             F.done = (unsigned char *)ctx->vf_done.p;
-            F.n_long = (int *)((unsigned char *)ctx->vf_done.p + (((size_t)B.n_reads + 3) & ~(size_t)3));
             F.cand_followup = (pre && mode == ADB_METHOD_CNN && (ntopk_per_read || given_ntopk > 1) && !ctx->opt_no_cand_followup) ? 1 : 0;
-            // without the candidate follow-up a long first candidate (mostly a wrong one) fails and goes to validate_kernel
-            // anyway: the LONG instance then only pays when many reads wait for it
-            F.long_min = (mode == ADB_METHOD_CNN && given_ntopk > 1 && !F.cand_followup) ? std::max(1, B.n_reads / 5) : 1;
-            CUDA_TRY(cudaFuncSetAttribute(validate_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
-            CUDA_TRY(cudaFuncSetAttribute(validate_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+            CUDA_TRY(cudaFuncSetAttribute(validate_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
             int focc = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&focc, validate_fast_kernel<false>, VF_THREADS, fsm));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&focc, validate_fast_kernel, VF_THREADS, fsm));
             if (focc < 1) focc = 1;
             const int fgrid = std::max(1, std::min(B.n_reads, ctx->sm_count * focc));
-            {
+            // the tensor-core histogram variant needs an accumulator per piece of the window: the ranges of the MVS check
+            // and of the median-shift check together can cut a read into more pieces than it has
+            const bool use_hist = ctx->opt_hist_validate && B.m <= 65535 && !(cfg.mvs_detect_check && cfg.detect_med_shift);
+            if (use_hist) {
+                const size_t hsm = vhist_smem_bytes();
+                CUDA_TRY(cudaFuncSetAttribute(validate_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
+                int hocc = 0;
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&hocc, validate_hist_kernel, VF_THREADS, hsm));
+                hocc = std::max(1, std::min(hocc, 4));  // 128 of the SM's 512 TMEM columns per CTA
+                const int hgrid = std::max(1, std::min(B.n_reads, ctx->sm_count * hocc));
                 KernelTimer t(ctx, 2, st);
-                validate_fast_kernel<false><<<fgrid, VF_THREADS, fsm, st>>>(F, cfg);
-            }
-            if (pre) {
-                // reads whose poly(A) series exceed the window memory (long-poly(A) stress sets); leaves at once otherwise.
-                // Timed with the hand-over kernels: it works on what the first launch left.
-                KernelTimer t(ctx, 7, st);
-                validate_fast_kernel<true><<<fgrid, VF_THREADS, fsm, st>>>(F, cfg);
-                ctx->launches += 1;
+                validate_hist_kernel<<<hgrid, VF_THREADS, hsm, st>>>(F, cfg);
+            } else {
+                KernelTimer t(ctx, 2, st);
+                validate_fast_kernel<<<fgrid, VF_THREADS, fsm, st>>>(F, cfg);
             }
             ctx->launches += 1;
             A.done = F.done;
@@ -702,6 +723,7 @@ extern "C" int adb_detect_pipelined_host(adb_ctx *ctx, const adb_batch *batch, c
     }
     if (ctx->twin) {
         ctx->twin->opt_no_fast_validate = ctx->opt_no_fast_validate;
+        ctx->twin->opt_hist_validate = ctx->opt_hist_validate;
         ctx->twin->opt_cnn_fp32 = ctx->opt_cnn_fp32;
         ctx->twin->opt_exact_gsel = ctx->opt_exact_gsel;
         ctx->twin->opt_no_cand_followup = ctx->opt_no_cand_followup;

@@ -212,6 +212,7 @@ extern "C" int adb_detect_files(adb_ctx *ctx, const adb_file_job *job, const adb
     CUDA_TRY(cudaSetDevice(ctx->device));
     if (!ctx->twin) { rc = adb_ctx_create(ctx->device, &ctx->twin); if (rc) return rc; }
     ctx->twin->opt_no_fast_validate = ctx->opt_no_fast_validate;
+        ctx->twin->opt_hist_validate = ctx->opt_hist_validate;
     ctx->twin->opt_cnn_fp32 = ctx->opt_cnn_fp32;
     ctx->twin->opt_exact_gsel = ctx->opt_exact_gsel;
         ctx->twin->opt_no_cand_followup = ctx->opt_no_cand_followup;

@@ -124,6 +124,7 @@ extern "C" int adb_detect_pipelined_svb_host(adb_ctx *ctx, const adb_svb_batch *
     }
     if (ctx->twin) {
         ctx->twin->opt_no_fast_validate = ctx->opt_no_fast_validate;
+        ctx->twin->opt_hist_validate = ctx->opt_hist_validate;
         ctx->twin->opt_cnn_fp32 = ctx->opt_cnn_fp32;
         ctx->twin->opt_exact_gsel = ctx->opt_exact_gsel;
         ctx->twin->opt_no_cand_followup = ctx->opt_no_cand_followup;

@@ -23,6 +23,7 @@
 #include "adb_common.cuh"
 #include "adb_gsample.cuh"
 #include "adb_validate.cuh"
+#include "adb_series_median.cuh"
 
 #define VF_THREADS 256
 #define VF_MAX_TASKS 12
@@ -708,8 +709,6 @@ struct VfastArgs {
     int given_stride;
     int given_ntopk;            // entries per read when ntopk_per_read == nullptr (-1: None)
     const int *ntopk_per_read;
-    int *n_long;                // device counter: reads left to the LONG instantiation
-    int long_min;               // the LONG instantiation runs only if at least that many reads wait for it
     int mode;                   // ADB_METHOD_*
     int win_bytes;              // capacity of the staged window (bytes)
     adb_record *out;
@@ -717,6 +716,7 @@ struct VfastArgs {
     const float *pre_var, *pre_mean;  // compact pools of precomputed moving statistics (mvs_series_kernel)
     const long long *pre_off;
     const int *pre_meta;
+    const float *series_med;    // [n_reads][2] medians of the two series of the row (series_median_kernel)
     unsigned char *done;        // [n_reads], zeroed before the launch; 1 = record written by this kernel,
                                 // 2 = record written with the FIRST poly(A) candidate's outcome, further candidates pending
     int cand_followup;          // 1: validate_cand_kernel runs behind this kernel (CNN path with several candidates)
@@ -817,14 +817,9 @@ __device__ float vf_mad_of(const VfRead &R, VfScratch &S, int q) {
     return __fdiv_rn(__fadd_rn(d0, d1), 2.0f);
 }
 
-// LONG = false: every read whose two moving-statistics series fit into the window memory (all but pathological reads).
-// LONG = true: a second launch for the others (poly(A) longer than about half the window) with the series bisected
-// from global memory; the two launches split the reads by the same predicate on the primary boundaries.
-template <bool LONG>
 __global__ void __launch_bounds__(VF_THREADS, 4) validate_fast_kernel(VfastArgs A, adb_config cfg) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *winbuf = smem;
-    const size_t win_cap = (((size_t)A.win_bytes + 48 + 15) & ~(size_t)15);
     __shared__ VfScratch S;
     __shared__ uint64_t bar_storage;
     uint64_t *bar = &bar_storage;
@@ -833,9 +828,6 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_fast_kernel(VfastArgs 
     __syncthreads();
     uint32_t phase = 0;
 
-    // nothing (or, with several poly(A) candidates per read, too little) to gain from the second launch: with top-k
-    // candidates a long first candidate is mostly a wrong one, the read fails it and goes to validate_kernel anyway
-    if (LONG && *A.n_long < A.long_min) return;
     for (int r = blockIdx.x; r < A.B.n_reads; r += gridDim.x) {
         const int mb = r / A.B.batch_size;
         adb_record *rec = A.out + r;
@@ -861,26 +853,12 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_fast_kernel(VfastArgs 
         const bool mvs_geom = cfg.mvs_detect_check && !(pe0 == 0 || a_end == 0 || pe0 < a_end || pe0 - a_end <= 2) &&
                               !(size < a_end + msw);
         const bool win_var = !(pe0 - a_end <= cfg.pA_var_window + 2), win_mean = !(pe0 - a_end <= cfg.pA_mean_window + 2);
-        const float *pv_series = nullptr, *pm_series = nullptr;
-        {
-            bool long_series = false;
-            if (mvs_geom && (win_var || win_mean)) {
-                int ga = a_end, gb = pe0;
-                clip_seg(ga, gb, size);
-                const int Lg = gb - ga;
-                const int gnv = win_var ? Lg - (cfg.pA_var_window - 1) : 0, gnm = win_mean ? Lg - (cfg.pA_mean_window - 1) : 0;
-                long_series = (size_t)(((gnv + 3) & ~3) + gnm) * 4 > win_cap;
-            }
-            if (long_series != LONG) {
-                if (!LONG && tid == 0) atomicAdd(A.n_long, 1);  // tells the second launch that it has work
-                continue;
-            }
-        }
+        float smed_var = 0.f, smed_mean = 0.f;  // medians of the two moving-statistics series (series_median_kernel)
         if (mvs_geom && (win_var || win_mean)) {
             const long long po = A.pre_off ? A.pre_off[r] : -1;
             if (!(po >= 0 && A.pre_meta[2 * r] == a_end && A.pre_meta[2 * r + 1] == pe0)) continue;  // not precomputed
-            pv_series = A.pre_var + po;
-            pm_series = A.pre_mean + po;
+            smed_var = A.series_med[2 * r];
+            smed_mean = A.series_med[2 * r + 1];
         }
         // ---- stage the preload window in shared memory (TMA bulk copy) ----
         VfRead R;
@@ -1053,14 +1031,8 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_fast_kernel(VfastArgs 
                 }
                 const float small_mean = S.ftmp[0], small_var = S.ftmp[1];
                 __syncthreads();
-                // the staged window is not needed any more: its memory now holds the ordered keys of the two series
-                float smed[2] = {0.f, 0.f};
-                const int nv = win_var ? L - (cfg.pA_var_window - 1) : 0, nm = win_mean ? L - (cfg.pA_mean_window - 1) : 0;
-                if (LONG) vf_series_medians<false>(S, pv_series, nv, pm_series, nm, (uint32_t *)winbuf, smed);
-                else if ((size_t)(((nv + 3) & ~3) + nm) * 4 > win_cap) defer = true;  // (cannot happen: split by the same predicate)
-                else if (nv > 0 || nm > 0) vf_series_medians<true>(S, pv_series, nv, pm_series, nm, (uint32_t *)winbuf, smed);
-                const float var32 = win_var ? smed[0] : small_var;
-                const float mean32 = win_mean ? smed[1] : small_mean;
+                const float var32 = win_var ? smed_var : small_var;
+                const float mean32 = win_mean ? smed_mean : small_mean;
                 const float shift32 = __fsub_rn(medAF, medBF);
                 mvs_v[0] = (double)mean32; mvs_v[1] = (double)var32; mvs_v[2] = (double)medP; mvs_v[3] = lrP; mvs_v[4] = (double)shift32;
                 const double mr[2] = {mlo, mhi};

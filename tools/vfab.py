@@ -9,6 +9,8 @@ from adapted_b200.config import flatten_config, get_chemistry_specific_config
 from adapted_b200.synth import make_reads_torch
 chem = sys.argv[2]; n = int(sys.argv[3]) if len(sys.argv) > 3 else 100000
 L = _lib.load(); ctx = _lib.Context(0)
+for kv in os.environ.get("ADB_OPTS", "").split(","):
+    if kv: _lib.check(L.adb_ctx_set_option(ctx.handle, kv.split("=")[0].encode(), int(kv.split("=")[1])))
 spc = get_chemistry_specific_config(chem); flat = flatten_config(spc); m = flat["sig_preload_size"]
 data = make_reads_torch(n, chem, m, seed=1234, device="cuda")
 cfg = _lib.fill_config(flat)
@@ -29,4 +31,4 @@ for _ in range(3): step()
 torch.cuda.synchronize()
 tim = (C.c_double * 16)(); L.adb_ctx_get_timing(ctx.handle, tim)
 names = ["gsb_pass", "gsb_small", "validate_fast", "llr_primary", "mvs_series", "cnn_conv", "cnn_prepost/sp", "handover"]
-print(os.path.basename(sys.argv[1]), chem, " ".join(f"{nm}={tim[2*i]/3:.2f}" for i, nm in enumerate(names) if tim[2*i+1] > 0), "checksum", int(rec.to(torch.int64).sum().item()))
+print(os.path.basename(sys.argv[1]), os.environ.get("ADB_OPTS", ""), chem, " ".join(f"{nm}={tim[2*i]/3:.2f}" for i, nm in enumerate(names) if tim[2*i+1] > 0), "checksum", int(rec.to(torch.int64).sum().item()))
