@@ -462,10 +462,13 @@ static int launch_validate(adb_ctx *ctx, const BatchDev &B, const adb_config &cf
             if (use_hist) {
                 const size_t hsm = vhist_smem_bytes();
                 CUDA_TRY(cudaFuncSetAttribute(validate_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
-                int hocc = 0;
-                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&hocc, validate_hist_kernel, VF_THREADS, hsm));
-                hocc = std::max(1, std::min(hocc, 4));  // 128 of the SM's 512 TMEM columns per CTA
+                // Four CTAs per SM: 128 of the SM's 512 TMEM columns, 64 registers x 256 threads and ~45 KB of shared memory
+                // each.  (cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for a kernel that allocates tensor
+                // memory; the CTAs do run side by side: 88.7 / 48.6 / 28.9 ms at 1 / 2 / 4 CTAs per SM.)
+                int hocc = 4;
+                if (const char *e = getenv("ADB_HIST_OCC")) hocc = std::max(1, std::min(atoi(e), 4));
                 const int hgrid = std::max(1, std::min(B.n_reads, ctx->sm_count * hocc));
+                if (getenv("ADB_DEBUG_OCC")) fprintf(stderr, "validate_hist_kernel: occupancy %d, grid %d, smem %zu\n", hocc, hgrid, hsm);
                 KernelTimer t(ctx, 2, st);
                 validate_hist_kernel<<<hgrid, VF_THREADS, hsm, st>>>(F, cfg);
             } else {
@@ -1159,3 +1162,12 @@ extern "C" int adb_open_pores_host(adb_ctx *ctx, const adb_batch *batch, const i
 #include "adb_ingest.cuh"
 #include "adb_files.cuh"
 
+
+#ifdef ADB_VH_STATS
+// instrumented builds only (tools/vhstats.py): per-phase cycle counters of validate_hist_kernel; reset != 0 clears them
+extern "C" int adb_vh_stats(unsigned long long *out, int reset) {
+    if (cudaMemcpyFromSymbol(out, vh_dbg, sizeof(unsigned long long) * 16) != cudaSuccess) return ADB_ERR_CUDA;
+    if (reset) { unsigned long long z[16] = {0}; if (cudaMemcpyToSymbol(vh_dbg, z, sizeof(z)) != cudaSuccess) return ADB_ERR_CUDA; }
+    return ADB_OK;
+}
+#endif

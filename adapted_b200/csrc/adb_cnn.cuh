@@ -18,6 +18,7 @@
 // is "boundaries within +-1 downscaled step" (north_star).  The FP32-pipe kernels accumulate every product with fmaf in
 // float32; the tensor-core kernels keep ~22 bits per operand (fp16 hi / lo split) and accumulate in float32.
 #pragma once
+#include "adb_series_median.cuh"
 #include <cuda_fp16.h>
 #include <float.h>
 
@@ -106,6 +107,97 @@ __global__ void __launch_bounds__(256) cnn_prep_kernel(BatchDev B, int A0, int f
             else if (v == -CUDART_INF_F) v = -FLT_MAX;
         }
         xr[b] = v;
+    }
+}
+
+// The same, one WARP per read (int16 sources): the downscaled row (1650 bins for RNA004) and its ordered keys live in
+// the warp's slice of shared memory, median and MAD are two warp-level selects (warp_select2, adb_series_median.cuh:
+// sampled opening bracket, bisection with warp counts, the last 64 keys ranked directly) -- no CTA barrier, 16 reads in
+// flight per SM.  Exact order statistics: identical to cnn_prep_kernel.
+#define PREP_WARPS 4
+__host__ __device__ inline size_t cnn_prep_warp_smem(int L) { return (size_t)PREP_WARPS * (2 * ((L + 3) & ~3) + SM_NCAND + 4) * 4; }
+__global__ void __launch_bounds__(PREP_WARPS * 32) cnn_prep_warp_kernel(BatchDev B, int A0, int f, int L, float *x) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Lp = (L + 3) & ~3;
+    float *ds = (float *)smem + (size_t)warp * (2 * Lp + SM_NCAND + 4);
+    uint32_t *keys = (uint32_t *)(ds + Lp), *cand = keys + Lp;
+    for (int r = blockIdx.x * PREP_WARPS + warp; r < B.n_reads; r += gridDim.x * PREP_WARPS) {
+        const ReadSrc src = make_src(B, r);
+        int nv;
+        {
+            const int span = B.m - A0;
+            if (span <= 0) nv = 0;
+            else if (src.n >= B.m) nv = L;
+            else nv = (src.n > A0) ? (src.n - A0) / f : 0;
+            nv = min(nv, L);
+        }
+        const int nvp = (nv + 3) & ~3;
+        if (lane == 0) {  // the window of this warp's next read travels to L2 while this one is worked on
+            const int rn = r + gridDim.x * PREP_WARPS;
+            if (rn < B.n_reads) {
+                const ReadSrc nx = make_src(B, rn);
+                if (nx.i16 != nullptr && nx.n > A0 + 16) {
+                    const uintptr_t p0 = ((uintptr_t)(nx.i16 + A0) + 15) & ~(uintptr_t)15;
+                    const uint32_t nbytes = (uint32_t)(((uintptr_t)(nx.i16 + min(nx.n, B.m)) - p0) & ~(uintptr_t)15);
+                    if (nbytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p0), "r"(nbytes) : "memory");
+                }
+            }
+        }
+        uint32_t mn = 0xffffffffu, mx = 0u;
+        for (int b = lane; b < nv; b += 64) {  // two bins per lane and round: twice the loads in flight
+            const int j0 = A0 + b * f, j1 = j0 + 32 * f;
+            const bool two = b + 32 < nv;
+            const float v0 = cnn_block_mean([&](int k) { const int j = j0 + k; return (j < B.m) ? src.pa(j) : 0.0f; }, f);
+            const float v1 = two ? cnn_block_mean([&](int k) { const int j = j1 + k; return (j < B.m) ? src.pa(j) : 0.0f; }, f) : 0.f;
+            ds[b] = v0;
+            const uint32_t k0 = f32_key(v0);
+            keys[b] = k0;
+            mn = min(mn, k0); mx = max(mx, k0);
+            if (two) {
+                ds[b + 32] = v1;
+                const uint32_t k1 = f32_key(v1);
+                keys[b + 32] = k1;
+                mn = min(mn, k1); mx = max(mx, k1);
+            }
+        }
+        if (lane < nvp - nv) keys[nv + lane] = 0xffffffffu;  // pad to full vectors with keys above every rank looked for
+        mn = __reduce_min_sync(ADB_FULL, mn);
+        mx = __reduce_max_sync(ADB_FULL, mx);
+        __syncwarp();
+        float med = CUDART_NAN_F, mad = CUDART_NAN_F;
+        if (nv > 0) {
+            const SmKeys K{reinterpret_cast<const uint4 *>(keys), nullptr};
+            const unsigned rank = (unsigned)(nv - 1) >> 1;
+            uint32_t a, b2;
+            bool hb;
+            warp_select2(K, nvp >> 2, 0u, false, nvp, rank, mn, mx, cand, a, b2, hb);
+            med = (nv & 1) ? key_f32(a) : __fdiv_rn(__fadd_rn(key_f32(a), key_f32(b2)), 2.0f);
+            __syncwarp();
+            mn = 0xffffffffu; mx = 0u;
+            for (int b = lane; b < nv; b += 32) {
+                const uint32_t k = f32_key(fabsf(__fsub_rn(ds[b], med)));
+                keys[b] = k;
+                mn = min(mn, k); mx = max(mx, k);
+            }
+            mn = __reduce_min_sync(ADB_FULL, mn);
+            mx = __reduce_max_sync(ADB_FULL, mx);
+            __syncwarp();
+            warp_select2(K, nvp >> 2, 0u, false, nvp, rank, mn, mx, cand, a, b2, hb);
+            mad = (nv & 1) ? key_f32(a) : __fdiv_rn(__fadd_rn(key_f32(a), key_f32(b2)), 2.0f);
+        }
+        float *xr = x + (size_t)r * L;
+        for (int b = lane; b < L; b += 32) {
+            float v = CNN_SCORE_EXCL;
+            if (b < nv) {
+                v = __fdiv_rn(__fsub_rn(ds[b], med), mad);
+                if (!(v == v)) v = CNN_SCORE_EXCL;          // torch.nan_to_num(nan=-5)
+                else if (v == CUDART_INF_F) v = FLT_MAX;
+                else if (v == -CUDART_INF_F) v = -FLT_MAX;
+            }
+            xr[b] = v;
+        }
+        __syncwarp();
     }
 }
 
@@ -724,7 +816,16 @@ static int cnn_primary_boundaries(adb_ctx *ctx, const BatchDev &B, const adb_con
         const size_t smem = (((size_t)D.Lx * 4 + 15) & ~(size_t)15) + ((ADB_SEL_SMEM_BYTES + 15) & ~15) + 64;
         CUDA_TRY(cudaFuncSetAttribute(cnn_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KernelTimer t(ctx, 6, st);
-        cnn_prep_kernel<<<n, 256, smem, st>>>(B, cfg.min_obs_adapter, cfg.downscale_factor, D.Lx, x);
+        const size_t wsm = cnn_prep_warp_smem(D.Lx);
+        if (B.sig_type == ADB_SIG_I16 && (int)wsm <= ctx->max_smem_optin && !getenv("ADB_PREP_CTA")) {
+            CUDA_TRY(cudaFuncSetAttribute(cnn_prep_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm));
+            int occ = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cnn_prep_warp_kernel, PREP_WARPS * 32, wsm));
+            const int grid = std::max(1, std::min((n + PREP_WARPS - 1) / PREP_WARPS, ctx->sm_count * std::max(occ, 1)));
+            cnn_prep_warp_kernel<<<grid, PREP_WARPS * 32, wsm, st>>>(B, cfg.min_obs_adapter, cfg.downscale_factor, D.Lx, x);
+        } else {
+            cnn_prep_kernel<<<n, 256, smem, st>>>(B, cfg.min_obs_adapter, cfg.downscale_factor, D.Lx, x);
+        }
         ctx->launches += 1;
     }
     int rc = cnn_forward_dev(ctx, x, n, D, w_dev, scores, st);

@@ -77,7 +77,7 @@ struct adb_ctx {
     DevBuf llr_cc;             // prefix sums of llr_primary_kernel (per resident CTA)
     DevBuf vf_done;            // per-read flags of validate_fast_kernel
     int opt_no_fast_validate = 0;
-    int opt_hist_validate = 0;  // adb_ctx_set_option("hist_validate"): tensor-core histogram validation (adb_vhist.cuh) instead of the counting passes
+    int opt_hist_validate = 1;  // adb_ctx_set_option("hist_validate", 0): counting passes (validate_fast_kernel) instead of the tensor-core histograms (adb_vhist.cuh)
     int opt_no_cand_followup = 0;  // adb_ctx_set_option("no_cand_followup"): further poly(A) candidates go to validate_kernel (A/B)
     int cnn_a0t_l1 = -1;       // L1 the tile-layout activation buffer was last zeroed for
     int opt_cnn_fp32 = 0;      // adb_ctx_set_option("cnn_fp32_pipe"): 64->64 convolutions on the FP32 pipe instead of tcgen05

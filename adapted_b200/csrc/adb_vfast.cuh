@@ -453,11 +453,10 @@ __device__ int vf_open_pores(const VfRead &R, VfScratch &S, int a, int b, int c2
 // numpy float32 mean of the `n` samples starting at a0 and at a1 (real_range_check: first / last mean_window samples)
 // in numpy's pairwise order.  For 128 < n <= 512 the (at most four) leaves of the pairwise tree are summed by
 // different threads and combined in tree order; other sizes by one thread per mean.  CTA-wide.
-__device__ void vf_mean_pair(const VfRead &R, VfScratch &S, int a0, int a1, int n, float &m0, float &m1) {
+template <class T>  // uint16_t: non-negative codes of the staged window; int16_t: any code (adb_vhist.cuh)
+__device__ void vf_mean_pair_t(const T *w, float coff, float cscale, VfScratch &S, int a0, int a1, int n, float &m0, float &m1) {
     __syncthreads();
     const int tid = threadIdx.x;
-    const uint16_t *w = R.W16 + R.s0;
-    const float coff = R.coff, cscale = R.cscale;
     if (n > 128 && n <= 512) {
         // tree: n -> (h0, n - h0); each part p > 128 -> (p2, p - p2)
         if (tid < 8) {
@@ -477,7 +476,7 @@ __device__ void vf_mean_pair(const VfRead &R, VfScratch &S, int a0, int a1, int 
             }
             float sum = 0.f;
             if (llen > 0) {
-                const uint16_t *p = w + base + lbase;
+                const T *p = w + base + lbase;
                 sum = np_sum_f32_leaf([&](int i) { return __fmul_rn(__fadd_rn((float)(int)p[i], coff), cscale); }, llen);
             }
             S.ftmp[tid] = sum;
@@ -494,7 +493,7 @@ __device__ void vf_mean_pair(const VfRead &R, VfScratch &S, int a0, int a1, int 
         m1 = combine(1);
     } else {
         if (tid == 0 || tid == 32) {
-            const uint16_t *p = w + (tid == 0 ? a0 : a1);
+            const T *p = w + (tid == 0 ? a0 : a1);
             const float s = np_sum_f32([&](int i) { return __fmul_rn(__fadd_rn((float)(int)p[i], coff), cscale); }, n);
             S.ftmp[tid == 0 ? 0 : 1] = __fdiv_rn(s, (float)n);
         }
@@ -503,6 +502,10 @@ __device__ void vf_mean_pair(const VfRead &R, VfScratch &S, int a0, int a1, int 
         m1 = S.ftmp[1];
     }
     __syncthreads();
+}
+
+__device__ __forceinline__ void vf_mean_pair(const VfRead &R, VfScratch &S, int a0, int a1, int n, float &m0, float &m1) {
+    vf_mean_pair_t<uint16_t>(R.W16 + R.s0, R.coff, R.cscale, S, a0, a1, n, m0, m1);
 }
 
 // exact integer sums of the codes of up to three segments [sa[i], sb[i]) (clipped; skipped unless on[i]) -> mean /

@@ -29,18 +29,30 @@
 #include "adb_cnn_tc.cuh"
 #include "adb_vfast.cuh"
 
-#define VH_BINS 2048
+#define VH_M 64                            // rows of the A tile = values of the high part of a code offset
+#define VH_BINS (VH_M * 16)
 #define VH_MAX_PIECES 8
-#define VH_A_LBO 2112                      // A tile: 2 K-groups (16 samples each) of 128 rows x 16 B, 64 B apart in banks
-#define VH_A_BYTES (VH_A_LBO + 2048)
+#define VH_A_LBO (VH_M * 16 + 64)          // A tile: 2 K-groups (16 samples each) of VH_M rows x 16 B, 64 B apart in banks
+#define VH_A_BYTES (VH_A_LBO + VH_M * 16)
 #define VH_B_LBO 320                       // B tile: 2 K-groups of 16 rows x 16 B
 #define VH_B_BYTES (VH_B_LBO + 256)
-#define VH_TILE_BYTES 4864                 // A + B of one warp, rounded to 128 B
+#define VH_TILE_BYTES ((VH_A_BYTES + VH_B_BYTES + 127) & ~127)  // A + B of one warp
 #define VH_WARPS (VF_THREADS / 32)
-#define VH_ARENA (VH_WARPS * VH_TILE_BYTES)  // 38 912 B >= VH_MAX_PIECES * VH_BINS * 2 (cumulative counts, u16)
-// instruction descriptor: D = f32, A = B = e4m3 (0), K-major, N = 16, M = 128
-#define VH_IDESC ((1u << 4) | ((16u >> 3) << 17) | ((128u >> 4) << 24))
+#define VH_SUB 2                           // MMAs (32 samples each) per batch of a warp: one fence, commit and wait for both
+#define VH_ARENA_TILES (VH_WARPS * VH_SUB * VH_TILE_BYTES)
+#define VH_ARENA_CUM (VH_MAX_PIECES * VH_BINS * 2)   // cumulative counts, u16
+#define VH_ARENA (VH_ARENA_TILES > VH_ARENA_CUM ? VH_ARENA_TILES : VH_ARENA_CUM)
+// instruction descriptor: D = f32, A = B = e4m3 (0), K-major, N = 16, M = VH_M
+#define VH_IDESC ((1u << 4) | ((16u >> 3) << 17) | (((unsigned)VH_M >> 4) << 24))
 #define VH_NQ 12
+#define VH_OP_WORDS 512                    // open-pore scan: 16 384 samples of adapter at most
+
+#ifdef ADB_VH_STATS
+__device__ unsigned long long vh_dbg[16];  // [0] reads, [1..] cycles of the phases (thread 0)
+#define VH_T(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&vh_dbg[i], (unsigned long long)(t_ - vh_t0)); vh_t0 = t_; } } while (0)
+#else
+#define VH_T(i) do { } while (0)
+#endif
 
 __host__ __device__ inline size_t vhist_smem_bytes() { return (size_t)VH_ARENA + 128; }
 
@@ -80,7 +92,7 @@ __device__ __forceinline__ void vh_tmem_ld16(uint32_t taddr, uint32_t v[16]) {
 
 struct VhShared {
     VfScratch S;                       // scratch of the helpers shared with adb_vfast.cuh
-    uint64_t bar[VH_WARPS];            // "the MMA of this warp's batch has read the tiles"
+    uint64_t bar[VH_WARPS];            // "the MMAs of this warp's batch have read the tiles"
     uint32_t tmem_slot;
     int cuts[VH_MAX_PIECES + 4];       // sorted cut points; piece p = samples [cuts[p], cuts[p + 1])
     int bstart[VH_MAX_PIECES + 2];     // first batch (32 samples) of piece p in the flattened batch space
@@ -89,6 +101,8 @@ struct VhShared {
     int unsettled;                     // an answer or a probe touched an end bin holding such samples
     int qv0[VH_NQ], qv1[VH_NQ], qn[VH_NQ];  // rank queries: codes at rank k and k + 1, samples of the range
     float mad[4];
+    uint32_t hitw[VH_OP_WORDS];        // vh_open_pores: bit i = sample i of the aligned window is an open-pore sample
+    unsigned long long psum[VH_MAX_PIECES][2];  // per piece: sum of (code - base), sum of (code - base)^2 (exact)
 };
 
 // samples of the pieces [p0, p1) whose clamped code offset is <= x
@@ -99,14 +113,20 @@ __device__ __forceinline__ int vh_cle(const uint16_t *cum, int p0, int p1, int x
     for (int p = p0; p < p1; p++) c += (int)cum[p * VH_BINS + x];
     return c;
 }
-// smallest offset x with vh_cle(x) > k (0 <= k < samples of the range)
-__device__ __forceinline__ int vh_select(const uint16_t *cum, int p0, int p1, int k) {
-    int lo = 0, hi = VH_BINS - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (vh_cle(cum, p0, p1, mid) > k) hi = mid; else lo = mid + 1;
+// smallest offset x with vh_cle(x) > k (0 <= k < samples of the range).  Warp-cooperative (all lanes, same arguments,
+// same result): a 32-way search, three rounds of one look-up per lane instead of eleven dependent ones.
+__device__ __forceinline__ int vh_wselect(const uint16_t *cum, int p0, int p1, int k) {
+    const int lane = threadIdx.x & 31;
+    constexpr int B1 = VH_BINS / 32;                   // bins per first-level block
+    unsigned m = __ballot_sync(ADB_FULL, vh_cle(cum, p0, p1, B1 * lane + B1 - 1) > k);
+    const int l1 = __ffs(m) - 1;                       // the block holding the answer (bit 31 is always set)
+    if (B1 == 32) {
+        m = __ballot_sync(ADB_FULL, vh_cle(cum, p0, p1, B1 * l1 + lane) > k);
+        return B1 * l1 + __ffs(m) - 1;
     }
-    return lo;
+    m = __ballot_sync(ADB_FULL, vh_cle(cum, p0, p1, B1 * l1 + 2 * lane + 1) > k);
+    const int x = B1 * l1 + 2 * (__ffs(m) - 1);
+    return (vh_cle(cum, p0, p1, x) > k) ? x : x + 1;
 }
 
 struct VhRange { int p0, p1; };  // pieces of a sample range
@@ -122,29 +142,24 @@ __device__ __forceinline__ VhRange vh_range(const VhShared &H, int a, int b, int
     return q;
 }
 
-// median(|x - med|) of a range from the cumulative counts: the candidate halving of vf_run (adb_vfast.cuh) with the
-// counts looked up.  One thread.
-__device__ float vh_mad(const VfRead &R, VhShared &H, const uint16_t *cum, VhRange q, int base, int n, float med) {
+// median(|x - med|) of a range from the cumulative counts.  Warp-cooperative (uniform arguments and result).
+// The candidates are the deviations of the codes on either side of the median (right: pv + i, left: pv - 1 - i, both
+// non-decreasing in i); d0 = the smallest candidate t with #(deviation <= t) > k.  "Candidate i of a side passes" is
+// monotone in i, so each side is a 32-way search for its first passing candidate (one candidate per lane and round:
+// exact float32 deviation, the matching end of the interval on the other side, two look-ups), and d0 is the smaller of
+// the two.  The decisive evaluations (first passing, last failing) are repeated with the end-bin check.
+__device__ float vh_wmad(const VfRead &R, VhShared &H, const uint16_t *cum, VhRange q, int base, int n, float med) {
+    const int lane = threadIdx.x & 31;
     if (n <= 0 || !(med == med)) return CUDART_NAN_F;
     const int n_low = H.n_low, n_high = H.n_high;
-    auto touch = [&](int x) { if ((x <= 0 && n_low > 0) || (x >= VH_BINS - 1 && n_high > 0)) H.unsettled = 1; };
-    const int xmin = vh_select(cum, q.p0, q.p1, 0), xmax = vh_select(cum, q.p0, q.p1, n - 1);
-    touch(xmin); touch(xmax);
-    const int smin = xmin + base, smax = xmax + base;
+    const int smin = vh_wselect(cum, q.p0, q.p1, 0) + base, smax = vh_wselect(cum, q.p0, q.p1, n - 1) + base;
     const int k = (n - 1) / 2;
     int ok = 1;
     int pv = gsb_code_at(med, false, R.coff, R.cscale, &ok);
     pv = min(max(pv, smin), smax + 1);
     const int nR = smax + 1 - pv, nL = pv - smin;
-    // samples with a code in [pA, pB]
-    auto count = [&](int pA, int pB) -> int {
-        if (pB < pA) return 0;
-        const int xa = pA - base, xb = pB - base;
-        touch(xb);
-        touch(xa - 1 < 0 ? 0 : xa);
-        return vh_cle(cum, q.p0, q.p1, xb) - vh_cle(cum, q.p0, q.p1, xa - 1);
-    };
     auto sdev = [&](bool right, int i) { return vf_dev(R, right ? pv + i : pv - 1 - i, med); };
+    // first index of a side whose deviation is > thr (strict) or >= thr
     auto sfirst = [&](bool right, int nn, float thr, bool strict) -> int {
         float gf = thr / R.cscale;
         int g = (gf == gf && gf < 1e9f) ? (int)gf : nn;
@@ -160,28 +175,43 @@ __device__ float vh_mad(const VfRead &R, VhShared &H, const uint16_t *cum, VhRan
         }
         return g;
     };
-    int rlo = 0, rhi = nR, llo = 0, lhi = nL, c_best = -1;
-    float t_best = CUDART_INF_F;
-    while (rlo < rhi || llo < lhi) {
-        // the middle candidate of the longer side: by symmetry of the two sides it halves the other one as well
-        const bool right = (rhi - rlo) >= (lhi - llo);
-        const int i = right ? (rlo + rhi) >> 1 : (llo + lhi) >> 1;
-        const float thr = sdev(right, i);
+    // samples deviating at most thr (check: flag the read if the interval runs into an end bin that holds outside codes)
+    auto count_le = [&](float thr, bool check) -> int {
         const int jR = sfirst(true, nR, thr, true), jL = sfirst(false, nL, thr, true);
-        const int c = count(pv - jL, pv + jR - 1);
-        if (c > k) {  // every candidate deviating at least thr passes
-            rhi = min(rhi, sfirst(true, nR, thr, false));
-            lhi = min(lhi, sfirst(false, nL, thr, false));
-            rlo = min(rlo, rhi);
-            llo = min(llo, lhi);
-            t_best = thr;
-            c_best = c;
-        } else {      // every candidate deviating at most thr fails
-            rlo = min(max(rlo, jR), rhi);
-            llo = min(max(llo, jL), lhi);
+        const int pA = pv - jL, pB = pv + jR - 1;
+        if (pB < pA) return 0;
+        const int xa = pA - base, xb = pB - base;
+        if (check && ((xa <= 0 && n_low > 0) || (xb >= VH_BINS - 1 && n_high > 0))) H.unsettled = 1;
+        return vh_cle(cum, q.p0, q.p1, xb) - vh_cle(cum, q.p0, q.p1, xa - 1);
+    };
+    // first passing candidate of a side (nn if none): answer in [lo, hi]
+    auto first_pass = [&](bool right, int nn) -> int {
+        int lo = 0, hi = nn;
+        while (lo < hi) {
+            const int step = (hi - lo + 31) >> 5;
+            const int i = lo + (lane + 1) * step - 1;     // lanes probe lo + step - 1, lo + 2 step - 1, ...
+            const bool pass = (i >= hi) || (count_le(sdev(right, min(i, nn - 1)), false) > k);
+            const unsigned m = __ballot_sync(ADB_FULL, pass);  // monotone in the lane
+            if (!m) { lo = hi; break; }                        // every candidate probed fails (the last probe was hi - 1)
+            const int f = __ffs(m) - 1;
+            // the answer lies in (lo + f step - 1, lo + (f + 1) step - 1]
+            const int nlo = lo + f * step, nhi = min(lo + (f + 1) * step - 1, hi);
+            lo = nlo; hi = nhi;
         }
+        return lo;
+    };
+    const int fR = first_pass(true, nR), fL = first_pass(false, nL);
+    float d0 = CUDART_INF_F;
+    if (fR < nR) d0 = fminf(d0, sdev(true, fR));
+    if (fL < nL) d0 = fminf(d0, sdev(false, fL));
+    // decisive evaluations with the end-bin check (lanes 0..3), and the count at d0
+    {
+        const bool right = lane < 2;
+        const int f = right ? fR : fL, nn = right ? nR : nL;
+        const int i = (lane & 1) ? f - 1 : f;
+        if (lane < 4 && i >= 0 && i < nn) (void)count_le(sdev(right, i), true);
     }
-    const float d0 = t_best;
+    const int c_best = count_le(d0, true);
     if (n & 1) return d0;
     float d1 = d0;
     if (!(c_best > k + 1)) {
@@ -193,12 +223,120 @@ __device__ float vh_mad(const VfRead &R, VhShared &H, const uint16_t *cum, VhRan
         while (lo < hi) { const int m = (lo + hi) >> 1; if (vf_dev(R, m, med) > d0) hi = m; else lo = m + 1; }
         const int r = lo - 1;
         d1 = CUDART_INF_F;
+        auto touch = [&](int x) { if ((x <= 0 && n_low > 0) || (x >= VH_BINS - 1 && n_high > 0)) H.unsettled = 1; };
         const int c_r = vh_cle(cum, q.p0, q.p1, r - base);          // samples with a code <= r
-        if (c_r < n) { const int x = vh_select(cum, q.p0, q.p1, c_r); touch(x); d1 = fminf(d1, vf_dev(R, x + base, med)); }
+        if (c_r < n) { const int x = vh_wselect(cum, q.p0, q.p1, c_r); touch(x); d1 = fminf(d1, vf_dev(R, x + base, med)); }
         const int c_l = vh_cle(cum, q.p0, q.p1, l - 1 - base);      // samples with a code < l
-        if (c_l > 0) { const int x = vh_select(cum, q.p0, q.p1, c_l - 1); touch(x); d1 = fminf(d1, vf_dev(R, x + base, med)); }
+        if (c_l > 0) { const int x = vh_wselect(cum, q.p0, q.p1, c_l - 1); touch(x); d1 = fminf(d1, vf_dev(R, x + base, med)); }
     }
     return __fdiv_rn(__fadd_rn(d0, d1), 2.0f);
+}
+
+// find_open_pores (anomalies.py:15-35) over the samples [0, b) of the window (b <= 32 * VH_OP_WORDS - 8), any int16
+// code.  Same results as vf_open_pores (adb_vfast.cuh), which scans per-thread chunks sample by sample; here the window
+// is read once with 16-byte loads into a bit mask (sample is an open-pore sample iff code >= c200) and everything else
+// is word arithmetic on the mask: a hit is a run start iff none of the 9 samples before it is a hit.
+__device__ int vh_open_pores(const VfRead &R, VhShared &H, int b, int c200, adb_record *rec, int *last) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    VfScratch &S = H.S;
+    int *sh = S.itmp;  // [0] hits, [1] first hit, [2] last hit, [3] run starts (the first hit excluded), [4] last run start
+    __syncthreads();
+    if (tid == 0) { sh[0] = 0; sh[1] = 0x7fffffff; sh[2] = -1; sh[3] = 0; sh[4] = -1; }
+    const int i0 = R.s0, i1 = R.s0 + b;               // aligned-window indices of the samples
+    const int nvec = (i1 + 7) >> 3, nwords = (nvec + 3) >> 2;
+    const uint4 *V = reinterpret_cast<const uint4 *>(R.W16);
+    uint8_t *hb = reinterpret_cast<uint8_t *>(H.hitw);
+    for (int v = tid; v < nwords * 4; v += VF_THREADS) {
+        unsigned m = 0;
+        if (v < nvec) {
+            uint4 q = make_uint4(0, 0, 0, 0);
+            if (((v + 1) << 3) <= R.s0 + R.n) q = __ldg(V + v);
+            else {  // the vector runs past the end of the read: sample by sample
+                unsigned short e[8];
+#pragma unroll
+                for (int t = 0; t < 8; t++) e[t] = ((v << 3) + t < R.s0 + R.n) ? R.W16[(v << 3) + t] : (unsigned short)0x8000;
+                q = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
+            }
+            const unsigned w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                m |= ((int)(int16_t)(w[t] & 0xffffu) >= c200 ? 1u : 0u) << (2 * t);
+                m |= ((int)(int16_t)(w[t] >> 16) >= c200 ? 1u : 0u) << (2 * t + 1);
+            }
+            const int ib = v << 3;                    // bits outside [i0, i1) off
+            if (ib < i0) m &= 0xffu << min(i0 - ib, 8);
+            if (ib + 8 > i1) m &= 0xffu >> min(ib + 8 - i1, 8);
+        }
+        hb[v] = (uint8_t)m;
+    }
+    __syncthreads();
+    // per word: hits, run starts
+    int hits = 0, first = 0x7fffffff, lastp = -1;
+    for (int w = tid; w < nwords; w += VF_THREADS) {
+        const uint32_t h = H.hitw[w];
+        if (h) { hits += __popc(h); first = min(first, 32 * w + __ffs(h) - 1); lastp = max(lastp, 32 * w + 31 - __clz(h)); }
+    }
+    hits = __reduce_add_sync(ADB_FULL, hits);
+    first = __reduce_min_sync(ADB_FULL, first);
+    lastp = __reduce_max_sync(ADB_FULL, lastp);
+    if (lane == 0 && hits) { atomicAdd(&sh[0], hits); atomicMin(&sh[1], first); atomicMax(&sh[2], lastp); }
+    __syncthreads();
+    const int tot_hits = sh[0], first_hit = sh[1], last_hit = sh[2];  // (aligned-window indices)
+    int result_n = 0;
+    if (tot_hits == 1) {
+        result_n = 1;
+        if (tid == 0) rec->open_pores[0] = first_hit - i0;
+        *last = first_hit - i0;
+    } else if (tot_hits > 1) {
+        // run starts other than the first hit, in order: counted per word, placed by a prefix sum over the words
+        // (nwords <= 512 = two words per thread)
+        uint32_t c[2] = {0, 0};
+        int n2 = 0;
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int w = 2 * tid + u;
+            if (w < nwords) {
+                const uint32_t h = H.hitw[w], pv = w ? H.hitw[w - 1] : 0u;
+                uint32_t near = 0;
+#pragma unroll
+                for (int k = 1; k <= 9; k++) near |= (h << k) | (pv >> (32 - k));
+                c[u] = h & ~near;
+                if ((first_hit >> 5) == w) c[u] &= ~(1u << (first_hit & 31));
+                n2 += __popc(c[u]);
+            }
+        }
+        int incl = n2;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(ADB_FULL, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) S.wtot[tid >> 5] = (unsigned)incl;
+        int lastc = -1;
+        if (c[1]) lastc = 32 * (2 * tid + 1) + 31 - __clz(c[1]); else if (c[0]) lastc = 32 * (2 * tid) + 31 - __clz(c[0]);
+        lastc = __reduce_max_sync(ADB_FULL, lastc);
+        if (lane == 0 && lastc >= 0) atomicMax(&sh[4], lastc);
+        __syncthreads();
+        int wbase = 0, total = 0;
+        for (int q = 0; q < VF_THREADS / 32; q++) { if (q < (tid >> 5)) wbase += (int)S.wtot[q]; total += (int)S.wtot[q]; }
+        if (total > 0) {
+            int pos = wbase + incl - n2;
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                uint32_t m = c[u];
+                while (m && pos < ADB_MAX_OPEN_PORES) {
+                    const int bit = __ffs(m) - 1;
+                    m &= m - 1;
+                    rec->open_pores[pos++] = 32 * (2 * tid + u) + bit - i0;
+                }
+            }
+            result_n = total;
+            *last = sh[4] - i0;
+        } else {
+            result_n = 1;
+            if (tid == 0) rec->open_pores[0] = last_hit - i0;
+            *last = last_hit - i0;
+        }
+    }
+    __syncthreads();
+    return result_n;
 }
 
 __global__ void __launch_bounds__(VF_THREADS, 4) validate_hist_kernel(VfastArgs A, adb_config cfg) {
@@ -213,16 +351,21 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_hist_kernel(VfastArgs 
     }
     for (int i = tid; i < VH_ARENA / 16; i += VF_THREADS) reinterpret_cast<uint4 *>(arena)[i] = make_uint4(0, 0, 0, 0);
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&H.tmem_slot)), "r"(128));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(&H.tmem_slot)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = H.tmem_slot;
-    unsigned char *tileA = arena + (size_t)warp * VH_TILE_BYTES, *tileB = tileA + VH_A_BYTES;
-    const uint32_t a_lo = tc_desc_lo(smem_u32(tileA), VH_A_LBO), b_lo = tc_desc_lo(smem_u32(tileB), VH_B_LBO);
+    unsigned char *tile0 = arena + (size_t)warp * VH_SUB * VH_TILE_BYTES;
     const uint32_t ab_hi = tc_desc_hi(128);
+    uint32_t a_lo[VH_SUB], b_lo[VH_SUB];
+#pragma unroll
+    for (int u = 0; u < VH_SUB; u++) {
+        a_lo[u] = tc_desc_lo(smem_u32(tile0 + u * VH_TILE_BYTES), VH_A_LBO);
+        b_lo[u] = tc_desc_lo(smem_u32(tile0 + u * VH_TILE_BYTES + VH_A_BYTES), VH_B_LBO);
+    }
     uint32_t phase = 0;  // parity of this warp's barrier
 
     for (int r = blockIdx.x; r < A.B.n_reads; r += gridDim.x) {
@@ -263,17 +406,35 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_hist_kernel(VfastArgs 
         R.n = size; R.coff = gsrc.coff; R.cscale = gsrc.cscale;
         R.kmin = 0; R.kmax = 0;
         const int16_t *W = gsrc.i16;
+        if (tid == 32) {  // the next read of this CTA: its window travels to L2 while this one is worked on
+            const int rn = r + gridDim.x;
+            if (rn < A.B.n_reads) {
+                const ReadSrc nx = make_src(A.B, rn);
+                if (nx.i16 != nullptr && nx.n > 8) {
+                    const uintptr_t p0 = ((uintptr_t)nx.i16 + 15) & ~(uintptr_t)15;
+                    const uint32_t nbytes = (uint32_t)(((uintptr_t)(nx.i16 + nx.n) - p0) & ~(uintptr_t)15);
+                    if (nbytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p0), "r"(nbytes) : "memory");
+                }
+            }
+        }
         int cok = 1;
-        const int base = gsb_code_at(-20.0f, false, R.coff, R.cscale, &cok);
+        const int base = gsb_code_at(VH_M == 128 ? -20.0f : 25.0f, false, R.coff, R.cscale, &cok);
         if (!cok) continue;
         for (int w = tid; w < (int)(sizeof(adb_record) / 4); w += blockDim.x) ((uint32_t *)rec)[w] = 0;
+#ifdef ADB_VH_STATS
+        long long vh_t0 = clock64();
+        if (tid == 0) atomicAdd(&vh_dbg[0], 1ull);
+#endif
 
         // ---- speculative inputs of the checks ----
         int n_open = 0, op_last = 0;
         if (haveA && cfg.detect_open_pores) {
             int ok = 1;
             const int c200 = gsb_code_at(200.0f, false, R.coff, R.cscale, &ok);
-            n_open = vf_open_pores(R, S, 0, a_end, c200, rec, &op_last);
+            int ob = a_end;
+            { int oa = 0; clip_seg(oa, ob, size); }
+            if (ob + 16 > 32 * VH_OP_WORDS) continue;  // (uniform) adapter longer than the scan's bit mask: validate_kernel
+            n_open = vh_open_pores(R, H, ob, c200, rec, &op_last);
         }
         const int a_start1 = (n_open > 0) ? op_last : 0;
         int ra = a_start1, rb = a_end;
@@ -281,7 +442,7 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_hist_kernel(VfastArgs 
         const int rlen = rb - ra;
         const bool rr_geom = haveA && cfg.real_signal_check && rlen >= 2 * cfg.mean_window;
         float rm0 = 0.f, rm1 = 0.f;
-        if (rr_geom) vf_mean_pair(R, S, ra, rb - cfg.mean_window, cfg.mean_window, rm0, rm1);
+        if (rr_geom) vf_mean_pair_t<int16_t>(W, R.coff, R.cscale, S, ra, rb - cfg.mean_window, cfg.mean_window, rm0, rm1);
         const int lrw = min(cfg.max_obs_local_range, rlen);
         const int nLR = lrw;
         const double vLR85 = __dmul_rn((double)(nLR - 1), 0.85), vLR15 = __dmul_rn((double)(nLR - 1), 0.15);
@@ -292,6 +453,7 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_hist_kernel(VfastArgs 
         const bool needP = mvs_geom || (pe_best > a_end);
         const bool ms_geom = cfg.detect_med_shift && haveA;
 
+        VH_T(1);
         // ---- the sample ranges of the statistics (query q works on [qa[q], qb[q]); empty: not wanted) ----
         int qa[VH_NQ], qb[VH_NQ];
 #pragma unroll
@@ -310,25 +472,40 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_hist_kernel(VfastArgs 
 #pragma unroll
         for (int q = 0; q < VH_NQ; q++) clip_seg(qa[q], qb[q], size);
         __syncthreads();
-        if (tid == 0) {
-            // cut points: sorted, distinct
-            int c[2 * VH_NQ + 2], nc = 0;
-            c[nc++] = 0; c[nc++] = size;
+        if (warp == 0) {
+            // cut points = the distinct range ends, sorted: lane l holds one end (lanes 24 / 25: 0 and size), its place is
+            // the number of distinct smaller ends
+            int v = (lane == 25) ? size : 0;
+            bool on = lane == 24 || lane == 25;
 #pragma unroll
-            for (int q = 0; q < VH_NQ; q++) if (qb[q] > qa[q]) { c[nc++] = qa[q]; c[nc++] = qb[q]; }
-            for (int i = 1; i < nc; i++) { const int v = c[i]; int j = i - 1; while (j >= 0 && c[j] > v) { c[j + 1] = c[j]; j--; } c[j + 1] = v; }
-            int m = 0;
-            for (int i = 0; i < nc; i++) if (m == 0 || c[i] != c[m - 1]) c[m++] = c[i];
-            const int np = m - 1;
-            H.np = np;
-            if (np <= VH_MAX_PIECES) {
-                int bs = 0;
-                for (int p = 0; p < np; p++) { H.cuts[p] = c[p]; H.bstart[p] = bs; bs += (c[p + 1] - c[p] + 31) >> 5; }
-                H.cuts[np] = c[np];
-                H.bstart[np] = bs;
+            for (int q = 0; q < VH_NQ; q++) {
+                if ((lane >> 1) == q) { v = (lane & 1) ? qb[q] : qa[q]; on = qb[q] > qa[q]; }
             }
-            H.n_low = 0; H.n_high = 0; H.unsettled = 0;
+            const unsigned onm = __ballot_sync(ADB_FULL, on);
+            bool first = on;
+            for (int j = 0; j < 26; j++) {
+                const int vj = __shfl_sync(ADB_FULL, v, j);
+                if (((onm >> j) & 1u) && j < lane && vj == v) first = false;
+            }
+            const unsigned fm = __ballot_sync(ADB_FULL, first);
+            int pos = 0;
+            for (int j = 0; j < 26; j++) {
+                const int vj = __shfl_sync(ADB_FULL, v, j);
+                if (((fm >> j) & 1u) && vj < v) pos++;
+            }
+            const int np = __popc(fm) - 1;
+            if (first && pos <= VH_MAX_PIECES) H.cuts[pos] = v;
+            __syncwarp();
+            if (np <= VH_MAX_PIECES) {
+                int nb = (lane < np) ? (H.cuts[lane + 1] - H.cuts[lane] + 32 * VH_SUB - 1) / (32 * VH_SUB) : 0;
+                int incl = nb;
+#pragma unroll
+                for (int o = 1; o < 16; o <<= 1) { const int t = __shfl_up_sync(ADB_FULL, incl, o); if (lane >= o) incl += t; }
+                if (lane <= np) H.bstart[lane] = incl - nb;   // (lane np: the total)
+            }
+            if (lane == 0) { H.np = np; H.n_low = 0; H.n_high = 0; H.unsettled = 0; }
         }
+        if (tid < 2 * VH_MAX_PIECES) (&H.psum[0][0])[tid] = 0ull;
         // ---- zero the accumulators ----
         {
             const uint32_t t0 = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(warp >> 2) * 64;
@@ -340,50 +517,97 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_hist_kernel(VfastArgs 
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int np = H.np;
+        VH_T(2);
         if (np > VH_MAX_PIECES) continue;  // (uniform) more ranges than accumulators: validate_kernel
-        // ---- one pass over the samples: one-hot tiles -> MMA -> clear ----
+        // ---- one pass over the samples: one-hot tiles -> MMA -> clear; sums of the codes per piece on the way ----
+        // A batch = 32 * VH_SUB consecutive samples of one piece (VH_SUB per lane, one MMA per 32); the batches of the
+        // pieces form one flattened space dealt round-robin to the warps.
         {
             const int nb_total = H.bstart[np];
-            int gb = warp, p = 0;
-            int code = 0;
-            bool valid = false;
-            auto fetch = [&](int gq, int &pp, int &cd, bool &vd) {
-                while (gq >= H.bstart[pp + 1]) pp++;
-                const int j = H.cuts[pp] + ((gq - H.bstart[pp]) << 5) + lane;
-                vd = j < H.cuts[pp + 1];
-                cd = vd ? (int)W[j] : 0;
+            constexpr int D = 2;                     // batches of this warp in flight as global loads
+            int q_code[D][VH_SUB], q_piece[D];
+            unsigned q_valid[D];                     // bit u: sub-sample u of the lane exists
+            int pf = 0;                              // piece cursor of the fetches (batches come in piece order)
+            auto fetch = [&](int gq, int (&cd)[VH_SUB], unsigned &vd, int &pp) {
+                vd = 0; pp = 0;
+#pragma unroll
+                for (int u = 0; u < VH_SUB; u++) cd[u] = 0;
+                if (gq >= nb_total) return;
+                while (gq >= H.bstart[pf + 1]) pf++;
+                const int j = H.cuts[pf] + (gq - H.bstart[pf]) * (32 * VH_SUB) + lane, jend = H.cuts[pf + 1];
+                pp = pf;
+#pragma unroll
+                for (int u = 0; u < VH_SUB; u++)
+                    if (j + 32 * u < jend) { vd |= 1u << u; cd[u] = (int)W[j + 32 * u]; }
             };
-            if (gb < nb_total) fetch(gb, p, code, valid);
-            int n_low = 0, n_high = 0;
-            while (gb < nb_total) {
-                const int g2 = gb + VH_WARPS;
-                int p2 = p, code2 = 0;
-                bool valid2 = false;
-                if (g2 < nb_total) fetch(g2, p2, code2, valid2);
-                int cp = code - base;
-                n_low += __popc(__ballot_sync(ADB_FULL, valid && cp < 0));
-                n_high += __popc(__ballot_sync(ADB_FULL, valid && cp > VH_BINS - 1));
-                cp = min(max(cp, 0), VH_BINS - 1);
-                unsigned char *pA8 = tileA + (lane >> 4) * VH_A_LBO + (cp >> 4) * 16 + (lane & 15);
-                unsigned char *pB8 = tileB + (lane >> 4) * VH_B_LBO + (cp & 15) * 16 + (lane & 15);
-                if (valid) { *pA8 = 0x38; *pB8 = 0x38; }
+#pragma unroll
+            for (int d = 0; d < D; d++) fetch(warp + d * VH_WARPS, q_code[d], q_valid[d], q_piece[d]);
+            unsigned outside = 0;                    // bit 0: a code below base seen, bit 1: one above base + VH_BINS - 1
+            int cur = -1;                            // piece of the running sums
+            int s1 = 0;                              // sum of (code - base) of this lane: |code - base| < 2^16, < 2^11 batches
+            unsigned long long s2 = 0;               // sum of their squares
+            auto flush = [&]() {
+                if (cur < 0) return;
+                long long t1 = s1;
+                unsigned long long t2 = s2;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { t1 += __shfl_xor_sync(ADB_FULL, t1, o); t2 += __shfl_xor_sync(ADB_FULL, t2, o); }
+                if (lane == 0) { atomicAdd(&H.psum[cur][0], (unsigned long long)t1); atomicAdd(&H.psum[cur][1], t2); }  // (two's complement)
+                s1 = 0; s2 = 0;
+            };
+            for (int gb = warp; gb < nb_total; gb += VH_WARPS) {
+                int code[VH_SUB];
+#pragma unroll
+                for (int u = 0; u < VH_SUB; u++) code[u] = q_code[0][u];
+                const int p = q_piece[0];
+                const unsigned valid = q_valid[0];
+#pragma unroll
+                for (int d = 0; d + 1 < D; d++) {
+#pragma unroll
+                    for (int u = 0; u < VH_SUB; u++) q_code[d][u] = q_code[d + 1][u];
+                    q_piece[d] = q_piece[d + 1]; q_valid[d] = q_valid[d + 1];
+                }
+                fetch(gb + D * VH_WARPS, q_code[D - 1], q_valid[D - 1], q_piece[D - 1]);
+                if (p != cur) { flush(); cur = p; }
+                unsigned char *pA8[VH_SUB], *pB8[VH_SUB];
+#pragma unroll
+                for (int u = 0; u < VH_SUB; u++) {
+                    const int dd = code[u] - base;
+                    const bool on = (valid >> u) & 1u;
+                    if (on) {
+                        outside |= (dd < 0 ? 1u : 0u) | (dd > VH_BINS - 1 ? 2u : 0u);
+                        const unsigned ud = (unsigned)abs(dd);
+                        s1 += dd;
+                        s2 += (unsigned long long)(ud * ud);
+                    }
+                    const int cp = min(max(dd, 0), VH_BINS - 1);
+                    unsigned char *tA = tile0 + u * VH_TILE_BYTES;
+                    pA8[u] = tA + (lane >> 4) * VH_A_LBO + (cp >> 4) * 16 + (lane & 15);
+                    pB8[u] = tA + VH_A_BYTES + (lane >> 4) * VH_B_LBO + (cp & 15) * 16 + (lane & 15);
+                    if (on) { *pA8[u] = 0x38; *pB8[u] = 0x38; }
+                }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (tc_elect_one()) {
-                    vh_mma_f8(tmem + (uint32_t)p * 16, a_lo, ab_hi, b_lo, ab_hi);
+#pragma unroll
+                    for (int u = 0; u < VH_SUB; u++) vh_mma_f8(tmem + (uint32_t)p * 16, a_lo[u], ab_hi, b_lo[u], ab_hi);
                     tc_commit(&H.bar[warp]);
                 }
                 __syncwarp();
                 mbar_wait(&H.bar[warp], phase);
                 phase ^= 1;
-                if (valid) { *pA8 = 0; *pB8 = 0; }
-                gb = g2; p = p2; code = code2; valid = valid2;
+#pragma unroll
+                for (int u = 0; u < VH_SUB; u++)
+                    if ((valid >> u) & 1u) { *pA8[u] = 0; *pB8[u] = 0; }
             }
-            if (lane == 0 && (n_low | n_high)) { atomicAdd(&H.n_low, n_low); atomicAdd(&H.n_high, n_high); }
+            flush();
+            const unsigned om = __reduce_or_sync(ADB_FULL, outside);
+            if (lane == 0 && om) { if (om & 1u) atomicAdd(&H.n_low, 1); if (om & 2u) atomicAdd(&H.n_high, 1); }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        VH_T(3);
         // ---- accumulators -> counts (u16) in the arena (the tiles are idle and all-zero) ----
         {
             const int quad = warp & 3;
@@ -399,9 +623,13 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_hist_kernel(VfastArgs 
                     const unsigned c1 = (unsigned)__float2int_rn(__uint_as_float(v[2 * i + 1]));
                     w[i] = (c0 & 0xffffu) | (c1 << 16);
                 }
-                uint4 *dst = reinterpret_cast<uint4 *>(cum + (size_t)p * VH_BINS + (quad * 32 + lane) * 16);
-                dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                // accumulator row of this thread's TMEM lane: M = 128 -> the lane; M = 64 -> 16 rows per 32-lane quarter
+                const int row = (VH_M == 128) ? quad * 32 + lane : quad * 16 + lane;
+                if (VH_M == 128 || lane < 16) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(cum + (size_t)p * VH_BINS + row * 16);
+                    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                }
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -427,50 +655,52 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_hist_kernel(VfastArgs 
             }
         }
         __syncthreads();
-        // ---- the statistics: lane q of warp 0 answers rank query q, then lanes 0..3 the four MADs ----
-        if (warp == 0) {
+        VH_T(4);
+        // ---- the statistics: rank query q on warp q % 8 (32-way searches), then the four MADs on warps 0..3 ----
+        {
             const int n_low = H.n_low, n_high = H.n_high;
-            if (lane < VH_NQ) {
+            for (int qq = warp; qq < VH_NQ; qq += VH_WARPS) {
                 int a = 0, b = 0;
 #pragma unroll
-                for (int q = 0; q < VH_NQ; q++) if (lane == q) { a = qa[q]; b = qb[q]; }
+                for (int q = 0; q < VH_NQ; q++) if (qq == q) { a = qa[q]; b = qb[q]; }
                 int v0 = 0, v1 = 0;
                 const int n = b - a;
                 if (n > 0) {
                     const VhRange q = vh_range(H, a, b, size);
                     int k = (n - 1) / 2;
                     bool two = (n & 1) == 0;
-                    if (lane == 2 || lane == 3 || lane == 5 || lane == 6) {  // np.percentile: floor of the virtual index
-                        const double vv = (lane == 2) ? vLR15 : (lane == 3) ? vLR85 : (lane == 5) ? vP15 : vP85;
+                    if (qq == 2 || qq == 3 || qq == 5 || qq == 6) {  // np.percentile: floor of the virtual index
+                        const double vv = (qq == 2) ? vLR15 : (qq == 3) ? vLR85 : (qq == 5) ? vP15 : vP85;
                         k = (int)floor(vv);
                         two = min(k + 1, n - 1) != k;
                     }
-                    const int x0 = vh_select(cum, q.p0, q.p1, k);
-                    const int x1 = two ? vh_select(cum, q.p0, q.p1, k + 1) : x0;
+                    const int x0 = vh_wselect(cum, q.p0, q.p1, k);
+                    const int x1 = two ? vh_wselect(cum, q.p0, q.p1, k + 1) : x0;
                     if (((x0 <= 0 || x1 <= 0) && n_low > 0) || ((x0 >= VH_BINS - 1 || x1 >= VH_BINS - 1) && n_high > 0)) H.unsettled = 1;
                     v0 = x0 + base;
                     v1 = x1 + base;
                 }
-                H.qv0[lane] = v0; H.qv1[lane] = v1; H.qn[lane] = n;
-            }
-            __syncwarp();
-            if (lane < 4) {
-                const int src = (lane == 0) ? 0 : (lane == 1) ? 1 : (lane == 2) ? 4 : 9;
-                int a = 0, b = 0;
-#pragma unroll
-                for (int q = 0; q < VH_NQ; q++) if (src == q) { a = qa[q]; b = qb[q]; }
-                const int n = b - a;
-                float mad = CUDART_NAN_F;
-                if (n > 0) {
-                    const float x0 = vf_pa(R, H.qv0[src]);
-                    const float med = (n & 1) ? x0 : __fdiv_rn(__fadd_rn(x0, vf_pa(R, H.qv1[src])), 2.0f);
-                    mad = vh_mad(R, H, cum, vh_range(H, a, b, size), base, n, med);
-                }
-                H.mad[lane] = mad;
+                if (lane == 0) { H.qv0[qq] = v0; H.qv1[qq] = v1; H.qn[qq] = n; }
             }
         }
         __syncthreads();
+        if (warp < 4) {
+            const int src = (warp == 0) ? 0 : (warp == 1) ? 1 : (warp == 2) ? 4 : 9;
+            int a = 0, b = 0;
+#pragma unroll
+            for (int q = 0; q < VH_NQ; q++) if (src == q) { a = qa[q]; b = qb[q]; }
+            const int n = b - a;
+            float mad = CUDART_NAN_F;
+            if (n > 0) {
+                const float x0 = vf_pa(R, H.qv0[src]);
+                const float med = (n & 1) ? x0 : __fdiv_rn(__fadd_rn(x0, vf_pa(R, H.qv1[src])), 2.0f);
+                mad = vh_wmad(R, H, cum, vh_range(H, a, b, size), base, n, med);
+            }
+            if (lane == 0) H.mad[warp] = mad;
+        }
+        __syncthreads();
         const bool unsettled = H.unsettled != 0;
+        VH_T(5);
         auto median_of = [&](int q) -> float {
             const int n = H.qn[q];
             if (n <= 0) return CUDART_NAN_F;
@@ -493,6 +723,7 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_hist_kernel(VfastArgs 
         __syncthreads();
         // the arena goes back to all-zero operand tiles for the next read
         for (int i = tid; i < VH_ARENA / 16; i += VF_THREADS) reinterpret_cast<uint4 *>(arena)[i] = make_uint4(0, 0, 0, 0);
+        VH_T(6);
         if (unsettled) continue;  // (uniform) codes outside the histogram range matter: validate_kernel
 
         // ---- the checks (combined.py:394-580), as in validate_fast_kernel ----
@@ -512,11 +743,28 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_hist_kernel(VfastArgs 
                 if (a_end - a_start < cfg.min_obs_adapter) { success = false; fail = ADB_FAIL_OPEN_PORE; }
             }
         }
+        // partition mean / std (signal_partitions.py:91-92) from the exact per-piece sums of the pass above: the same
+        // integers and the same float64 formulas as vf_mean_std3
         double pmean[3], pstd[3];
         {
             const int sa[3] = {a_start, a_end, pe_best}, sb[3] = {a_end, pe_best, size};
             const bool on[3] = {a_end > a_start, pe_best > a_end, size > pe_best};
-            vf_mean_std3(R, S, sa, sb, on, pmean, pstd);
+            for (int sgm = 0; sgm < 3; sgm++) {
+                int a = sa[sgm], b = sb[sgm];
+                clip_seg(a, b, size);
+                const int n = on[sgm] ? b - a : 0;
+                if (n <= 0) { pmean[sgm] = CUDART_NAN; pstd[sgm] = CUDART_NAN; continue; }
+                const VhRange q = vh_range(H, a, b, size);
+                long long d1 = 0, d2 = 0;
+                for (int p = q.p0; p < q.p1; p++) { d1 += (long long)H.psum[p][0]; d2 += (long long)H.psum[p][1]; }
+                const long long s1 = d1 + (long long)n * base;                                   // sum of the codes
+                const long long s2 = d2 + 2ll * base * d1 + (long long)n * base * (long long)base;  // sum of their squares
+                const double mk = (double)s1 / n;
+                double vk = (double)s2 / n - mk * mk;
+                if (vk < 0) vk = 0;
+                pmean[sgm] = (double)(float)((mk + (double)R.coff) * (double)R.cscale);
+                pstd[sgm] = (double)(float)(sqrt(vk) * fabs((double)R.cscale));
+            }
         }
         if (success && cfg.real_signal_check) {
             if (rlen < 2 * cfg.mean_window) {
@@ -654,9 +902,10 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_hist_kernel(VfastArgs 
             __threadfence();
             A.done[r] = followup ? 2 : 1;
         }
+        VH_T(7);
     }
     __syncthreads();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem));
 }
