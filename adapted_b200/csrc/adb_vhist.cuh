@@ -152,8 +152,11 @@ __device__ float vh_wmad(const VfRead &R, VhShared &H, const uint16_t *cum, VhRa
     const int lane = threadIdx.x & 31;
     if (n <= 0 || !(med == med)) return CUDART_NAN_F;
     const int n_low = H.n_low, n_high = H.n_high;
-    const int smin = vh_wselect(cum, q.p0, q.p1, 0) + base, smax = vh_wselect(cum, q.p0, q.p1, n - 1) + base;
+    // candidates: every code of the histogram range (codes nobody holds are harmless: the count only changes at codes that
+    // are held, so the first passing candidate of the side that decides is a held one)
+    const int smin = base, smax = base + VH_BINS - 1;
     const int k = (n - 1) / 2;
+    const float rscale = 1.0f / R.cscale;
     int ok = 1;
     int pv = gsb_code_at(med, false, R.coff, R.cscale, &ok);
     pv = min(max(pv, smin), smax + 1);
@@ -161,7 +164,7 @@ __device__ float vh_wmad(const VfRead &R, VhShared &H, const uint16_t *cum, VhRa
     auto sdev = [&](bool right, int i) { return vf_dev(R, right ? pv + i : pv - 1 - i, med); };
     // first index of a side whose deviation is > thr (strict) or >= thr
     auto sfirst = [&](bool right, int nn, float thr, bool strict) -> int {
-        float gf = thr / R.cscale;
+        float gf = thr * rscale;  // (a guess: corrected below by evaluating the deviations exactly)
         int g = (gf == gf && gf < 1e9f) ? (int)gf : nn;
         g = min(max(g, 0), nn);
         int guard = 0;
@@ -360,12 +363,10 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_hist_kernel(VfastArgs 
     const uint32_t tmem = H.tmem_slot;
     unsigned char *tile0 = arena + (size_t)warp * VH_SUB * VH_TILE_BYTES;
     const uint32_t ab_hi = tc_desc_hi(128);
-    uint32_t a_lo[VH_SUB], b_lo[VH_SUB];
-#pragma unroll
-    for (int u = 0; u < VH_SUB; u++) {
-        a_lo[u] = tc_desc_lo(smem_u32(tile0 + u * VH_TILE_BYTES), VH_A_LBO);
-        b_lo[u] = tc_desc_lo(smem_u32(tile0 + u * VH_TILE_BYTES + VH_A_BYTES), VH_B_LBO);
-    }
+    // descriptors of sub-tile 0 (sub-tile u: + u * VH_TILE_BYTES >> 4 in the address field); this lane's byte of a tile row
+    const uint32_t a_lo0 = tc_desc_lo(smem_u32(tile0), VH_A_LBO), b_lo0 = tc_desc_lo(smem_u32(tile0 + VH_A_BYTES), VH_B_LBO);
+    unsigned char *laneA = tile0 + (lane >> 4) * VH_A_LBO + (lane & 15);
+    unsigned char *laneB = tile0 + VH_A_BYTES + (lane >> 4) * VH_B_LBO + (lane & 15);
     uint32_t phase = 0;  // parity of this warp's barrier
 
     for (int r = blockIdx.x; r < A.B.n_reads; r += gridDim.x) {
@@ -520,89 +521,71 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_hist_kernel(VfastArgs 
         VH_T(2);
         if (np > VH_MAX_PIECES) continue;  // (uniform) more ranges than accumulators: validate_kernel
         // ---- one pass over the samples: one-hot tiles -> MMA -> clear; sums of the codes per piece on the way ----
-        // A batch = 32 * VH_SUB consecutive samples of one piece (VH_SUB per lane, one MMA per 32); the batches of the
-        // pieces form one flattened space dealt round-robin to the warps.
+        // A batch = 32 * VH_SUB consecutive samples of one piece (VH_SUB per lane, one MMA per 32); the batches of all
+        // pieces are dealt round-robin to the warps, the samples of a warp's next batch are loaded one batch ahead.
         {
-            const int nb_total = H.bstart[np];
-            constexpr int D = 2;                     // batches of this warp in flight as global loads
-            int q_code[D][VH_SUB], q_piece[D];
-            unsigned q_valid[D];                     // bit u: sub-sample u of the lane exists
-            int pf = 0;                              // piece cursor of the fetches (batches come in piece order)
-            auto fetch = [&](int gq, int (&cd)[VH_SUB], unsigned &vd, int &pp) {
-                vd = 0; pp = 0;
+            int cmin = 0x7fffffff, cmax = -0x7fffffff;   // code range seen by this lane
+            int boff = 0;                                // batches of the pieces before p
+            for (int p = 0; p < np; p++) {
+                const int c0 = H.cuts[p], c1 = H.cuts[p + 1];
+                const int nb = (c1 - c0 + 32 * VH_SUB - 1) / (32 * VH_SUB);
+                int bt = (warp - boff) & (VH_WARPS - 1);  // this warp's first batch of the piece
+                boff += nb;
+                if (bt >= nb) continue;
+                const uint32_t dcol = tmem + (uint32_t)p * 16;
+                int j = c0 + bt * (32 * VH_SUB) + lane;
+                int nxt[VH_SUB];
 #pragma unroll
-                for (int u = 0; u < VH_SUB; u++) cd[u] = 0;
-                if (gq >= nb_total) return;
-                while (gq >= H.bstart[pf + 1]) pf++;
-                const int j = H.cuts[pf] + (gq - H.bstart[pf]) * (32 * VH_SUB) + lane, jend = H.cuts[pf + 1];
-                pp = pf;
+                for (int u = 0; u < VH_SUB; u++) nxt[u] = (j + 32 * u < c1) ? (int)W[j + 32 * u] : 0;
+                int s1 = 0;                              // sum of (code - base) of this lane: |code - base| < 2^16, < 2^11 batches
+                unsigned long long s2 = 0;               // sum of their squares
+                for (; bt < nb; bt += VH_WARPS, j += VH_WARPS * 32 * VH_SUB) {
+                    int code[VH_SUB];
 #pragma unroll
-                for (int u = 0; u < VH_SUB; u++)
-                    if (j + 32 * u < jend) { vd |= 1u << u; cd[u] = (int)W[j + 32 * u]; }
-            };
+                    for (int u = 0; u < VH_SUB; u++) code[u] = nxt[u];
+                    const int jn = j + VH_WARPS * 32 * VH_SUB;
 #pragma unroll
-            for (int d = 0; d < D; d++) fetch(warp + d * VH_WARPS, q_code[d], q_valid[d], q_piece[d]);
-            unsigned outside = 0;                    // bit 0: a code below base seen, bit 1: one above base + VH_BINS - 1
-            int cur = -1;                            // piece of the running sums
-            int s1 = 0;                              // sum of (code - base) of this lane: |code - base| < 2^16, < 2^11 batches
-            unsigned long long s2 = 0;               // sum of their squares
-            auto flush = [&]() {
-                if (cur < 0) return;
+                    for (int u = 0; u < VH_SUB; u++) nxt[u] = (jn + 32 * u < c1) ? (int)W[jn + 32 * u] : 0;
+                    unsigned char *pA8[VH_SUB], *pB8[VH_SUB];
+#pragma unroll
+                    for (int u = 0; u < VH_SUB; u++) {
+                        const bool on = j + 32 * u < c1;
+                        const int dd = code[u] - base;
+                        if (on) {
+                            cmin = min(cmin, dd); cmax = max(cmax, dd);
+                            const unsigned ud = (unsigned)abs(dd);
+                            s1 += dd;
+                            s2 += (unsigned long long)(ud * ud);
+                        }
+                        const int cp = min(max(dd, 0), VH_BINS - 1);
+                        pA8[u] = laneA + u * VH_TILE_BYTES + (cp >> 4) * 16;
+                        pB8[u] = laneB + u * VH_TILE_BYTES + (cp & 15) * 16;
+                        if (on) { *pA8[u] = 0x38; *pB8[u] = 0x38; }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (tc_elect_one()) {
+#pragma unroll
+                        for (int u = 0; u < VH_SUB; u++)
+                            vh_mma_f8(dcol, a_lo0 + u * (VH_TILE_BYTES >> 4), ab_hi, b_lo0 + u * (VH_TILE_BYTES >> 4), ab_hi);
+                        tc_commit(&H.bar[warp]);
+                    }
+                    __syncwarp();
+                    mbar_wait(&H.bar[warp], phase);
+                    phase ^= 1;
+#pragma unroll
+                    for (int u = 0; u < VH_SUB; u++)
+                        if (j + 32 * u < c1) { *pA8[u] = 0; *pB8[u] = 0; }
+                }
+                // this warp's share of the piece's sums
                 long long t1 = s1;
                 unsigned long long t2 = s2;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) { t1 += __shfl_xor_sync(ADB_FULL, t1, o); t2 += __shfl_xor_sync(ADB_FULL, t2, o); }
-                if (lane == 0) { atomicAdd(&H.psum[cur][0], (unsigned long long)t1); atomicAdd(&H.psum[cur][1], t2); }  // (two's complement)
-                s1 = 0; s2 = 0;
-            };
-            for (int gb = warp; gb < nb_total; gb += VH_WARPS) {
-                int code[VH_SUB];
-#pragma unroll
-                for (int u = 0; u < VH_SUB; u++) code[u] = q_code[0][u];
-                const int p = q_piece[0];
-                const unsigned valid = q_valid[0];
-#pragma unroll
-                for (int d = 0; d + 1 < D; d++) {
-#pragma unroll
-                    for (int u = 0; u < VH_SUB; u++) q_code[d][u] = q_code[d + 1][u];
-                    q_piece[d] = q_piece[d + 1]; q_valid[d] = q_valid[d + 1];
-                }
-                fetch(gb + D * VH_WARPS, q_code[D - 1], q_valid[D - 1], q_piece[D - 1]);
-                if (p != cur) { flush(); cur = p; }
-                unsigned char *pA8[VH_SUB], *pB8[VH_SUB];
-#pragma unroll
-                for (int u = 0; u < VH_SUB; u++) {
-                    const int dd = code[u] - base;
-                    const bool on = (valid >> u) & 1u;
-                    if (on) {
-                        outside |= (dd < 0 ? 1u : 0u) | (dd > VH_BINS - 1 ? 2u : 0u);
-                        const unsigned ud = (unsigned)abs(dd);
-                        s1 += dd;
-                        s2 += (unsigned long long)(ud * ud);
-                    }
-                    const int cp = min(max(dd, 0), VH_BINS - 1);
-                    unsigned char *tA = tile0 + u * VH_TILE_BYTES;
-                    pA8[u] = tA + (lane >> 4) * VH_A_LBO + (cp >> 4) * 16 + (lane & 15);
-                    pB8[u] = tA + VH_A_BYTES + (lane >> 4) * VH_B_LBO + (cp & 15) * 16 + (lane & 15);
-                    if (on) { *pA8[u] = 0x38; *pB8[u] = 0x38; }
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (tc_elect_one()) {
-#pragma unroll
-                    for (int u = 0; u < VH_SUB; u++) vh_mma_f8(tmem + (uint32_t)p * 16, a_lo[u], ab_hi, b_lo[u], ab_hi);
-                    tc_commit(&H.bar[warp]);
-                }
-                __syncwarp();
-                mbar_wait(&H.bar[warp], phase);
-                phase ^= 1;
-#pragma unroll
-                for (int u = 0; u < VH_SUB; u++)
-                    if ((valid >> u) & 1u) { *pA8[u] = 0; *pB8[u] = 0; }
+                if (lane == 0) { atomicAdd(&H.psum[p][0], (unsigned long long)t1); atomicAdd(&H.psum[p][1], t2); }  // (two's complement)
             }
-            flush();
-            const unsigned om = __reduce_or_sync(ADB_FULL, outside);
-            if (lane == 0 && om) { if (om & 1u) atomicAdd(&H.n_low, 1); if (om & 2u) atomicAdd(&H.n_high, 1); }
+            const bool lo_out = __any_sync(ADB_FULL, cmin < 0), hi_out = __any_sync(ADB_FULL, cmax > VH_BINS - 1);
+            if (lane == 0) { if (lo_out) atomicAdd(&H.n_low, 1); if (hi_out) atomicAdd(&H.n_high, 1); }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
@@ -721,8 +704,8 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_hist_kernel(VfastArgs 
         const double lrP = local_range(5, 6, vP15, vP85);
         const float madA0 = H.mad[0], madA1 = H.mad[1], madP = H.mad[2], madR = H.mad[3];
         __syncthreads();
-        // the arena goes back to all-zero operand tiles for the next read
-        for (int i = tid; i < VH_ARENA / 16; i += VF_THREADS) reinterpret_cast<uint4 *>(arena)[i] = make_uint4(0, 0, 0, 0);
+        // the part of the arena that held the cumulative counts goes back to all-zero operand tiles for the next read
+        for (int i = tid; i < np * (VH_BINS * 2 / 16); i += VF_THREADS) reinterpret_cast<uint4 *>(arena)[i] = make_uint4(0, 0, 0, 0);
         VH_T(6);
         if (unsettled) continue;  // (uniform) codes outside the histogram range matter: validate_kernel
 
