@@ -361,6 +361,12 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_hist_kernel(VfastArgs 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = H.tmem_slot;
+    {
+        const uint32_t t0 = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(warp >> 2) * 64;
+        vh_tmem_zero32(t0);
+        vh_tmem_zero32(t0 + 32);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
     unsigned char *tile0 = arena + (size_t)warp * VH_SUB * VH_TILE_BYTES;
     const uint32_t ab_hi = tc_desc_hi(128);
     // descriptors of sub-tile 0 (sub-tile u: + u * VH_TILE_BYTES >> 4 in the address field); this lane's byte of a tile row
@@ -507,13 +513,7 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_hist_kernel(VfastArgs 
             if (lane == 0) { H.np = np; H.n_low = 0; H.n_high = 0; H.unsettled = 0; }
         }
         if (tid < 2 * VH_MAX_PIECES) (&H.psum[0][0])[tid] = 0ull;
-        // ---- zero the accumulators ----
-        {
-            const uint32_t t0 = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(warp >> 2) * 64;
-            vh_tmem_zero32(t0);
-            vh_tmem_zero32(t0 + 32);
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        }
+        // (the accumulators are all-zero: cleared by the warps that read them, right after the previous read's readout)
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -614,6 +614,11 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_hist_kernel(VfastArgs 
                     dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
                 }
             }
+            // this warp's part of the accumulators (the lanes and columns it has just read) back to zero for the next read
+            const uint32_t t0 = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(warp >> 2) * 64;
+            vh_tmem_zero32(t0);
+            vh_tmem_zero32(t0 + 32);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
@@ -882,8 +887,7 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_hist_kernel(VfastArgs 
             for (int i = 0; i < 3; i++) rec->real[i] = real_v[i];
             rec->med_shift = med_shift;
             if (followup) *reinterpret_cast<float *>(rec->_reserved) = medA0;  // scales the mean range of the later candidates
-            __threadfence();
-            A.done[r] = followup ? 2 : 1;
+            A.done[r] = followup ? 2 : 1;  // (read by the kernels launched behind this one: no fence needed)
         }
         VH_T(7);
     }

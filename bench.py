@@ -231,7 +231,7 @@ def bind_to_gpu_local_cpus(local_rank: int):
     return info
 
 
-CLS_NAMES = ["global_select_pass", "global_select_small", "validate_fast_kernel", "llr_primary_kernel", "mvs_series_kernel",
+CLS_NAMES = ["global_select_pass", "global_select_small", "validate_hist_kernel", "llr_primary_kernel", "mvs_series_kernel + series_median_kernel",
              "cnn_conv_kernels", "cnn_pre_post | start_peak | svb16_decode", "handover_kernels"]
 
 
