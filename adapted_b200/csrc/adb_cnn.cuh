@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(256) cnn_prep_kernel(BatchDev B, int A0, int f
 // sampled opening bracket, bisection with warp counts, the last 64 keys ranked directly) -- no CTA barrier, 16 reads in
 // flight per SM.  Exact order statistics: identical to cnn_prep_kernel.
 #define PREP_WARPS 4
+#define PREP_CHUNK_BINS 320   // bins per staged chunk: 320 x downscale factor 10 x 2 B = 6400 B <= the warp's key area
 __host__ __device__ inline size_t cnn_prep_warp_smem(int L) { return (size_t)PREP_WARPS * (2 * ((L + 3) & ~3) + SM_NCAND + 4) * 4; }
 __global__ void __launch_bounds__(PREP_WARPS * 32) cnn_prep_warp_kernel(BatchDev B, int A0, int f, int L, float *x) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -122,6 +123,10 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) cnn_prep_warp_kernel(BatchDev
     const int Lp = (L + 3) & ~3;
     float *ds = (float *)smem + (size_t)warp * (2 * Lp + SM_NCAND + 4);
     uint32_t *keys = (uint32_t *)(ds + Lp), *cand = keys + Lp;
+    __shared__ uint64_t pbar[PREP_WARPS];
+    if (threadIdx.x < PREP_WARPS) mbar_init(&pbar[threadIdx.x], 1);
+    __syncthreads();
+    uint32_t pphase = 0;
     for (int r = blockIdx.x * PREP_WARPS + warp; r < B.n_reads; r += gridDim.x * PREP_WARPS) {
         const ReadSrc src = make_src(B, r);
         int nv;
@@ -145,21 +150,43 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) cnn_prep_warp_kernel(BatchDev
             }
         }
         uint32_t mn = 0xffffffffu, mx = 0u;
-        for (int b = lane; b < nv; b += 64) {  // two bins per lane and round: twice the loads in flight
-            const int j0 = A0 + b * f, j1 = j0 + 32 * f;
-            const bool two = b + 32 < nv;
-            const float v0 = cnn_block_mean([&](int k) { const int j = j0 + k; return (j < B.m) ? src.pa(j) : 0.0f; }, f);
-            const float v1 = two ? cnn_block_mean([&](int k) { const int j = j1 + k; return (j < B.m) ? src.pa(j) : 0.0f; }, f) : 0.f;
-            ds[b] = v0;
-            const uint32_t k0 = f32_key(v0);
-            keys[b] = k0;
-            mn = min(mn, k0); mx = max(mx, k0);
-            if (two) {
-                ds[b + 32] = v1;
-                const uint32_t k1 = f32_key(v1);
-                keys[b + 32] = k1;
-                mn = min(mn, k1); mx = max(mx, k1);
+        // The raw samples of the NaN-free bins travel to the warp's slice in chunks of PREP_CHUNK_BINS bins (the 16-byte
+        // aligned interior of a chunk by one TMA bulk copy, the few samples around it by ordinary loads; the `keys` area
+        // is free until the row is complete), the block means are formed from shared memory: ten conflict-free 2-byte
+        // loads per bin instead of ten strided global loads.
+        {
+            int16_t *raw = reinterpret_cast<int16_t *>(keys);
+            const int16_t *g0 = src.i16 + A0;                     // first sample of bin 0
+            const int cbins = min(PREP_CHUNK_BINS, (Lp * 4 - 16) / (2 * f));  // bins per chunk that fit the key area
+            const int n_have = min(src.n, B.m) - A0;              // samples that exist behind A0
+            for (int b0 = 0; b0 < nv; b0 += cbins) {
+                const int nbin = min(cbins, nv - b0), ns = min(nbin * f, n_have - b0 * f);
+                const int16_t *gs = g0 + (size_t)b0 * f;          // first sample of the chunk
+                const int shift = (int)(((uintptr_t)gs & 15) >> 1);  // the chunk sits at raw[shift ...): same 16-byte phase
+                const int head = min((8 - shift) & 7, ns);         // samples before the aligned interior
+                const int body = (ns - head) & ~7;                 // samples of the interior (a multiple of 8)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0 && body > 0) {
+                    mbar_expect_tx(&pbar[warp], (uint32_t)body * 2);
+                    tma_bulk_g2s(raw + shift + head, gs + head, (uint32_t)body * 2, &pbar[warp]);
+                }
+                for (int i = lane; i < head; i += 32) raw[shift + i] = gs[i];
+                for (int i = head + body + lane; i < ns; i += 32) raw[shift + i] = gs[i];
+                if (body > 0) { mbar_wait(&pbar[warp], pphase); pphase ^= 1; }
+                __syncwarp();
+                const int16_t *rs = raw + shift;
+                for (int b = lane; b < nbin; b += 32) {
+                    const int16_t *p = rs + b * f;
+                    const int left = ns - b * f;                   // staged samples from the bin's start (< f: ragged last bin)
+                    const float v = cnn_block_mean([&](int k) { return (k < left) ? __fmul_rn(__fadd_rn((float)(int)p[k], src.coff), src.cscale) : 0.0f; }, f);
+                    ds[b0 + b] = v;
+                    const uint32_t k0 = f32_key(v);
+                    mn = min(mn, k0); mx = max(mx, k0);
+                }
+                __syncwarp();
             }
+            for (int b = lane; b < nv; b += 32) keys[b] = f32_key(ds[b]);
         }
         if (lane < nvp - nv) keys[nv + lane] = 0xffffffffu;  // pad to full vectors with keys above every rank looked for
         mn = __reduce_min_sync(ADB_FULL, mn);
@@ -817,7 +844,8 @@ static int cnn_primary_boundaries(adb_ctx *ctx, const BatchDev &B, const adb_con
         CUDA_TRY(cudaFuncSetAttribute(cnn_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KernelTimer t(ctx, 6, st);
         const size_t wsm = cnn_prep_warp_smem(D.Lx);
-        if (B.sig_type == ADB_SIG_I16 && (int)wsm <= ctx->max_smem_optin && !getenv("ADB_PREP_CTA")) {
+        if (B.sig_type == ADB_SIG_I16 && (int)wsm <= ctx->max_smem_optin && !getenv("ADB_PREP_CTA") &&
+            (((D.Lx + 3) & ~3) * 4 - 16) / (2 * cfg.downscale_factor) >= 32) {
             CUDA_TRY(cudaFuncSetAttribute(cnn_prep_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm));
             int occ = 0;
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cnn_prep_warp_kernel, PREP_WARPS * 32, wsm));

@@ -208,15 +208,22 @@ __device__ float warp_series_median(const float *__restrict__ g, int n, uint32_t
         // whole row from the pool.
         bool done = false;
         {
-            for (int i = lane; i < SM_NSAMP; i += 32) kbuf[i] = f32_key(__ldg(g + (size_t)(((long long)i * n) / SM_NSAMP)));
+            uint32_t smn = 0xffffffffu, smx = 0u;
+            for (int i = lane; i < SM_NSAMP; i += 32) {
+                const uint32_t k = f32_key(__ldg(g + (size_t)(((long long)i * n) / SM_NSAMP)));
+                kbuf[i] = k;
+                smn = min(smn, k); smx = max(smx, k);
+            }
+            smn = __reduce_min_sync(ADB_FULL, smn);
+            smx = __reduce_max_sync(ADB_FULL, smx);
             __syncwarp();
             const SmKeys KS{K4, G4};
             const int rs = (int)(((long long)rank * SM_NSAMP) / n);
             const int r_lo = rs - SM_SPREAD, r_hi = rs + SM_SPREAD + 1;
             uint32_t s_lo = 0u, s_hi = 0xffffffffu, t0, t1;
             bool hb;
-            if (r_lo >= 0) warp_select2(KS, SM_NSAMP / 4, 0, false, SM_NSAMP, (unsigned)r_lo, 0u, 0xffffffffu, cand, s_lo, t0, hb);
-            if (r_hi < SM_NSAMP) warp_select2(KS, SM_NSAMP / 4, 0, false, SM_NSAMP, (unsigned)r_hi, 0u, 0xffffffffu, cand, s_hi, t1, hb);
+            if (r_lo >= 0) warp_select2(KS, SM_NSAMP / 4, 0, false, SM_NSAMP, (unsigned)r_lo, smn, smx, cand, s_lo, t0, hb);
+            if (r_hi < SM_NSAMP) warp_select2(KS, SM_NSAMP / 4, 0, false, SM_NSAMP, (unsigned)r_hi, smn, smx, cand, s_hi, t1, hb);
             __syncwarp();
             // one pass: keys below s_lo are counted, keys in [s_lo, s_hi] staged
             const int nv = n >> 2;
