@@ -101,6 +101,7 @@ struct VhShared {
     int unsettled;                     // an answer or a probe touched an end bin holding such samples
     int qv0[VH_NQ], qv1[VH_NQ], qn[VH_NQ];  // rank queries: codes at rank k and k + 1, samples of the range
     float mad[4];
+    int mfp[4][2];                     // first passing candidate of the right / left side of the four MAD ranges
     uint32_t hitw[VH_OP_WORDS];        // vh_open_pores: bit i = sample i of the aligned window is an open-pore sample
     unsigned long long psum[VH_MAX_PIECES][2];  // per piece: sum of (code - base), sum of (code - base)^2 (exact)
 };
@@ -142,28 +143,35 @@ __device__ __forceinline__ VhRange vh_range(const VhShared &H, int a, int b, int
     return q;
 }
 
-// median(|x - med|) of a range from the cumulative counts.  Warp-cooperative (uniform arguments and result).
+// median(|x - med|) of a range from the cumulative counts.  Warp-cooperative (uniform arguments and results).
 // The candidates are the deviations of the codes on either side of the median (right: pv + i, left: pv - 1 - i, both
 // non-decreasing in i); d0 = the smallest candidate t with #(deviation <= t) > k.  "Candidate i of a side passes" is
 // monotone in i, so each side is a 32-way search for its first passing candidate (one candidate per lane and round:
-// exact float32 deviation, the matching end of the interval on the other side, two look-ups), and d0 is the smaller of
-// the two.  The decisive evaluations (first passing, last failing) are repeated with the end-bin check.
-__device__ float vh_wmad(const VfRead &R, VhShared &H, const uint16_t *cum, VhRange q, int base, int n, float med) {
-    const int lane = threadIdx.x & 31;
-    if (n <= 0 || !(med == med)) return CUDART_NAN_F;
-    const int n_low = H.n_low, n_high = H.n_high;
-    // candidates: every code of the histogram range (codes nobody holds are harmless: the count only changes at codes that
-    // are held, so the first passing candidate of the side that decides is a held one)
-    const int smin = base, smax = base + VH_BINS - 1;
-    const int k = (n - 1) / 2;
-    const float rscale = 1.0f / R.cscale;
-    int ok = 1;
-    int pv = gsb_code_at(med, false, R.coff, R.cscale, &ok);
-    pv = min(max(pv, smin), smax + 1);
-    const int nR = smax + 1 - pv, nL = pv - smin;
-    auto sdev = [&](bool right, int i) { return vf_dev(R, right ? pv + i : pv - 1 - i, med); };
+// exact float32 deviation, the matching end of the interval on the other side, two look-ups) -- the two sides of a range
+// run on two warps -- and d0 is the smaller of the two.  The decisive evaluations (first passing, last failing) are
+// repeated with the end-bin check.  Candidates are all codes of the histogram range (codes nobody holds are harmless:
+// the count only changes at codes that are held, so the first passing candidate of the side that decides is a held one).
+struct VhMad {
+    const VfRead &R;
+    VhShared &H;
+    const uint16_t *cum;
+    VhRange q;
+    int base, n, k, pv, nR, nL, n_low, n_high;
+    float med, rscale;
+    __device__ VhMad(const VfRead &R_, VhShared &H_, const uint16_t *cum_, VhRange q_, int base_, int n_, float med_)
+        : R(R_), H(H_), cum(cum_), q(q_), base(base_), n(n_), med(med_) {
+        n_low = H.n_low; n_high = H.n_high;
+        k = (n - 1) / 2;
+        rscale = 1.0f / R.cscale;
+        int ok = 1;
+        pv = gsb_code_at(med, false, R.coff, R.cscale, &ok);
+        pv = min(max(pv, base), base + VH_BINS);
+        nR = base + VH_BINS - pv;
+        nL = pv - base;
+    }
+    __device__ __forceinline__ float sdev(bool right, int i) const { return vf_dev(R, right ? pv + i : pv - 1 - i, med); }
     // first index of a side whose deviation is > thr (strict) or >= thr
-    auto sfirst = [&](bool right, int nn, float thr, bool strict) -> int {
+    __device__ int sfirst(bool right, int nn, float thr, bool strict) const {
         float gf = thr * rscale;  // (a guess: corrected below by evaluating the deviations exactly)
         int g = (gf == gf && gf < 1e9f) ? (int)gf : nn;
         g = min(max(g, 0), nn);
@@ -177,18 +185,20 @@ __device__ float vh_wmad(const VfRead &R, VhShared &H, const uint16_t *cum, VhRa
             if (strict ? !(d > thr) : !(d >= thr)) g++; else break;
         }
         return g;
-    };
+    }
     // samples deviating at most thr (check: flag the read if the interval runs into an end bin that holds outside codes)
-    auto count_le = [&](float thr, bool check) -> int {
+    __device__ int count_le(float thr, bool check) const {
         const int jR = sfirst(true, nR, thr, true), jL = sfirst(false, nL, thr, true);
         const int pA = pv - jL, pB = pv + jR - 1;
         if (pB < pA) return 0;
         const int xa = pA - base, xb = pB - base;
         if (check && ((xa <= 0 && n_low > 0) || (xb >= VH_BINS - 1 && n_high > 0))) H.unsettled = 1;
         return vh_cle(cum, q.p0, q.p1, xb) - vh_cle(cum, q.p0, q.p1, xa - 1);
-    };
-    // first passing candidate of a side (nn if none): answer in [lo, hi]
-    auto first_pass = [&](bool right, int nn) -> int {
+    }
+    // first passing candidate of a side (its number of candidates if none)
+    __device__ int first_pass(bool right) const {
+        const int lane = threadIdx.x & 31;
+        const int nn = right ? nR : nL;
         int lo = 0, hi = nn;
         while (lo < hi) {
             const int step = (hi - lo + 31) >> 5;
@@ -202,38 +212,40 @@ __device__ float vh_wmad(const VfRead &R, VhShared &H, const uint16_t *cum, VhRa
             lo = nlo; hi = nhi;
         }
         return lo;
-    };
-    const int fR = first_pass(true, nR), fL = first_pass(false, nL);
-    float d0 = CUDART_INF_F;
-    if (fR < nR) d0 = fminf(d0, sdev(true, fR));
-    if (fL < nL) d0 = fminf(d0, sdev(false, fL));
-    // decisive evaluations with the end-bin check (lanes 0..3), and the count at d0
-    {
-        const bool right = lane < 2;
-        const int f = right ? fR : fL, nn = right ? nR : nL;
-        const int i = (lane & 1) ? f - 1 : f;
-        if (lane < 4 && i >= 0 && i < nn) (void)count_le(sdev(right, i), true);
     }
-    const int c_best = count_le(d0, true);
-    if (n & 1) return d0;
-    float d1 = d0;
-    if (!(c_best > k + 1)) {
-        // the next larger deviation: the first occupied code on either side of the interval [l, r] deviating <= d0
-        int lo = smin, hi = pv;
-        while (lo < hi) { const int m = (lo + hi) >> 1; if (vf_dev(R, m, med) <= d0) hi = m; else lo = m + 1; }
-        const int l = lo;
-        lo = pv; hi = smax + 1;
-        while (lo < hi) { const int m = (lo + hi) >> 1; if (vf_dev(R, m, med) > d0) hi = m; else lo = m + 1; }
-        const int r = lo - 1;
-        d1 = CUDART_INF_F;
-        auto touch = [&](int x) { if ((x <= 0 && n_low > 0) || (x >= VH_BINS - 1 && n_high > 0)) H.unsettled = 1; };
-        const int c_r = vh_cle(cum, q.p0, q.p1, r - base);          // samples with a code <= r
-        if (c_r < n) { const int x = vh_wselect(cum, q.p0, q.p1, c_r); touch(x); d1 = fminf(d1, vf_dev(R, x + base, med)); }
-        const int c_l = vh_cle(cum, q.p0, q.p1, l - 1 - base);      // samples with a code < l
-        if (c_l > 0) { const int x = vh_wselect(cum, q.p0, q.p1, c_l - 1); touch(x); d1 = fminf(d1, vf_dev(R, x + base, med)); }
+    __device__ float finish(int fR, int fL) const {
+        const int lane = threadIdx.x & 31;
+        float d0 = CUDART_INF_F;
+        if (fR < nR) d0 = fminf(d0, sdev(true, fR));
+        if (fL < nL) d0 = fminf(d0, sdev(false, fL));
+        // decisive evaluations with the end-bin check (lanes 0..3), and the count at d0
+        {
+            const bool right = lane < 2;
+            const int f = right ? fR : fL, nn = right ? nR : nL;
+            const int i = (lane & 1) ? f - 1 : f;
+            if (lane < 4 && i >= 0 && i < nn) (void)count_le(sdev(right, i), true);
+        }
+        const int c_best = count_le(d0, true);
+        if (n & 1) return d0;
+        float d1 = d0;
+        if (!(c_best > k + 1)) {
+            // the next larger deviation: the first occupied code on either side of the interval [l, r] deviating <= d0
+            int lo = base, hi = pv;
+            while (lo < hi) { const int m = (lo + hi) >> 1; if (vf_dev(R, m, med) <= d0) hi = m; else lo = m + 1; }
+            const int l = lo;
+            lo = pv; hi = base + VH_BINS;
+            while (lo < hi) { const int m = (lo + hi) >> 1; if (vf_dev(R, m, med) > d0) hi = m; else lo = m + 1; }
+            const int r = lo - 1;
+            d1 = CUDART_INF_F;
+            auto touch = [&](int x) { if ((x <= 0 && n_low > 0) || (x >= VH_BINS - 1 && n_high > 0)) H.unsettled = 1; };
+            const int c_r = vh_cle(cum, q.p0, q.p1, r - base);          // samples with a code <= r
+            if (c_r < n) { const int x = vh_wselect(cum, q.p0, q.p1, c_r); touch(x); d1 = fminf(d1, vf_dev(R, x + base, med)); }
+            const int c_l = vh_cle(cum, q.p0, q.p1, l - 1 - base);      // samples with a code < l
+            if (c_l > 0) { const int x = vh_wselect(cum, q.p0, q.p1, c_l - 1); touch(x); d1 = fminf(d1, vf_dev(R, x + base, med)); }
+        }
+        return __fdiv_rn(__fadd_rn(d0, d1), 2.0f);
     }
-    return __fdiv_rn(__fadd_rn(d0, d1), 2.0f);
-}
+};
 
 // find_open_pores (anomalies.py:15-35) over the samples [0, b) of the window (b <= 32 * VH_OP_WORDS - 8), any int16
 // code.  Same results as vf_open_pores (adb_vfast.cuh), which scans per-thread chunks sample by sample; here the window
@@ -672,223 +684,244 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_hist_kernel(VfastArgs 
             }
         }
         __syncthreads();
-        if (warp < 4) {
-            const int src = (warp == 0) ? 0 : (warp == 1) ? 1 : (warp == 2) ? 4 : 9;
+        // the four MADs (ranges 0, 1, 4, 9): warp w searches the right side of range w & 3 (w < 4) or its left side
+        {
+            const int t = warp & 3;
+            const int src = (t == 0) ? 0 : (t == 1) ? 1 : (t == 2) ? 4 : 9;
             int a = 0, b = 0;
 #pragma unroll
             for (int q = 0; q < VH_NQ; q++) if (src == q) { a = qa[q]; b = qb[q]; }
             const int n = b - a;
-            float mad = CUDART_NAN_F;
+            float med = CUDART_NAN_F;
             if (n > 0) {
                 const float x0 = vf_pa(R, H.qv0[src]);
-                const float med = (n & 1) ? x0 : __fdiv_rn(__fadd_rn(x0, vf_pa(R, H.qv1[src])), 2.0f);
-                mad = vh_wmad(R, H, cum, vh_range(H, a, b, size), base, n, med);
+                med = (n & 1) ? x0 : __fdiv_rn(__fadd_rn(x0, vf_pa(R, H.qv1[src])), 2.0f);
             }
-            if (lane == 0) H.mad[warp] = mad;
+            const bool live = n > 0 && med == med;
+            const VhMad M(R, H, cum, vh_range(H, a, b, size), base, max(n, 1), live ? med : 0.0f);
+            if (live) { const int f = M.first_pass(warp < 4); if (lane == 0) H.mfp[t][warp >> 2] = f; }
+            __syncthreads();
+            if (warp < 4) {
+                const float mad = live ? M.finish(H.mfp[t][0], H.mfp[t][1]) : CUDART_NAN_F;
+                if (lane == 0) H.mad[t] = mad;
+            }
         }
         __syncthreads();
         const bool unsettled = H.unsettled != 0;
         VH_T(5);
-        auto median_of = [&](int q) -> float {
-            const int n = H.qn[q];
-            if (n <= 0) return CUDART_NAN_F;
-            const float x0 = vf_pa(R, H.qv0[q]);
-            if (n & 1) return x0;
-            return __fdiv_rn(__fadd_rn(x0, vf_pa(R, H.qv1[q])), 2.0f);
-        };
-        const float medA0 = median_of(0), medA1 = median_of(1), medP = median_of(4), medR = median_of(9);
-        const float medAF = median_of(7), medBF = median_of(8), medMA = median_of(10), medMB = median_of(11);
-        auto local_range = [&](int q15, int q85, double v15, double v85) -> double {
-            if (H.qn[q15] <= 0 || H.qn[q85] <= 0) return CUDART_NAN;
-            const int l15 = (int)floor(v15), l85 = (int)floor(v85);
-            const double p85 = np_lerp_f32(vf_pa(R, H.qv0[q85]), vf_pa(R, H.qv1[q85]), __dsub_rn(v85, (double)l85));
-            const double p15 = np_lerp_f32(vf_pa(R, H.qv0[q15]), vf_pa(R, H.qv1[q15]), __dsub_rn(v15, (double)l15));
-            return __dsub_rn(p85, p15);
-        };
-        const double lrA = local_range(2, 3, vLR15, vLR85);
-        const double lrP = local_range(5, 6, vP15, vP85);
-        const float madA0 = H.mad[0], madA1 = H.mad[1], madP = H.mad[2], madR = H.mad[3];
         __syncthreads();
         // the part of the arena that held the cumulative counts goes back to all-zero operand tiles for the next read
         for (int i = tid; i < np * (VH_BINS * 2 / 16); i += VF_THREADS) reinterpret_cast<uint4 *>(arena)[i] = make_uint4(0, 0, 0, 0);
         VH_T(6);
         if (unsettled) continue;  // (uniform) codes outside the histogram range matter: validate_kernel
 
-        // ---- the checks (combined.py:394-580), as in validate_fast_kernel ----
-        int a_start = 0;
-        bool success = true;
-        int fail = ADB_FAIL_NONE, fail_mask = 0;
-        uint32_t valid = ADB_V_FIELDS;
-        double mvs_v[5] = {0, 0, 0, 0, 0}, real_v[3] = {0, 0, 0}, med_shift = 0.0;
-        int n_open_rep = 0;
-        if (a_end == 0) { success = false; fail = ADB_FAIL_NO_ADAPTER; }
-        if (success && (madA0 != 0.0f) && !in_range_d((double)madA0, cfg.adapter_mad_range)) { success = false; fail = ADB_FAIL_ADAPTER_MAD; }
-        if (success && cfg.detect_open_pores) {
-            n_open_rep = n_open;
-            valid |= ADB_V_OPEN_PORES;
-            if (n_open > 0) {
-                a_start = op_last;
-                if (a_end - a_start < cfg.min_obs_adapter) { success = false; fail = ADB_FAIL_OPEN_PORE; }
-            }
-        }
-        // partition mean / std (signal_partitions.py:91-92) from the exact per-piece sums of the pass above: the same
-        // integers and the same float64 formulas as vf_mean_std3
-        double pmean[3], pstd[3];
-        {
-            const int sa[3] = {a_start, a_end, pe_best}, sb[3] = {a_end, pe_best, size};
-            const bool on[3] = {a_end > a_start, pe_best > a_end, size > pe_best};
-            for (int sgm = 0; sgm < 3; sgm++) {
-                int a = sa[sgm], b = sb[sgm];
-                clip_seg(a, b, size);
-                const int n = on[sgm] ? b - a : 0;
-                if (n <= 0) { pmean[sgm] = CUDART_NAN; pstd[sgm] = CUDART_NAN; continue; }
-                const VhRange q = vh_range(H, a, b, size);
-                long long d1 = 0, d2 = 0;
-                for (int p = q.p0; p < q.p1; p++) { d1 += (long long)H.psum[p][0]; d2 += (long long)H.psum[p][1]; }
-                const long long s1 = d1 + (long long)n * base;                                   // sum of the codes
-                const long long s2 = d2 + 2ll * base * d1 + (long long)n * base * (long long)base;  // sum of their squares
-                const double mk = (double)s1 / n;
-                double vk = (double)s2 / n - mk * mk;
-                if (vk < 0) vk = 0;
-                pmean[sgm] = (double)(float)((mk + (double)R.coff) * (double)R.cscale);
-                pstd[sgm] = (double)(float)(sqrt(vk) * fabs((double)R.cscale));
-            }
-        }
-        if (success && cfg.real_signal_check) {
-            if (rlen < 2 * cfg.mean_window) {
-                success = false; fail = ADB_FAIL_REAL_RANGE;
-            } else {
-                real_v[0] = (double)rm0; real_v[1] = (double)rm1;
-                valid |= ADB_V_REAL_MEANS;
-                if (in_range_d((double)rm0, cfg.mean_start_range) && in_range_d((double)rm1, cfg.mean_end_range)) {
-                    real_v[2] = lrA;
-                    valid |= ADB_V_REAL_RANGE;
-                    if (!in_range_d(lrA, cfg.local_range)) { success = false; fail = ADB_FAIL_REAL_RANGE; }
-                } else {
-                    success = false; fail = ADB_FAIL_REAL_RANGE;
+        // ---- the checks (combined.py:394-580), as in validate_fast_kernel, on warp 0 only ----
+        // (scalar work with float64 in it: on every warp it would queue at the SM's few FP64 units and take issue slots
+        // from the other CTAs; the other warps wait at the top of the loop)
+        if (warp == 0) do {
+            auto median_of = [&](int q) -> float {
+                const int n = H.qn[q];
+                if (n <= 0) return CUDART_NAN_F;
+                const float x0 = vf_pa(R, H.qv0[q]);
+                if (n & 1) return x0;
+                return __fdiv_rn(__fadd_rn(x0, vf_pa(R, H.qv1[q])), 2.0f);
+            };
+            const float medA0 = median_of(0), medA1 = median_of(1), medP = median_of(4), medR = median_of(9);
+            const float medAF = median_of(7), medBF = median_of(8), medMA = median_of(10), medMB = median_of(11);
+            auto local_range = [&](int q15, int q85, double v15, double v85) -> double {
+                if (H.qn[q15] <= 0 || H.qn[q85] <= 0) return CUDART_NAN;
+                const int l15 = (int)floor(v15), l85 = (int)floor(v85);
+                const double p85 = np_lerp_f32(vf_pa(R, H.qv0[q85]), vf_pa(R, H.qv1[q85]), __dsub_rn(v85, (double)l85));
+                const double p15 = np_lerp_f32(vf_pa(R, H.qv0[q15]), vf_pa(R, H.qv1[q15]), __dsub_rn(v15, (double)l15));
+                return __dsub_rn(p85, p15);
+            };
+            const double lrA = local_range(2, 3, vLR15, vLR85);
+            const double lrP = local_range(5, 6, vP15, vP85);
+            const float madA0 = H.mad[0], madA1 = H.mad[1], madP = H.mad[2], madR = H.mad[3];
+            int a_start = 0;
+            bool success = true;
+            int fail = ADB_FAIL_NONE, fail_mask = 0;
+            uint32_t valid = ADB_V_FIELDS;
+            double mvs_v[5] = {0, 0, 0, 0, 0}, real_v[3] = {0, 0, 0}, med_shift = 0.0;
+            int n_open_rep = 0;
+            if (a_end == 0) { success = false; fail = ADB_FAIL_NO_ADAPTER; }
+            if (success && (madA0 != 0.0f) && !in_range_d((double)madA0, cfg.adapter_mad_range)) { success = false; fail = ADB_FAIL_ADAPTER_MAD; }
+            if (success && cfg.detect_open_pores) {
+                n_open_rep = n_open;
+                valid |= ADB_V_OPEN_PORES;
+                if (n_open > 0) {
+                    a_start = op_last;
+                    if (a_end - a_start < cfg.min_obs_adapter) { success = false; fail = ADB_FAIL_OPEN_PORE; }
                 }
             }
-        }
-        bool exception = false, defer = false, need_mvs = false, followup = false;
-        double mlo = cfg.pA_mean_range[0], mhi = cfg.pA_mean_range[1];
-        if (success && cfg.mvs_detect_check) {
-            if (pe_best == 0) {
-                success = false; fail = ADB_FAIL_NO_POLYA;
-            } else {
-                if (cfg.pA_mean_range_empty && !cfg.pA_mean_scale_range_empty) {
-                    mlo = __dmul_rn(cfg.pA_mean_scale_range[0], (double)medA0);
-                    mhi = __dmul_rn(cfg.pA_mean_scale_range[1], (double)medA0);
-                } else if (cfg.pA_mean_range_empty) {
-                    exception = true; fail = ADB_FAIL_EXC_PA_MEAN_RANGE;
-                }
-                if (!exception && n_topk < 0) { exception = true; fail = ADB_FAIL_EXC_TOPK_NONE; }
-                need_mvs = !exception && n_topk >= 1 && pe0 != 0;
-            }
-        }
-        if (need_mvs) {
-            valid |= ADB_V_MVS;
-            bool ok = false;
-            if (mvs_geom) {
-                const int L = nP;
-                __syncthreads();
-                if (!win_var || !win_mean) {
-                    // exact numpy mean / variance of a short segment (one thread, pairwise order)
-                    if (tid == 0) {
-                        const int16_t *p = W + pa_;
-                        const float co = R.coff, cs = R.cscale;
-                        const float mean = __fdiv_rn(np_sum_f32([&](int i) { return __fmul_rn(__fadd_rn((float)(int)p[i], co), cs); }, L), (float)L);
-                        S.ftmp[0] = mean;
-                        S.ftmp[1] = __fdiv_rn(np_sum_f32([&](int i) { const float d = __fsub_rn(__fmul_rn(__fadd_rn((float)(int)p[i], co), cs), mean); return __fmul_rn(d, d); }, L), (float)L);
+            // partition mean / std (signal_partitions.py:91-92) from the exact per-piece sums of the pass above: the same
+            // integers and the same float64 formulas as vf_mean_std3
+            double pmean[3], pstd[3];
+            {
+                const int sa[3] = {a_start, a_end, pe_best}, sb[3] = {a_end, pe_best, size};
+                const bool on[3] = {a_end > a_start, pe_best > a_end, size > pe_best};
+                // (three threads, one partition each: the float64 divisions / square root would otherwise run on every
+                // warp of the CTA through the SM's few FP64 units)
+                __syncwarp();
+                if (tid < 3) {
+                    const int sgm = tid;
+                    int a = sa[sgm], b = sb[sgm];
+                    clip_seg(a, b, size);
+                    const int n = on[sgm] ? b - a : 0;
+                    double pm = CUDART_NAN, ps = CUDART_NAN;
+                    if (n > 0) {
+                        const VhRange q = vh_range(H, a, b, size);
+                        long long d1 = 0, d2 = 0;
+                        for (int p = q.p0; p < q.p1; p++) { d1 += (long long)H.psum[p][0]; d2 += (long long)H.psum[p][1]; }
+                        const long long s1 = d1 + (long long)n * base;                                   // sum of the codes
+                        const long long s2 = d2 + 2ll * base * d1 + (long long)n * base * (long long)base;  // sum of their squares
+                        const double mk = (double)s1 / n;
+                        double vk = (double)s2 / n - mk * mk;
+                        if (vk < 0) vk = 0;
+                        pm = (double)(float)((mk + (double)R.coff) * (double)R.cscale);
+                        ps = (double)(float)(sqrt(vk) * fabs((double)R.cscale));
                     }
-                    __syncthreads();
+                    S.dtmp[sgm] = pm; S.dtmp[3 + sgm] = ps;
                 }
-                const float small_mean = S.ftmp[0], small_var = S.ftmp[1];
-                __syncthreads();
-                const float var32 = win_var ? smed_var : small_var;
-                const float mean32 = win_mean ? smed_mean : small_mean;
-                const float shift32 = __fsub_rn(medAF, medBF);
-                mvs_v[0] = (double)mean32; mvs_v[1] = (double)var32; mvs_v[2] = (double)medP; mvs_v[3] = lrP; mvs_v[4] = (double)shift32;
-                const double mr[2] = {mlo, mhi};
-                int mask = 0;
-                if (!in_range_d(mvs_v[0], mr)) mask |= 1;
-                if (!in_range_d(mvs_v[1], cfg.pA_var_range)) mask |= 2;
-                if (!in_range_d(mvs_v[2], cfg.polyA_med_range)) mask |= 4;
-                if (!in_range_d(mvs_v[3], cfg.polyA_local_range)) mask |= 8;
-                if (!in_range_d(mvs_v[4], cfg.median_shift_range)) mask |= 16;
-                ok = (mask == 0);
-                if (!ok) {
-                    success = false;
-                    if (mvs_v[0] == 0.0) { fail = ADB_FAIL_MVS_NOT_ENOUGH; fail_mask = 0; }  // combined.py:492-495 keys on the value
-                    else { fail = ADB_FAIL_MVS_CHECKS; fail_mask = mask; }
+                __syncwarp();
+                for (int sgm = 0; sgm < 3; sgm++) { pmean[sgm] = S.dtmp[sgm]; pstd[sgm] = S.dtmp[3 + sgm]; }
+            }
+            if (success && cfg.real_signal_check) {
+                if (rlen < 2 * cfg.mean_window) {
+                    success = false; fail = ADB_FAIL_REAL_RANGE;
+                } else {
+                    real_v[0] = (double)rm0; real_v[1] = (double)rm1;
+                    valid |= ADB_V_REAL_MEANS;
+                    if (in_range_d((double)rm0, cfg.mean_start_range) && in_range_d((double)rm1, cfg.mean_end_range)) {
+                        real_v[2] = lrA;
+                        valid |= ADB_V_REAL_RANGE;
+                        if (!in_range_d(lrA, cfg.local_range)) { success = false; fail = ADB_FAIL_REAL_RANGE; }
+                    } else {
+                        success = false; fail = ADB_FAIL_REAL_RANGE;
+                    }
                 }
-            } else {
-                success = false; fail = ADB_FAIL_MVS_NOT_ENOUGH; fail_mask = 0;
             }
-            if (!ok && topk1 != 0) {
-                if (A.cand_followup != 0) followup = true; else defer = true;
+            bool exception = false, defer = false, need_mvs = false, followup = false;
+            double mlo = cfg.pA_mean_range[0], mhi = cfg.pA_mean_range[1];
+            if (success && cfg.mvs_detect_check) {
+                if (pe_best == 0) {
+                    success = false; fail = ADB_FAIL_NO_POLYA;
+                } else {
+                    if (cfg.pA_mean_range_empty && !cfg.pA_mean_scale_range_empty) {
+                        mlo = __dmul_rn(cfg.pA_mean_scale_range[0], (double)medA0);
+                        mhi = __dmul_rn(cfg.pA_mean_scale_range[1], (double)medA0);
+                    } else if (cfg.pA_mean_range_empty) {
+                        exception = true; fail = ADB_FAIL_EXC_PA_MEAN_RANGE;
+                    }
+                    if (!exception && n_topk < 0) { exception = true; fail = ADB_FAIL_EXC_TOPK_NONE; }
+                    need_mvs = !exception && n_topk >= 1 && pe0 != 0;
+                }
             }
-        }
-        if (!exception && success && cfg.detect_med_shift) {
-            const float sh = __fsub_rn(medMA, medMB);
-            med_shift = (double)sh;
-            valid |= ADB_V_MED_SHIFT;
-            if (!in_range_d(med_shift, cfg.med_shift_range)) { success = false; fail = ADB_FAIL_MED_SHIFT; }
-        }
-        if (A.mode == ADB_METHOD_CNN && cfg.fallback_to_llr_short_reads && !exception && !success && a_end > 0 && pe_best > 0 &&
-            pe_best - a_end > 1000 && full_len < 2 * cfg.max_obs_adapter)
-            defer = true;  // "hail mary" LLR fallback (combined.py:251-301) lives in validate_kernel
-        if (defer) continue;  // (uniform) validate_kernel redoes this read from scratch
-        __syncthreads();
-        if (!(valid & ADB_V_OPEN_PORES) || exception) {
-            if (tid < ADB_MAX_OPEN_PORES) rec->open_pores[tid] = 0;  // the scan was speculative
-        }
-        if (exception) {
+            if (need_mvs) {
+                valid |= ADB_V_MVS;
+                bool ok = false;
+                if (mvs_geom) {
+                    const int L = nP;
+                    __syncwarp();
+                    if (!win_var || !win_mean) {
+                        // exact numpy mean / variance of a short segment (one thread, pairwise order)
+                        if (tid == 0) {
+                            const int16_t *p = W + pa_;
+                            const float co = R.coff, cs = R.cscale;
+                            const float mean = __fdiv_rn(np_sum_f32([&](int i) { return __fmul_rn(__fadd_rn((float)(int)p[i], co), cs); }, L), (float)L);
+                            S.ftmp[0] = mean;
+                            S.ftmp[1] = __fdiv_rn(np_sum_f32([&](int i) { const float d = __fsub_rn(__fmul_rn(__fadd_rn((float)(int)p[i], co), cs), mean); return __fmul_rn(d, d); }, L), (float)L);
+                        }
+                        __syncwarp();
+                    }
+                    const float small_mean = S.ftmp[0], small_var = S.ftmp[1];
+                    __syncwarp();
+                    const float var32 = win_var ? smed_var : small_var;
+                    const float mean32 = win_mean ? smed_mean : small_mean;
+                    const float shift32 = __fsub_rn(medAF, medBF);
+                    mvs_v[0] = (double)mean32; mvs_v[1] = (double)var32; mvs_v[2] = (double)medP; mvs_v[3] = lrP; mvs_v[4] = (double)shift32;
+                    const double mr[2] = {mlo, mhi};
+                    int mask = 0;
+                    if (!in_range_d(mvs_v[0], mr)) mask |= 1;
+                    if (!in_range_d(mvs_v[1], cfg.pA_var_range)) mask |= 2;
+                    if (!in_range_d(mvs_v[2], cfg.polyA_med_range)) mask |= 4;
+                    if (!in_range_d(mvs_v[3], cfg.polyA_local_range)) mask |= 8;
+                    if (!in_range_d(mvs_v[4], cfg.median_shift_range)) mask |= 16;
+                    ok = (mask == 0);
+                    if (!ok) {
+                        success = false;
+                        if (mvs_v[0] == 0.0) { fail = ADB_FAIL_MVS_NOT_ENOUGH; fail_mask = 0; }  // combined.py:492-495 keys on the value
+                        else { fail = ADB_FAIL_MVS_CHECKS; fail_mask = mask; }
+                    }
+                } else {
+                    success = false; fail = ADB_FAIL_MVS_NOT_ENOUGH; fail_mask = 0;
+                }
+                if (!ok && topk1 != 0) {
+                    if (A.cand_followup != 0) followup = true; else defer = true;
+                }
+            }
+            if (!exception && success && cfg.detect_med_shift) {
+                const float sh = __fsub_rn(medMA, medMB);
+                med_shift = (double)sh;
+                valid |= ADB_V_MED_SHIFT;
+                if (!in_range_d(med_shift, cfg.med_shift_range)) { success = false; fail = ADB_FAIL_MED_SHIFT; }
+            }
+            if (A.mode == ADB_METHOD_CNN && cfg.fallback_to_llr_short_reads && !exception && !success && a_end > 0 && pe_best > 0 &&
+                pe_best - a_end > 1000 && full_len < 2 * cfg.max_obs_adapter)
+                defer = true;  // "hail mary" LLR fallback (combined.py:251-301) lives in validate_kernel
+            if (defer) break;       // (uniform) validate_kernel redoes this read from scratch
+            __syncwarp();
+            if (!(valid & ADB_V_OPEN_PORES) || exception) {
+                for (int i = lane; i < ADB_MAX_OPEN_PORES; i += 32) rec->open_pores[i] = 0;  // the scan was speculative
+            }
+            if (exception) {
+                if (tid == 0) {
+                    rec->success = 0; rec->fail_code = fail; rec->mvs_fail_mask = 0; rec->valid = 0;
+                    rec->signal_len = full_len; rec->preloaded = min(full_len, size);
+                    A.done[r] = 1;
+                }
+                break;
+            }
             if (tid == 0) {
-                rec->success = 0; rec->fail_code = fail; rec->mvs_fail_mask = 0; rec->valid = 0;
-                rec->signal_len = full_len; rec->preloaded = min(full_len, size);
-                A.done[r] = 1;
+                double st[3][4];
+                for (int p = 0; p < 3; p++) for (int q = 0; q < 4; q++) st[p][q] = 0.0;
+                if (a_end > a_start) {
+                    st[0][0] = pmean[0]; st[0][1] = pstd[0];
+                    st[0][2] = (double)(a_start == 0 ? medA0 : medA1);
+                    st[0][3] = (double)(a_start == 0 ? madA0 : madA1);
+                    valid |= ADB_V_ADAPTER_STATS;
+                }
+                if (pe_best > a_end) {
+                    st[1][0] = pmean[1]; st[1][1] = pstd[1]; st[1][2] = (double)medP; st[1][3] = (double)madP;
+                    valid |= ADB_V_POLYA_STATS;
+                }
+                if (size > pe_best) {
+                    st[2][0] = pmean[2]; st[2][1] = pstd[2]; st[2][2] = (double)medR; st[2][3] = (double)madR;
+                    valid |= ADB_V_RNA_STATS;
+                }
+                rec->success = success ? 1 : 0;
+                rec->fail_code = fail;
+                rec->mvs_fail_mask = fail_mask;
+                rec->valid = valid | (n_topk >= 0 ? ADB_V_CAND : 0);
+                rec->signal_len = full_len;
+                rec->preloaded = min(full_len, size);
+                rec->adapter_start = a_start;
+                rec->adapter_end = a_end;
+                rec->polya_end = pe_best;
+                rec->primary_adapter_end = a_end;
+                rec->primary_polya_end = pe_best;
+                rec->mvs_adapter_end = 0;
+                rec->n_cand = max(n_topk, 0);
+                for (int t = 0; t < ADB_MAX_CAND; t++) rec->cand[t] = (t < n_topk) ? g[1 + t] : 0;
+                rec->n_open_pores = n_open_rep;
+                for (int p = 0; p < 3; p++) for (int q = 0; q < 4; q++) rec->stats[p][q] = st[p][q];
+                for (int i = 0; i < 5; i++) rec->mvs[i] = mvs_v[i];
+                for (int i = 0; i < 3; i++) rec->real[i] = real_v[i];
+                rec->med_shift = med_shift;
+                if (followup) *reinterpret_cast<float *>(rec->_reserved) = medA0;  // scales the mean range of the later candidates
+                A.done[r] = followup ? 2 : 1;  // (read by the kernels launched behind this one: no fence needed)
             }
-            continue;
-        }
-        if (tid == 0) {
-            double st[3][4];
-            for (int p = 0; p < 3; p++) for (int q = 0; q < 4; q++) st[p][q] = 0.0;
-            if (a_end > a_start) {
-                st[0][0] = pmean[0]; st[0][1] = pstd[0];
-                st[0][2] = (double)(a_start == 0 ? medA0 : medA1);
-                st[0][3] = (double)(a_start == 0 ? madA0 : madA1);
-                valid |= ADB_V_ADAPTER_STATS;
-            }
-            if (pe_best > a_end) {
-                st[1][0] = pmean[1]; st[1][1] = pstd[1]; st[1][2] = (double)medP; st[1][3] = (double)madP;
-                valid |= ADB_V_POLYA_STATS;
-            }
-            if (size > pe_best) {
-                st[2][0] = pmean[2]; st[2][1] = pstd[2]; st[2][2] = (double)medR; st[2][3] = (double)madR;
-                valid |= ADB_V_RNA_STATS;
-            }
-            rec->success = success ? 1 : 0;
-            rec->fail_code = fail;
-            rec->mvs_fail_mask = fail_mask;
-            rec->valid = valid | (n_topk >= 0 ? ADB_V_CAND : 0);
-            rec->signal_len = full_len;
-            rec->preloaded = min(full_len, size);
-            rec->adapter_start = a_start;
-            rec->adapter_end = a_end;
-            rec->polya_end = pe_best;
-            rec->primary_adapter_end = a_end;
-            rec->primary_polya_end = pe_best;
-            rec->mvs_adapter_end = 0;
-            rec->n_cand = max(n_topk, 0);
-            for (int t = 0; t < ADB_MAX_CAND; t++) rec->cand[t] = (t < n_topk) ? g[1 + t] : 0;
-            rec->n_open_pores = n_open_rep;
-            for (int p = 0; p < 3; p++) for (int q = 0; q < 4; q++) rec->stats[p][q] = st[p][q];
-            for (int i = 0; i < 5; i++) rec->mvs[i] = mvs_v[i];
-            for (int i = 0; i < 3; i++) rec->real[i] = real_v[i];
-            rec->med_shift = med_shift;
-            if (followup) *reinterpret_cast<float *>(rec->_reserved) = medA0;  // scales the mean range of the later candidates
-            A.done[r] = followup ? 2 : 1;  // (read by the kernels launched behind this one: no fence needed)
-        }
+        } while (0);
         VH_T(7);
     }
     __syncthreads();
