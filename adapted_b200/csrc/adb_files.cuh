@@ -15,6 +15,7 @@
 // Container "ADBSIG02" (adapted_b200/ingest.py writes it): a 128-byte header, then 64-byte aligned sections.
 // Included at the end of adb_api.cu.
 #pragma once
+#include <sched.h>
 #include <dlfcn.h>
 #include <fcntl.h>
 #include <sys/mman.h>
@@ -32,6 +33,14 @@
 #include "adb_ingest.cuh"
 
 namespace adbf {
+
+// CPUs this process may run on (a rank of a multi-GPU job is bound to its GPU's PCIe-local set: bench.py)
+static unsigned usable_cpus() {
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) { const int n = CPU_COUNT(&set); if (n > 0) return (unsigned)n; }
+    return std::max(1u, std::thread::hardware_concurrency());
+}
 
 #pragma pack(push, 1)
 struct Header {
@@ -193,7 +202,7 @@ extern "C" int adb_detect_files(adb_ctx *ctx, const adb_file_job *job, const adb
     const int chunk_batches = std::max(1, job->chunk_batches > 0 ? job->chunk_batches : 16);
     const int chunk_reads = chunk_batches * mbs;
     // (measured on the 16-core box, 400 000 RNA004 reads: 4 / 8 / 12 copy threads -> 1.15 / 1.46 / 1.47 M reads/s file -> tables)
-    int n_copy_thr = std::max(1, job->n_copy_threads > 0 ? job->n_copy_threads : (int)std::min(8u, std::max(2u, std::thread::hardware_concurrency() / 2)));
+    int n_copy_thr = std::max(1, job->n_copy_threads > 0 ? job->n_copy_threads : (int)std::min(8u, std::max(2u, usable_cpus() / 2)));
     if (const char *e = getenv("ADB_COPY_THREADS")) n_copy_thr = std::max(1, atoi(e));  // (experiments)
     const int n_fmt_thr = std::max(1, job->n_format_threads > 0 ? job->n_format_threads : (int)std::min(16u, std::max(2u, std::thread::hardware_concurrency() / 2)));
     const bool write_csv = job->write_csv != 0 && job->out_dir != nullptr;
