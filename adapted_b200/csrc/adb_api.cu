@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -37,6 +38,22 @@ extern "C" int adb_device_count(void) {
     return n;
 }
 
+// slots of the constant bank adb_c_convT (adb_cnn.cuh): one per live context and device, -1 when none is left (the
+// context then keeps the transposed convolution's weights in shared memory)
+static std::mutex g_ct_mu;
+static unsigned g_ct_used[64];
+static int ct_slot_take(int device) {
+    std::lock_guard<std::mutex> lk(g_ct_mu);
+    if (device < 0 || device >= 64) return -1;
+    for (int s = 0; s < ADB_CT_SLOTS; s++)
+        if (!(g_ct_used[device] & (1u << s))) { g_ct_used[device] |= 1u << s; return s; }
+    return -1;
+}
+static void ct_slot_give(int device, int slot) {
+    std::lock_guard<std::mutex> lk(g_ct_mu);
+    if (device >= 0 && device < 64 && slot >= 0) g_ct_used[device] &= ~(1u << slot);
+}
+
 extern "C" int adb_ctx_create(int device, adb_ctx **out) {
     if (!out) return ADB_ERR_ARG;
     *out = nullptr;
@@ -57,6 +74,7 @@ extern "C" int adb_ctx_create(int device, adb_ctx **out) {
     c->sm_count = prop.multiProcessorCount;
     c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     if (const char *e = getenv("ADB_HIST_VALIDATE")) c->opt_hist_validate = atoi(e);  // A/B switch of the validation kernel
+    c->ct_slot = ct_slot_take(device);
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int k = 0; k < 2; k++) {
@@ -72,11 +90,13 @@ extern "C" void adb_ctx_destroy(adb_ctx *c) {
     if (!c) return;
     if (c->twin) { adb_ctx_destroy(c->twin); c->twin = nullptr; }
     cudaSetDevice(c->device);
+    ct_slot_give(c->device, c->ct_slot);
+    c->ct_slot = -1;
     if (c->file_ring && c->file_ring_free) { c->file_ring_free(c->file_ring); c->file_ring = nullptr; }
     DevBuf *all[] = {&c->states, &c->hist, &c->series, &c->given, &c->status, &c->cnn_x, &c->cnn_act0,
                      &c->cnn_act1, &c->cnn_scores, &c->cnn_w, &c->cnn_aux, &c->cnn_post, &c->sp_rows, &c->h_signal, &c->h_offsets,
                      &c->h_lens, &c->h_coff, &c->h_cscale, &c->h_records, &c->h_misc, &c->h_misc2, &c->h_misc3,
-                     &c->gsb_plan, &c->gsb_hist, &c->gsb_tab, &c->gsb_bases, &c->gsb_active, &c->vf_done, &c->mvs_perm, &c->cnn_wtc, &c->cnn_a0t, &c->llr_cc};
+                     &c->gsb_plan, &c->gsb_hist, &c->gsb_tab, &c->gsb_bases, &c->gsb_active, &c->vf_done, &c->mvs_perm, &c->cnn_wtc, &c->cnn_a0t, &c->cnn_ct, &c->llr_cc};
     for (DevBuf *b : all) b->release();
     for (int k = 0; k < 2; k++) {
         DevBuf *pb[] = {&c->p_signal[k], &c->p_offsets[k], &c->p_lens[k], &c->p_coff[k], &c->p_cscale[k], &c->p_records[k], &c->p_status[k],

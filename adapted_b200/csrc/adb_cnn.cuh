@@ -720,8 +720,27 @@ static CnnDims cnn_dims(int m, int A0, int f) {
 // tensor-core version of the two 64 -> 64 convolutions (adb_cnn_tc.cuh)
 __global__ void cnn_tc_pack_weights_kernel(const float *w, __half *packed);
 static int cnn_tc_launch_setup();
+// Layer 3's epilogue multiplies every activation with the 14 weights of the transposed convolution.  From shared memory
+// that is two 16-byte broadcast loads per channel and thread -- 512 B of register-file writes per warp and load, the
+// bottleneck of the epilogue.  From the CONSTANT bank the weights reach the FFMAs through the uniform datapath (ULDC +
+// uniform-register operands): no vector register is written.  One slot per context ([co][ci][8] weights + the 64 layer-3
+// biases), filled stream-ordered by a device-to-device copy into the symbol (cnn_ct_pack_kernel -> cudaMemcpyToSymbolAsync).
+#define ADB_CT_SLOTS 4
+#define ADB_CT_FLOATS (2 * 64 * 8 + 64)
+__constant__ float adb_c_convT[ADB_CT_SLOTS][ADB_CT_FLOATS];
+
+__global__ void cnn_ct_pack_kernel(const float *w4 /* torch layout [ci][co][k] */, const float *b3, float *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 1024) {
+        const int co = i >> 9, ci = (i >> 3) & 63, k = i & 7;
+        out[i] = (k < CNN_K) ? w4[(ci * 2 + co) * CNN_K + k] : 0.0f;
+    } else if (i < ADB_CT_FLOATS) {
+        out[i] = b3[i - 1024];
+    }
+}
+
 static void cnn_tc_launch(int layer, const void *in, void *out, const __half *wp, const float *bias, const float *w1,
-                          const float *b1, int n_reads, int Lx, int L1, int LP, int *redo, int sm_count, cudaStream_t st);
+                          const float *b1, int n_reads, int Lx, int L1, int LP, int *redo, int sm_count, cudaStream_t st, int cslot = -1);
 static size_t cnn_tc_a0t_bytes_per_read(int L1);
 static int cnn_tc_a0t_rows_host(int L1);
 
@@ -748,6 +767,7 @@ static int cnn_forward_dev(adb_ctx *ctx, const float *x, int n, const CnnDims &D
     __half *wtc = nullptr;
     unsigned char *a0t = nullptr;
     int *redo = nullptr;
+    int cslot = -1;  // slot of the constant bank holding the transposed convolution's weights (-1: shared memory)
     if (use_tc) {
         // split fp16 weights of both layers, then the per-read "outside the fp16 range" flags of one chunk
         const size_t wbytes = sizeof(__half) * 2 * CNN_K * 2 * 4096;
@@ -759,6 +779,15 @@ static int cnn_forward_dev(adb_ctx *ctx, const float *x, int n, const CnnDims &D
             cnn_tc_pack_weights_kernel<<<(2 * CNN_K * 4096 + 255) / 256, 256, 0, st>>>(w_dev, wtc);
         }
         ctx->launches += 1;
+        if (ctx->ct_slot >= 0 && !getenv("ADB_NO_CONST_CONVT")) {
+            // the transposed convolution's weights + layer 3's biases into this context's slot of the constant bank
+            if (ctx->cnn_ct.ensure(sizeof(float) * ADB_CT_FLOATS)) { set_err("cudaMalloc cnn constants"); return ADB_ERR_CUDA; }
+            cnn_ct_pack_kernel<<<(ADB_CT_FLOATS + 255) / 256, 256, 0, st>>>(w_dev + CNN_W4, w_dev + CNN_B3, (float *)ctx->cnn_ct.p);
+            CUDA_TRY(cudaMemcpyToSymbolAsync(adb_c_convT, ctx->cnn_ct.p, sizeof(float) * ADB_CT_FLOATS,
+                                             sizeof(float) * ADB_CT_FLOATS * (size_t)ctx->ct_slot, cudaMemcpyDeviceToDevice, st));
+            ctx->launches += 1;
+            cslot = ctx->ct_slot;
+        }
         if (cnn_tc_launch_setup()) { set_err("cudaFuncSetAttribute cnn tc"); return ADB_ERR_CUDA; }
         // layer 2 -> layer 3 activations in layer 3's tile layout; the padding rows are never written: zero them whenever
         // the buffer is (re)allocated
@@ -788,7 +817,7 @@ static int cnn_forward_dev(adb_ctx *ctx, const float *x, int n, const CnnDims &D
                 // layer 3 + the transposed convolution: scores straight from the epilogue
                 cnn_tc_launch(3, a0t, scores + (size_t)r0 * 2 * D.Lout, wtc + (size_t)CNN_K * 2 * 4096, w_dev + CNN_B3,
                               w_dev + CNN_W4, w_dev + CNN_B4, nc, D.Lout, D.L1, cnn_tc_a0t_rows_host(D.L1), redo,
-                              ctx->sm_count, st);
+                              ctx->sm_count, st, cslot);
             }
             {
                 // reads with a value outside the fp16 range (flagged by either layer): both layers again on the FP32 pipe

@@ -170,7 +170,7 @@ __host__ __device__ inline size_t cnn_tc_smem_bytes_layer(int layer) {
 //   a 256-byte shared buffer, one named barrier per tile).  `w1` / `b1` carry W4 / b4, `Lx` carries Lout.
 // wp  : packed weights of this layer, [7][2][4096] fp16 (cnn_tc_pack_weights_kernel)
 // redo: [N] set to 1 for reads with a value outside the fp16 range (recomputed on the FP32 pipe afterwards)
-template <int LAYER>
+template <int LAYER, int CSLOT = -1>  // CSLOT >= 0 (layer 3): transposed-convolution weights from that slot of adb_c_convT
 __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const void *in, void *out, const __half *wp,
                                                                      const float *bias, const float *w1, const float *b1,
                                                                      int n_reads, int Lx, int L1, int LP, int *redo) {
@@ -330,13 +330,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const void
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accfree[tb])) : "memory");
                 }
+                if (CSLOT >= 0) {
+                    // weights and biases from the constant bank; with the slot a template parameter and the branch on co
+                    // (uniform per warp) every address is a compile-time constant: the FFMAs / FADDs take their second
+                    // operand straight from the bank (c[3][imm]), no load instruction at all
+                    auto acc = [&](const float *cw, const float *cb) {
 #pragma unroll
-                for (int c = 0; c < 32; c++) {
-                    const int ci = hh * 32 + c;
-                    const float a = live ? fmaxf(__fadd_rn(__uint_as_float(v[c]), Bs[ci]), 0.0f) : 0.0f;
-                    const float4 w0 = wv[ci * 2], w1v = wv[ci * 2 + 1];
-                    P[0] = fmaf(a, w0.x, P[0]); P[1] = fmaf(a, w0.y, P[1]); P[2] = fmaf(a, w0.z, P[2]); P[3] = fmaf(a, w0.w, P[3]);
-                    P[4] = fmaf(a, w1v.x, P[4]); P[5] = fmaf(a, w1v.y, P[5]); P[6] = fmaf(a, w1v.z, P[6]);
+                        for (int c = 0; c < 32; c++) {
+                            const int ci = hh * 32 + c;
+                            const float a = live ? fmaxf(__fadd_rn(__uint_as_float(v[c]), cb[ci]), 0.0f) : 0.0f;
+#pragma unroll
+                            for (int j = 0; j < CNN_K; j++) P[j] = fmaf(a, cw[ci * 8 + j], P[j]);
+                        }
+                    };
+                    constexpr int SL = CSLOT >= 0 ? CSLOT : 0;
+                    if (co == 0) acc(&adb_c_convT[SL][0], &adb_c_convT[SL][1024]);
+                    else acc(&adb_c_convT[SL][512], &adb_c_convT[SL][1024]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; c++) {
+                        const int ci = hh * 32 + c;
+                        const float a = live ? fmaxf(__fadd_rn(__uint_as_float(v[c]), Bs[ci]), 0.0f) : 0.0f;
+                        const float4 w0 = wv[ci * 2], w1v = wv[ci * 2 + 1];
+                        P[0] = fmaf(a, w0.x, P[0]); P[1] = fmaf(a, w0.y, P[1]); P[2] = fmaf(a, w0.z, P[2]); P[3] = fmaf(a, w0.w, P[3]);
+                        P[4] = fmaf(a, w1v.x, P[4]); P[5] = fmaf(a, w1v.y, P[5]); P[6] = fmaf(a, w1v.z, P[6]);
+                    }
                 }
             }
             // neighbours: P0..P2 of row q + 1, P6 of row q - 1
@@ -444,16 +462,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const void
 static int cnn_tc_launch_setup() {
     if (cudaFuncSetAttribute(cnn_conv64_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cnn_tc_smem_bytes_layer(2)) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(cnn_conv64_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cnn_tc_smem_bytes_layer(3)) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(cnn_conv64_tc_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cnn_tc_smem_bytes_layer(3)) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(cnn_conv64_tc_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cnn_tc_smem_bytes_layer(3)) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(cnn_conv64_tc_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cnn_tc_smem_bytes_layer(3)) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(cnn_conv64_tc_kernel<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cnn_tc_smem_bytes_layer(3)) != cudaSuccess) return -1;
     return 0;
 }
 
 // layer 2: in = x, out = A0T;  layer 3: in = A0T, out = scores [N][2][Lout] (w1 / b1 = W4 / b4, Lx = Lout)
 static void cnn_tc_launch(int layer, const void *in, void *out, const __half *wp, const float *bias, const float *w1,
-                          const float *b1, int n_reads, int Lx, int L1, int LP, int *redo, int sm_count, cudaStream_t st) {
+                          const float *b1, int n_reads, int Lx, int L1, int LP, int *redo, int sm_count, cudaStream_t st,
+                          int cslot) {
     const int jobs = n_reads * (layer == 3 ? (L1 + TC_L3_STRIDE - 1) / TC_L3_STRIDE : (L1 + TC_ROWS - 1) / TC_ROWS);
     const int grid = std::max(1, std::min(jobs, sm_count));
     const size_t smem = cnn_tc_smem_bytes_layer(layer);
     if (layer == 2) cnn_conv64_tc_kernel<2><<<grid, TC_THREADS, smem, st>>>(in, out, wp, bias, w1, b1, n_reads, Lx, L1, LP, redo);
+    else if (cslot == 0) cnn_conv64_tc_kernel<3, 0><<<grid, TC_THREADS, smem, st>>>(in, out, wp, bias, w1, b1, n_reads, Lx, L1, LP, redo);
+    else if (cslot == 1) cnn_conv64_tc_kernel<3, 1><<<grid, TC_THREADS, smem, st>>>(in, out, wp, bias, w1, b1, n_reads, Lx, L1, LP, redo);
+    else if (cslot == 2) cnn_conv64_tc_kernel<3, 2><<<grid, TC_THREADS, smem, st>>>(in, out, wp, bias, w1, b1, n_reads, Lx, L1, LP, redo);
+    else if (cslot == 3) cnn_conv64_tc_kernel<3, 3><<<grid, TC_THREADS, smem, st>>>(in, out, wp, bias, w1, b1, n_reads, Lx, L1, LP, redo);
     else cnn_conv64_tc_kernel<3><<<grid, TC_THREADS, smem, st>>>(in, out, wp, bias, w1, b1, n_reads, Lx, L1, LP, redo);
 }
 

@@ -76,6 +76,7 @@ struct adb_ctx {
     DevBuf mvs_perm;           // length-sorted read order of mvs_series_kernel
     DevBuf llr_cc;             // prefix sums of llr_primary_kernel (per resident CTA)
     DevBuf vf_done;            // per-read flags of validate_fast_kernel
+    int ct_slot = -1;          // this context's slot of the constant bank adb_c_convT (adb_cnn_tc.cuh), -1: none left
     int opt_no_fast_validate = 0;
     int opt_hist_validate = 1;  // adb_ctx_set_option("hist_validate", 0): counting passes (validate_fast_kernel) instead of the tensor-core histograms (adb_vhist.cuh)
     int opt_no_cand_followup = 0;  // adb_ctx_set_option("no_cand_followup"): further poly(A) candidates go to validate_kernel (A/B)
@@ -84,7 +85,7 @@ struct adb_ctx {
     int vf_last_reads = 0;
     int gsb_last_batches = 0;
     int opt_exact_gsel = 0;  // adb_ctx_set_option("exact_global_select"): always use the multi-pass select
-    DevBuf cnn_x, cnn_act0, cnn_act1, cnn_scores, cnn_w, cnn_aux, cnn_post, sp_rows, cnn_wtc, cnn_a0t;
+    DevBuf cnn_x, cnn_act0, cnn_act1, cnn_scores, cnn_w, cnn_aux, cnn_post, sp_rows, cnn_wtc, cnn_a0t, cnn_ct;
     // staging for the *_host entry points
     DevBuf h_signal, h_offsets, h_lens, h_coff, h_cscale, h_records, h_misc, h_misc2, h_misc3;
 };
