@@ -381,7 +381,8 @@ class Runner:
             if args.file_reads != 0 and label == "main":
                 from adapted_b200.ingest import detect_files_native, write_container_v2
 
-                nf = n if args.file_reads < 0 else min(n, args.file_reads)
+                # (several ranks share the box's temporary storage: half the container per rank there)
+                nf = n if args.file_reads < 0 else min(n, args.file_reads if self.world == 1 else min(args.file_reads, 200000))
                 nf = max(mbs, nf // mbs * mbs)
                 tmp = tempfile.mkdtemp(prefix=f"adb_bench_r{self.rank}_", dir=args.file_dir or None)
                 try:
