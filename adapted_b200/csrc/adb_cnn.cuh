@@ -522,8 +522,7 @@ __global__ void __launch_bounds__(128) cnn_topk_kernel(const float *scores, int 
                                                        int *ncand) {
     __shared__ long long pos[CNN_WS_CAP];   // flattened positions, ascending
     __shared__ float hgt[CNN_WS_CAP];
-    __shared__ unsigned short ord[CNN_WS_SORT];  // indices sorted by priority (ascending height, ties: lower index first)
-    __shared__ unsigned short prio[CNN_WS_CAP];  // rank of every peak in that order
+    __shared__ unsigned short ord[CNN_WS_CAP];   // survivors of this row (compaction scratch)
     __shared__ unsigned char keep[CNN_WS_CAP];   // 2 undecided, 1 kept, 0 removed
     __shared__ int n_sh;
     const int r = blockIdx.x;
@@ -581,31 +580,10 @@ __global__ void __launch_bounds__(128) cnn_topk_kernel(const float *scores, int 
         }
         n = min(n + c, CNN_WS_CAP);
     }
-    // priority order (np.argsort of the heights; scipy walks it from the back): bitonic sort of the indices by
-    // (height, index) ascending; padding entries sort last
-    int np2 = 2;
-    while (np2 < n) np2 <<= 1;
-    for (int i = threadIdx.x; i < np2; i += blockDim.x) ord[i] = (i < n) ? (unsigned short)i : (unsigned short)0xffff;
-    __syncthreads();
-    auto before = [&](unsigned a, unsigned b) {  // does entry a sort before entry b
-        if (a == 0xffffu) return false;
-        if (b == 0xffffu) return true;
-        const float ha = hgt[a], hb = hgt[b];
-        return (ha < hb) || (ha == hb && a < b);
-    };
-    for (int kk = 2; kk <= np2; kk <<= 1) {
-        for (int j = kk >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < (np2 >> 1); t += blockDim.x) {
-                const int i = ((t / j) * 2 * j) + (t % j), p = i + j;
-                const bool up = (i & kk) == 0;
-                const unsigned a = ord[i], b = ord[p];
-                const bool swap = up ? before(b, a) : before(a, b);
-                if (swap) { ord[i] = (unsigned short)b; ord[p] = (unsigned short)a; }
-            }
-            __syncthreads();
-        }
-    }
-    for (int q = threadIdx.x; q < n; q += blockDim.x) prio[ord[q]] = (unsigned short)q;
+    // priority order (np.argsort of the heights, stable: ties keep the lower index first; scipy walks it from the back):
+    // peak t has priority over peak i iff (height, index) of t is the larger pair.  Only peaks closer than `dist` are
+    // ever compared, so no sorted order is materialised.
+    auto over = [&](int t, int i) { const float ht = hgt[t], hi_ = hgt[i]; return (ht > hi_) || (ht == hi_ && t > i); };
     __syncthreads();
     // _select_by_peak_distance: in priority order a kept peak removes everything closer than `dist`; equivalently a peak
     // is kept iff no KEPT peak of higher priority lies within the distance.  Resolved in parallel rounds: a peak
@@ -620,11 +598,10 @@ __global__ void __launch_bounds__(128) cnn_topk_kernel(const float *scores, int 
                 unsigned char st = keep[i];
                 if (st == 2) {
                     bool killed = false, wait = false;
-                    const unsigned pi = prio[i];
                     for (int t = i - 1; t >= 0 && pos[i] - pos[t] < dist; t--)
-                        if (prio[t] > pi) { const unsigned char s2 = keep[t]; killed |= (s2 == 1); wait |= (s2 == 2); }
+                        if (over(t, i)) { const unsigned char s2 = keep[t]; killed |= (s2 == 1); wait |= (s2 == 2); }
                     for (int t = i + 1; t < n && pos[t] - pos[i] < dist; t++)
-                        if (prio[t] > pi) { const unsigned char s2 = keep[t]; killed |= (s2 == 1); wait |= (s2 == 2); }
+                        if (over(t, i)) { const unsigned char s2 = keep[t]; killed |= (s2 == 1); wait |= (s2 == 2); }
                     if (killed) st = 0;
                     else if (!wait) st = 1;
                     else pending = true;
