@@ -478,6 +478,7 @@ __global__ void __launch_bounds__(128) cnn_peaks_kernel(const float *scores, int
     FlatView V{scores, Lout, mb * batch_size, min(batch_size, n_reads - mb * batch_size)};
     const long long N = V.size();
     const long long g0 = (long long)(r - V.r0) * Lout;
+    const float *rowp = scores + ((size_t)r * 2 + 1) * Lout;  // the poly(A) channel of this read
     if (threadIdx.x == 0) base_sh = 0;
     __syncthreads();
     for (int jb = 0; jb < Lout; jb += blockDim.x) {
@@ -486,11 +487,14 @@ __global__ void __launch_bounds__(128) cnn_peaks_kernel(const float *scores, int
         if (j < Lout) {
             const long long i = g0 + j;
             if (i >= 1 && i < N - 1) {
-                const float xi = V.at(i);
-                if (V.at(i - 1) < xi) {
+                // elements of this row straight from its pointer; only the neighbours across a row end go through the
+                // flattened view (a 64-bit division per element)
+                auto val = [&](long long g) { const long long jj = g - g0; return (jj >= 0 && jj < Lout) ? rowp[jj] : V.at(g); };
+                const float xi = rowp[j];
+                if (val(i - 1) < xi) {
                     long long ia = i + 1;
-                    while (ia < N - 1 && V.at(ia) == xi) ia++;
-                    if (V.at(ia) < xi) mid = (i + ia - 1) / 2;
+                    while (ia < N - 1 && val(ia) == xi) ia++;
+                    if (val(ia) < xi) mid = (i + ia - 1) / 2;
                 }
             }
         }
