@@ -5,25 +5,29 @@
 // Every order statistic the reference asks for (medians, MADs, p15 / p85 of up to a dozen sample ranges of a read) is
 // a function of the histogram of the ADC codes of the range.  Shared-memory atomics build such a histogram at 2 cycles
 // per sample and SM (profiles/r1_validate_kernel_v3.txt), counting passes need ~20 passes over the window
-// (adb_vfast.cuh).  Here the tensor core does the scatter-add: for a batch of K = 32 consecutive samples a warp writes
-// two ONE-HOT operand tiles in shared memory,
-//     A[hi][k] = 1 iff (code_k - base) >> 4 == hi      (M = 128 rows)
+// (adb_vfast.cuh).  Here the tensor core does the scatter-add: for 32 consecutive samples a warp writes two ONE-HOT
+// operand tiles in shared memory,
+//     A[hi][k] = 1 iff (code_k - base) >> 4 == hi      (M = 64 rows)
 //     B[lo][k] = 1 iff (code_k - base) & 15 == lo      (N = 16 rows)
-// (one byte store per sample and tile, e4m3 1.0 = 0x38) and one tcgen05.mma.kind::f8f6f4 accumulates
+// (one byte store per sample and tile, e4m3 1.0 = 0x38) and one tcgen05.mma.kind::f8f6f4 (K = 32) accumulates
 //     D[hi][lo] += sum_k A[hi][k] * B[lo][k]  =  number of samples of the batch with code - base == 16 * hi + lo
-// into a float32 accumulator in TMEM (exact: counts stay below 2^24) -- a 2048-bin histogram per accumulator, 32
-// samples per MMA, no atomics, no conflicts between samples of equal value.  After the MMA has read the tiles the warp
-// clears the bytes it set (the tiles are all-zero between batches).
+// into a float32 accumulator in TMEM (exact: counts stay below 2^24) -- a 1024-bin histogram per accumulator, no
+// atomics, no conflicts between samples of equal value.  A warp batch is 64 samples (two MMAs, one fence, one commit);
+// after the MMAs have read the tiles the warp clears the bytes it set (the tiles are all-zero between batches).  The
+// tensor core reads the whole (mostly zero) tiles: 80 B of shared memory per sample -- the floor of this formulation
+// (M >= 64 for tcgen05), reached by the stream phase.
 //
 // The ranges of a read overlap (adapter, its tail windows, poly(A), the windows around adapter_end, the rest), so the
 // window is cut at every range boundary into at most VH_MAX_PIECES disjoint PIECES, one accumulator each (16 TMEM
-// columns); a range is a run of consecutive pieces.  The samples are read ONCE from global memory (no staging of the
-// window in shared memory).  The accumulators are then copied to shared memory as per-piece cumulative counts and
-// every statistic is a handful of binary searches in them (lanes of warp 0, one query each): ranks by bisection on the
-// code, MADs by the candidate halving of adb_vfast.cuh with the counts looked up instead of counted.
+// columns, 128 columns per CTA, four CTAs per SM); a range is a run of consecutive pieces.  The samples are read ONCE
+// from global memory (no staging of the window in shared memory; the next read's window is prefetched into L2), the
+// exact sums of the codes and of their squares per piece are taken on the way.  The accumulators are then copied to
+// shared memory as per-piece cumulative counts and every statistic is a few look-ups in them: ranks by 32-way searches
+// (one warp per query), MADs by 32-way searches for the first candidate deviation whose count exceeds the middle rank
+// (the two sides of a median on two warps), with exact float32 deviations.  The checks and the record run on warp 0.
 //
-// Codes outside [base, base + 2047] (base = the code of -20 pA: the range covers -20 .. +339 pA at a typical
-// calibration) fall into the end bins; a read is handed to validate_kernel (same results) whenever an answer or a probe
+// Codes outside [base, base + 1023] (base = the code of 25 pA: the range covers 25 .. 205 pA at a typical calibration)
+// fall into the end bins; a read is handed to validate_kernel (same results) whenever an answer or a decisive probe
 // touches an end bin that holds such codes.  Also handed over: what validate_fast_kernel hands over.
 #pragma once
 #include "adb_cnn_tc.cuh"
@@ -95,7 +99,6 @@ struct VhShared {
     uint64_t bar[VH_WARPS];            // "the MMAs of this warp's batch have read the tiles"
     uint32_t tmem_slot;
     int cuts[VH_MAX_PIECES + 4];       // sorted cut points; piece p = samples [cuts[p], cuts[p + 1])
-    int bstart[VH_MAX_PIECES + 2];     // first batch (32 samples) of piece p in the flattened batch space
     int np;
     int n_low, n_high;                 // samples of the read below base / above base + 2047
     int unsettled;                     // an answer or a probe touched an end bin holding such samples
@@ -515,13 +518,6 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_hist_kernel(VfastArgs 
             const int np = __popc(fm) - 1;
             if (first && pos <= VH_MAX_PIECES) H.cuts[pos] = v;
             __syncwarp();
-            if (np <= VH_MAX_PIECES) {
-                int nb = (lane < np) ? (H.cuts[lane + 1] - H.cuts[lane] + 32 * VH_SUB - 1) / (32 * VH_SUB) : 0;
-                int incl = nb;
-#pragma unroll
-                for (int o = 1; o < 16; o <<= 1) { const int t = __shfl_up_sync(ADB_FULL, incl, o); if (lane >= o) incl += t; }
-                if (lane <= np) H.bstart[lane] = incl - nb;   // (lane np: the total)
-            }
             if (lane == 0) { H.np = np; H.n_low = 0; H.n_high = 0; H.unsettled = 0; }
         }
         if (tid < 2 * VH_MAX_PIECES) (&H.psum[0][0])[tid] = 0ull;
