@@ -268,11 +268,14 @@ __device__ int vh_open_pores(const VfRead &R, VhShared &H, int b, int c200, adb_
         unsigned m = 0;
         if (v < nvec) {
             uint4 q = make_uint4(0, 0, 0, 0);
-            if (((v + 1) << 3) <= R.s0 + R.n) q = __ldg(V + v);
-            else {  // the vector runs past the end of the read: sample by sample
+            if ((v << 3) >= R.s0 && ((v + 1) << 3) <= R.s0 + R.n) q = __ldg(V + v);
+            else {  // the vector reaches beyond the read (before its first or past its last sample): sample by sample
                 unsigned short e[8];
 #pragma unroll
-                for (int t = 0; t < 8; t++) e[t] = ((v << 3) + t < R.s0 + R.n) ? R.W16[(v << 3) + t] : (unsigned short)0x8000;
+                for (int t = 0; t < 8; t++) {
+                    const int ii = (v << 3) + t;
+                    e[t] = (ii >= R.s0 && ii < R.s0 + R.n) ? R.W16[ii] : (unsigned short)0x8000;
+                }
                 q = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
             }
             const unsigned w[4] = {q.x, q.y, q.z, q.w};
