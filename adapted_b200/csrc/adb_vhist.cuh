@@ -760,8 +760,7 @@ __global__ void __launch_bounds__(VF_THREADS, 4) validate_hist_kernel(VfastArgs 
             {
                 const int sa[3] = {a_start, a_end, pe_best}, sb[3] = {a_end, pe_best, size};
                 const bool on[3] = {a_end > a_start, pe_best > a_end, size > pe_best};
-                // (three threads, one partition each: the float64 divisions / square root would otherwise run on every
-                // warp of the CTA through the SM's few FP64 units)
+                // (three lanes, one partition each)
                 __syncwarp();
                 if (tid < 3) {
                     const int sgm = tid;
