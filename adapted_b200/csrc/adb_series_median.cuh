@@ -17,8 +17,7 @@
 #define SM_WARPS 4
 #define SM_CAP 3072      // keys per warp slice (12 KB)
 #define SM_NCAND 64
-#define SM_NSAMP 2048    // subsample of a row longer than the slice
-#define SM_SPREAD 80     // half-width of the bracket in sample ranks (3.5 sigma of the subsample's middle rank; a miss is caught and redone)
+#define SM_NSAMP 2048    // largest subsample of a row longer than the slice
 
 struct SeriesMedianArgs {
     BatchDev B;
@@ -208,22 +207,40 @@ __device__ float warp_series_median(const float *__restrict__ g, int n, uint32_t
         // whole row from the pool.
         bool done = false;
         {
+            const int nv_all = n >> 2;
+            const int ns = min(nv_all, SM_NSAMP);
             uint32_t smn = 0xffffffffu, smx = 0u;
-            for (int i = lane; i < SM_NSAMP; i += 32) {
-                const uint32_t k = f32_key(__ldg(g + (size_t)(((long long)i * n) / SM_NSAMP)));
-                kbuf[i] = k;
-                smn = min(smn, k); smx = max(smx, k);
+            if (nv_all <= SM_NSAMP) {
+                // rows up to 4 SM_NSAMP keys: the first key of every vector, read in one COALESCED pass over the row (which
+                // also brings it into L2 for the pass that follows)
+                for (int v = lane; v < nv_all; v += 32) {
+                    const uint32_t k = f32_key(__ldg(G4 + v).x);
+                    kbuf[v] = k;
+                    smn = min(smn, k); smx = max(smx, k);
+                }
+            } else {
+                // longer rows: SM_NSAMP keys spread evenly (one sector each: less traffic than a whole pass)
+                for (int i = lane; i < SM_NSAMP; i += 32) {
+                    const uint32_t k = f32_key(__ldg(g + (size_t)(((long long)i * n) / SM_NSAMP)));
+                    kbuf[i] = k;
+                    smn = min(smn, k); smx = max(smx, k);
+                }
             }
+            const int nsp = (ns + 3) & ~3;                           // padded to full vectors with keys above every rank
+            if (lane < nsp - ns) kbuf[ns + lane] = 0xffffffffu;
             smn = __reduce_min_sync(ADB_FULL, smn);
             smx = __reduce_max_sync(ADB_FULL, smx);
             __syncwarp();
             const SmKeys KS{K4, G4};
-            const int rs = (int)(((long long)rank * SM_NSAMP) / n);
-            const int r_lo = rs - SM_SPREAD, r_hi = rs + SM_SPREAD + 1;
+            // half-width of the bracket in sample ranks: 3.5 sigma of the middle rank of the subsample (+ 2); a miss is
+            // caught by the exact counts below and the row redone
+            const int spread = (int)(1.75f * sqrtf((float)ns)) + 2;
+            const int rs = (int)(((long long)rank * ns) / n);
+            const int r_lo = rs - spread, r_hi = rs + spread + 1;
             uint32_t s_lo = 0u, s_hi = 0xffffffffu, t0, t1;
             bool hb;
-            if (r_lo >= 0) warp_select2(KS, SM_NSAMP / 4, 0, false, SM_NSAMP, (unsigned)r_lo, smn, smx, cand, s_lo, t0, hb);
-            if (r_hi < SM_NSAMP) warp_select2(KS, SM_NSAMP / 4, 0, false, SM_NSAMP, (unsigned)r_hi, smn, smx, cand, s_hi, t1, hb);
+            if (r_lo >= 0) warp_select2(KS, nsp >> 2, 0, false, nsp, (unsigned)r_lo, smn, smx, cand, s_lo, t0, hb);
+            if (r_hi < ns) warp_select2(KS, nsp >> 2, 0, false, nsp, (unsigned)r_hi, smn, smx, cand, s_hi, t1, hb);
             __syncwarp();
             // one pass: keys below s_lo are counted, keys in [s_lo, s_hi] staged
             const int nv = n >> 2;
