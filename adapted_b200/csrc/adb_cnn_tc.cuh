@@ -35,6 +35,7 @@
 
 #define TC_WORKERS 256                   // 8 worker warps
 #define TC_THREADS (TC_WORKERS + 64)      // + the MMA issuer warp + the tile loader warp (layer 3)
+#define TC_THREADS2 (2 * TC_WORKERS + 64)  // layer 2: 8 warps build the tiles, 8 more drain the accumulators, + issuer (+ idle loader)
 #define TC_ROWS 128                      // output positions per job (one M = 128 tile)
 #define TC_RA (TC_ROWS + 8)              // rows of the activation tile (6 halo rows, rounded to a multiple of 8)
 #define TC_NQ (TC_ROWS + 6)              // rows actually filled
@@ -171,10 +172,11 @@ __host__ __device__ inline size_t cnn_tc_smem_bytes_layer(int layer) {
 // wp  : packed weights of this layer, [7][2][4096] fp16 (cnn_tc_pack_weights_kernel)
 // redo: [N] set to 1 for reads with a value outside the fp16 range (recomputed on the FP32 pipe afterwards)
 template <int LAYER, int CSLOT = -1>  // CSLOT >= 0 (layer 3): transposed-convolution weights from that slot of adb_c_convT
-__global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const void *in, void *out, const __half *wp,
+__global__ void __launch_bounds__(LAYER == 2 ? TC_THREADS2 : TC_THREADS, 1) cnn_conv64_tc_kernel(const void *in, void *out, const __half *wp,
                                                                      const float *bias, const float *w1, const float *b1,
                                                                      int n_reads, int Lx, int L1, int LP, int *redo) {
     constexpr int NBUF = LAYER == 3 ? 3 : 2;
+    constexpr int NWW = LAYER == 2 ? 2 * TC_WORKERS / 32 : TC_WORKERS / 32;  // worker warps (layer 2: builders + drainers)
     const int a0t_rows = LP;                                    // rows per octet of A0T (cnn_tc_a0t_rows)
     const size_t a0t_read_bytes = (size_t)2 * 8 * a0t_rows * 16;
     extern __shared__ __align__(1024) unsigned char tsm[];
@@ -314,7 +316,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const void
         const int t0 = LAYER == 3 ? (job % jobs_per_read) * TC_L3_STRIDE - 1 : (job % jobs_per_read) * TC_ROWS;
         mbar_wait(&accb[tb], phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int q = (warp & 3) * 32 + lane, ch0 = (warp >> 2) * 32;
+        const int q = (warp & 3) * 32 + lane, ch0 = ((warp >> 2) & 1) * 32;  // (layer 2: the drainers are warps 8 .. 15)
         const int p = t0 + q;
         uint32_t v[32];
         if (LAYER == 3) {
@@ -402,7 +404,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const void
         }
     };
 
-    if (warp == TC_WORKERS / 32) {
+    if (warp == NWW) {
         // ---- MMA issuer ----
         if (tc_elect_one()) {
             uint32_t it = 0;
@@ -416,7 +418,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const void
             }
         }
         __syncwarp();
-    } else if (warp == TC_WORKERS / 32 + 1) {
+    } else if (warp == NWW + 1) {
         // ---- tile loader (layer 3): runs up to NBUF tiles ahead; tile it reuses the buffer of tile it - NBUF, whose
         // next release needs the tile loaded here, so the parity wait cannot be overtaken ----
         if (LAYER == 3 && lane == 0) {
@@ -430,29 +432,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_conv64_tc_kernel(const void
         __syncwarp();
     } else {
         // ---- workers ----
-        int job = blockIdx.x;
-        if (LAYER == 2 && job < n_jobs) {
-            prefetch(job);
-            build(job, 0);
-        }
-        int prev_job = -1;
-        uint32_t it = 0;
-        for (; job < n_jobs; job += gridDim.x, it++) {
-            const int b = (int)(it & 1u);
-            const int next = job + (int)gridDim.x;
-            const bool has_next = next < n_jobs;
-            if (LAYER == 2 && has_next) prefetch(next);
-            if (prev_job >= 0) {  // layer 2: also proves tile buffer b^1 is free
-                epilogue(prev_job, b ^ 1, ((it - 1) >> 1) & 1u, b ^ 1);
-                if (LAYER == 2) {  // (layer 3 hands the accumulator back inside its epilogue)
+        if (LAYER == 2) {
+            // Layer 2 splits its workers: warps 0 .. 7 BUILD the operand tiles (x window -> layer 1 -> hi / lo planes),
+            // warps 8 .. 15 DRAIN the accumulators (bias + ReLU + split -> A0T).  Both loops run side by side, so a tile
+            // costs max(build, drain) instead of their sum (the tensor pipe was idle 45 % of the time behind eight
+            // warps doing both).  A tile buffer is rebuilt once the MMAs that read it are complete: the builders wait on
+            // the same accumulator barrier as the drainers (parity waits do not consume it).
+            if (warp < TC_WORKERS / 32) {
+                int job = blockIdx.x;
+                if (job < n_jobs) {
+                    prefetch(job);
+                    build(job, 0);
+                }
+                uint32_t it = 0;
+                for (; job < n_jobs; job += gridDim.x, it++) {
+                    const int b = (int)(it & 1u);
+                    const int next = job + (int)gridDim.x;
+                    if (next < n_jobs) {
+                        prefetch(next);
+                        if (it >= 1) mbar_wait(&accb[b ^ 1], ((it - 1) >> 1) & 1u);  // tile it - 1 (buffer b ^ 1) has been multiplied
+                        build(next, b ^ 1);
+                    }
+                }
+            } else {
+                uint32_t it = 0;
+                for (int job = blockIdx.x; job < n_jobs; job += gridDim.x, it++) {
+                    const int tb = (int)(it & 1u);
+                    epilogue(job, tb, (it >> 1) & 1u, tb);
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accfree[b ^ 1])) : "memory");
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accfree[tb])) : "memory");
                 }
             }
-            if (LAYER == 2 && has_next) build(next, b ^ 1);
-            prev_job = job;
+        } else {
+            int prev_job = -1;
+            uint32_t it = 0;
+            for (int job = blockIdx.x; job < n_jobs; job += gridDim.x, it++) {
+                const int b = (int)(it & 1u);
+                if (prev_job >= 0) epilogue(prev_job, b ^ 1, ((it - 1) >> 1) & 1u, b ^ 1);  // (hands the accumulator back itself)
+                prev_job = job;
+            }
+            if (prev_job >= 0) epilogue(prev_job, (int)((it - 1) & 1u), ((it - 1) >> 1) & 1u, (int)((it - 1) & 1u));
         }
-        if (prev_job >= 0) epilogue(prev_job, (int)((it - 1) & 1u), ((it - 1) >> 1) & 1u, (int)((it - 1) & 1u));
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -476,7 +496,7 @@ static void cnn_tc_launch(int layer, const void *in, void *out, const __half *wp
     const int jobs = n_reads * (layer == 3 ? (L1 + TC_L3_STRIDE - 1) / TC_L3_STRIDE : (L1 + TC_ROWS - 1) / TC_ROWS);
     const int grid = std::max(1, std::min(jobs, sm_count));
     const size_t smem = cnn_tc_smem_bytes_layer(layer);
-    if (layer == 2) cnn_conv64_tc_kernel<2><<<grid, TC_THREADS, smem, st>>>(in, out, wp, bias, w1, b1, n_reads, Lx, L1, LP, redo);
+    if (layer == 2) cnn_conv64_tc_kernel<2><<<grid, TC_THREADS2, smem, st>>>(in, out, wp, bias, w1, b1, n_reads, Lx, L1, LP, redo);
     else if (cslot == 0) cnn_conv64_tc_kernel<3, 0><<<grid, TC_THREADS, smem, st>>>(in, out, wp, bias, w1, b1, n_reads, Lx, L1, LP, redo);
     else if (cslot == 1) cnn_conv64_tc_kernel<3, 1><<<grid, TC_THREADS, smem, st>>>(in, out, wp, bias, w1, b1, n_reads, Lx, L1, LP, redo);
     else if (cslot == 2) cnn_conv64_tc_kernel<3, 2><<<grid, TC_THREADS, smem, st>>>(in, out, wp, bias, w1, b1, n_reads, Lx, L1, LP, redo);
