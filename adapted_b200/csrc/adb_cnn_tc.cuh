@@ -47,9 +47,12 @@
 #define TC_ROUNDS ((TC_ITEMS + TC_WORKERS - 1) / TC_WORKERS)
 // instruction descriptor (cute/arch/mma_sm100_desc.hpp): D = f32 [4,6) = 1, A = B = f16 (0), both K-major,
 // N >> 3 at [17,23), M >> 4 at [24,29)
-#define TC_IDESC ((1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24))
+#define TC_IDESC ((1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24))    // N = 64
+#define TC_IDESC2 ((1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24))  // N = 128: [W_hi | W_lo] side by side
 
-// weights: torch layout w[co][ci][k] -> [layer][tap][hi, lo][ci / 8][co][ci % 8] fp16
+// weights: torch layout w[co][ci][k] -> [layer][tap][ci / 8][hi, lo][co][ci % 8] fp16: per tap and channel octet the 64
+// rows of the hi part are followed by the 64 rows of the lo part, so that ONE N = 128 operand [W_hi | W_lo] serves the
+// products hi * hi and hi * lo of an activation tile (the activation tile is read from shared memory once for both)
 __global__ void cnn_tc_pack_weights_kernel(const float *w, __half *packed) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 2 * CNN_K * 4096) return;
@@ -59,9 +62,9 @@ __global__ void cnn_tc_pack_weights_kernel(const float *w, __half *packed) {
     const int ci = kc * 8 + j;
     const float v = (w + (layer == 0 ? CNN_W2 : CNN_W3))[(co * CNN_C + ci) * CNN_K + k];
     const __half hi = __float2half_rn(v);
-    __half *dst = packed + ((size_t)(layer * CNN_K + k) * 2) * 4096;
-    dst[e] = hi;
-    dst[4096 + e] = __float2half_rn(__fsub_rn(v, __half2float(hi)));
+    __half *dst = packed + ((size_t)(layer * CNN_K + k) * 2) * 4096 + (size_t)kc * 1024 + co * 8 + j;
+    dst[0] = hi;
+    dst[512] = __float2half_rn(__fsub_rn(v, __half2float(hi)));
 }
 
 // SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start >> 4 [0,14), LBO >> 4 [16,30), SBO >> 4 [32,46), version 1
@@ -73,7 +76,7 @@ __device__ __forceinline__ uint32_t tc_desc_lo(uint32_t saddr, uint32_t lbo_byte
 __device__ __forceinline__ uint32_t tc_desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3fffu) | (1u << 14); }
 
 __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                           uint32_t accumulate) {
+                                           uint32_t accumulate, uint32_t idesc = TC_IDESC) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -83,7 +86,7 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint32_t a_lo, uint3
         "setp.ne.b32 p, %6, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
         "}\n" ::"r"(d_tmem),
-        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(TC_IDESC), "r"(accumulate)
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 
@@ -212,7 +215,7 @@ __global__ void __launch_bounds__(LAYER == 2 ? TC_THREADS2 : TC_THREADS, 1) cnn_
     }
     if (tid < CNN_C) Bs[tid] = bias[tid];
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the weights were written with generic stores
@@ -290,22 +293,25 @@ __global__ void __launch_bounds__(LAYER == 2 ? TC_THREADS2 : TC_THREADS, 1) cnn_
         for (int pk = 0; pk < 16; pk++)  // pk = plane * 8 + octet
             tma_bulk_g2s(dst + (size_t)pk * (TC_RA * 16), src + (size_t)pk * ((size_t)a0t_rows * 16), TC_TILE_RUN, &afull[b]);
     };
-    // ---- the 84 MMAs of one tile: 7 taps x 4 K-steps of 16 channels x (hi*hi, lo*hi, hi*lo) ----
-    const uint32_t w_lo0 = tc_desc_lo(smem_u32(Wsm), 64 * 16), w_hi = tc_desc_hi(128);
+    // ---- the 56 MMAs of one tile: 7 taps x 4 K-steps of 16 channels x { A_hi x [W_hi | W_lo] (N = 128), A_lo x W_hi
+    // (N = 64) }.  Columns 0 .. 63 of the accumulator collect hi * hi + lo * hi, columns 64 .. 127 hi * lo (added by the
+    // epilogue).  Three separate N = 64 products read 18 KB of operands from shared memory per tap and K-step -- more
+    // than the SM's shared memory delivers in the 96 cycles the tensor core needs for them (the kernels were bound by
+    // exactly that: tensor pipe 55 - 61 % active); side by side the activation tile is read once for two products: 14 KB.
+    const uint32_t w_lo0 = tc_desc_lo(smem_u32(Wsm), 128 * 16), w_hi = tc_desc_hi(128);
     const uint32_t a_hi_word = tc_desc_hi(128);
     auto issue = [&](int sb, int tb) {
         const uint32_t ah0 = tc_desc_lo(smem_u32(Abuf + (size_t)sb * 2 * TC_PLANE), TC_RA * 16);
         const uint32_t al0 = ah0 + (TC_PLANE >> 4);
-        const uint32_t d = tmem + (uint32_t)(tb * 64);
+        const uint32_t d = tmem + (uint32_t)(tb * 128);
 #pragma unroll
         for (int k = 0; k < CNN_K; k++) {
 #pragma unroll
             for (int kp = 0; kp < 4; kp++) {
                 const uint32_t a_off = (uint32_t)((2 * kp) * TC_RA + k);              // 16-byte units
-                const uint32_t w_off = (uint32_t)(((k * 2) * TC_WPART + 2 * kp * 64 * 16) >> 4);
-                tc_mma_f16(d, ah0 + a_off, a_hi_word, w_lo0 + w_off, w_hi, (k > 0 || kp > 0) ? 1u : 0u);
-                tc_mma_f16(d, al0 + a_off, a_hi_word, w_lo0 + w_off, w_hi, 1u);
-                tc_mma_f16(d, ah0 + a_off, a_hi_word, w_lo0 + w_off + (TC_WPART >> 4), w_hi, 1u);
+                const uint32_t w_off = (uint32_t)(((k * 2) * TC_WPART + 2 * kp * 128 * 16) >> 4);  // (tap, octet 2 kp): hi rows, lo rows
+                tc_mma_f16(d, ah0 + a_off, a_hi_word, w_lo0 + w_off, w_hi, (k > 0 || kp > 0) ? 1u : 0u, TC_IDESC2);
+                tc_mma_f16(d, al0 + a_off, a_hi_word, w_lo0 + w_off, w_hi, 1u, TC_IDESC);
             }
         }
         tc_commit(&accb[tb]);
@@ -321,13 +327,19 @@ __global__ void __launch_bounds__(LAYER == 2 ? TC_THREADS2 : TC_THREADS, 1) cnn_
         uint32_t v[32];
         if (LAYER == 3) {
             const int co = warp >> 2, wq = warp & 3;
-            const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(tb * 64);
+            const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(tb * 128);
             const bool live = p >= 0 && p < L1;   // rows outside the read are zero padding for the transposed convolution
             float P[CNN_K] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             const float4 *wv = reinterpret_cast<const float4 *>(W4s + co * 512);
 #pragma unroll
             for (int hh = 0; hh < 2; hh++) {
                 tc_ld32(taddr + (uint32_t)(hh * 32), v);
+                {   // + the hi * lo products (columns 64 ..)
+                    uint32_t v2[32];
+                    tc_ld32(taddr + (uint32_t)(64 + hh * 32), v2);
+#pragma unroll
+                    for (int c = 0; c < 32; c++) v[c] = __float_as_uint(__fadd_rn(__uint_as_float(v[c]), __uint_as_float(v2[c])));
+                }
                 if (hh == 1) {  // both halves are in registers: hand the accumulator back
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accfree[tb])) : "memory");
@@ -378,8 +390,14 @@ __global__ void __launch_bounds__(LAYER == 2 ? TC_THREADS2 : TC_THREADS, 1) cnn_
             }
         } else {
             // bias + ReLU, split, and straight into layer 3's tile layout (rows >= L1: zeros = its padding)
-            const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(tb * 64 + ch0);
+            const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(tb * 128 + ch0);
             tc_ld32(taddr, v);
+            {   // + the hi * lo products (columns 64 ..)
+                uint32_t v2[32];
+                tc_ld32(taddr + 64u, v2);
+#pragma unroll
+                for (int c = 0; c < 32; c++) v[c] = __float_as_uint(__fadd_rn(__uint_as_float(v[c]), __uint_as_float(v2[c])));
+            }
             unsigned char *base = (unsigned char *)out + (size_t)r * a0t_read_bytes + (size_t)(p + TC_A0T_PAD) * 16;
             bool bad = false;
 #pragma unroll
@@ -476,7 +494,7 @@ __global__ void __launch_bounds__(LAYER == 2 ? TC_THREADS2 : TC_THREADS, 1) cnn_
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
 }
 
 static int cnn_tc_launch_setup() {
