@@ -457,19 +457,21 @@ __global__ void __launch_bounds__(LAYER == 2 ? TC_THREADS2 : TC_THREADS, 1) cnn_
             // warps doing both).  A tile buffer is rebuilt once the MMAs that read it are complete: the builders wait on
             // the same accumulator barrier as the drainers (parity waits do not consume it).
             if (warp < TC_WORKERS / 32) {
+                // (the x window of a tile is loaded into registers a whole tile ahead of the build that consumes it)
                 int job = blockIdx.x;
                 if (job < n_jobs) {
                     prefetch(job);
                     build(job, 0);
+                    if (job + (int)gridDim.x < n_jobs) prefetch(job + (int)gridDim.x);
                 }
                 uint32_t it = 0;
                 for (; job < n_jobs; job += gridDim.x, it++) {
                     const int b = (int)(it & 1u);
                     const int next = job + (int)gridDim.x;
                     if (next < n_jobs) {
-                        prefetch(next);
                         if (it >= 1) mbar_wait(&accb[b ^ 1], ((it - 1) >> 1) & 1u);  // tile it - 1 (buffer b ^ 1) has been multiplied
                         build(next, b ^ 1);
+                        if (next + (int)gridDim.x < n_jobs) prefetch(next + (int)gridDim.x);
                     }
                 }
             } else {
